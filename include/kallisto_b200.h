@@ -1,0 +1,130 @@
+/* kallisto_b200 -- C ABI of the B200-native `kallisto quant` / `kallisto bus` hot path.
+ *
+ * kallisto (the reference, /root/reference) has no plugin or FFI layer: the hot path sits between
+ * its CLI, its index file and its output files.  This header is the boundary a
+ * maintainer would bind to from the reference's own C++: every entry point
+ * names the reference function whose work it takes over.  Plain pointers and sizes only; all
+ * buffers are caller-allocated HOST memory unless the name says `_device`; opaque handles are
+ * freed with the matching `_free`.  Every function returns 0 on success and a negative code on
+ * failure; kb_last_error() then returns a message for the calling thread.  There is no CPU
+ * implementation behind any of these calls: without a CUDA device they fail with KB_ERR_NO_DEVICE.
+ */
+#ifndef KALLISTO_B200_H
+#define KALLISTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_OK 0
+#define KB_ERR_INVALID (-1)   /* bad argument */
+#define KB_ERR_INDEX (-2)     /* unreadable / unsupported index file */
+#define KB_ERR_NO_DEVICE (-3) /* no CUDA device: there is no CPU path */
+#define KB_ERR_CUDA (-4)      /* CUDA runtime or device-side failure */
+#define KB_ERR_IO (-5)        /* file could not be read or written */
+
+typedef struct kb_index kb_index; /* KmerIndex after load(), resident in HBM */
+typedef struct kb_quant kb_quant; /* MinCollector + MasterProcessor state of one run */
+
+const char* kb_last_error(void);
+const char* kb_version(void);
+
+/* ---- index: replaces KmerIndex::load (src/KmerIndex.cpp:1330-1559) ---------------------------
+ * Reads an index file written by the reference `kallisto index` (format v13), flattens the
+ * compacted de Bruijn graph + mosaic equivalence classes and builds the k-mer table on the
+ * device.  load_positions != 0 keeps per-transcript positions (needed only by single-end quant
+ * without --single-overhang, KmerIndex.h:78). */
+int kb_index_load(const char* path, int device, int load_positions, int threads, kb_index** out);
+void kb_index_free(kb_index* ix);
+
+typedef struct kb_index_info {
+  int32_t k;
+  uint32_t n_targets;
+  uint32_t n_unitigs;
+  uint32_t n_ec_blocks;
+  uint32_t n_ec_sets;      /* distinct transcript sets among the blocks */
+  uint64_t n_kmers;        /* "[index] number of k-mers" */
+  uint64_t table_slots;    /* capacity of the device k-mer table (32 B per slot) */
+  double load_seconds;     /* file parse */
+  double build_seconds;    /* device upload + table build */
+} kb_index_info;
+int kb_index_get_info(const kb_index* ix, kb_index_info* info);
+/* target_names_ / target_lens_ (src/KmerIndex.h:136-138) */
+const char* kb_index_target_name(const kb_index* ix, uint32_t i);
+int kb_index_target_lens(const kb_index* ix, uint32_t* lens_out /* n_targets */);
+
+/* ---- a quantification run ------------------------------------------------------------------- */
+typedef struct kb_quant_opts {
+  int32_t paired;            /* 1: reads come as interleaved mate pairs (kallisto quant default); 0: --single */
+  int32_t strand_mode;       /* 0 unstranded, 1 --fr-stranded, 2 --rf-stranded (ProgramOptions::StrandType) */
+  int32_t collect_fld;       /* 1: estimate the fragment-length distribution from the first 10000 unique pairs */
+  uint32_t max_batch_reads;  /* largest batch (reads) that will be submitted; 0 = default (4 Mi) */
+  uint64_t max_batch_bases;  /* largest batch (bases); 0 = default (512 Mi) */
+} kb_quant_opts;
+int kb_quant_create(kb_index* ix, const kb_quant_opts* opts, kb_quant** out);
+void kb_quant_free(kb_quant* q);
+
+/* Replaces ReadProcessor::processBuffer (src/ProcessReads.cpp:968-1237) for one batch of parsed
+ * reads, i.e. per fragment KmerIndex::match x2 (src/KmerIndex.cpp:1698-1940) +
+ * MinCollector::intersectKmers (src/MinCollector.cpp:160-218) + [doStrandSpecificity] + the
+ * ecmapinv lookup / count (ProcessReads.cpp:1148-1161) + KmerIndex::mapPair fragment-length
+ * sampling (1174-1181).
+ *   bases    concatenated ASCII read sequences (as in the reference's `seqs` buffer, without the NULs)
+ *   offsets  n_reads + 1 offsets into bases, or NULL if every read has exactly fixed_len bases
+ *   n_reads  reads in the batch; mates interleaved (r1,r2,r1,r2,...) when the run is paired
+ *   ec_out   optional: one int32 per fragment, an opaque set handle >= 0, or -1 if not pseudoaligned
+ *            (translate with kb_quant_ec_table after the run)
+ * Host buffers; the host->device copy, the kernels and the copy back are all inside the call. */
+int kb_pseudoalign_batch(kb_quant* q, const char* bases, const uint32_t* offsets, uint32_t n_reads,
+                         uint32_t fixed_len, int32_t* ec_out);
+/* Same with DEVICE pointers (inputs already resident in HBM); asynchronous on the run's stream. */
+int kb_pseudoalign_batch_device(kb_quant* q, const void* d_bases, const uint32_t* d_offsets, uint32_t n_reads,
+                                uint32_t fixed_len, uint32_t max_read_len);
+int kb_quant_sync(kb_quant* q);
+
+/* Replaces MasterProcessor::update + the tail flush + MinCollector::increaseCount
+ * (src/ProcessReads.cpp:323-334,424-483; src/MinCollector.cpp:251-269): equivalence classes in
+ * order of first occurrence (the ids the reference assigns with -t 1), their transcript sets and counts. */
+typedef struct kb_run_stats {
+  uint64_t n_processed, n_pseudoaligned, n_unique;
+  uint64_t n_ecs, n_ec_entries;
+  uint64_t n_probes;        /* k-mer table lookups executed (dbg.find equivalents) */
+  uint64_t n_slot_visits;   /* 32-byte slots touched by those lookups */
+  uint64_t n_resolved;      /* fragments finished by the warp-level intersection kernel */
+  uint64_t n_memo_hits;
+} kb_run_stats;
+int kb_quant_finalize(kb_quant* q, kb_run_stats* stats);
+int kb_quant_ec_table(kb_quant* q, uint64_t* ec_offsets /* n_ecs+1 */, uint32_t* tids /* n_ec_entries */,
+                      uint32_t* counts /* n_ecs */, int32_t* handles /* n_ecs, may be NULL */);
+/* tc.flens (fragment-length histogram, 1000 bins) */
+int kb_quant_get_flens(kb_quant* q, uint32_t* flens_out);
+int kb_quant_set_flens(kb_quant* q, const uint32_t* flens_in);
+
+/* Replaces compute_mean_frag_lens_trunc / init_mean_fl_trunc + get_frag_len_means + calc_eff_lens +
+ * calc_weights + EMAlgorithm::run(10000, 50) (src/MinCollector.cpp:629-651, src/weights.cpp,
+ * src/EMAlgorithm.h:95-221).  fld_mean == 0 uses the estimated distribution, otherwise the
+ * truncated Gaussian of -l/-s.  Outputs have n_targets entries. */
+int kb_em_run(kb_quant* q, double fld_mean, double fld_sd, double* est_counts_out, double* eff_lens_out,
+              int32_t* rounds_out, double* seconds_out);
+/* Same, on an explicit EC table (e.g. the table merged across ranks). */
+int kb_em_run_table(kb_quant* q, uint32_t n_ecs, const uint64_t* ec_offsets, const uint32_t* tids,
+                    const uint32_t* counts, double fld_mean, double fld_sd, double* est_counts_out,
+                    double* eff_lens_out, int32_t* rounds_out, double* seconds_out);
+
+/* Replaces the bootstrap loop of main.cpp:2743-2782 (seeds from mt19937_64(seed); per bootstrap
+ * Multinomial::sample + Bootstrap::run_em).  est_counts_out is n_bootstrap x n_targets, row-major;
+ * samples_out (optional) n_bootstrap x n_ecs resampled counts; rounds_out (optional) n_bootstrap. */
+int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed, int32_t n_bootstrap,
+                     double* est_counts_out, uint32_t* samples_out, int32_t* rounds_out);
+
+/* counts_to_tpm (src/PlaintextWriter.cpp:5-27) -- host arithmetic, here so that callers format
+ * identical numbers. */
+int kb_counts_to_tpm(const double* est_counts, const double* eff_lens, uint32_t n, double* tpm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KALLISTO_B200_H */

@@ -1,0 +1,235 @@
+// extern "C" boundary: include/kallisto_b200.h implemented on top of kb::Index / kb::Quant.
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "../../include/kallisto_b200.h"
+#include "engine.hpp"
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+template <class F> int guarded(F&& f) {
+  try {
+    f();
+    return KB_OK;
+  } catch (const kb::Error& e) {
+    const std::string m = e.what();
+    int code = KB_ERR_CUDA;
+    if (m.find("no CUDA device") != std::string::npos) code = KB_ERR_NO_DEVICE;
+    return fail(code, m);
+  } catch (const std::bad_alloc&) {
+    return fail(KB_ERR_CUDA, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(KB_ERR_INDEX, e.what());
+  }
+}
+}  // namespace
+
+struct kb_index {
+  std::unique_ptr<kb::Index> ix;
+};
+struct kb_quant {
+  std::unique_ptr<kb::Quant> q;
+  kb_index* owner;
+};
+
+extern "C" {
+
+const char* kb_last_error(void) { return g_err.c_str(); }
+const char* kb_version(void) { return "kallisto_b200 0.1.0 (reference: kallisto 0.51.1, index format 13)"; }
+
+int kb_index_load(const char* path, int device, int load_positions, int threads, kb_index** out) {
+  if (!path || !out) return fail(KB_ERR_INVALID, "kb_index_load: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    auto ix = kb::Index::load(path, device, load_positions != 0, threads > 0 ? threads : 1);
+    kb_index* h = new kb_index();
+    h->ix = std::move(ix);
+    *out = h;
+  });
+}
+
+void kb_index_free(kb_index* ix) { delete ix; }
+
+int kb_index_get_info(const kb_index* ix, kb_index_info* info) {
+  if (!ix || !info) return fail(KB_ERR_INVALID, "kb_index_get_info: null argument");
+  const kb::FlatIndex& f = ix->ix->flat;
+  info->k = f.k;
+  info->n_targets = f.num_targets();
+  info->n_unitigs = f.n_unitigs();
+  info->n_ec_blocks = (uint32_t)f.blk_lb.size();
+  info->n_ec_sets = f.n_ec();
+  info->n_kmers = f.n_kmers;
+  info->table_slots = ix->ix->table_cap;
+  info->load_seconds = ix->ix->load_seconds;
+  info->build_seconds = ix->ix->build_seconds;
+  return KB_OK;
+}
+
+const char* kb_index_target_name(const kb_index* ix, uint32_t i) {
+  if (!ix || i >= ix->ix->flat.num_targets()) return nullptr;
+  return ix->ix->flat.target_name[i].c_str();
+}
+
+int kb_index_target_lens(const kb_index* ix, uint32_t* lens_out) {
+  if (!ix || !lens_out) return fail(KB_ERR_INVALID, "kb_index_target_lens: null argument");
+  const auto& v = ix->ix->flat.target_len;
+  memcpy(lens_out, v.data(), v.size() * sizeof(uint32_t));
+  return KB_OK;
+}
+
+int kb_quant_create(kb_index* ix, const kb_quant_opts* opts, kb_quant** out) {
+  if (!ix || !out) return fail(KB_ERR_INVALID, "kb_quant_create: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    kb::QuantOptions o;
+    if (opts) {
+      o.paired = opts->paired;
+      o.strand_mode = opts->strand_mode;
+      o.collect_fld = opts->collect_fld;
+      if (opts->max_batch_reads) o.max_batch_reads = opts->max_batch_reads;
+      if (opts->max_batch_bases) o.max_batch_bases = opts->max_batch_bases;
+    }
+    if (o.strand_mode < 0 || o.strand_mode > 2) throw std::invalid_argument("kb_quant_create: bad strand_mode");
+    kb_quant* h = new kb_quant();
+    h->owner = ix;
+    h->q.reset(new kb::Quant(*ix->ix, o));
+    *out = h;
+  });
+}
+
+void kb_quant_free(kb_quant* q) { delete q; }
+
+int kb_pseudoalign_batch(kb_quant* q, const char* bases, const uint32_t* offsets, uint32_t n_reads,
+                         uint32_t fixed_len, int32_t* ec_out) {
+  if (!q || (!bases && n_reads)) return fail(KB_ERR_INVALID, "kb_pseudoalign_batch: null argument");
+  if (!offsets && fixed_len == 0 && n_reads) return fail(KB_ERR_INVALID, "kb_pseudoalign_batch: need offsets or fixed_len");
+  return guarded([&] { q->q->pseudoalign_host(bases, offsets, n_reads, fixed_len, ec_out); });
+}
+
+int kb_pseudoalign_batch_device(kb_quant* q, const void* d_bases, const uint32_t* d_offsets, uint32_t n_reads,
+                                uint32_t fixed_len, uint32_t max_read_len) {
+  if (!q || (!d_bases && n_reads)) return fail(KB_ERR_INVALID, "kb_pseudoalign_batch_device: null argument");
+  return guarded([&] {
+    q->q->pseudoalign_device((const uint8_t*)d_bases, d_offsets, n_reads, fixed_len,
+                             d_offsets ? max_read_len : fixed_len);
+  });
+}
+
+int kb_quant_sync(kb_quant* q) {
+  if (!q) return fail(KB_ERR_INVALID, "kb_quant_sync: null argument");
+  return guarded([&] { q->q->sync(); });
+}
+
+int kb_quant_finalize(kb_quant* q, kb_run_stats* stats) {
+  if (!q) return fail(KB_ERR_INVALID, "kb_quant_finalize: null argument");
+  return guarded([&] {
+    const kb::EcTable& e = q->q->finalize_ecs();
+    if (stats) {
+      const kb::Stats s = q->q->stats();
+      stats->n_processed = s.n_processed;
+      stats->n_pseudoaligned = s.n_pseudoaligned;
+      stats->n_unique = s.n_unique;
+      stats->n_ecs = e.n();
+      stats->n_ec_entries = e.tid.size();
+      stats->n_probes = s.n_probes;
+      stats->n_slot_visits = s.n_slot_visits;
+      stats->n_resolved = s.n_resolved;
+      stats->n_memo_hits = s.n_memo_hits;
+    }
+  });
+}
+
+int kb_quant_ec_table(kb_quant* q, uint64_t* ec_offsets, uint32_t* tids, uint32_t* counts, int32_t* handles) {
+  if (!q || !ec_offsets || !tids || !counts) return fail(KB_ERR_INVALID, "kb_quant_ec_table: null argument");
+  return guarded([&] {
+    const kb::EcTable& e = q->q->finalize_ecs();
+    memcpy(ec_offsets, e.off.data(), e.off.size() * sizeof(uint64_t));
+    memcpy(tids, e.tid.data(), e.tid.size() * sizeof(uint32_t));
+    memcpy(counts, e.count.data(), e.count.size() * sizeof(uint32_t));
+    if (handles) memcpy(handles, e.handle.data(), e.handle.size() * sizeof(int32_t));
+  });
+}
+
+int kb_quant_get_flens(kb_quant* q, uint32_t* flens_out) {
+  if (!q || !flens_out) return fail(KB_ERR_INVALID, "kb_quant_get_flens: null argument");
+  memcpy(flens_out, q->q->flens().data(), 1000 * sizeof(uint32_t));
+  return KB_OK;
+}
+
+int kb_quant_set_flens(kb_quant* q, const uint32_t* flens_in) {
+  if (!q || !flens_in) return fail(KB_ERR_INVALID, "kb_quant_set_flens: null argument");
+  q->q->set_flens(flens_in);
+  return KB_OK;
+}
+
+static void em_common(kb_quant* q, const kb::EcTable& ecs, double fld_mean, double fld_sd, double* est, double* eff,
+                      int32_t* rounds, double* seconds) {
+  const auto fl = q->q->mean_fl_trunc(fld_mean, fld_sd);
+  kb::EmResult r = q->q->run_em(ecs, fl);
+  if (est) memcpy(est, r.alpha.data(), r.alpha.size() * sizeof(double));
+  if (eff) memcpy(eff, r.eff_lens.data(), r.eff_lens.size() * sizeof(double));
+  if (rounds) *rounds = r.rounds;
+  if (seconds) *seconds = r.seconds;
+}
+
+int kb_em_run(kb_quant* q, double fld_mean, double fld_sd, double* est_counts_out, double* eff_lens_out,
+              int32_t* rounds_out, double* seconds_out) {
+  if (!q) return fail(KB_ERR_INVALID, "kb_em_run: null argument");
+  return guarded([&] {
+    em_common(q, q->q->finalize_ecs(), fld_mean, fld_sd, est_counts_out, eff_lens_out, rounds_out, seconds_out);
+  });
+}
+
+int kb_em_run_table(kb_quant* q, uint32_t n_ecs, const uint64_t* ec_offsets, const uint32_t* tids,
+                    const uint32_t* counts, double fld_mean, double fld_sd, double* est_counts_out,
+                    double* eff_lens_out, int32_t* rounds_out, double* seconds_out) {
+  if (!q || !ec_offsets || (!tids && n_ecs) || (!counts && n_ecs))
+    return fail(KB_ERR_INVALID, "kb_em_run_table: null argument");
+  return guarded([&] {
+    kb::EcTable t;
+    t.off.assign(ec_offsets, ec_offsets + n_ecs + 1);
+    t.tid.assign(tids, tids + ec_offsets[n_ecs]);
+    t.count.assign(counts, counts + n_ecs);
+    const uint32_t T = q->q->index().flat.num_targets();
+    for (uint32_t v : t.tid)
+      if (v >= T) throw std::invalid_argument("kb_em_run_table: transcript id out of range");
+    em_common(q, t, fld_mean, fld_sd, est_counts_out, eff_lens_out, rounds_out, seconds_out);
+  });
+}
+
+int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed, int32_t n_bootstrap,
+                     double* est_counts_out, uint32_t* samples_out, int32_t* rounds_out) {
+  if (!q || !est_counts_out || n_bootstrap < 0) return fail(KB_ERR_INVALID, "kb_bootstrap_run: bad argument");
+  return guarded([&] {
+    const kb::EcTable& ecs = q->q->finalize_ecs();
+    const auto fl = q->q->mean_fl_trunc(fld_mean, fld_sd);
+    std::vector<double> alpha;
+    std::vector<uint32_t> samples;
+    std::vector<int> rounds = q->q->run_bootstrap(ecs, fl, seed, n_bootstrap, alpha, samples_out ? &samples : nullptr);
+    memcpy(est_counts_out, alpha.data(), alpha.size() * sizeof(double));
+    if (samples_out) memcpy(samples_out, samples.data(), samples.size() * sizeof(uint32_t));
+    if (rounds_out)
+      for (int b = 0; b < n_bootstrap; ++b) rounds_out[b] = rounds[b];
+  });
+}
+
+int kb_counts_to_tpm(const double* est_counts, const double* eff_lens, uint32_t n, double* tpm_out) {
+  if (!est_counts || !eff_lens || !tpm_out) return fail(KB_ERR_INVALID, "kb_counts_to_tpm: null argument");
+  const double MILLION = 1e6;
+  double total_mass = 0.0;
+  for (uint32_t i = 0; i < n; ++i) {
+    tpm_out[i] = est_counts[i] / eff_lens[i];
+    total_mass += tpm_out[i];
+  }
+  for (uint32_t i = 0; i < n; ++i) tpm_out[i] = (tpm_out[i] / total_mass) * MILLION;
+  return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,658 @@
+// Host-side engine: see engine.hpp.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <random>
+
+namespace kb {
+
+namespace {
+
+inline void ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw Error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+#define KB_CK(x) ck((x), #x)
+
+inline uint64_t pow2_ge(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+template <class T> void DBuf<T>::alloc(size_t count) {
+  release();
+  n = count;
+  if (count) KB_CK(cudaMalloc((void**)&p, count * sizeof(T)));
+}
+template <class T> void DBuf<T>::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  n = 0;
+}
+template <class T> void DBuf<T>::upload(const T* src, size_t count, cudaStream_t st) {
+  if (count > n) alloc(count);
+  if (count) KB_CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+template <class T> void DBuf<T>::download(T* dst, size_t count, size_t offset, cudaStream_t st) const {
+  if (count) KB_CK(cudaMemcpyAsync(dst, p + offset, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+}
+template <class T> void DBuf<T>::zero(cudaStream_t st) {
+  if (n) KB_CK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
+}
+
+// ------------------------------------------------------------------------------------------
+// Index
+// ------------------------------------------------------------------------------------------
+Index::~Index() {}
+
+std::unique_ptr<Index> Index::load(const std::string& path, int device, bool load_positions, int threads) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw Error("kallisto_b200: no CUDA device available (this build has no CPU path)");
+  if (device < 0 || device >= ndev) throw Error("kallisto_b200: invalid CUDA device ordinal");
+  KB_CK(cudaSetDevice(device));
+
+  std::unique_ptr<Index> ix(new Index());
+  ix->device = device;
+  const double t0 = now_s();
+  load_index_v13(path, ix->flat, load_positions, threads);
+  const double t1 = now_s();
+  ix->load_seconds = t1 - t0;
+  FlatIndex& f = ix->flat;
+  if (f.dlist_n != 0)
+    throw Error("kallisto_b200: indices with a D-list (distinguishing flanking k-mers) are not supported yet");
+  if (f.onlist.size() != f.target_len.size())
+    throw Error("kallisto_b200: indices whose on-list does not cover every target are not supported yet");
+  if (f.ec_tid.size() >= 0xFFFFFFFFull) throw Error("kallisto_b200: index EC sets exceed 2^32 entries");
+  if (f.num_targets() >= (1u << 24)) throw Error("kallisto_b200: more than 2^24 targets are not supported");
+
+  const uint32_t nU = f.n_unitigs();
+  std::vector<uint64_t> kstart(nU + 1, 0);
+  for (uint32_t u = 0; u < nU; ++u) kstart[u + 1] = kstart[u] + (f.ulen[u] - f.k + 1);
+  if (kstart[nU] != f.n_kmers) throw Error("kallisto_b200: k-mer count mismatch");
+
+  cudaStream_t st = 0;
+  // permanent arrays
+  std::vector<uint32_t> ec_off32(f.ec_off.size());
+  for (size_t i = 0; i < f.ec_off.size(); ++i) ec_off32[i] = (uint32_t)f.ec_off[i];
+  ix->ec_off.upload(ec_off32.data(), ec_off32.size(), st);
+  ix->n_index_tids = (uint32_t)f.ec_tid.size();
+  ix->index_pool.alloc(std::max<size_t>(1, f.ec_tid.size()));
+  ix->index_pool.upload(f.ec_tid.data(), f.ec_tid.size(), st);
+  ix->blk_ec.upload(f.blk_ec.data(), f.blk_ec.size(), st);
+  ix->blk_strand_off.upload(f.blk_strand_off.data(), f.blk_strand_off.size(), st);
+  ix->strand.alloc(std::max<size_t>(1, f.strand.size()));
+  ix->strand.upload(f.strand.data(), f.strand.size(), st);
+  for (uint32_t e = 0; e < f.n_ec(); ++e) {
+    const uint32_t len = (uint32_t)(f.ec_off[e + 1] - f.ec_off[e]);
+    if (len == 0) ix->empty_ec = e;
+    ix->max_set_len = std::max(ix->max_set_len, len);
+  }
+
+  // k-mer table: load factor <= 0.5
+  ix->table_cap = pow2_ge(std::max<uint64_t>(1024, f.n_kmers * 2));
+  ix->slots.alloc(ix->table_cap);
+  DBuf<int> err;
+  err.alloc(1);
+  err.zero(st);
+  {
+    DBuf<uint8_t> d_useq;
+    DBuf<uint64_t> d_byteoff, d_skmer, d_kstart, d_blkoff;
+    DBuf<uint32_t> d_lb, d_ub;
+    d_useq.upload(f.useq.data(), f.useq.size(), st);
+    d_byteoff.upload(f.useq_byteoff.data(), f.useq_byteoff.size(), st);
+    d_skmer.alloc(std::max<size_t>(1, f.skmer.size()));
+    d_skmer.upload(f.skmer.data(), f.skmer.size(), st);
+    d_kstart.upload(kstart.data(), kstart.size(), st);
+    d_blkoff.upload(f.blk_off.data(), f.blk_off.size(), st);
+    d_lb.upload(f.blk_lb.data(), f.blk_lb.size(), st);
+    d_ub.upload(f.blk_ub.data(), f.blk_ub.size(), st);
+    TableBuildArgs a{};
+    a.useq = d_useq.p; a.useq_byteoff = d_byteoff.p; a.skmer = d_skmer.p; a.kstart = d_kstart.p;
+    a.blk_off = d_blkoff.p; a.blk_lb = d_lb.p; a.blk_ub = d_ub.p; a.blk_ec = ix->blk_ec.p;
+    a.n_long = f.n_long; a.n_unitigs = nU; a.k = f.k; a.n_kmers = f.n_kmers;
+    a.slots = ix->slots.p; a.mask = ix->table_cap - 1; a.error = err.p;
+    launch_build_table(a, st);
+    KB_CK(cudaGetLastError());
+    KB_CK(cudaStreamSynchronize(st));
+  }
+  // set dictionary, initial state: the index's own EC sets
+  ix->dict_cap = pow2_ge((uint64_t)f.n_ec() * 4 + (1u << 20));
+  ix->dslots_init.alloc(ix->dict_cap);
+  launch_fill_u64(ix->dslots_init.p, ix->dict_cap, ~0ULL, st);
+  ix->ec_handle.alloc(std::max<uint32_t>(1, f.n_ec()));
+  {
+    DictInitArgs a{};
+    a.ec_off = ix->ec_off.p; a.pool = ix->index_pool.p; a.n_ec = f.n_ec();
+    a.dslots = ix->dslots_init.p; a.dmask = ix->dict_cap - 1; a.ec_handle = ix->ec_handle.p;
+    launch_dict_init(a, st);
+    KB_CK(cudaGetLastError());
+  }
+  int herr = 0;
+  err.download(&herr, 1, 0, st);
+  KB_CK(cudaStreamSynchronize(st));
+  if (herr & KB_DEVERR_TABLE_DUP) throw Error("kallisto_b200: corrupt index (a k-mer occurs in two unitigs)");
+
+  DevIndex& d = ix->dev;
+  d.slots = ix->slots.p;
+  d.mask = ix->table_cap - 1;
+  d.k = f.k;
+  d.n_ec = f.n_ec();
+  d.n_targets = f.num_targets();
+  d.ec_off = ix->ec_off.p;
+  d.ec_handle = ix->ec_handle.p;
+  d.blk_ec = ix->blk_ec.p;
+  d.blk_strand_off = ix->blk_strand_off.p;
+  d.strand = ix->strand.p;
+  ix->build_seconds = now_s() - t1;
+  return ix;
+}
+
+// ------------------------------------------------------------------------------------------
+// Quant
+// ------------------------------------------------------------------------------------------
+Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(1000, 0) {
+  KB_CK(cudaSetDevice(ix_.device));
+  KB_CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  cudaStream_t st = stream_;
+  const uint64_t nE = ix_.flat.n_ec();
+  // pools and tables of this run
+  const uint64_t pool_cap =
+      std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)ix_.n_index_tids + std::max<uint64_t>(1u << 24, 4ull * ix_.n_index_tids));
+  pool_.alloc(pool_cap);
+  KB_CK(cudaMemcpyAsync(pool_.p, ix_.index_pool.p, (size_t)ix_.n_index_tids * 4, cudaMemcpyDeviceToDevice, st));
+  dslots_.alloc(ix_.dict_cap);
+  KB_CK(cudaMemcpyAsync(dslots_.p, ix_.dslots_init.p, ix_.dict_cap * 8, cudaMemcpyDeviceToDevice, st));
+  count_.alloc(ix_.dict_cap);
+  count_.zero(st);
+  first_.alloc(ix_.dict_cap);
+  launch_fill_u64(first_.p, ix_.dict_cap, ~0ULL, st);
+  const uint64_t m2_cap = pow2_ge(nE * 8 + (1u << 20));
+  const uint64_t mn_cap = pow2_ge(nE * 4 + (1u << 20));
+  m2_key_.alloc(m2_cap);
+  launch_fill_u64(m2_key_.p, m2_cap, ~0ULL, st);
+  m2_val_.alloc(m2_cap);
+  launch_fill_i32(m2_val_.p, m2_cap, KB_H_NOTREADY, st);
+  mn_key_.alloc(mn_cap);
+  launch_fill_u64(mn_key_.p, mn_cap, ~0ULL, st);
+  mn_val_.alloc(mn_cap);
+  launch_fill_i32(mn_val_.p, mn_cap, KB_H_NOTREADY, st);
+  const uint64_t tpool_cap = mn_cap * 8;
+  tpool_.alloc(tpool_cap);
+  counters_.alloc(8);
+  {
+    unsigned long long init[8] = {ix_.n_index_tids, 0, 0, 0, 0, 0, 0, 0};
+    KB_CK(cudaMemcpyAsync(counters_.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    KB_CK(cudaStreamSynchronize(st));   // init is a stack array
+  }
+  error_.alloc(1);
+  error_.zero(st);
+
+  dd_.pool = pool_.p; dd_.pool_top = counters_.p + 0; dd_.pool_cap = pool_cap;
+  dd_.dslots = dslots_.p; dd_.dmask = ix_.dict_cap - 1;
+  dd_.count = count_.p; dd_.first = first_.p;
+  dd_.m2_key = m2_key_.p; dd_.m2_val = m2_val_.p; dd_.m2_mask = m2_cap - 1;
+  dd_.mn_key = mn_key_.p; dd_.mn_val = mn_val_.p; dd_.mn_mask = mn_cap - 1;
+  dd_.tpool = tpool_.p; dd_.tpool_top = counters_.p + 1; dd_.tpool_cap = tpool_cap;
+  dd_.error = error_.p; dd_.stats = counters_.p + 2;
+
+  // batch staging
+  const uint32_t max_frag = opt_.max_batch_reads;
+  d_handles_.alloc(max_frag);
+  d_tl_.alloc(max_frag);
+  d_qcount_.alloc(1);
+  d_qentries_.alloc((size_t)max_frag * KB_Q_STRIDE);
+  // resolve-kernel scratch: 2 x max_set_len words per warp, at most ~1 GiB in total
+  const uint64_t stride = std::max<uint64_t>(64, 2ull * ix_.max_set_len);
+  uint64_t warps = (1ull << 28) / stride;
+  warps = std::min<uint64_t>(148 * 16, std::max<uint64_t>(64, warps));
+  n_resolve_warps_ = (uint32_t)(warps / 4 * 4);
+  d_scratch_.alloc((size_t)n_resolve_warps_ * stride);
+  KB_CK(cudaStreamSynchronize(st));
+}
+
+Quant::~Quant() {
+  if (h_off_pinned_) cudaFreeHost(h_off_pinned_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Quant::sync() { KB_CK(cudaStreamSynchronize(stream_)); }
+
+void Quant::check_device_errors() {
+  int herr = 0;
+  error_.download(&herr, 1, 0, stream_);
+  KB_CK(cudaStreamSynchronize(stream_));
+  if (herr == 0) return;
+  std::string m = "kallisto_b200: device-side failure:";
+  if (herr & KB_DEVERR_POOL_FULL) m += " set pool exhausted;";
+  if (herr & KB_DEVERR_DICT_FULL) m += " set dictionary full;";
+  if (herr & KB_DEVERR_MEMO_FULL) m += " memo table full;";
+  if (herr & KB_DEVERR_TPOOL_FULL) m += " tuple pool exhausted;";
+  if (herr & KB_DEVERR_E_OVERFLOW) m += " a fragment hit more than 16 distinct EC sets;";
+  throw Error(m);
+}
+
+void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
+                      uint32_t max_read_len) {
+  const uint32_t n_frag = opt_.paired ? n_reads / 2 : n_reads;
+  if (opt_.paired && (n_reads & 1)) throw Error("kallisto_b200: odd number of reads in a paired batch");
+  if (n_frag > d_handles_.n) throw Error("kallisto_b200: batch larger than max_batch_reads");
+  if (n_frag == 0) return;
+  ecs_valid_ = false;
+  BatchArgs ba{};
+  ba.bases = d_bases;
+  ba.off = d_off;
+  ba.fixed_len = fixed_len;
+  ba.n_frag = n_frag;
+  ba.paired = opt_.paired;
+  ba.strand_mode = opt_.strand_mode;
+  ba.frag_base = n_frag_total_;
+  ba.handle_out = d_handles_.p;
+  const bool want_fld = opt_.paired && opt_.collect_fld && tlencount_ < 10000;   // ProcessReads.cpp:981-1017
+  ba.tl_out = want_fld ? d_tl_.p : nullptr;
+  ba.q_count = d_qcount_.p;
+  ba.q_entries = d_qentries_.p;
+  ba.bwords = (max_read_len + 31) / 32 + 1;
+  ba.iwords = ba.bwords / 2 + 1;
+  ba.empty_ec = ix_.empty_ec;
+  ResolveArgs ra{};
+  ra.scratch = d_scratch_.p;
+  ra.scratch_stride = (uint32_t)(d_scratch_.n / n_resolve_warps_);
+  ra.n_warps = n_resolve_warps_;
+
+  int tpb = opt_.threads_per_block;
+  const size_t per_thread = (size_t)(ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 2) * 4;
+  while (tpb > 32 && per_thread * tpb > 48 * 1024) tpb >>= 1;
+  if (per_thread * tpb > 48 * 1024) throw Error("kallisto_b200: read too long for the short-read kernel");
+  launch_pseudoalign(ix_.dev, dd_, ba, ra, tpb, stream_);
+  KB_CK(cudaGetLastError());
+  if (want_fld) {
+    launch_fld_finalize(dd_, ba, stream_);
+    h_tl_.resize(n_frag);
+    d_tl_.download(h_tl_.data(), n_frag, 0, stream_);
+    KB_CK(cudaStreamSynchronize(stream_));
+    // first (10000 - tlencount) qualifying fragments of this batch, in read order
+    int goal = 10000 - (int)tlencount_;
+    uint32_t local = 0;
+    for (uint32_t i = 0; i < n_frag && goal > 0; ++i) {
+      const uint16_t tl = h_tl_[i];
+      if (tl > 0) { ++flens_[tl]; --goal; ++local; }
+    }
+    tlencount_ += local;
+  }
+  n_frag_total_ += n_frag;
+}
+
+void Quant::pseudoalign_device(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
+                               uint32_t max_read_len) {
+  KB_CK(cudaSetDevice(ix_.device));
+  run_batch(d_bases, d_off, n_reads, fixed_len, max_read_len);
+}
+
+void Quant::pseudoalign_host(const char* bases, const uint32_t* off, uint32_t n_reads, uint32_t fixed_len,
+                             int32_t* handles_out) {
+  KB_CK(cudaSetDevice(ix_.device));
+  if (n_reads == 0) return;
+  uint64_t n_bases;
+  uint32_t maxlen = fixed_len;
+  if (off) {
+    n_bases = off[n_reads];
+    maxlen = 0;
+    for (uint32_t i = 0; i < n_reads; ++i) maxlen = std::max(maxlen, off[i + 1] - off[i]);
+    if (off[0] != 0) throw Error("kallisto_b200: offsets must start at 0");
+  } else {
+    n_bases = (uint64_t)n_reads * fixed_len;
+  }
+  if (d_bases_.n < n_bases + 16) d_bases_.alloc(std::max<uint64_t>(n_bases + 16, opt_.max_batch_bases));
+  KB_CK(cudaMemcpyAsync(d_bases_.p, bases, n_bases, cudaMemcpyHostToDevice, stream_));
+  if (off) {
+    if (d_off_.n < (size_t)n_reads + 1) d_off_.alloc(std::max<size_t>((size_t)n_reads + 1, (size_t)opt_.max_batch_reads * 2 + 1));
+    KB_CK(cudaMemcpyAsync(d_off_.p, off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, stream_));
+  }
+  run_batch(d_bases_.p, off ? d_off_.p : nullptr, n_reads, fixed_len, maxlen);
+  if (handles_out) {
+    const uint32_t n_frag = opt_.paired ? n_reads / 2 : n_reads;
+    d_handles_.download(handles_out, n_frag, 0, stream_);
+  }
+  KB_CK(cudaStreamSynchronize(stream_));
+}
+
+void Quant::set_flens(const uint32_t* f) { flens_.assign(f, f + 1000); }
+
+namespace {
+__global__ void gather_used_kernel(DevDict dd, const uint32_t* used, uint32_t n, uint32_t* cnt, unsigned long long* first,
+                                   unsigned long long* word) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t h = used[i];
+  cnt[i] = dd.count[h];
+  first[i] = dd.first[h];
+  word[i] = dd.dslots[h];
+}
+}  // namespace
+
+const EcTable& Quant::finalize_ecs() {
+  if (ecs_valid_) return ecs_;
+  KB_CK(cudaSetDevice(ix_.device));
+  check_device_errors();
+  DBuf<uint32_t> d_used, d_n, d_cnt;
+  DBuf<unsigned long long> d_first, d_word;
+  d_used.alloc(ix_.dict_cap);
+  d_n.alloc(1);
+  launch_collect_used(dd_, d_used.p, d_n.p, stream_);
+  uint32_t n_used = 0;
+  d_n.download(&n_used, 1, 0, stream_);
+  unsigned long long pool_top = 0;
+  KB_CK(cudaMemcpyAsync(&pool_top, dd_.pool_top, 8, cudaMemcpyDeviceToHost, stream_));
+  KB_CK(cudaStreamSynchronize(stream_));
+  std::vector<uint32_t> used(n_used), cnt(n_used);
+  std::vector<unsigned long long> first(n_used), word(n_used);
+  if (n_used) {
+    d_cnt.alloc(n_used);
+    d_first.alloc(n_used);
+    d_word.alloc(n_used);
+    gather_used_kernel<<<(n_used + 255) / 256, 256, 0, stream_>>>(dd_, d_used.p, n_used, d_cnt.p, d_first.p, d_word.p);
+    d_used.download(used.data(), n_used, 0, stream_);
+    d_cnt.download(cnt.data(), n_used, 0, stream_);
+    d_first.download(first.data(), n_used, 0, stream_);
+    d_word.download(word.data(), n_used, 0, stream_);
+  }
+  // sets discovered at run time
+  std::vector<uint32_t> dyn;
+  if (pool_top > ix_.n_index_tids) {
+    dyn.resize(pool_top - ix_.n_index_tids);
+    pool_.download(dyn.data(), dyn.size(), ix_.n_index_tids, stream_);
+  }
+  KB_CK(cudaStreamSynchronize(stream_));
+  std::vector<uint32_t> order(n_used);
+  std::iota(order.begin(), order.end(), 0u);
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return first[a] < first[b]; });
+  ecs_ = EcTable();
+  ecs_.off.reserve(n_used + 1);
+  ecs_.off.push_back(0);
+  for (uint32_t oi = 0; oi < n_used; ++oi) {
+    const uint32_t i = order[oi];
+    const uint32_t off = (uint32_t)word[i];
+    const uint32_t len = (uint32_t)((word[i] >> 32) & 0xFFFFFFu);
+    const uint32_t* src = off < ix_.n_index_tids ? ix_.flat.ec_tid.data() + off : dyn.data() + (off - ix_.n_index_tids);
+    ecs_.tid.insert(ecs_.tid.end(), src, src + len);
+    ecs_.off.push_back(ecs_.tid.size());
+    ecs_.count.push_back(cnt[i]);
+    ecs_.handle.push_back((int32_t)used[i]);
+  }
+  ecs_valid_ = true;
+  return ecs_;
+}
+
+Stats Quant::stats() {
+  const EcTable& e = finalize_ecs();
+  Stats s;
+  s.n_processed = n_frag_total_;
+  for (uint32_t i = 0; i < e.n(); ++i) {
+    s.n_pseudoaligned += e.count[i];
+    if (e.off[i + 1] - e.off[i] == 1) s.n_unique += e.count[i];
+  }
+  unsigned long long st[4];
+  KB_CK(cudaMemcpy(st, dd_.stats, sizeof(st), cudaMemcpyDeviceToHost));
+  s.n_probes = st[0];
+  s.n_resolved = st[1];
+  s.n_memo_hits = st[2];
+  s.n_slot_visits = st[3];
+  return s;
+}
+
+// MinCollector::compute_mean_frag_lens_trunc (src/MinCollector.cpp:629-651) when fld_mean == 0,
+// MinCollector::init_mean_fl_trunc + trunc_gaussian_fld (src/MinCollector.cpp:583-627,
+// src/weights.cpp:248-296) otherwise.
+std::vector<double> Quant::mean_fl_trunc(double fld_mean, double fld_sd) const {
+  const int MAXF = 1000;
+  std::vector<double> out(MAXF, 0.0);
+  if (fld_mean == 0.0) {
+    std::vector<int> counts(MAXF, 0);
+    std::vector<double> mass(MAXF, 0.0);
+    counts[0] = (int)flens_[0];
+    for (size_t i = 1; i < (size_t)MAXF; ++i) {
+      mass[i] = static_cast<double>(flens_[i] * i) + mass[i - 1];
+      counts[i] = (int)flens_[i] + counts[i - 1];
+      if (counts[i] > 0) out[i] = mass[i] / static_cast<double>(counts[i]);
+    }
+  } else {
+    // trunc_gaussian_fld(0, MAX_FRAG_LEN, mean, sd), src/weights.cpp:248-271
+    std::vector<double> mean_fl(MAXF, 0.0);
+    double total_mass = 0.0, total_density = 0.0;
+    for (size_t i = 0; i < (size_t)MAXF; ++i) {
+      double x = static_cast<double>(0 + i);
+      x = (x - fld_mean) / fld_sd;
+      const double cur_density = std::exp(-0.5 * x * x) / fld_sd;
+      total_mass += cur_density * i;
+      total_density += cur_density;
+      if (total_mass > 0) mean_fl[i] = total_mass / total_density;
+    }
+    out = mean_fl;
+  }
+  return out;
+}
+
+namespace {
+struct EmHost {
+  std::vector<uint32_t> multi_ec, m_off, m_tid, t_off, t_midx;
+  std::vector<double> m_w, t_w, eff;
+  std::vector<int32_t> t_single;
+};
+
+// get_frag_len_means + calc_eff_lens + calc_weights (src/weights.cpp:7-28,58-79,220-246)
+void em_setup(const FlatIndex& f, const EcTable& ecs, const std::vector<double>& fl_trunc, EmHost& h) {
+  const uint32_t T = f.num_targets();
+  h.eff.resize(T);
+  const double marginal = fl_trunc[999];
+  for (uint32_t t = 0; t < T; ++t) {
+    const double mean = f.target_len[t] >= 1000 ? marginal : fl_trunc[f.target_len[t]];
+    const double len = static_cast<double>(f.target_len[t]);
+    double e = len - mean + 1;
+    if (e < 1.0) e = len;
+    h.eff[t] = e;
+  }
+  h.t_single.assign(T, -1);
+  h.m_off.push_back(0);
+  std::vector<uint32_t> deg(T + 1, 0);
+  for (uint32_t e = 0; e < ecs.n(); ++e) {
+    const uint64_t b = ecs.off[e], n = ecs.off[e + 1] - b;
+    if (n == 1) {
+      h.t_single[ecs.tid[b]] = (int32_t)e;
+      continue;
+    }
+    h.multi_ec.push_back(e);
+    for (uint64_t j = 0; j < n; ++j) {
+      const uint32_t t = ecs.tid[b + j];
+      h.m_tid.push_back(t);
+      h.m_w.push_back(static_cast<double>(ecs.count[e]) / h.eff[t]);
+      ++deg[t + 1];
+    }
+    h.m_off.push_back((uint32_t)h.m_tid.size());
+  }
+  h.t_off.assign(T + 1, 0);
+  for (uint32_t t = 0; t < T; ++t) h.t_off[t + 1] = h.t_off[t] + deg[t + 1];
+  h.t_midx.resize(h.m_tid.size());
+  h.t_w.resize(h.m_tid.size());
+  std::vector<uint32_t> fill(h.t_off.begin(), h.t_off.end() - 1);
+  for (uint32_t r = 0; r < h.multi_ec.size(); ++r)
+    for (uint32_t j = h.m_off[r]; j < h.m_off[r + 1]; ++j) {
+      const uint32_t t = h.m_tid[j];
+      h.t_midx[fill[t]] = r;
+      h.t_w[fill[t]] = h.m_w[j];
+      ++fill[t];
+    }
+}
+
+struct EmDevice {
+  DBuf<uint32_t> multi_ec, m_off, m_tid, t_off, t_midx, counts;
+  DBuf<double> m_w, t_w, alpha, norm;
+  DBuf<int32_t> t_single;
+  DBuf<int> rounds, state;
+  DBuf<unsigned int> chcount, barrier;
+};
+
+void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, EmProblem& p, cudaStream_t st) {
+  const size_t nm = h.multi_ec.size(), nnz = h.m_tid.size();
+  d.multi_ec.alloc(std::max<size_t>(1, nm)); d.multi_ec.upload(h.multi_ec.data(), nm, st);
+  d.m_off.upload(h.m_off.data(), h.m_off.size(), st);
+  d.m_tid.alloc(std::max<size_t>(1, nnz)); d.m_tid.upload(h.m_tid.data(), nnz, st);
+  d.m_w.alloc(std::max<size_t>(1, nnz)); d.m_w.upload(h.m_w.data(), nnz, st);
+  d.t_off.upload(h.t_off.data(), h.t_off.size(), st);
+  d.t_midx.alloc(std::max<size_t>(1, nnz)); d.t_midx.upload(h.t_midx.data(), nnz, st);
+  d.t_w.alloc(std::max<size_t>(1, nnz)); d.t_w.upload(h.t_w.data(), nnz, st);
+  d.t_single.upload(h.t_single.data(), h.t_single.size(), st);
+  d.counts.alloc(std::max<size_t>(1, (size_t)nb * n_ec));
+  d.alpha.alloc((size_t)nb * T);
+  d.norm.alloc(std::max<size_t>(1, (size_t)nb * nm));
+  d.rounds.alloc(nb); d.rounds.zero(st);
+  d.state.alloc(nb); d.state.zero(st);
+  d.chcount.alloc((size_t)nb * 2); d.chcount.zero(st);
+  d.barrier.alloc(4); d.barrier.zero(st);
+  p = EmProblem();
+  p.n_ec = n_ec; p.n_targets = T; p.n_multi = (uint32_t)nm;
+  p.multi_ec = d.multi_ec.p; p.m_off = d.m_off.p; p.m_tid = d.m_tid.p; p.m_w = d.m_w.p;
+  p.t_off = d.t_off.p; p.t_midx = d.t_midx.p; p.t_w = d.t_w.p; p.t_single = d.t_single.p;
+  p.nb = nb; p.counts = d.counts.p; p.alpha = d.alpha.p; p.norm = d.norm.p;
+  p.rounds = d.rounds.p; p.state = d.state.p; p.chcount = d.chcount.p; p.barrier = d.barrier.p;
+}
+
+void em_fetch(const EmProblem& p, EmDevice& d, int nb, uint32_t T, std::vector<double>& alpha, std::vector<int>& rounds,
+              cudaStream_t st) {
+  alpha.resize((size_t)nb * T);
+  rounds.resize(nb);
+  std::vector<int> state(nb);
+  d.alpha.download(alpha.data(), alpha.size(), 0, st);
+  d.rounds.download(rounds.data(), nb, 0, st);
+  d.state.download(state.data(), nb, 0, st);
+  KB_CK(cudaStreamSynchronize(st));
+  for (int b = 0; b < nb; ++b)
+    if (state[b] == 3)   // stop detected on the last allowed iteration: zero small alphas (EMAlgorithm.h:213-216)
+      for (uint32_t t = 0; t < T; ++t)
+        if (alpha[(size_t)b * T + t] < 1e-7 / 10.0) alpha[(size_t)b * T + t] = 0.0;
+}
+}  // namespace
+
+EmResult Quant::run_em(const EcTable& ecs, const std::vector<double>& fl_trunc, int max_iter, int min_rounds) {
+  KB_CK(cudaSetDevice(ix_.device));
+  const FlatIndex& f = ix_.flat;
+  const uint32_t T = f.num_targets();
+  EmHost h;
+  em_setup(f, ecs, fl_trunc, h);
+  EmDevice d;
+  EmProblem p;
+  em_upload(h, ecs.n(), T, 1, d, p, stream_);
+  d.counts.upload(ecs.count.data(), ecs.n(), stream_);
+  std::vector<double> a0(T, 1.0 / T);   // uniform start (EMAlgorithm.h:38)
+  d.alpha.upload(a0.data(), T, stream_);
+  p.max_iter = max_iter;
+  p.min_rounds = min_rounds;
+  cudaEvent_t e0, e1;
+  KB_CK(cudaEventCreate(&e0));
+  KB_CK(cudaEventCreate(&e1));
+  KB_CK(cudaEventRecord(e0, stream_));
+  launch_em(p, 256, stream_);
+  KB_CK(cudaGetLastError());
+  KB_CK(cudaEventRecord(e1, stream_));
+  EmResult r;
+  std::vector<int> rounds;
+  em_fetch(p, d, 1, T, r.alpha, rounds, stream_);
+  float ms = 0;
+  KB_CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  r.seconds = ms * 1e-3;
+  last_em_seconds = r.seconds;
+  r.rounds = rounds[0];
+  r.eff_lens = h.eff;
+  return r;
+}
+
+std::vector<int> Quant::run_bootstrap(const EcTable& ecs, const std::vector<double>& fl_trunc, uint64_t seed, int B,
+                                      std::vector<double>& alpha_out, std::vector<uint32_t>* samples_out) {
+  KB_CK(cudaSetDevice(ix_.device));
+  const FlatIndex& f = ix_.flat;
+  const uint32_t T = f.num_targets();
+  const uint32_t nE = ecs.n();
+  std::vector<int> rounds;
+  if (B <= 0) { alpha_out.clear(); return rounds; }
+  // seeds (src/main.cpp:2746-2752)
+  std::mt19937_64 rnd;
+  rnd.seed(seed);
+  std::vector<uint32_t> x0(B);
+  for (int b = 0; b < B; ++b) {
+    const uint64_t s = rnd();
+    uint32_t x = (uint32_t)(s % 2147483647ull);      // minstd_rand0 seeding (libstdc++ linear_congruential_engine::seed)
+    if (x == 0) x = 1;
+    x0[b] = x;
+  }
+  // std::discrete_distribution<int>(counts): normalised probabilities and their partial sums
+  std::vector<double> cp;
+  uint64_t N = 0;
+  for (uint32_t e = 0; e < nE; ++e) N += ecs.count[e];
+  const int n_draws = (int)N;   // Multinomial::n_ is an int
+  if (nE >= 2) {
+    std::vector<double> prob(ecs.count.begin(), ecs.count.end());
+    const double sum = std::accumulate(prob.begin(), prob.end(), 0.0);
+    for (auto& v : prob) v /= sum;
+    cp.resize(nE);
+    std::partial_sum(prob.begin(), prob.end(), cp.begin());
+    cp[nE - 1] = 1.0;
+  }
+  EmHost h;
+  em_setup(f, ecs, fl_trunc, h);
+  EmDevice d;
+  EmProblem p;
+  em_upload(h, nE, T, B, d, p, stream_);
+  if (nE >= 2) {
+    DBuf<double> d_cp;
+    DBuf<uint32_t> d_x0;
+    d_cp.upload(cp.data(), nE, stream_);
+    d_x0.upload(x0.data(), B, stream_);
+    ResampleArgs ra{};
+    ra.cp = d_cp.p; ra.n_ec = nE; ra.n_draws = n_draws > 0 ? (uint64_t)n_draws : 0; ra.nb = B; ra.x0 = d_x0.p;
+    ra.samp = d.counts.p;
+    launch_resample(ra, stream_);
+    KB_CK(cudaGetLastError());
+    KB_CK(cudaStreamSynchronize(stream_));
+  } else {
+    // a single class: discrete_distribution returns 0 without consuming the engine
+    std::vector<uint32_t> s((size_t)B * nE, 0);
+    for (int b = 0; b < B && nE == 1; ++b) s[b] = n_draws > 0 ? (uint32_t)n_draws : 0;
+    d.counts.upload(s.data(), s.size(), stream_);
+    KB_CK(cudaStreamSynchronize(stream_));
+  }
+  if (samples_out) {
+    samples_out->resize((size_t)B * nE);
+    d.counts.download(samples_out->data(), samples_out->size(), 0, stream_);
+  }
+  std::vector<double> a0((size_t)B * T, 1.0 / T);
+  d.alpha.upload(a0.data(), a0.size(), stream_);
+  p.max_iter = 10000;
+  p.min_rounds = 50;
+  launch_em(p, 256, stream_);
+  KB_CK(cudaGetLastError());
+  em_fetch(p, d, B, T, alpha_out, rounds, stream_);
+  return rounds;
+}
+
+template struct DBuf<uint8_t>;
+template struct DBuf<uint16_t>;
+template struct DBuf<uint32_t>;
+template struct DBuf<int32_t>;
+template struct DBuf<uint64_t>;
+template struct DBuf<unsigned long long>;
+template struct DBuf<double>;
+template struct DBuf<KmerSlot>;
+
+}  // namespace kb

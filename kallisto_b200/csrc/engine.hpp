@@ -1,0 +1,163 @@
+// Host-side engine: owns the device tables of one index and the device state of one
+// quantification run.  This is the C++ layer right under the C ABI (include/kallisto_b200.h);
+// it mirrors the reference objects that sit on the hot path:
+//
+//   kb::Index  <->  KmerIndex after KmerIndex::load            (src/KmerIndex.cpp:1330-1559)
+//   kb::Quant  <->  MinCollector + MasterProcessor/ReadProcessor (src/MinCollector.h:17-119,
+//                   src/ProcessReads.cpp:307-483, 934-1237) followed by EMAlgorithm / Bootstrap
+//
+// There is no CPU implementation of any of the per-read or per-iteration work in here:
+// without a CUDA device every entry point throws.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "index_v13.hpp"
+#include "kernels.hpp"
+
+namespace kb {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  void alloc(size_t count);
+  void release();
+  void upload(const T* src, size_t count, cudaStream_t st = 0);
+  void download(T* dst, size_t count, size_t offset = 0, cudaStream_t st = 0) const;
+  void zero(cudaStream_t st = 0);
+};
+
+class Index {
+ public:
+  static std::unique_ptr<Index> load(const std::string& path, int device, bool load_positions, int threads);
+  ~Index();
+
+  FlatIndex flat;
+  int device = 0;
+  DevIndex dev{};
+  uint64_t table_cap = 0;
+  uint64_t dict_cap = 0;          // set-dictionary capacity used by every run on this index
+  uint32_t empty_ec = 0xFFFFFFFFu;
+  uint32_t max_set_len = 0;
+  uint32_t n_index_tids = 0;      // pool entries occupied by the index's own EC sets
+  double load_seconds = 0, build_seconds = 0;
+
+  DBuf<KmerSlot> slots;
+  DBuf<uint32_t> ec_off;
+  DBuf<uint32_t> index_pool;      // the index's EC sets (copied to the front of every run's pool)
+  DBuf<unsigned long long> dslots_init;
+  DBuf<int32_t> ec_handle;
+  DBuf<uint32_t> blk_ec;
+  DBuf<uint64_t> blk_strand_off;
+  DBuf<uint8_t> strand;
+};
+
+struct QuantOptions {
+  int paired = 1;          // !opt.single_end
+  int strand_mode = 0;     // 0 unstranded, 1 --fr-stranded, 2 --rf-stranded
+  int collect_fld = 1;     // opt.fld == 0: estimate the fragment-length distribution from the data
+  uint32_t max_batch_reads = 1u << 22;     // staging capacity (reads per batch)
+  uint64_t max_batch_bases = 1ull << 29;   // staging capacity (bases per batch)
+  int threads_per_block = 128;
+};
+
+// Equivalence classes of a finished run, ids in order of first occurrence (== reference -t 1).
+struct EcTable {
+  std::vector<uint64_t> off;      // n_ec + 1
+  std::vector<uint32_t> tid;
+  std::vector<uint32_t> count;
+  std::vector<int32_t> handle;    // device handle of each EC (to translate per-fragment results)
+  uint32_t n() const { return (uint32_t)count.size(); }
+};
+
+struct EmResult {
+  std::vector<double> alpha;      // est_counts
+  std::vector<double> eff_lens;
+  int rounds = 0;
+  double seconds = 0;
+};
+
+struct Stats {
+  uint64_t n_processed = 0, n_pseudoaligned = 0, n_unique = 0;
+  uint64_t n_probes = 0, n_slot_visits = 0, n_resolved = 0, n_memo_hits = 0;
+};
+
+class Quant {
+ public:
+  Quant(Index& ix, const QuantOptions& opt);
+  ~Quant();
+
+  // One batch of reads (mates interleaved when paired).  `off` has n_reads+1 entries or is null
+  // when every read has `fixed_len` bases.  Pointers are HOST memory; the copy to the device, the
+  // kernels and (if handles_out != null) the copy back of one handle per fragment happen inside.
+  void pseudoalign_host(const char* bases, const uint32_t* off, uint32_t n_reads, uint32_t fixed_len,
+                        int32_t* handles_out);
+  // Same, inputs already resident in device memory; handles stay on the device
+  // (device_handles(), valid until the next batch).
+  void pseudoalign_device(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
+                          uint32_t max_read_len);
+  const int32_t* device_handles() const { return d_handles_.p; }
+  void sync();
+
+  // MasterProcessor tail flush + EC id assignment.
+  const EcTable& finalize_ecs();
+  const std::vector<uint32_t>& flens() const { return flens_; }
+  void set_flens(const uint32_t* f);     // e.g. after an all-reduce across ranks
+  Stats stats();
+
+  // Effective lengths from the fragment-length distribution (or a given mean/sd), then the EM.
+  std::vector<double> mean_fl_trunc(double fld_mean, double fld_sd) const;
+  EmResult run_em(const EcTable& ecs, const std::vector<double>& fl_trunc, int max_iter = 10000, int min_rounds = 50);
+  // B bootstrap EMs (Bootstrap::run_em): alpha_out is B x n_targets.  Returns rounds per bootstrap.
+  std::vector<int> run_bootstrap(const EcTable& ecs, const std::vector<double>& fl_trunc, uint64_t seed, int B,
+                                 std::vector<double>& alpha_out, std::vector<uint32_t>* samples_out = nullptr);
+
+  Index& index() { return ix_; }
+  const QuantOptions& options() const { return opt_; }
+  cudaStream_t stream() const { return stream_; }
+  double last_em_seconds = 0;
+
+ private:
+  void run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
+                 uint32_t max_read_len);
+  void check_device_errors();
+
+  Index& ix_;
+  QuantOptions opt_;
+  cudaStream_t stream_ = nullptr;
+  DevDict dd_{};
+  // run state on the device
+  DBuf<uint32_t> pool_;
+  DBuf<unsigned long long> dslots_, first_, m2_key_, mn_key_, counters_;   // counters_: pool_top, tpool_top, stats[4]
+  DBuf<uint32_t> count_, tpool_;
+  DBuf<int32_t> m2_val_, mn_val_;
+  DBuf<int> error_;
+  // batch staging
+  DBuf<uint8_t> d_bases_;
+  DBuf<uint32_t> d_off_, d_qcount_, d_qentries_, d_scratch_;
+  DBuf<int32_t> d_handles_;
+  DBuf<uint16_t> d_tl_;
+  uint32_t n_resolve_warps_ = 0;
+  uint32_t* h_off_pinned_ = nullptr;
+  // host-side run state
+  uint64_t n_frag_total_ = 0;
+  std::vector<uint32_t> flens_;
+  uint32_t tlencount_ = 0;
+  std::vector<uint16_t> h_tl_;
+  EcTable ecs_;
+  bool ecs_valid_ = false;
+};
+
+}  // namespace kb

@@ -1,0 +1,202 @@
+// K4/K5: fp64 EM over the sparse EC x transcript layout, and bootstrap resampling.
+//
+// EMAlgorithm::run (src/EMAlgorithm.h:95-221) restated as two segmented passes per iteration
+// inside ONE persistent cooperative kernel (no atomics, no dense contraction, no tensor cores):
+//   pass A  per multi-transcript EC (CSR by EC):     denom = sum_j alpha[t_j] * w_j ; norm = count/denom
+//   pass B  per transcript (CSC, entries by EC id):  next[t] = count(singleton {t}) + sum (w*alpha[t]) * norm
+//           + the convergence test and alpha <- next
+// Every row is accumulated sequentially in the reference's own order (transcript ids ascending
+// inside an EC, EC ids ascending inside a transcript) with separate IEEE multiply and add
+// (the reference is built without FMA contraction: no -march on src/), so alpha is
+// bit-identical to the CPU result, iteration count included.  A batch dimension runs the B
+// bootstrap EMs of Bootstrap::run_em (src/Bootstrap.cpp:4-13) concurrently over the same structure.
+#include <cooperative_groups.h>
+
+#include "kb_device.cuh"
+#include "kernels.hpp"
+
+namespace cg = cooperative_groups;
+
+namespace kb {
+
+namespace {
+constexpr double kAlphaLimit = 1e-7;          // EMAlgorithm.h:101
+constexpr double kAlphaChangeLimit = 1e-2;    // :102
+constexpr double kAlphaChange = 1e-2;         // :103
+constexpr double kTolerance = 4.9406564584124654e-324;   // std::numeric_limits<double>::denorm_min()
+}
+
+__global__ void __launch_bounds__(256) em_kernel(EmProblem p) {
+  cg::grid_group grid = cg::this_grid();
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t nA = (uint64_t)p.nb * p.n_multi;
+  const uint64_t nB = (uint64_t)p.nb * p.n_targets;
+  const double zero_below = kAlphaLimit / 10.0;
+
+  for (int it = 0; it < p.max_iter; ++it) {
+    // ---------------- pass A: denominators ----------------
+    for (uint64_t i = gtid; i < nA; i += gstride) {
+      const uint32_t b = (uint32_t)(i / p.n_multi), r = (uint32_t)(i % p.n_multi);
+      const int st = p.state[b];
+      if (st >= 2) continue;
+      const uint32_t c = p.counts[(size_t)b * p.n_ec + p.multi_ec[r]];
+      double nrm = 0.0;
+      if (c != 0) {
+        const double* al = p.alpha + (size_t)b * p.n_targets;
+        double denom = 0.0;
+        const uint32_t e0 = p.m_off[r], e1 = p.m_off[r + 1];
+        for (uint32_t j = e0; j < e1; ++j) {
+          double a = al[p.m_tid[j]];
+          if (st == 1 && a < zero_below) a = 0.0;          // alpha zeroed before the final round (:213-216)
+          denom = __dadd_rn(denom, __dmul_rn(a, p.m_w[j]));
+        }
+        if (!(denom < kTolerance)) nrm = __ddiv_rn((double)c, denom);
+      }
+      p.norm[(size_t)b * p.n_multi + r] = nrm;
+    }
+    // "all problems finished" flag, double-buffered by iteration parity so that the reset below
+    // can never overtake a slow thread still reading the previous iteration's verdict.
+    int* done_flag = reinterpret_cast<int*>(p.barrier) + (it & 1);
+    if (gtid == 0) *done_flag = 1;
+    grid.sync();
+    // ---------------- pass B: numerators, convergence test, alpha <- next ----------------
+    for (uint64_t i0 = gtid - lane; i0 < nB; i0 += gstride) {
+      const uint64_t i = i0 + lane;
+      bool changed = false;
+      uint32_t b = 0;
+      int st = 2;
+      if (i < nB) {
+        b = (uint32_t)(i / p.n_targets);
+        const uint32_t t = (uint32_t)(i % p.n_targets);
+        st = p.state[b];
+        if (st < 2) {
+          double* al = p.alpha + (size_t)b * p.n_targets;
+          double a = al[t];
+          if (st == 1 && a < zero_below) a = 0.0;
+          const int32_t s = p.t_single[t];
+          double acc = s >= 0 ? (double)p.counts[(size_t)b * p.n_ec + s] : 0.0;     // :119-123
+          const double* nr = p.norm + (size_t)b * p.n_multi;
+          const uint32_t e0 = p.t_off[t], e1 = p.t_off[t + 1];
+          for (uint32_t j = e0; j < e1; ++j)
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(p.t_w[j], a), nr[p.t_midx[j]]));   // :154-156
+          changed = acc > kAlphaChangeLimit && (fabs(__dadd_rn(acc, -a)) / acc) > kAlphaChange;   // :178
+          al[t] = acc;
+        }
+      }
+      // one atomic per warp when the warp sits inside one problem (the common case)
+      const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, b, 0), b31 = __shfl_sync(0xFFFFFFFFu, b, 31);
+      const bool full = (i0 + 31 < nB) && b0 == b31;
+      if (full) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, changed);
+        if (lane == 0 && m) atomicAdd(&p.chcount[2 * b0 + (it & 1)], (unsigned)__popc(m));
+      } else if (changed) {
+        atomicAdd(&p.chcount[2 * b + (it & 1)], 1u);
+      }
+    }
+    grid.sync();
+    // ---------------- state machine per problem (:202-221) ----------------
+    for (uint64_t b = gtid; b < (uint64_t)p.nb; b += gstride) {
+      int st = p.state[b];
+      if (st < 2) {
+        const unsigned ch = p.chcount[2 * b + (it & 1)];
+        p.chcount[2 * b + (it & 1)] = 0;
+        if (st == 1) { st = 2; p.rounds[b] = it; }                      // if (finalRound) break;
+        else if (ch == 0 && it > p.min_rounds) st = 1;                  // stopEM -> finalRound
+        if (st < 2 && it + 1 == p.max_iter) {
+          // loop runs out: i == n_iter.  If the stop was detected on the very last iteration the
+          // reference still zeroes the small alphas (:213-216); the host does that for state 3.
+          p.rounds[b] = p.max_iter;
+          st = (st == 1) ? 3 : 2;
+        }
+        p.state[b] = st;
+        if (st < 2) *done_flag = 0;
+      }
+    }
+    grid.sync();
+    if (*reinterpret_cast<volatile int*>(done_flag)) break;
+  }
+}
+
+int em_max_blocks(int tpb) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel, tpb, 0);
+  return sms * per_sm;
+}
+
+void launch_em(const EmProblem& p, int tpb, cudaStream_t st) {
+  const int maxb = em_max_blocks(tpb);
+  const uint64_t work = (uint64_t)p.nb * (p.n_multi > p.n_targets ? p.n_multi : p.n_targets);
+  int blocks = (int)((work + tpb - 1) / tpb);
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  EmProblem pp = p;
+  void* args[] = {&pp};
+  cudaLaunchCooperativeKernel((void*)em_kernel, dim3(blocks), dim3(tpb), args, 0, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multinomial::sample (src/Multinomial.hpp:33-51): N draws of std::discrete_distribution<int>
+// driven by std::default_random_engine (libstdc++: minstd_rand0, x <- 16807 x mod 2^31-1), two
+// engine calls per draw (generate_canonical<double,53>).  The engine is a pure multiplicative
+// LCG, so draw i starts from 16807^(2i) x0: every thread jumps to its own chunk of the stream
+// and the result is bit-identical to the sequential CPU loop.
+namespace {
+constexpr uint32_t kM = 2147483647u;
+__device__ __forceinline__ uint32_t mulmod(uint32_t a, uint32_t b) {
+  uint64_t p = (uint64_t)a * b;
+  p = (p & kM) + (p >> 31);
+  p = (p & kM) + (p >> 31);
+  return p >= kM ? (uint32_t)(p - kM) : (uint32_t)p;
+}
+__device__ __forceinline__ uint32_t powmod(uint32_t a, uint64_t e) {
+  uint32_t r = 1;
+  while (e) {
+    if (e & 1) r = mulmod(r, a);
+    a = mulmod(a, a);
+    e >>= 1;
+  }
+  return r;
+}
+constexpr int kDrawsPerThread = 64;
+}
+
+__global__ void __launch_bounds__(256) resample_kernel(ResampleArgs a) {
+  const uint32_t b = blockIdx.y;
+  const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t d0 = chunk * kDrawsPerThread;
+  if (d0 >= a.n_draws) return;
+  const uint64_t d1 = min(a.n_draws, d0 + kDrawsPerThread);
+  uint32_t x = mulmod(a.x0[b], powmod(16807u, 2 * d0));
+  uint32_t* samp = a.samp + (size_t)b * a.n_ec;
+  const double R = 2147483646.0;
+  const double RR = __dmul_rn(R, R);
+  for (uint64_t d = d0; d < d1; ++d) {
+    x = mulmod(x, 16807u);
+    const double u0 = (double)(x - 1);
+    x = mulmod(x, 16807u);
+    const double u1 = (double)(x - 1);
+    double u = __ddiv_rn(__dadd_rn(u0, __dmul_rn(u1, R)), RR);
+    if (u >= 1.0) u = 0.99999999999999988897769753748;   // nextafter(1.0, 0.0)
+    // std::lower_bound(cp.begin(), cp.end(), u): first index with cp[idx] >= u
+    uint32_t lo = 0, hi = a.n_ec;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (a.cp[mid] < u) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&samp[lo], 1u);
+  }
+}
+
+void launch_resample(const ResampleArgs& a, cudaStream_t st) {
+  cudaMemsetAsync(a.samp, 0, (size_t)a.nb * a.n_ec * sizeof(uint32_t), st);
+  if (a.n_draws == 0 || a.nb == 0) return;
+  const uint64_t chunks = (a.n_draws + kDrawsPerThread - 1) / kDrawsPerThread;
+  dim3 grid((unsigned)((chunks + 255) / 256), (unsigned)a.nb);
+  resample_kernel<<<grid, 256, 0, st>>>(a);
+}
+
+}  // namespace kb
