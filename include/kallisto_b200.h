@@ -52,6 +52,8 @@ typedef struct kb_index_info {
   double build_seconds;    /* device upload + table build */
 } kb_index_info;
 int kb_index_get_info(const kb_index* ix, kb_index_info* info);
+/* Host-only: parse the file and report its sizes without touching a device (tooling, CI). */
+int kb_index_inspect(const char* path, kb_index_info* info);
 /* target_names_ / target_lens_ (src/KmerIndex.h:136-138) */
 const char* kb_index_target_name(const kb_index* ix, uint32_t i);
 int kb_index_target_lens(const kb_index* ix, uint32_t* lens_out /* n_targets */);

@@ -1,0 +1,256 @@
+"""kallisto_b200 -- host-side Python mirror of the C ABI (include/kallisto_b200.h).
+
+The product is the shared library ``libkallisto_b200.so`` (hand-written sm_100a CUDA behind an
+``extern "C"`` boundary) and the ``kallisto_b200`` command-line binary; this module is the thin
+ctypes binding used by the tests and ``bench.py``.  Class and method names follow the reference
+objects they stand in for: ``KmerIndex`` (src/KmerIndex.h), ``MinCollector``/``MasterProcessor``
+(src/MinCollector.h, src/ProcessReads.h) and ``EMAlgorithm`` (src/EMAlgorithm.h).
+
+There is no CPU fallback: if the library is missing, or no CUDA device is present, every call
+that would compute something raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkallisto_b200.so")
+
+KB_OK = 0
+KB_ERR_NO_DEVICE = -3
+
+
+class KallistoB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("kallisto_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class kb_index_info(C.Structure):
+    _fields_ = [("k", C.c_int32), ("n_targets", C.c_uint32), ("n_unitigs", C.c_uint32), ("n_ec_blocks", C.c_uint32),
+                ("n_ec_sets", C.c_uint32), ("n_kmers", C.c_uint64), ("table_slots", C.c_uint64),
+                ("load_seconds", C.c_double), ("build_seconds", C.c_double)]
+
+
+class kb_quant_opts(C.Structure):
+    _fields_ = [("paired", C.c_int32), ("strand_mode", C.c_int32), ("collect_fld", C.c_int32),
+                ("max_batch_reads", C.c_uint32), ("max_batch_bases", C.c_uint64)]
+
+
+class kb_run_stats(C.Structure):
+    _fields_ = [("n_processed", C.c_uint64), ("n_pseudoaligned", C.c_uint64), ("n_unique", C.c_uint64),
+                ("n_ecs", C.c_uint64), ("n_ec_entries", C.c_uint64), ("n_probes", C.c_uint64),
+                ("n_slot_visits", C.c_uint64), ("n_resolved", C.c_uint64), ("n_memo_hits", C.c_uint64)]
+
+
+# every symbol declared in include/kallisto_b200.h
+EXPORTED_SYMBOLS = [
+    "kb_last_error", "kb_version", "kb_index_load", "kb_index_free", "kb_index_get_info", "kb_index_target_name",
+    "kb_index_target_lens", "kb_index_inspect", "kb_quant_create", "kb_quant_free", "kb_pseudoalign_batch",
+    "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
+    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_counts_to_tpm",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libkallisto_b200.so (built in-tree by __graft_entry__.build() / make)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KallistoB200Error(-5, "%s not found: build it with `make -C kallisto_b200/csrc` "
+                                    "(there is no Python/CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, i32, u64, dbl = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64, C.c_double
+    L.kb_last_error.restype = C.c_char_p
+    L.kb_version.restype = C.c_char_p
+    L.kb_index_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.kb_index_free.argtypes = [vp]
+    L.kb_index_get_info.argtypes = [vp, C.POINTER(kb_index_info)]
+    L.kb_index_inspect.argtypes = [C.c_char_p, C.POINTER(kb_index_info)]
+    L.kb_index_target_name.argtypes = [vp, u32]
+    L.kb_index_target_name.restype = C.c_char_p
+    L.kb_index_target_lens.argtypes = [vp, vp]
+    L.kb_quant_create.argtypes = [vp, C.POINTER(kb_quant_opts), C.POINTER(vp)]
+    L.kb_quant_free.argtypes = [vp]
+    L.kb_pseudoalign_batch.argtypes = [vp, vp, vp, u32, u32, vp]
+    L.kb_pseudoalign_batch_device.argtypes = [vp, vp, vp, u32, u32, u32]
+    L.kb_quant_sync.argtypes = [vp]
+    L.kb_quant_finalize.argtypes = [vp, C.POINTER(kb_run_stats)]
+    L.kb_quant_ec_table.argtypes = [vp, vp, vp, vp, vp]
+    L.kb_quant_get_flens.argtypes = [vp, vp]
+    L.kb_quant_set_flens.argtypes = [vp, vp]
+    L.kb_em_run.argtypes = [vp, dbl, dbl, vp, vp, C.POINTER(i32), C.POINTER(dbl)]
+    L.kb_em_run_table.argtypes = [vp, u32, vp, vp, vp, dbl, dbl, vp, vp, C.POINTER(i32), C.POINTER(dbl)]
+    L.kb_bootstrap_run.argtypes = [vp, dbl, dbl, u64, i32, vp, vp, vp]
+    L.kb_counts_to_tpm.argtypes = [vp, vp, u32, vp]
+    _lib = L
+    return L
+
+
+def _ck(rc):
+    if rc != KB_OK:
+        raise KallistoB200Error(rc, lib().kb_last_error().decode(errors="replace"))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def inspect_index(path):
+    """Parse an index file on the host only (no device needed): sizes for tooling and tests."""
+    info = kb_index_info()
+    _ck(lib().kb_index_inspect(os.fsencode(path), C.byref(info)))
+    return {f: getattr(info, f) for f, _ in kb_index_info._fields_}
+
+
+class KmerIndex:
+    """KmerIndex::load (src/KmerIndex.cpp:1330-1559) -> flat tables resident in HBM."""
+
+    def __init__(self, path, device=0, load_positions=False, threads=4):
+        self._h = C.c_void_p()
+        _ck(lib().kb_index_load(os.fsencode(path), device, int(load_positions), threads, C.byref(self._h)))
+        info = kb_index_info()
+        _ck(lib().kb_index_get_info(self._h, C.byref(info)))
+        self.info = {f: getattr(info, f) for f, _ in kb_index_info._fields_}
+        self.k = info.k
+        self.num_trans = info.n_targets
+        self.target_lens_ = np.zeros(self.num_trans, np.uint32)
+        _ck(lib().kb_index_target_lens(self._h, _p(self.target_lens_)))
+        self.target_names_ = [lib().kb_index_target_name(self._h, i).decode() for i in range(self.num_trans)]
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().kb_index_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MinCollector:
+    """One quantification run: per-batch pseudoalignment, EC bookkeeping, EM, bootstrap.
+
+    Stands in for MinCollector + MasterProcessor/ReadProcessor (src/ProcessReads.cpp) followed by
+    EMAlgorithm / Bootstrap."""
+
+    def __init__(self, index, paired=True, strand=None, collect_fld=True, max_batch_reads=0, max_batch_bases=0):
+        self.index = index
+        self.paired = bool(paired)
+        o = kb_quant_opts()
+        o.paired = int(self.paired)
+        o.strand_mode = {None: 0, "unstranded": 0, "fr": 1, "rf": 2, 0: 0, 1: 1, 2: 2}[strand]
+        o.collect_fld = int(collect_fld)
+        o.max_batch_reads = max_batch_reads
+        o.max_batch_bases = max_batch_bases
+        self._h = C.c_void_p()
+        _ck(lib().kb_quant_create(index._h, C.byref(o), C.byref(self._h)))
+        self._stats = None
+
+    def close(self):
+        if self._h:
+            lib().kb_quant_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- ReadProcessor::processBuffer ------------------------------------------------------
+    def process_buffer(self, bases, offsets=None, fixed_len=0, want_handles=True):
+        """Host arrays in, one set handle per fragment out (or None)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+            n_reads = len(offsets) - 1
+        else:
+            n_reads = len(bases) // fixed_len if fixed_len else 0
+        n_frag = n_reads // 2 if self.paired else n_reads
+        out = np.full(n_frag, -1, np.int32) if want_handles else None
+        _ck(lib().kb_pseudoalign_batch(self._h, _p(bases), _p(offsets), n_reads, fixed_len, _p(out)))
+        self._stats = None
+        return out
+
+    def process_buffer_ptr(self, bases_ptr, offsets_ptr, n_reads, fixed_len, out_ptr=None):
+        """Same, raw host pointers (e.g. pinned torch tensors)."""
+        _ck(lib().kb_pseudoalign_batch(self._h, bases_ptr, offsets_ptr, n_reads, fixed_len, out_ptr))
+        self._stats = None
+
+    def process_buffer_device(self, d_bases_ptr, d_offsets_ptr, n_reads, fixed_len, max_read_len=0):
+        _ck(lib().kb_pseudoalign_batch_device(self._h, d_bases_ptr, d_offsets_ptr, n_reads, fixed_len, max_read_len))
+        self._stats = None
+
+    def sync(self):
+        _ck(lib().kb_quant_sync(self._h))
+
+    # -- MasterProcessor::update / increaseCount --------------------------------------------
+    def finalize(self):
+        s = kb_run_stats()
+        _ck(lib().kb_quant_finalize(self._h, C.byref(s)))
+        self._stats = {f: getattr(s, f) for f, _ in kb_run_stats._fields_}
+        return self._stats
+
+    def ec_table(self):
+        """-> (offsets uint64[n+1], tids uint32, counts uint32[n], handles int32[n]); ids in order of
+        first occurrence."""
+        st = self._stats or self.finalize()
+        n, m = st["n_ecs"], st["n_ec_entries"]
+        off = np.zeros(n + 1, np.uint64)
+        tids = np.zeros(max(1, m), np.uint32)
+        counts = np.zeros(max(1, n), np.uint32)
+        handles = np.zeros(max(1, n), np.int32)
+        _ck(lib().kb_quant_ec_table(self._h, _p(off), _p(tids), _p(counts), _p(handles)))
+        return off, tids[:m], counts[:n], handles[:n]
+
+    @property
+    def flens(self):
+        f = np.zeros(1000, np.uint32)
+        _ck(lib().kb_quant_get_flens(self._h, _p(f)))
+        return f
+
+    def set_flens(self, f):
+        f = np.ascontiguousarray(f, np.uint32)
+        assert len(f) == 1000
+        _ck(lib().kb_quant_set_flens(self._h, _p(f)))
+
+    # -- EMAlgorithm::run / Bootstrap::run_em --------------------------------------------------
+    def run_em(self, fld_mean=0.0, fld_sd=0.0, table=None):
+        T = self.index.num_trans
+        est = np.zeros(T, np.float64)
+        eff = np.zeros(T, np.float64)
+        rounds = C.c_int32(0)
+        secs = C.c_double(0)
+        if table is None:
+            _ck(lib().kb_em_run(self._h, fld_mean, fld_sd, _p(est), _p(eff), C.byref(rounds), C.byref(secs)))
+        else:
+            off, tids, counts = (np.ascontiguousarray(table[0], np.uint64), np.ascontiguousarray(table[1], np.uint32),
+                                 np.ascontiguousarray(table[2], np.uint32))
+            _ck(lib().kb_em_run_table(self._h, len(counts), _p(off), _p(tids), _p(counts), fld_mean, fld_sd, _p(est),
+                                      _p(eff), C.byref(rounds), C.byref(secs)))
+        return dict(est_counts=est, eff_lens=eff, rounds=rounds.value, seconds=secs.value)
+
+    def run_bootstrap(self, n_bootstrap, seed=42, fld_mean=0.0, fld_sd=0.0, want_samples=False):
+        T = self.index.num_trans
+        st = self._stats or self.finalize()
+        est = np.zeros((n_bootstrap, T), np.float64)
+        samples = np.zeros((n_bootstrap, max(1, st["n_ecs"])), np.uint32) if want_samples else None
+        rounds = np.zeros(max(1, n_bootstrap), np.int32)
+        _ck(lib().kb_bootstrap_run(self._h, fld_mean, fld_sd, seed, n_bootstrap, _p(est), _p(samples), _p(rounds)))
+        return dict(est_counts=est, samples=samples, rounds=rounds[:n_bootstrap])
+
+
+def counts_to_tpm(est_counts, eff_lens):
+    est_counts = np.ascontiguousarray(est_counts, np.float64)
+    eff_lens = np.ascontiguousarray(eff_lens, np.float64)
+    out = np.zeros(len(est_counts), np.float64)
+    _ck(lib().kb_counts_to_tpm(_p(est_counts), _p(eff_lens), len(est_counts), _p(out)))
+    return out

@@ -72,6 +72,23 @@ int kb_index_get_info(const kb_index* ix, kb_index_info* info) {
   return KB_OK;
 }
 
+int kb_index_inspect(const char* path, kb_index_info* info) {
+  if (!path || !info) return fail(KB_ERR_INVALID, "kb_index_inspect: null argument");
+  return guarded([&] {
+    kb::FlatIndex f;
+    kb::load_index_v13(path, f, false, 1);
+    info->k = f.k;
+    info->n_targets = f.num_targets();
+    info->n_unitigs = f.n_unitigs();
+    info->n_ec_blocks = (uint32_t)f.blk_lb.size();
+    info->n_ec_sets = f.n_ec();
+    info->n_kmers = f.n_kmers;
+    info->table_slots = 0;
+    info->load_seconds = 0;
+    info->build_seconds = 0;
+  });
+}
+
 const char* kb_index_target_name(const kb_index* ix, uint32_t i) {
   if (!ix || i >= ix->ix->flat.num_targets()) return nullptr;
   return ix->ix->flat.target_name[i].c_str();

@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library loads, exports every symbol include/kallisto_b200.h declares, parses
+index files on the host, and fails LOUDLY (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import kallisto_b200 as K
+from tests import util
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(util.ROOT, "include", "kallisto_b200.h")).read()
+    declared = set(re.findall(r"\b(kb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = K.lib()
+    for sym in sorted(declared):
+        assert hasattr(L, sym), "missing export: " + sym
+    assert declared == set(K.EXPORTED_SYMBOLS)
+
+
+def test_inspect_index_matches_reference_log_lines():
+    # "[index] number of targets: 14", "[index] number of k-mers: 22,118", 21 contigs
+    info = K.inspect_index(util.dataset("config1")["index"])
+    assert info["k"] == 31 and info["n_targets"] == 14 and info["n_kmers"] == 22118 and info["n_unitigs"] == 21
+    assert info["n_ec_blocks"] == 27
+
+
+def test_bad_index_is_rejected():
+    with pytest.raises(K.KallistoB200Error):
+        K.inspect_index(os.path.join(util.ROOT, "include", "kallisto_b200.h"))
+    with pytest.raises(K.KallistoB200Error):
+        K.inspect_index("/nonexistent/file.kidx")
+
+
+def test_counts_to_tpm_host():
+    est = np.array([10.0, 0.0, 5.0])
+    eff = np.array([100.0, 50.0, 25.0])
+    tpm = K.counts_to_tpm(est, eff)
+    x = est / eff
+    np.testing.assert_allclose(tpm, x / x.sum() * 1e6, rtol=0, atol=0)
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_have_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_device_fails_loudly():
+    with pytest.raises(K.KallistoB200Error) as ei:
+        K.KmerIndex(util.dataset("config1")["index"])
+    assert ei.value.code == K.KB_ERR_NO_DEVICE

@@ -1,0 +1,85 @@
+"""CPU: the oracle restatement (oracle/kb_oracle.cpp) against the fixtures produced by the
+UNMODIFIED reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import util
+
+
+@pytest.mark.parametrize("name", ["config1", "synth_small"])
+@pytest.mark.parametrize("mode", list(util.MODES))
+def test_per_fragment_ecs_match_reference(name, mode):
+    ds = util.dataset(name)
+    paired, strand, _ = util.MODES[mode]
+    g = util.golden_ecs(ds, mode)
+    ix = O.OracleIndex(ds["index"])
+    run = O.OracleRun(ix, paired, strand, collect_fld=True)
+    bases, off = util.batch(ds, paired)
+    frag = run.pseudoalign(bases, off)
+    assert len(frag) == int(g["n_processed"])
+    np.testing.assert_array_equal(frag, g["frag_ec"])          # bit-exact, ids in first-occurrence order
+    eo, et, ec = run.ec_table()
+    assert util.ec_sets(eo, et) == util.ec_sets(g["ec_off"], g["ec_tids"])
+    assert int(ec.sum()) == int(g["n_pseudoaligned"])
+    if paired and "flens" in g.files:
+        np.testing.assert_array_equal(run.flens(), g["flens"])
+
+
+@pytest.mark.parametrize("name", ["config1", "synth_small"])
+def test_quant_text_identical_to_reference(name):
+    """abundance.tsv of `kallisto quant --plaintext -t 1`, byte for byte (6 significant digits)."""
+    ds = util.dataset(name)
+    ix = O.OracleIndex(ds["index"])
+    run = O.OracleRun(ix, True, 0, True)
+    bases, off = util.batch(ds, True)
+    run.pseudoalign(bases, off)
+    eo, et, ec = run.ec_table()
+    fl = O.mean_fl_trunc(run.flens())
+    eff = O.eff_lens(ix.target_lens, fl)
+    alpha, rounds = O.em(eo, et, ec, eff, ix.n_targets)
+    txt = O.abundance_tsv(ix.target_names, ix.target_lens, eff, alpha, O.tpm(alpha, eff))
+    ref = open(os.path.join(ds["dir"], "ref_quant_paired", "abundance.tsv")).read()
+    assert txt == ref
+    if name == "config1":
+        # the number quoted in SURVEY.md 8(c) / BASELINE.md
+        assert hashlib.md5(txt.encode()).hexdigest() == "0bd5087aba9db4b681073bb84de3fe5f"
+        assert rounds == 52
+
+
+@pytest.mark.parametrize("name", ["config1", "synth_small"])
+def test_bootstrap_text_identical_to_reference(name):
+    ds = util.dataset(name)
+    ix = O.OracleIndex(ds["index"])
+    run = O.OracleRun(ix, True, 0, True)
+    bases, off = util.batch(ds, True)
+    run.pseudoalign(bases, off)
+    eo, et, ec = run.ec_table()
+    fl = O.mean_fl_trunc(run.flens())
+    eff = O.eff_lens(ix.target_lens, fl)
+    for b in range(3):
+        samp = O.bootstrap_sample(ec, 42, b)
+        assert samp.sum() == ec.sum()
+        alpha, _ = O.em(eo, et, samp, eff, ix.n_targets, counts_w=ec)
+        txt = O.abundance_tsv(ix.target_names, ix.target_lens, eff, alpha, O.tpm(alpha, eff))
+        ref = open(os.path.join(ds["dir"], "ref_quant_paired", "bs_abundance_%d.tsv" % b)).read()
+        assert txt == ref
+
+
+def test_single_overhang_quant_matches_reference():
+    """--single --single-overhang -l 200 -s 20: truncated-Gaussian effective lengths."""
+    ds = util.dataset("synth_small")
+    ix = O.OracleIndex(ds["index"])
+    run = O.OracleRun(ix, False, 0, False)
+    bases, off = util.batch(ds, False)
+    run.pseudoalign(bases, off)
+    eo, et, ec = run.ec_table()
+    fl = O.mean_fl_trunc(np.zeros(1000, np.uint32), 200.0, 20.0)
+    eff = O.eff_lens(ix.target_lens, fl)
+    alpha, _ = O.em(eo, et, ec, eff, ix.n_targets)
+    txt = O.abundance_tsv(ix.target_names, ix.target_lens, eff, alpha, O.tpm(alpha, eff))
+    ref = open(os.path.join(ds["dir"], "ref_quant_single_overhang", "abundance.tsv")).read()
+    assert txt == ref
