@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- paired reads/s of the `kallisto quant` hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config.workload): BASELINE config 2 -- a human-GENCODE-v44-like transcriptome index
+(built by the unmodified reference `kallisto index`, k=31; synthetic stand-in, see benchdata.py)
+and synthetic 2x100 bp paired reads.  One step = one batch of `pairs_per_step` read pairs through
+pseudoalignment (k-mer probes + EC intersection + EC counting); after the K timed steps the EC
+table is finalised and the EM is run ONCE, inside the timed region (it is part of the job).
+  value  = K * pairs_per_step * N / time, reads resident in HBM before the timed region starts;
+  e2e    = same job through kb_pseudoalign_batch with pinned HOST buffers (H2D inside), results
+           (est_counts) copied back to the host;
+  roofline  = match_kernel: algorithmic bytes (SURVEY.md 8d / DESIGN.md) / CUDA-event time, vs
+           MEASURED_PEAKS.json hbm_gbs;
+  cpu_baseline / --impl reference = oracle/_ref/kallisto (the unmodified reference, built from
+           /root/reference by oracle/Makefile) `quant -t <all cores>` on a bounded FASTQ sample of
+           the same reads, index-load time subtracted.
+Every step uses different reads and each batch (pairs_per_step x 200 B) is larger than L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import benchdata  # noqa: E402
+
+DATA = os.path.join(ROOT, "bench_data")
+READ_LEN = 100
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# workload: index + transcriptome (cached under bench_data/, rebuilt with the reference if absent)
+# ---------------------------------------------------------------------------------------------
+def workload(genes):
+    os.makedirs(DATA, exist_ok=True)
+    idx = os.path.join(DATA, "g%d.kidx" % genes)
+    txf = os.path.join(DATA, "g%d.tx.npz" % genes)
+    if not (os.path.exists(idx) and os.path.exists(txf)):
+        from oracle import oracle as O
+        log("building workload for %d genes (one-off, cached in bench_data/)" % genes)
+        t0 = time.time()
+        tx = benchdata.make_transcriptome(genes, seed=44)
+        codes = np.zeros(256, np.uint8)
+        for i, c in enumerate(b"ACGT"):
+            codes[c] = i
+        c = codes[tx.concat]
+        pad = (-len(c)) % 4
+        c = np.concatenate([c, np.zeros(pad, np.uint8)]).reshape(-1, 4)
+        packed = (c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)).astype(np.uint8)
+        np.savez(txf + ".tmp.npz", packed=packed, lens=tx.lens)
+        os.replace(txf + ".tmp.npz", txf)
+        if not os.path.exists(idx):
+            O.build()
+            with tempfile.TemporaryDirectory(dir=DATA) as td:
+                fa = os.path.join(td, "tx.fa")
+                tx.write_fasta(fa)
+                O.ref_run(["index", "-t", str(min(32, os.cpu_count() or 8)), "-i", idx + ".tmp", fa])
+            os.replace(idx + ".tmp", idx)
+        log("workload built in %.0f s" % (time.time() - t0))
+    z = np.load(txf)
+    packed, lens = z["packed"], z["lens"]
+    concat = np.empty(len(packed) * 4, np.uint8)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    for j in range(4):
+        concat[j::4] = lut[(packed >> (2 * j)) & 3]
+    concat = concat[: int(lens.sum())]
+    return idx, concat, lens
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            a = [x.strip() for x in r.split(",")]
+            if len(a) < 9:
+                continue
+            try:
+                sm.append(float(a[1]))
+                mx.append(float(a[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, a[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference's CPU path on the host cores
+# ---------------------------------------------------------------------------------------------
+def reference_run(idx, concat, lens, sample_pairs, repeats, device):
+    """-> (pairs/s, info).  Runs `kallisto quant -t <cores>` on `repeats` copies of a FASTQ sample
+    of `sample_pairs` pairs and subtracts the time of a run on one pair (index load + start-up)."""
+    import torch
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    sim = benchdata.TorchSimulator(concat, lens, device, read_len=READ_LEN)
+    reads = sim.pairs(sample_pairs, seed=1000).cpu().numpy()
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else DATA
+    with tempfile.TemporaryDirectory(dir=shm) as td:
+        f1, f2 = os.path.join(td, "s_1.fq"), os.path.join(td, "s_2.fq")
+        benchdata.write_fastq_fast(f1, reads[:, 0], 1)
+        benchdata.write_fastq_fast(f2, reads[:, 1], 2)
+        t1, t2 = os.path.join(td, "t_1.fq"), os.path.join(td, "t_2.fq")
+        benchdata.write_fastq_fast(t1, reads[:1, 0], 1)
+        benchdata.write_fastq_fast(t2, reads[:1, 1], 2)
+        # warm the page cache for the index
+        with open(idx, "rb") as f:
+            while f.read(1 << 26):
+                pass
+
+        def run(files):
+            t0 = time.perf_counter()
+            O.ref_run(["quant", "-i", idx, "-o", os.path.join(td, "out"), "--plaintext", "-t", str(cores)] + files,
+                      check=False)
+            return time.perf_counter() - t0
+        t_load = min(run([t1, t2]) for _ in range(1))
+        t_total = run([f1, f2] * repeats)
+    t_work = max(1e-9, t_total - t_load)
+    return sample_pairs * repeats / t_work, dict(cores=cores, t_load_s=round(t_load, 2), t_total_s=round(t_total, 2),
+                                                 sample_pairs=sample_pairs, repeats=repeats)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=15)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genes", type=int, default=int(os.environ.get("KB_BENCH_GENES", "62000")))
+    ap.add_argument("--pairs-per-step", type=int, default=int(os.environ.get("KB_BENCH_PAIRS", "2000000")))
+    ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("KB_BENCH_CPU_PAIRS", "2000000")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N = args.gpus
+    K, W, P = args.steps, max(args.warmup, 0), args.pairs_per_step
+    workload_name = ("human-GENCODE-v44-like synthetic transcriptome (%d genes, seed 44; reference-built k=31 index), "
+                     "synthetic 2x100bp pairs" % args.genes)
+
+    import torch
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        idx, concat, lens = workload(args.genes)
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        sample = min(args.cpu_sample_pairs, P)
+        reps = max(1, min(K + W, 4))
+        v, info = reference_run(idx, concat, lens, sample, reps, dev)
+        line = {
+            "metric": "paired reads/sec quant", "value": v, "unit": "pairs/s", "n_gpus": N, "steps": K, "warmup": W,
+            "ms_per_step": P / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64/f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name, "pairs_per_step": P, "read_len": READ_LEN,
+                       "reference": "oracle/_ref/kallisto quant --plaintext -t %d, plain FASTQ from /dev/shm, index-load "
+                                    "run subtracted" % info["cores"], **info},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": info["cores"], "kind": "reference",
+                             "sample": "%d pairs x %d repeats" % (sample, reps)},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------------------------- our arm ----------------------------------
+    import torch.distributed as dist
+    import kallisto_b200 as K200
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    idx, concat, lens = workload(args.genes)
+    t0 = time.time()
+    index = K200.KmerIndex(idx, device=local_rank, threads=min(16, os.cpu_count() or 4))
+    log("rank %d: index loaded in %.1f s (parse %.1f s, device build %.1f s): %s" % (
+        rank, time.time() - t0, index.info["load_seconds"], index.info["build_seconds"], index.info))
+    sim = benchdata.TorchSimulator(concat, lens, dev, read_len=READ_LEN)
+    nsteps = K + W
+    t0 = time.time()
+    d_batches = [sim.pairs(P, seed=1000 + rank * 100003 + s) for s in range(nsteps)]
+    torch.cuda.synchronize()
+    log("rank %d: %d x %d pairs simulated on the device in %.1f s" % (rank, nsteps, P, time.time() - t0))
+    h_batches = [torch.empty((P, 2, READ_LEN), dtype=torch.uint8, pin_memory=True) for _ in range(nsteps)]
+    for h, d in zip(h_batches, d_batches):
+        h.copy_(d)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    n_reads = 2 * P
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def new_run():
+        mc = K200.MinCollector(index, paired=True, max_batch_reads=P, max_batch_bases=P * 2 * READ_LEN + 64)
+        mc.set_stream(stream.cuda_stream)
+        return mc
+
+    # warm-up on a scratch run (dictionary, memo, clocks, allocator); the timed job starts cold
+    mc = new_run()
+    for s in range(W):
+        mc.process_buffer_device(d_batches[s].data_ptr(), None, n_reads, READ_LEN)
+    if W:
+        mc.run_em()
+    mc.close()
+
+    # ---- value: inputs resident in HBM ----
+    mc = new_run()
+    mc.enable_timing(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ev0.record(stream)
+    for s in range(W, W + K):
+        mc.process_buffer_device(d_batches[s].data_ptr(), None, n_reads, READ_LEN)
+    ev1.record(stream)
+    em = mc.run_em()        # finalises the EC table (D2H of the used sets), builds CSR/CSC, runs the EM kernel
+    ev2.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    t_align_ms = ev0.elapsed_time(ev1)
+    t_total_ms = ev0.elapsed_time(ev2)
+    tt = torch.tensor([t_total_ms, t_align_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_total_ms, t_align_ms = float(tt[0]), float(tt[1])
+    st = mc.finalize()
+    tm = mc.timings()
+    mc.close()
+
+    # ---- e2e: pinned host buffers through the C ABI, H2D inside, est_counts back on the host ----
+    mc2 = new_run()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        mc2.process_buffer_ptr(h_batches[s].data_ptr(), None, n_reads, READ_LEN, None)
+    em2 = mc2.run_em()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te[0])
+    mc2.close()
+
+    total_pairs = K * P * world
+    value = total_pairs / (t_total_ms * 1e-3)
+    e2e_value = total_pairs / t_e2e
+
+    # ---- roofline of the dominant kernel (match_kernel) ----
+    probes_per_pair = st["n_probes"] / max(1, st["n_processed"])
+    visits_per_pair = st["n_slot_visits"] / max(1, st["n_processed"])
+    # algorithmic bytes per pair: read bases + one 32-byte sector per executed probe +
+    # the per-pair result; EC-list bytes are only touched by the (rare) resolve kernel
+    bytes_per_pair = 2 * READ_LEN + probes_per_pair * 32 + 16
+    peak, peak_src = measured_peak()
+    match_ms_per_launch = tm["match_ms"] / max(1, tm["match_launches"])
+    achieved = bytes_per_pair * P / (match_ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "match_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "bytes_per_pair": bytes_per_pair, "probes_per_pair": probes_per_pair,
+                "slot_visits_per_pair": visits_per_pair, "ms_per_launch": match_ms_per_launch,
+                "resolve_ms_per_launch": tm["resolve_ms"] / max(1, tm["resolve_launches"]), "em_ms": tm["em_ms"],
+                "em_rounds": em["rounds"]}
+    prof = os.path.join(ROOT, "profiles", "match_kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+
+    if rank != 0:
+        return 0
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, info = reference_run(idx, concat, lens, min(args.cpu_sample_pairs, P), 1, dev)
+            cpu = {"value": v, "unit": "pairs/s", "cores": info["cores"], "kind": "reference",
+                   "sample": "%d pairs, oracle/_ref/kallisto quant -t %d, index-load run (%.1f s) subtracted" % (
+                       info["sample_pairs"], info["cores"], info["t_load_s"])}
+        except Exception as e:   # the baseline must never take the measurement down
+            cpu = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % e}
+    line = {
+        "metric": "paired reads/sec quant", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64/f64", "data": "synthetic",
+        "config": {"workload": workload_name, "pairs_per_step": P, "read_len": READ_LEN, "parallelism": "dp%d" % world,
+                   "l2": "every step reads a different %d MB batch (> 126 MB L2)" % (P * 2 * READ_LEN // 1000000),
+                   "em_in_timed_region": True, "align_ms": t_align_ms, "total_ms": t_total_ms,
+                   "n_ecs": st["n_ecs"], "n_ec_entries": st["n_ec_entries"],
+                   "p_pseudoaligned": st["n_pseudoaligned"] / max(1, st["n_processed"]),
+                   "index": {k: index.info[k] for k in ("n_targets", "n_kmers", "n_unitigs", "n_ec_sets", "table_slots")}},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": P * 2 * READ_LEN,
+                "d2h_bytes_per_step": int(index.num_trans * 16 / K), "seconds": t_e2e,
+                "api": "kb_pseudoalign_batch (pinned host bases) x K, kb_em_run"},
+        "gpu_launches": int(tm["match_launches"] + tm["resolve_launches"] + 4),
+        "roofline": roofline,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -130,3 +130,103 @@ def interleave(r1, r2):
     out[:, 0, :] = r1
     out[:, 1, :] = r2
     return out.reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------
+# Same read model on the GPU with torch ops (bench plumbing: inputs must already be resident in
+# HBM when the timed region starts, and 30 M pairs are too slow to simulate with numpy).
+# ---------------------------------------------------------------------------------------------
+def _abundance_weights(lens, fl_mean=200.0, abundance_seed=7):
+    ab = np.random.default_rng(abundance_seed).gamma(0.5, 1.0, len(lens))
+    w = ab * np.maximum(lens - fl_mean + 1, 1.0)
+    return w / w.sum()
+
+
+class TorchSimulator:
+    def __init__(self, concat, lens, device, read_len=100, err=0.005, n_frac=0.001, random_frac=0.05, fl_mean=200.0,
+                 fl_sd=30.0):
+        import torch
+        self.torch = torch
+        self.dev = device
+        self.L = read_len
+        self.err, self.n_frac, self.random_frac, self.fl_mean, self.fl_sd = err, n_frac, random_frac, fl_mean, fl_sd
+        self.concat = torch.from_numpy(np.ascontiguousarray(concat)).to(device)
+        lens = np.asarray(lens, np.int64)
+        starts = np.zeros(len(lens), np.int64)
+        np.cumsum(lens[:-1], out=starts[1:])
+        self.lens = torch.from_numpy(lens).to(device)
+        self.starts = torch.from_numpy(starts).to(device)
+        w = _abundance_weights(lens, fl_mean)
+        self.cdf = torch.from_numpy(np.cumsum(w)).to(device)
+        self.comp = torch.from_numpy(COMP).to(device)
+        self.acgt = torch.from_numpy(ACGT.copy()).to(device)
+
+    def pairs(self, n_pairs, seed):
+        """-> uint8 tensor (n_pairs, 2, L) on the device: mates interleaved, ready for
+        kb_pseudoalign_batch(_device) with fixed_len = L."""
+        torch = self.torch
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(int(seed))
+        L = self.L
+        u = torch.rand(n_pairs, generator=g, device=self.dev, dtype=torch.float64)
+        t = torch.searchsorted(self.cdf, u).clamp_(max=len(self.lens) - 1)
+        fl = torch.normal(self.fl_mean, self.fl_sd, (n_pairs,), generator=g, device=self.dev).round_().clamp_(L, 999).long()
+        tl = self.lens[t]
+        fl = torch.minimum(fl, tl)
+        ok = fl >= L
+        start = (torch.rand(n_pairs, generator=g, device=self.dev, dtype=torch.float64) * (tl - fl + 1).double()).long()
+        base = self.starts[t] + start
+        ar = torch.arange(L, device=self.dev)
+        nmax = self.concat.numel() - 1
+        out = torch.empty((n_pairs, 2, L), dtype=torch.uint8, device=self.dev)
+        CH = 1 << 20
+        for c0 in range(0, n_pairs, CH):
+            c1 = min(n_pairs, c0 + CH)
+            b = torch.where(ok[c0:c1], base[c0:c1], torch.zeros_like(base[c0:c1]))
+            f = torch.where(ok[c0:c1], fl[c0:c1], torch.full_like(fl[c0:c1], L))
+            r1 = self.concat[(b[:, None] + ar[None, :]).clamp_(max=nmax)]
+            r2 = self.comp[self.concat[((b + f - 1)[:, None] - ar[None, :]).clamp_(0, nmax)].long()]
+            flip = torch.rand(c1 - c0, generator=g, device=self.dev) < 0.5
+            out[c0:c1, 0] = torch.where(flip[:, None], r2, r1)
+            out[c0:c1, 1] = torch.where(flip[:, None], r1, r2)
+            rnd = (torch.rand(c1 - c0, generator=g, device=self.dev) < self.random_frac) | ~ok[c0:c1]
+            rnd_bases = self.acgt[torch.randint(0, 4, (c1 - c0, 2, L), generator=g, device=self.dev)]
+            out[c0:c1] = torch.where(rnd[:, None, None], rnd_bases, out[c0:c1])
+            m = torch.rand((c1 - c0, 2, L), generator=g, device=self.dev) < self.err
+            sub = self.acgt[torch.randint(0, 4, (c1 - c0, 2, L), generator=g, device=self.dev)]
+            out[c0:c1] = torch.where(m, sub, out[c0:c1])
+            nn = torch.rand((c1 - c0, 2), generator=g, device=self.dev) < self.n_frac
+            pos = torch.randint(0, L, (c1 - c0, 2), generator=g, device=self.dev)
+            nmask = torch.zeros((c1 - c0, 2, L), dtype=torch.bool, device=self.dev)
+            nmask.scatter_(2, pos[:, :, None], nn[:, :, None])
+            out[c0:c1] = torch.where(nmask, torch.full_like(out[c0:c1], ord("N")), out[c0:c1])
+        return out
+
+
+def write_fastq_fast(path, reads, tag):
+    """Vectorised FASTQ writer: fixed-width names @r%09d/<tag>, constant quality 'I'."""
+    n, L = reads.shape
+    name_w = 1 + 1 + 9 + 2   # '@' 'r' digits '/' tag
+    row = name_w + 1 + L + 1 + 2 + L + 1
+    with open(path, "wb") as f:
+        CH = 500000
+        for c0 in range(0, n, CH):
+            c1 = min(n, c0 + CH)
+            m = c1 - c0
+            buf = np.empty((m, row), np.uint8)
+            buf[:, 0] = ord("@")
+            buf[:, 1] = ord("r")
+            idx = np.arange(c0, c1, dtype=np.int64)
+            for d in range(9):
+                buf[:, 2 + d] = ord("0") + (idx // 10 ** (8 - d)) % 10
+            buf[:, 11] = ord("/")
+            buf[:, 12] = ord("0") + tag
+            buf[:, 13] = ord("\n")
+            buf[:, 14:14 + L] = reads[c0:c1]
+            o = 14 + L
+            buf[:, o] = ord("\n")
+            buf[:, o + 1] = ord("+")
+            buf[:, o + 2] = ord("\n")
+            buf[:, o + 3:o + 3 + L] = ord("I")
+            buf[:, o + 3 + L] = ord("\n")
+            f.write(buf.tobytes())

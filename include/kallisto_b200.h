@@ -86,6 +86,15 @@ int kb_pseudoalign_batch(kb_quant* q, const char* bases, const uint32_t* offsets
 int kb_pseudoalign_batch_device(kb_quant* q, const void* d_bases, const uint32_t* d_offsets, uint32_t n_reads,
                                 uint32_t fixed_len, uint32_t max_read_len);
 int kb_quant_sync(kb_quant* q);
+/* Run the kernels of this run on the caller's CUDA stream (cudaStream_t) instead of a private one. */
+int kb_quant_set_stream(kb_quant* q, void* cuda_stream);
+/* Per-kernel device time measured with CUDA events on the launching stream (for the roofline). */
+typedef struct kb_kernel_timings {
+  double match_ms, resolve_ms, em_ms;
+  uint64_t match_launches, resolve_launches;
+} kb_kernel_timings;
+int kb_quant_enable_timing(kb_quant* q, int on);
+int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out);
 
 /* Replaces MasterProcessor::update + the tail flush + MinCollector::increaseCount
  * (src/ProcessReads.cpp:323-334,424-483; src/MinCollector.cpp:251-269): equivalence classes in

@@ -38,6 +38,11 @@ class kb_quant_opts(C.Structure):
                 ("max_batch_reads", C.c_uint32), ("max_batch_bases", C.c_uint64)]
 
 
+class kb_kernel_timings(C.Structure):
+    _fields_ = [("match_ms", C.c_double), ("resolve_ms", C.c_double), ("em_ms", C.c_double),
+                ("match_launches", C.c_uint64), ("resolve_launches", C.c_uint64)]
+
+
 class kb_run_stats(C.Structure):
     _fields_ = [("n_processed", C.c_uint64), ("n_pseudoaligned", C.c_uint64), ("n_unique", C.c_uint64),
                 ("n_ecs", C.c_uint64), ("n_ec_entries", C.c_uint64), ("n_probes", C.c_uint64),
@@ -48,7 +53,8 @@ class kb_run_stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "kb_last_error", "kb_version", "kb_index_load", "kb_index_free", "kb_index_get_info", "kb_index_target_name",
     "kb_index_target_lens", "kb_index_inspect", "kb_quant_create", "kb_quant_free", "kb_pseudoalign_batch",
-    "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
+    "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_set_stream", "kb_quant_enable_timing",
+    "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
     "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_counts_to_tpm",
 ]
 
@@ -79,6 +85,9 @@ def lib():
     L.kb_pseudoalign_batch.argtypes = [vp, vp, vp, u32, u32, vp]
     L.kb_pseudoalign_batch_device.argtypes = [vp, vp, vp, u32, u32, u32]
     L.kb_quant_sync.argtypes = [vp]
+    L.kb_quant_set_stream.argtypes = [vp, vp]
+    L.kb_quant_enable_timing.argtypes = [vp, C.c_int]
+    L.kb_quant_get_timings.argtypes = [vp, C.POINTER(kb_kernel_timings)]
     L.kb_quant_finalize.argtypes = [vp, C.POINTER(kb_run_stats)]
     L.kb_quant_ec_table.argtypes = [vp, vp, vp, vp, vp]
     L.kb_quant_get_flens.argtypes = [vp, vp]
@@ -191,6 +200,17 @@ class MinCollector:
 
     def sync(self):
         _ck(lib().kb_quant_sync(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        _ck(lib().kb_quant_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def enable_timing(self, on=True):
+        _ck(lib().kb_quant_enable_timing(self._h, int(on)))
+
+    def timings(self):
+        t = kb_kernel_timings()
+        _ck(lib().kb_quant_get_timings(self._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in kb_kernel_timings._fields_}
 
     # -- MasterProcessor::update / increaseCount --------------------------------------------
     def finalize(self):

@@ -144,6 +144,29 @@ int kb_quant_sync(kb_quant* q) {
   return guarded([&] { q->q->sync(); });
 }
 
+int kb_quant_set_stream(kb_quant* q, void* cuda_stream) {
+  if (!q) return fail(KB_ERR_INVALID, "kb_quant_set_stream: null argument");
+  return guarded([&] { q->q->set_stream((cudaStream_t)cuda_stream); });
+}
+
+int kb_quant_enable_timing(kb_quant* q, int on) {
+  if (!q) return fail(KB_ERR_INVALID, "kb_quant_enable_timing: null argument");
+  q->q->enable_timing(on != 0);
+  return KB_OK;
+}
+
+int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out) {
+  if (!q || !out) return fail(KB_ERR_INVALID, "kb_quant_get_timings: null argument");
+  return guarded([&] {
+    const kb::Quant::Timings t = q->q->timings();
+    out->match_ms = t.match_ms;
+    out->resolve_ms = t.resolve_ms;
+    out->match_launches = t.match_launches;
+    out->resolve_launches = t.resolve_launches;
+    out->em_ms = q->q->last_em_seconds * 1e3;
+  });
+}
+
 int kb_quant_finalize(kb_quant* q, kb_run_stats* stats) {
   if (!q) return fail(KB_ERR_INVALID, "kb_quant_finalize: null argument");
   return guarded([&] {

@@ -223,7 +223,31 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
 
 Quant::~Quant() {
   if (h_off_pinned_) cudaFreeHost(h_off_pinned_);
-  if (stream_) cudaStreamDestroy(stream_);
+  for (auto ev : events_) cudaEventDestroy(ev);
+  if (stream_ && own_stream_) cudaStreamDestroy(stream_);
+}
+
+void Quant::set_stream(cudaStream_t st) {
+  KB_CK(cudaStreamSynchronize(stream_));
+  if (stream_ && own_stream_) cudaStreamDestroy(stream_);
+  stream_ = st;
+  own_stream_ = false;
+}
+
+Quant::Timings Quant::timings() {
+  KB_CK(cudaStreamSynchronize(stream_));
+  for (size_t i = 0; i + 2 < events_.size(); i += 3) {
+    float a = 0, b = 0;
+    KB_CK(cudaEventElapsedTime(&a, events_[i], events_[i + 1]));
+    KB_CK(cudaEventElapsedTime(&b, events_[i + 1], events_[i + 2]));
+    tacc_.match_ms += a;
+    tacc_.resolve_ms += b;
+    ++tacc_.match_launches;
+    ++tacc_.resolve_launches;
+  }
+  for (auto ev : events_) cudaEventDestroy(ev);
+  events_.clear();
+  return tacc_;
 }
 
 void Quant::sync() { KB_CK(cudaStreamSynchronize(stream_)); }
@@ -274,7 +298,14 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   const size_t per_thread = (size_t)(ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 2) * 4;
   while (tpb > 32 && per_thread * tpb > 48 * 1024) tpb >>= 1;
   if (per_thread * tpb > 48 * 1024) throw Error("kallisto_b200: read too long for the short-read kernel");
-  launch_pseudoalign(ix_.dev, dd_, ba, ra, tpb, stream_);
+  cudaEvent_t* ev = nullptr;
+  if (timing_) {
+    const size_t base = events_.size();
+    events_.resize(base + 3);
+    for (int i = 0; i < 3; ++i) KB_CK(cudaEventCreate(&events_[base + i]));
+    ev = events_.data() + base;
+  }
+  launch_pseudoalign(ix_.dev, dd_, ba, ra, tpb, stream_, ev);
   KB_CK(cudaGetLastError());
   if (want_fld) {
     launch_fld_finalize(dd_, ba, stream_);

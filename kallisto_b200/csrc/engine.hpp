@@ -124,6 +124,13 @@ class Quant {
   std::vector<int> run_bootstrap(const EcTable& ecs, const std::vector<double>& fl_trunc, uint64_t seed, int B,
                                  std::vector<double>& alpha_out, std::vector<uint32_t>* samples_out = nullptr);
 
+  // Run on a caller-provided stream (e.g. the framework's current stream) instead of the run's own.
+  void set_stream(cudaStream_t st);
+  // Per-kernel device time, measured with CUDA events on the launching stream.
+  struct Timings { double match_ms = 0, resolve_ms = 0; uint64_t match_launches = 0, resolve_launches = 0; };
+  void enable_timing(bool on) { timing_ = on; }
+  Timings timings();
+
   Index& index() { return ix_; }
   const QuantOptions& options() const { return opt_; }
   cudaStream_t stream() const { return stream_; }
@@ -137,6 +144,10 @@ class Quant {
   Index& ix_;
   QuantOptions opt_;
   cudaStream_t stream_ = nullptr;
+  bool own_stream_ = true;
+  bool timing_ = false;
+  std::vector<cudaEvent_t> events_;   // triples
+  Timings tacc_;
   DevDict dd_{};
   // run state on the device
   DBuf<uint32_t> pool_;

@@ -64,8 +64,9 @@ void launch_dict_init(const DictInitArgs& a, cudaStream_t st);
 
 // Pseudoalignment of one batch: match kernel (thread per fragment) + resolve kernel (warp per
 // queued fragment) [+ fragment-length finalisation].
+// ev (optional): three events recorded before match_kernel, between the kernels, after resolve_kernel.
 void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& ba, const ResolveArgs& ra,
-                        int threads_per_block, cudaStream_t st);
+                        int threads_per_block, cudaStream_t st, cudaEvent_t* ev = nullptr);
 void launch_fld_finalize(const DevDict& dd, const BatchArgs& ba, cudaStream_t st);
 // Compact the handles with count > 0: used[0..*n_used)
 void launch_collect_used(const DevDict& dd, uint32_t* used, uint32_t* n_used, cudaStream_t st);

@@ -652,13 +652,16 @@ __global__ void collect_used_kernel(DevDict dd, uint32_t* used, uint32_t* n_used
 }
 
 void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& ba, const ResolveArgs& ra,
-                        int tpb, cudaStream_t st) {
+                        int tpb, cudaStream_t st, cudaEvent_t* ev) {
   if (ba.n_frag == 0) return;
   cudaMemsetAsync(ba.q_count, 0, sizeof(uint32_t), st);
   const size_t smem = (size_t)tpb * ((size_t)(ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 2) * 4);
   const unsigned blocks = (ba.n_frag + tpb - 1) / tpb;
+  if (ev) cudaEventRecord(ev[0], st);
   match_kernel<<<blocks, tpb, smem, st>>>(ix, dd, ba);
+  if (ev) cudaEventRecord(ev[1], st);
   resolve_kernel<<<(ra.n_warps * 32 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra);
+  if (ev) cudaEventRecord(ev[2], st);
 }
 
 void launch_fld_finalize(const DevDict& dd, const BatchArgs& ba, cudaStream_t st) {
