@@ -163,16 +163,25 @@ def reference_run(idx, concat, lens, sample_pairs, repeats, device):
             while f.read(1 << 26):
                 pass
 
-        def run(files):
+        def run(files, threads):
             t0 = time.perf_counter()
-            O.ref_run(["quant", "-i", idx, "-o", os.path.join(td, "out"), "--plaintext", "-t", str(cores)] + files,
+            O.ref_run(["quant", "-i", idx, "-o", os.path.join(td, "out"), "--plaintext", "-t", str(threads)] + files,
                       check=False)
             return time.perf_counter() - t0
-        t_load = min(run([t1, t2]) for _ in range(1))
-        t_total = run([f1, f2] * repeats)
-    t_work = max(1e-9, t_total - t_load)
-    return sample_pairs * repeats / t_work, dict(cores=cores, t_load_s=round(t_load, 2), t_total_s=round(t_total, 2),
-                                                 sample_pairs=sample_pairs, repeats=repeats)
+        # the reference's reader lock makes very high thread counts slower, so give it its best shot:
+        # try all cores and a few smaller counts, keep the fastest
+        best = None
+        tried = {}
+        for threads in sorted({cores, min(cores, 32), min(cores, 16)}, reverse=True):
+            t_load = run([t1, t2], threads)
+            t_total = run([f1, f2] * repeats, threads)
+            rate = sample_pairs * repeats / max(1e-9, t_total - t_load)
+            tried[threads] = round(rate)
+            if best is None or rate > best[0]:
+                best = (rate, threads, t_load, t_total)
+    rate, threads, t_load, t_total = best
+    return rate, dict(cores=threads, host_cores=cores, t_load_s=round(t_load, 2), t_total_s=round(t_total, 2),
+                      sample_pairs=sample_pairs, repeats=repeats, pairs_per_s_by_threads=tried)
 
 
 def main():
@@ -183,7 +192,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genes", type=int, default=int(os.environ.get("KB_BENCH_GENES", "62000")))
     ap.add_argument("--pairs-per-step", type=int, default=int(os.environ.get("KB_BENCH_PAIRS", "2000000")))
-    ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("KB_BENCH_CPU_PAIRS", "2000000")))
+    ap.add_argument("--cpu-sample-pairs", type=int, default=int(os.environ.get("KB_BENCH_CPU_PAIRS", "1000000")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -334,8 +343,9 @@ def main():
         try:
             v, info = reference_run(idx, concat, lens, min(args.cpu_sample_pairs, P), 1, dev)
             cpu = {"value": v, "unit": "pairs/s", "cores": info["cores"], "kind": "reference",
-                   "sample": "%d pairs, oracle/_ref/kallisto quant -t %d, index-load run (%.1f s) subtracted" % (
-                       info["sample_pairs"], info["cores"], info["t_load_s"])}
+                   "sample": "%d pairs, oracle/_ref/kallisto quant -t %d (best of %s on %d cores), index-load run (%.1f s) "
+                             "subtracted" % (info["sample_pairs"], info["cores"], info["pairs_per_s_by_threads"],
+                                             info["host_cores"], info["t_load_s"])}
         except Exception as e:   # the baseline must never take the measurement down
             cpu = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % e}
     line = {
@@ -345,7 +355,8 @@ def main():
         "config": {"workload": workload_name, "pairs_per_step": P, "read_len": READ_LEN, "parallelism": "dp%d" % world,
                    "l2": "every step reads a different %d MB batch (> 126 MB L2)" % (P * 2 * READ_LEN // 1000000),
                    "em_in_timed_region": True, "align_ms": t_align_ms, "total_ms": t_total_ms,
-                   "n_ecs": st["n_ecs"], "n_ec_entries": st["n_ec_entries"],
+                   "n_ecs": st["n_ecs"], "n_ec_entries": st["n_ec_entries"], "n_resolved": st["n_resolved"],
+                   "n_memo_hits": st["n_memo_hits"],
                    "p_pseudoaligned": st["n_pseudoaligned"] / max(1, st["n_processed"]),
                    "index": {k: index.info[k] for k in ("n_targets", "n_kmers", "n_unitigs", "n_ec_sets", "table_slots")}},
         "clocks": clocks,

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkallisto_b200.so")
+LIB_PATH = os.environ.get("KB_LIB_PATH") or os.path.join(_HERE, "libkallisto_b200.so")   # KB_LIB_PATH: experiments only
 
 KB_OK = 0
 KB_ERR_NO_DEVICE = -3

@@ -61,6 +61,7 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
     throw Error("kallisto_b200: no CUDA device available (this build has no CPU path)");
   if (device < 0 || device >= ndev) throw Error("kallisto_b200: invalid CUDA device ordinal");
   KB_CK(cudaSetDevice(device));
+  if (const char* s = getenv("KB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s));   // experiment knob
 
   std::unique_ptr<Index> ix(new Index());
   ix->device = device;
@@ -89,7 +90,6 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   ix->n_index_tids = (uint32_t)f.ec_tid.size();
   ix->index_pool.alloc(std::max<size_t>(1, f.ec_tid.size()));
   ix->index_pool.upload(f.ec_tid.data(), f.ec_tid.size(), st);
-  ix->blk_ec.upload(f.blk_ec.data(), f.blk_ec.size(), st);
   ix->blk_strand_off.upload(f.blk_strand_off.data(), f.blk_strand_off.size(), st);
   ix->strand.alloc(std::max<size_t>(1, f.strand.size()));
   ix->strand.upload(f.strand.data(), f.strand.size(), st);
@@ -98,6 +98,31 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
     if (len == 0) ix->empty_ec = e;
     ix->max_set_len = std::max(ix->max_set_len, len);
   }
+
+  cudaStream_t st0 = st;
+  // set dictionary, initial state: the index's own EC sets.  Done first: the k-mer slots store the
+  // dictionary handle of their block's set, not its index-local id.
+  ix->dict_cap = pow2_ge((uint64_t)f.n_ec() * 4 + (1u << 20));
+  ix->dslots_init.alloc(ix->dict_cap);
+  launch_fill_u64(ix->dslots_init.p, ix->dict_cap, ~0ULL, st0);
+  ix->ec_handle.alloc(std::max<uint32_t>(1, f.n_ec()));
+  {
+    DictInitArgs a{};
+    a.ec_off = ix->ec_off.p; a.pool = ix->index_pool.p; a.n_ec = f.n_ec();
+    a.dslots = ix->dslots_init.p; a.dmask = ix->dict_cap - 1; a.ec_handle = ix->ec_handle.p;
+    launch_dict_init(a, st0);
+    KB_CK(cudaGetLastError());
+  }
+  ix->h_ec_handle.resize(f.n_ec());
+  ix->ec_handle.download(ix->h_ec_handle.data(), f.n_ec(), 0, st0);
+  KB_CK(cudaStreamSynchronize(st0));
+  {
+    std::vector<uint32_t> blk_handle(f.blk_ec.size());
+    for (size_t i = 0; i < blk_handle.size(); ++i) blk_handle[i] = (uint32_t)ix->h_ec_handle[f.blk_ec[i]];
+    ix->blk_ec.upload(blk_handle.data(), blk_handle.size(), st0);
+    KB_CK(cudaStreamSynchronize(st0));
+  }
+  if (ix->empty_ec != 0xFFFFFFFFu) ix->empty_ec = (uint32_t)ix->h_ec_handle[ix->empty_ec];
 
   // k-mer table: load factor <= 0.5
   ix->table_cap = pow2_ge(std::max<uint64_t>(1024, f.n_kmers * 2));
@@ -126,18 +151,6 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
     KB_CK(cudaGetLastError());
     KB_CK(cudaStreamSynchronize(st));
   }
-  // set dictionary, initial state: the index's own EC sets
-  ix->dict_cap = pow2_ge((uint64_t)f.n_ec() * 4 + (1u << 20));
-  ix->dslots_init.alloc(ix->dict_cap);
-  launch_fill_u64(ix->dslots_init.p, ix->dict_cap, ~0ULL, st);
-  ix->ec_handle.alloc(std::max<uint32_t>(1, f.n_ec()));
-  {
-    DictInitArgs a{};
-    a.ec_off = ix->ec_off.p; a.pool = ix->index_pool.p; a.n_ec = f.n_ec();
-    a.dslots = ix->dslots_init.p; a.dmask = ix->dict_cap - 1; a.ec_handle = ix->ec_handle.p;
-    launch_dict_init(a, st);
-    KB_CK(cudaGetLastError());
-  }
   int herr = 0;
   err.download(&herr, 1, 0, st);
   KB_CK(cudaStreamSynchronize(st));
@@ -162,6 +175,7 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
 // Quant
 // ------------------------------------------------------------------------------------------
 Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(1000, 0) {
+  if (const char* s = getenv("KB_REFILL_MIN")) opt_.refill_min = std::max(1, std::min(32, atoi(s)));   // tuning knob
   KB_CK(cudaSetDevice(ix_.device));
   KB_CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   cudaStream_t st = stream_;
@@ -179,10 +193,8 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
   launch_fill_u64(first_.p, ix_.dict_cap, ~0ULL, st);
   const uint64_t m2_cap = pow2_ge(nE * 8 + (1u << 20));
   const uint64_t mn_cap = pow2_ge(nE * 4 + (1u << 20));
-  m2_key_.alloc(m2_cap);
-  launch_fill_u64(m2_key_.p, m2_cap, ~0ULL, st);
-  m2_val_.alloc(m2_cap);
-  launch_fill_i32(m2_val_.p, m2_cap, KB_H_NOTREADY, st);
+  m2_.alloc(m2_cap);
+  launch_fill_memo2(m2_.p, m2_cap, st);
   mn_key_.alloc(mn_cap);
   launch_fill_u64(mn_key_.p, mn_cap, ~0ULL, st);
   mn_val_.alloc(mn_cap);
@@ -201,7 +213,7 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
   dd_.pool = pool_.p; dd_.pool_top = counters_.p + 0; dd_.pool_cap = pool_cap;
   dd_.dslots = dslots_.p; dd_.dmask = ix_.dict_cap - 1;
   dd_.count = count_.p; dd_.first = first_.p;
-  dd_.m2_key = m2_key_.p; dd_.m2_val = m2_val_.p; dd_.m2_mask = m2_cap - 1;
+  dd_.m2 = m2_.p; dd_.m2_mask = m2_cap - 1;
   dd_.mn_key = mn_key_.p; dd_.mn_val = mn_val_.p; dd_.mn_mask = mn_cap - 1;
   dd_.tpool = tpool_.p; dd_.tpool_top = counters_.p + 1; dd_.tpool_cap = tpool_cap;
   dd_.error = error_.p; dd_.stats = counters_.p + 2;
@@ -286,18 +298,26 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.tl_out = want_fld ? d_tl_.p : nullptr;
   ba.q_count = d_qcount_.p;
   ba.q_entries = d_qentries_.p;
-  ba.bwords = (max_read_len + 31) / 32 + 1;
+  ba.nb = std::max<uint32_t>(1, (max_read_len + 31) / 32);
+  ba.bwords = ba.nb + 1;
   ba.iwords = ba.bwords / 2 + 1;
+  ba.pstride = (3 * ba.nb + 7) & ~7u;
+  {
+    const size_t need = (size_t)n_reads * ba.pstride;
+    if (d_packed_.n < need) d_packed_.alloc(std::max(need, (size_t)opt_.max_batch_reads * 2 * 16));
+  }
+  ba.packed = d_packed_.p;
   ba.empty_ec = ix_.empty_ec;
+  ba.refill_min = opt_.refill_min;
   ResolveArgs ra{};
   ra.scratch = d_scratch_.p;
   ra.scratch_stride = (uint32_t)(d_scratch_.n / n_resolve_warps_);
   ra.n_warps = n_resolve_warps_;
 
   int tpb = opt_.threads_per_block;
-  const size_t per_thread = (size_t)(ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 2) * 4;
-  while (tpb > 32 && per_thread * tpb > 48 * 1024) tpb >>= 1;
-  if (per_thread * tpb > 48 * 1024) throw Error("kallisto_b200: read too long for the short-read kernel");
+  const size_t per_thread = (size_t)2 * (ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 8) * 4;
+  while (tpb > 32 && per_thread * tpb > 200 * 1024) tpb >>= 1;
+  if (per_thread * tpb > 200 * 1024) throw Error("kallisto_b200: read too long for the short-read kernel");
   cudaEvent_t* ev = nullptr;
   if (timing_) {
     const size_t base = events_.size();
@@ -685,5 +705,6 @@ template struct DBuf<uint64_t>;
 template struct DBuf<unsigned long long>;
 template struct DBuf<double>;
 template struct DBuf<KmerSlot>;
+template struct DBuf<Memo2Entry>;
 
 }  // namespace kb

@@ -59,6 +59,7 @@ class Index {
   DBuf<uint32_t> index_pool;      // the index's EC sets (copied to the front of every run's pool)
   DBuf<unsigned long long> dslots_init;
   DBuf<int32_t> ec_handle;
+  std::vector<int32_t> h_ec_handle;   // host copy: index EC-set id -> dictionary handle
   DBuf<uint32_t> blk_ec;
   DBuf<uint64_t> blk_strand_off;
   DBuf<uint8_t> strand;
@@ -70,7 +71,8 @@ struct QuantOptions {
   int collect_fld = 1;     // opt.fld == 0: estimate the fragment-length distribution from the data
   uint32_t max_batch_reads = 1u << 22;     // staging capacity (reads per batch)
   uint64_t max_batch_bases = 1ull << 29;   // staging capacity (bases per batch)
-  int threads_per_block = 128;
+  int threads_per_block = 256;
+  int refill_min = 16;     // match_kernel: finished lanes per warp that trigger a finalise + refill round
 };
 
 // Equivalence classes of a finished run, ids in order of first occurrence (== reference -t 1).
@@ -151,13 +153,14 @@ class Quant {
   DevDict dd_{};
   // run state on the device
   DBuf<uint32_t> pool_;
-  DBuf<unsigned long long> dslots_, first_, m2_key_, mn_key_, counters_;   // counters_: pool_top, tpool_top, stats[4]
+  DBuf<Memo2Entry> m2_;
+  DBuf<unsigned long long> dslots_, first_, mn_key_, counters_;   // counters_: pool_top, tpool_top, stats[4]
   DBuf<uint32_t> count_, tpool_;
-  DBuf<int32_t> m2_val_, mn_val_;
+  DBuf<int32_t> mn_val_;
   DBuf<int> error_;
   // batch staging
   DBuf<uint8_t> d_bases_;
-  DBuf<uint32_t> d_off_, d_qcount_, d_qentries_, d_scratch_;
+  DBuf<uint32_t> d_off_, d_qcount_, d_qentries_, d_scratch_, d_packed_;
   DBuf<int32_t> d_handles_;
   DBuf<uint16_t> d_tl_;
   uint32_t n_resolve_warps_ = 0;

@@ -21,6 +21,7 @@ namespace kb {
 
 static constexpr uint64_t KB_EMPTY_KEY = ~0ULL;
 static constexpr int KB_MAX_E = 16;          // distinct EC sets tracked per fragment on the fast path
+static constexpr int KB_SCAN_W = 4;         // independent k-mer lookups in flight while scanning a stretch of misses
 static constexpr int32_t KB_H_UNMAPPED = -1;
 static constexpr int32_t KB_H_PENDING = -2;  // fragment queued for the resolve kernel
 static constexpr int32_t KB_H_NOTREADY = -3; // memo slot claimed, value not yet published
@@ -29,7 +30,7 @@ struct __align__(32) KmerSlot {
   uint64_t key;        // canonical k-mer, right-aligned 2k bits; KB_EMPTY_KEY = free
   uint32_t unitig;     // global unitig id (long, then short, then abundant)
   uint32_t blk;        // global EC-block id
-  uint32_t ec;         // content-deduplicated EC-set id of that block
+  uint32_t ec;         // EC set of that block, as its dictionary handle (equal handles <=> equal transcript sets)
   uint32_t dist_flag;  // bits 0..30: k-mer offset in unitig-forward coordinates; bit 31: forward k-mer is the canonical one
   uint32_t lb, ub;     // EC block [lb, ub) in k-mer coordinates of the unitig
 };
@@ -43,9 +44,15 @@ struct DevIndex {
   uint32_t n_targets;
   const uint32_t* ec_off;    // n_ec + 1 offsets into pool (index sets occupy pool[0 .. ec_off[n_ec]))
   const int32_t* ec_handle;  // n_ec: handle (dictionary slot) of each index set
-  const uint32_t* blk_ec;    // per block: EC-set id (strand filter)
+  const uint32_t* blk_ec;    // per block: set handle of its EC (strand filter)
   const uint64_t* blk_strand_off;  // per block offset into strand bytes (stranded modes)
   const uint8_t* strand;
+};
+
+struct __align__(16) Memo2Entry {
+  unsigned long long key;   // ~0 = free
+  int32_t val;              // KB_H_NOTREADY until published
+  uint32_t pad;
 };
 
 // Run-time state of one quantification run, resident on the device.
@@ -57,9 +64,8 @@ struct DevDict {
   uint64_t dmask;
   uint32_t* count;           // per handle
   unsigned long long* first; // per handle: smallest global fragment index that produced it
-  // memo for tuples of exactly two EC sets: key = lo<<32|hi
-  unsigned long long* m2_key;
-  int32_t* m2_val;
+  // memo for tuples of exactly two EC sets: key = lo<<32|hi ; 16-byte entries, two per 32-byte block
+  Memo2Entry* m2;
   uint64_t m2_mask;
   // memo for longer tuples (and tuples carrying strand words): word = tag(32)<<32 | tuple offset
   unsigned long long* mn_key;

@@ -14,7 +14,7 @@ struct TableBuildArgs {
   const uint64_t* blk_off;
   const uint32_t* blk_lb;
   const uint32_t* blk_ub;
-  const uint32_t* blk_ec;
+  const uint32_t* blk_ec;     // per block: set handle
   uint32_t n_long, n_unitigs;
   int k;
   uint64_t n_kmers;
@@ -47,7 +47,11 @@ struct BatchArgs {
   uint32_t* q_count;        // resolve queue
   uint32_t* q_entries;      // stride KB_Q_STRIDE
   uint32_t bwords, iwords;  // shared-memory words per read (2-bit bases / invalid mask)
-  uint32_t empty_ec;        // id of the empty index EC set, or 0xFFFFFFFF
+  const uint32_t* packed;   // pack_kernel output: per read, nb 64-bit base words then nb 32-bit invalid masks
+  uint32_t nb;              // 32-base words per packed read = ceil(max_read_len / 32)
+  uint32_t pstride;         // 32-bit words per packed read (multiple of 8 = 32 bytes)
+  uint32_t empty_ec;        // handle of the empty index EC set, or 0xFFFFFFFF
+  int refill_min;           // finished lanes of a warp that trigger a finalise + refill round
 };
 static constexpr int KB_Q_STRIDE = 2 + KB_MAX_E + 2;
 
@@ -59,6 +63,7 @@ struct ResolveArgs {
 
 void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st);
 void launch_fill_i32(int32_t* p, uint64_t n, int32_t v, cudaStream_t st);
+void launch_fill_memo2(Memo2Entry* p, uint64_t n, cudaStream_t st);
 void launch_build_table(const TableBuildArgs& a, cudaStream_t st);
 void launch_dict_init(const DictInitArgs& a, cudaStream_t st);
 

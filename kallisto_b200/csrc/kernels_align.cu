@@ -20,14 +20,13 @@
 #include "kb_device.cuh"
 #include "kernels.hpp"
 
+#ifndef KB_MATCH_MIN_BLOCKS
+#define KB_MATCH_MIN_BLOCKS 3
+#endif
+
 namespace kb {
 
 namespace {
-
-struct Hit {
-  uint32_t unitig, blk, ec, dist, lb, ub;
-  bool strand;
-};
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -39,42 +38,26 @@ __device__ __forceinline__ int32_t ld_relaxed_s32(const int32_t* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-
-// One lookup in the k-mer table: dbg.find(km) + get_mc_contig + ec[dist] of the reference.
-// `strand` = the k-mer as it appears in the read equals the unitig-forward k-mer
-// (CompactedDBG.tcc:1049-1107).
-__device__ __forceinline__ bool probe(const DevIndex& ix, uint64_t fwd, Hit& h, uint32_t& n_visits) {
-  const uint64_t rc = kb_revcomp(fwd, ix.k);
-  const bool is_canon = fwd < rc;
-  const uint64_t canon = is_canon ? fwd : rc;
-  uint64_t s = kb_mix64(canon) & ix.mask;
-  for (;;) {
-    const uint4* sp = reinterpret_cast<const uint4*>(ix.slots + s);
-    const uint4 a = __ldg(sp);
-    ++n_visits;
-    const uint64_t key = (uint64_t)a.x | ((uint64_t)a.y << 32);
-    if (key == canon) {
-      const uint4 b = __ldg(sp + 1);
-      h.unitig = a.z;
-      h.blk = a.w;
-      h.ec = b.x;
-      h.dist = b.y & 0x7FFFFFFFu;
-      const bool fic = (b.y >> 31) != 0;
-      h.strand = (is_canon == fic);
-      h.lb = b.z;
-      h.ub = b.w;
-      return true;
-    }
-    if (key == KB_EMPTY_KEY) return false;
-    s = (s + 1) & ix.mask;
-  }
+// One 256-bit read-only load (LDG.E.256 on sm_100a): a whole k-mer slot, half a packed read, or a
+// block of memo entries per instruction.  The address must be 32-byte aligned.
+__device__ __forceinline__ void ld256_nc(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+// Same for memory other blocks may be writing during the kernel (memo tables): L2-coherent.
+__device__ __forceinline__ void ld256_cg(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p)
+               : "memory");
 }
 
-// Per-thread view of the read currently being matched: 2-bit bases and an invalid-base mask in
-// shared memory, word w of thread t at [w * blockDim.x + t] (bank-conflict free).
+// Per-lane view of the read being matched: 2-bit bases and an invalid-base mask in shared memory,
+// word w of lane t at [w * stride + t] (bank-conflict free).
 struct ReadView {
-  uint64_t* bw;   // base words: base i in bits 62-2*(i&31) of word i>>5
-  uint64_t* iv;   // invalid mask: bit (i&63) of word i>>6
+  const uint64_t* bw;   // base words: base i in bits 62-2*(i&31) of word i>>5
+  const uint64_t* iv;   // invalid mask: bit (i&63) of word i>>6
   int stride;
   int len;
   int k;
@@ -102,170 +85,28 @@ struct ReadView {
   }
 };
 
-__device__ __forceinline__ void load_read(const BatchArgs& ba, uint32_t read_idx, ReadView& rv) {
-  uint64_t off;
-  int len;
-  if (ba.off) {
-    off = ba.off[read_idx];
-    len = (int)(ba.off[read_idx + 1] - ba.off[read_idx]);
-  } else {
-    off = (uint64_t)read_idx * ba.fixed_len;
-    len = (int)ba.fixed_len;
-  }
-  const int nbw = (int)ba.bwords, niw = (int)ba.iwords;   // host guarantees niw == nbw/2 + 1
-  const int maxlen = (nbw - 1) * 32;
-  if (len > maxlen) len = maxlen;   // cannot happen: the host sizes bwords from the longest read
-  rv.len = len;
-  const uint8_t* s = ba.bases + off;
-  for (int w2 = 0; w2 < niw; ++w2) {
-    uint64_t inv64 = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int w = 2 * w2 + half;
-      uint32_t inv32 = ~0u;
-      if (w < nbw) {
-        uint64_t bwv = 0;
-        const int base = w * 32;
-        if (base < len) {
-          const int n = min(32, len - base);
-          inv32 = 0;
-          for (int j = 0; j < n; ++j) {
-            const uint32_t c = __ldg(s + base + j);
-            const uint32_t x = (c & 4) >> 1;
-            const uint32_t code = x + ((x ^ (c & 2)) >> 1);          // Kmer::set_kmer
-            const uint32_t u = c & 0xDF;                               // KmerIterator: mask lowercase bit
-            const bool ok = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');   // isDNA, Common.hpp:45-50
-            bwv |= (uint64_t)code << (62 - 2 * j);
-            inv32 |= (ok ? 0u : 1u) << j;
-          }
-          if (n < 32) inv32 |= ~0u << n;
-        }
-        rv.bw[w * rv.stride] = bwv;
-      }
-      inv64 |= (uint64_t)inv32 << (32 * half);
-    }
-    rv.iv[w2 * rv.stride] = inv64;
-  }
-}
-
-struct MateInfo {
-  bool v_nonempty;     // match() returned at least one hit
-  bool s_nonempty;     // at least one hit with a non-empty EC set
-  // first hit (smallest read position): findFirstMappingKmer / mapPair
-  uint32_t f_unitig, f_blk, f_ec, f_dist, f_ub;
-  int f_pos;
-  bool f_strand;
-};
-
-struct FragState {
-  uint32_t* elist;   // shared memory, strided
-  int stride;
-  int n_e;
-  bool overflow;
-  uint32_t empty_ec;
-};
-
-__device__ __forceinline__ void push_hit(FragState& fs, MateInfo& mi, const Hit& h, int pos) {
-  if (!mi.v_nonempty) {
-    mi.v_nonempty = true;
-    mi.f_unitig = h.unitig; mi.f_blk = h.blk; mi.f_ec = h.ec; mi.f_dist = h.dist; mi.f_ub = h.ub;
-    mi.f_pos = pos; mi.f_strand = h.strand;
-  }
-  if (h.ec == fs.empty_ec) return;   // "Don't intersect empty EC", MinCollector.cpp:468-469
-  mi.s_nonempty = true;
-  for (int i = 0; i < fs.n_e; ++i)
-    if (fs.elist[i * fs.stride] == h.ec) return;
-  if (fs.n_e == KB_MAX_E) { fs.overflow = true; return; }
-  fs.elist[fs.n_e * fs.stride] = h.ec;
-  ++fs.n_e;
-}
-
-__device__ __forceinline__ bool same_ue(const Hit& a, const Hit& b) {
-  // um.isSameReferenceUnitig(um2) && ec[um.dist] == ec[um2.dist]   (KmerIndex.cpp:1810-1811)
-  return a.unitig == b.unitig && a.ec == b.ec;
-}
-
-// KmerIndex::match for one read, default flags (no shade/union/no_jump/cfc, empty D-list).
-// `partial` only short-circuits reads whose running intersection empties; the final result is
-// the same either way, so it is not modelled.
-__device__ void match_read(const DevIndex& ix, const ReadView& rv, FragState& fs, MateInfo& mi,
-                           uint32_t& n_probes, uint32_t& n_visits) {
-  const int k = rv.k, l = rv.len;
-  int p = rv.next_valid(0);
-  while (p >= 0) {
-    Hit h;
-    ++n_probes;
-    if (probe(ix, rv.kmer(p), h, n_visits)) {
-      push_hit(fs, mi, h, p);
-      const int off = (int)(h.dist - h.lb), blen = (int)(h.ub - h.lb);
-      const int dist = h.strand ? (blen - 1 - off) : off;                    // 1780-1788
-      if (dist >= 2) {
-        const int nextPos = (p + dist >= l - k) ? (l - k) : (p + dist);      // 1793-1798
-        const int adv = nextPos - p;
-        const int p2 = adv == 0 ? p : rv.next_valid(p + adv);                // kit2 += nextPos-pos
-        if (p2 < 0) break;                                                   // 1882-1886
-        Hit h2;
-        ++n_probes;
-        const bool f2 = probe(ix, rv.kmer(p2), h2, n_visits);
-        bool found2 = false;
-        int found2pos = p + dist;
-        if (!f2) { found2 = true; found2pos = p; }
-        else if (same_ue(h, h2)) { found2 = true; found2pos = p + dist; }
-        if (found2) {
-          if (found2pos >= l - k) { push_hit(fs, mi, h, l - k); break; }
-          push_hit(fs, mi, h, found2pos);
-          p = p2;
-        } else {
-          bool foundMiddle = false;
-          if (dist > 4) {
-            const int middlePos = (p + nextPos) / 2;
-            const int adv3 = middlePos - p;
-            const int p3 = adv3 == 0 ? p : rv.next_valid(p + adv3);
-            if (p3 >= 0) {
-              Hit h3;
-              ++n_probes;
-              if (probe(ix, rv.kmer(p3), h3, n_visits)) {
-                int found3pos = p + dist;
-                if (same_ue(h, h3)) { foundMiddle = true; found3pos = middlePos; }
-                else if (same_ue(h2, h3)) { foundMiddle = true; found3pos = p + dist; }
-                if (foundMiddle) push_hit(fs, mi, h3, found3pos);
-              }
-              if (foundMiddle) {
-                if (nextPos >= l - k) break;
-                p = p2;
-              }
-            }
-          }
-          if (!foundMiddle) {
-            p = rv.next_valid(p + 1);          // ++kit; backOff: exactly one probe (outer nextPos == 0)
-            if (p < 0) break;
-            Hit h4;
-            ++n_probes;
-            if (probe(ix, rv.kmer(p), h4, n_visits)) push_hit(fs, mi, h4, p);
-          }
-        }
-      }
-    }
-    p = rv.next_valid(p + 1);
-  }
-}
-
 __device__ __forceinline__ uint64_t tuple_hash(const uint32_t* w, int n, int stride) {
   uint64_t h = 0x243F6A8885A308D3ULL ^ (uint64_t)n;
   for (int i = 0; i < n; ++i) h = kb_mix64(h ^ ((uint64_t)w[i * stride] + 0x9E3779B97F4A7C15ULL * (i + 1)));
   return h;
 }
 
-// Memo lookups.  Return KB_H_NOTREADY on a miss.
+// Memo lookups used by the resolve kernel (one lane).  Return KB_H_NOTREADY on a miss.
 __device__ __forceinline__ int32_t memo2_lookup(const DevDict& dd, uint32_t e0, uint32_t e1) {
   const unsigned long long key = ((unsigned long long)e0 << 32) | e1;
   uint64_t s = kb_mix64(key) & dd.m2_mask;
   for (;;) {
-    const unsigned long long kk = __ldcg(&dd.m2_key[s]);
-    if (kk == key) return ld_relaxed_s32(&dd.m2_val[s]);
+    const unsigned long long kk = __ldcg(&dd.m2[s].key);
+    if (kk == key) return ld_relaxed_s32(&dd.m2[s].val);
     if (kk == ~0ULL) return KB_H_NOTREADY;
     s = (s + 1) & dd.m2_mask;
   }
+}
+__device__ __forceinline__ bool tuple_equal(const DevDict& dd, uint32_t toff, const uint32_t* w, int n, int stride) {
+  const uint32_t* t = dd.tpool + toff;
+  bool eq = __ldcg(t) == (uint32_t)n;
+  for (int i = 0; eq && i < n; ++i) eq = __ldcg(t + 1 + i) == w[i * stride];
+  return eq;
 }
 __device__ __forceinline__ int32_t memon_lookup(const DevDict& dd, const uint32_t* w, int n, int stride) {
   const uint64_t th = tuple_hash(w, n, stride);
@@ -274,135 +115,426 @@ __device__ __forceinline__ int32_t memon_lookup(const DevDict& dd, const uint32_
   for (;;) {
     const unsigned long long word = ld_acquire_u64(&dd.mn_key[s]);
     if (word == ~0ULL) return KB_H_NOTREADY;
-    if ((uint32_t)(word >> 32) == tag) {
-      const uint32_t* t = dd.tpool + (uint32_t)word;
-      bool eq = __ldcg(t) == (uint32_t)n;
-      for (int i = 0; eq && i < n; ++i) eq = __ldcg(t + 1 + i) == w[i * stride];
-      if (eq) return ld_relaxed_s32(&dd.mn_val[s]);
-    }
+    if ((uint32_t)(word >> 32) == tag && tuple_equal(dd, (uint32_t)word, w, n, stride)) return ld_relaxed_s32(&dd.mn_val[s]);
     s = (s + 1) & dd.mn_mask;
   }
 }
 
-// Warp-aggregated per-handle accounting (valid for any subset of participating lanes that calls
-// it convergently with the full mask).
-__device__ __forceinline__ void account(const DevDict& dd, int32_t handle, uint64_t frag, unsigned lane) {
-  const unsigned grp = __match_any_sync(0xFFFFFFFFu, handle);
-  if (handle >= 0) {
-    const unsigned leader = __ffs(grp) - 1;
-    if (lane == leader) {
-      atomicAdd(&dd.count[handle], (uint32_t)__popc(grp));
-      atomicMin(&dd.first[handle], (unsigned long long)frag);   // lowest lane = lowest fragment index
-    }
-  }
-}
+// Lane states of match_kernel.
+enum : int {
+  S_MAIN = 0, S_JUMP = 1, S_MIDDLE = 2, S_BACKOFF = 3,   // k-mer table lookups (KmerIndex::match control flow)
+  S_FIN = 4,                                             // fragment finished, waiting for the next service round
+  S_EMPTY = 5                                            // no fragment assigned
+};
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) match_kernel(DevIndex ix, DevDict dd, BatchArgs ba) {
+// ---------------------------------------------------------------------------------------------
+// pack_kernel: ASCII reads -> 2-bit bases + invalid-base masks, one thread per (read, 32-base word).
+// Streaming and fully convergent: aligned 32-bit loads (whatever the byte offset of the read), 4
+// bases at a time with SWAR arithmetic
+//   code  = ((c >> 1) & 3) ^ (((c >> 1) & 3) >> 1)          == Kmer::set_kmer (Kmer.cpp:92-107) on A/C/G/T
+//   valid = (c & 0xDF) in {A,C,G,T}                          == isDNA(c & 0xDF)  (KmerIterator.cpp:12-14)
+// Packed read = nb 64-bit base words, then nb 32-bit invalid masks, padded (with "invalid") to a
+// multiple of 32 bytes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_kernel(BatchArgs ba, uint32_t n_reads, uint32_t* out) {
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nb = ba.nb;
+  const uint64_t total = (uint64_t)n_reads * nb;
+  if (gid >= total) return;
+  const uint32_t r = (uint32_t)(gid / nb), w = (uint32_t)(gid % nb);
+  uint64_t off;
+  int len;
+  if (ba.off) {
+    const uint32_t o0 = ba.off[r], o1 = ba.off[r + 1];
+    off = o0;
+    len = (int)(o1 - o0);
+  } else {
+    off = (uint64_t)r * ba.fixed_len;
+    len = (int)ba.fixed_len;
+  }
+  const int base = (int)w * 32;
+  uint64_t bwv = 0;
+  uint32_t inv32 = ~0u;
+  if (base < len) {
+    const int n = min(32, len - base);
+    const uint64_t a = off + (uint64_t)base;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(ba.bases + (a & ~3ull));
+    const int sh = (int)(a & 3) * 8;
+    const int ng = (n + 3) >> 2;
+    uint32_t cur = __ldg(wp);
+    inv32 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q < ng) {
+        int m = n - 4 * q;
+        m = m > 4 ? 4 : m;
+        uint32_t nxt = 0;
+        if (((int)(a & 3) + m > 4) || (q + 1 < ng)) nxt = __ldg(wp + q + 1);
+        const uint32_t four = sh ? __funnelshift_r(cur, nxt, sh) : cur;
+        cur = nxt;
+        uint32_t x = (four >> 1) & 0x03030303u;
+        x ^= (x >> 1) & 0x01010101u;
+        const uint32_t code8 = (x * 0x40100401u) >> 24;                     // b0<<6 | b1<<4 | b2<<2 | b3
+        const uint32_t u = four & 0xDFDFDFDFu;
+        uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) |
+                      __vcmpeq4(u, 0x54545454u);
+        if (m < 4) ok &= 0xFFFFFFFFu >> (8 * (4 - m));
+        const uint32_t inv4 = (((~ok) & 0x01010101u) * 0x01020408u) >> 24;   // bit j = base j invalid
+        bwv |= (uint64_t)code8 << (56 - 8 * q);
+        inv32 |= inv4 << (4 * q);
+      } else {
+        inv32 |= 0xFu << (4 * q);
+      }
+    }
+  }
+  uint32_t* dst = out + (size_t)r * ba.pstride;
+  reinterpret_cast<uint2*>(dst)[w] = make_uint2((uint32_t)bwv, (uint32_t)(bwv >> 32));
+  dst[2 * nb + w] = inv32;
+  if (w == 0)
+    for (uint32_t j = 3 * nb; j < ba.pstride; ++j) dst[j] = ~0u;   // padding reads as "invalid"
+}
+
+// ---------------------------------------------------------------------------------------------
+// match_kernel: persistent warps, 32 independent fragment state machines per warp.
+//
+// KmerIndex::match (src/KmerIndex.cpp:1698-1940, default flags, empty D-list) is a chain of
+// dependent k-mer lookups whose length varies from 2 (clean read inside one EC block) to >100
+// (unmappable read: every k-mer is probed).  As straight-line per-thread code a warp pays the
+// maximum over its lanes, and lanes sitting at different call sites serialise.  Here each lane
+// keeps an explicit state and every iteration of the warp's loop performs exactly ONE lookup per
+// active lane through a single convergent site: canonical k-mer + hash, one LDG.E.256 of the
+// 32-byte slot, then the reference's control flow as a state transition
+//   MAIN     the k-mer at p.  Miss: next valid k-mer.  Hit: record it, distance to the end of its EC
+//            block (1780-1788); if >= 2 go to JUMP.
+//   JUMP     the jump target (1793-1827).  Absent or same (unitig, EC set): accepted, scanning resumes
+//            after the target.  Otherwise MIDDLE (dist > 4) or BACKOFF.
+//   MIDDLE   the middle k-mer (1831-1873).
+//   BACKOFF  the k-mer after p, once (1876-1925: the outer nextPos is never updated, so the back-off
+//            loop runs a single iteration), then MAIN.
+// (linear-probing collisions cost one more iteration in the same state).  Lanes whose fragment is
+// finished wait until `refill_min` of them can be served together: the rare, expensive steps --
+// pair combination, memo lookup, accounting, loading the next packed reads -- then run convergent
+// over many lanes instead of once per lane.  The lookups executed are exactly the reference's,
+// in the same order per read.  `partial` (single-end early exit) does not change the result and
+// is not modelled; the pushes of the anchor hit at synthetic positions (1820, 1824) add no new EC
+// set and are dropped.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevIndex ix, DevDict dd, BatchArgs ba) {
   extern __shared__ uint64_t smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const unsigned lane = tid & 31;
-  const uint32_t f = blockIdx.x * nt + tid;
-  const bool active = f < ba.n_frag;
+  const int nb = (int)ba.nb, nbw = nb + 1, niw = nbw / 2 + 1;
+  const int k = ix.k;
+  // shared memory per lane: two reads (base words, invalid words), the tuple of EC-set handles,
+  // 6 words of first-mate information
+  uint64_t* s_bw = smem + tid;                               // [mate][nbw]
+  uint64_t* s_iv = smem + (size_t)2 * nbw * nt + tid;        // [mate][niw]
+  uint32_t* elist = reinterpret_cast<uint32_t*>(smem + (size_t)2 * (nbw + niw) * nt) + tid;
+  uint32_t* msave = elist + (size_t)(KB_MAX_E + 2) * nt;
+  for (int mt = 0; mt < 2; ++mt) {   // words the packed reads never overwrite
+    s_bw[(mt * nbw + nb) * nt] = 0;
+    for (int w = (nb + 1) / 2; w < niw; ++w) s_iv[(mt * niw + w) * nt] = ~0ULL;
+  }
 
-  ReadView rv;
-  rv.bw = smem + tid;
-  rv.iv = smem + (size_t)ba.bwords * nt + tid;
-  rv.stride = nt;
-  rv.k = ix.k;
-  rv.len = 0;
-  FragState fs;
-  fs.elist = reinterpret_cast<uint32_t*>(smem + (size_t)(ba.bwords + ba.iwords) * nt) + tid;
-  fs.stride = nt;
-  fs.n_e = 0;
-  fs.overflow = false;
-  fs.empty_ec = ba.empty_ec;
+  // contiguous chunk of fragments owned by this warp
+  const uint32_t n_warps = (gridDim.x * nt) >> 5;
+  const uint32_t gw = (blockIdx.x * nt + tid) >> 5;
+  const uint32_t chunk = (ba.n_frag + n_warps - 1) / n_warps;
+  uint32_t next = min(ba.n_frag, gw * chunk);
+  const uint32_t end = min(ba.n_frag, next + chunk);
+  const int n_mates = ba.paired ? 2 : 1;
+  const int n_chunks = (int)(ba.pstride >> 3);   // 32-byte pieces per packed read
 
-  MateInfo m[2];
-  m[0].v_nonempty = m[0].s_nonempty = false;
-  m[1].v_nonempty = m[1].s_nonempty = false;
+  int st = S_EMPTY;
+  uint32_t frag = 0;
+  int mate = 0;
+  int p = -1, p2 = -1, p3 = -1, np = 0, dist = 0;   // np = the reference's nextPos
+  int len1 = 0;
+  uint32_t hu = 0, he = 0, h2u = 0, h2e = 0;
+  int n_e = 0;
+  bool overflow = false, need_prep = false;
+  // first hit of the mate being matched (findFirstMappingKmer / mapPair) and hit flags of both mates
+  bool v_cur = false, s_cur = false, v_first = false, s_first = false, f_strand = false;
+  uint32_t f_unitig = 0, f_blk = 0, f_ec = 0, f_dist = 0, f_ub = 0;
+  int f_pos = 0;
+  uint64_t canon = 0, slot = 0;
+  bool is_canon = false;
   uint32_t n_probes = 0, n_visits = 0, n_memo = 0;
+  ReadView rv;
+  rv.stride = nt;
+  rv.k = k;
+  rv.len = 0;
+  rv.bw = s_bw;
+  rv.iv = s_iv;
 
-  int32_t handle = KB_H_UNMAPPED;
-  bool queued = false;
-  if (active) {
-    const int nm = ba.paired ? 2 : 1;
-    for (int mate = 0; mate < nm; ++mate) {
-      load_read(ba, ba.paired ? 2 * f + mate : f, rv);
-      match_read(ix, rv, fs, m[mate], n_probes, n_visits);
-    }
-    // ---- MinCollector::intersectKmers, net effect (MinCollector.cpp:160-218) ----
-    bool mapped = m[0].v_nonempty || m[1].v_nonempty;
-    if ((m[0].v_nonempty && !m[0].s_nonempty) || (m[1].v_nonempty && !m[1].s_nonempty)) mapped = false;
-    if (mapped && fs.n_e == 0) mapped = false;
-    if (mapped) {
-      // sort the distinct EC-set ids (insertion sort, <= 16 entries)
-      for (int i = 1; i < fs.n_e; ++i) {
-        const uint32_t v = fs.elist[i * nt];
-        int j = i - 1;
-        while (j >= 0 && fs.elist[j * nt] > v) { fs.elist[(j + 1) * nt] = fs.elist[j * nt]; --j; }
-        fs.elist[(j + 1) * nt] = v;
-      }
-      uint32_t sw0 = 0, sw1 = 0;
-      if (fs.overflow) {
-        atomicOr(dd.error, KB_DEVERR_E_OVERFLOW);
-        handle = KB_H_UNMAPPED;
-      } else if (ba.strand_mode == 0 && fs.n_e == 1) {
-        handle = ix.ec_handle[fs.elist[0]];
-      } else {
-        int32_t r;
-        if (ba.strand_mode == 0 && fs.n_e == 2) {
-          r = memo2_lookup(dd, fs.elist[0], fs.elist[nt]);
-        } else {
-          int n = fs.n_e;
-          if (ba.strand_mode != 0) {
-            // the strand filter depends on the first hit of each mate: (block, orientation)
-            sw0 = m[0].v_nonempty ? (m[0].f_blk * 2u + (m[0].f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
-            sw1 = m[1].v_nonempty ? (m[1].f_blk * 2u + (m[1].f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
-            fs.elist[n * nt] = sw0;          // elist has KB_MAX_E + 2 words per thread
-            fs.elist[(n + 1) * nt] = sw1;
-            n += 2;
+  for (;;) {
+    // ------------------------------------------------------------------ service round
+    const unsigned fin = __ballot_sync(0xFFFFFFFFu, st == S_FIN);
+    const unsigned idle = fin | __ballot_sync(0xFFFFFFFFu, st == S_EMPTY);
+    const bool work_left = next < end;
+    if (idle == 0xFFFFFFFFu && fin == 0 && !work_left) break;
+    if (idle == 0xFFFFFFFFu || (work_left && __popc(idle) >= ba.refill_min)) {
+      if (st == S_FIN) {
+        // ---- MinCollector::intersectKmers, net effect (MinCollector.cpp:160-218) ----
+        bool v0 = v_cur, s0 = s_cur, v1 = false, s1 = false;
+        if (mate == 1) { v0 = v_first; s0 = s_first; v1 = v_cur; s1 = s_cur; }
+        bool mapped = v0 || v1;
+        if ((v0 && !s0) || (v1 && !s1)) mapped = false;
+        if (mapped && n_e == 0) mapped = false;
+        int32_t handle = KB_H_UNMAPPED;
+        if (mapped) {
+          for (int i = 1; i < n_e; ++i) {   // sort the distinct set handles (<= 16 entries)
+            const uint32_t x = elist[i * nt];
+            int j = i - 1;
+            while (j >= 0 && elist[j * nt] > x) { elist[(j + 1) * nt] = elist[j * nt]; --j; }
+            elist[(j + 1) * nt] = x;
           }
-          r = memon_lookup(dd, fs.elist, n, nt);
+          if (overflow) {
+            atomicOr(dd.error, KB_DEVERR_E_OVERFLOW);
+          } else if (ba.strand_mode == 0 && n_e == 1) {
+            handle = (int32_t)elist[0];            // a single EC set: its handle is stored in the slot
+          } else {
+            int n = n_e;
+            int32_t r;
+            if (ba.strand_mode == 0 && n_e == 2) {
+              r = memo2_lookup(dd, elist[0], elist[nt]);
+            } else {
+              if (ba.strand_mode != 0) {
+                // the strand filter depends on the first hit of each mate: (block, orientation)
+                uint32_t w0, w1 = 0xFFFFFFFFu;
+                if (mate == 1) {
+                  w0 = v_first ? (msave[nt] * 2u + (msave[3 * nt] >> 31)) : 0xFFFFFFFFu;
+                  w1 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
+                } else {
+                  w0 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
+                }
+                elist[n * nt] = w0;
+                elist[(n + 1) * nt] = w1;
+                n += 2;
+              }
+              r = memon_lookup(dd, elist, n, nt);
+            }
+            if (r == KB_H_NOTREADY) {
+              handle = KB_H_PENDING;
+              const uint32_t q = atomicAdd(ba.q_count, 1u);
+              uint32_t* e = ba.q_entries + (size_t)q * KB_Q_STRIDE;
+              e[0] = frag;
+              e[1] = (uint32_t)n;
+              for (int i = 0; i < n; ++i) e[2 + i] = elist[i * nt];
+            } else {
+              handle = r;
+              ++n_memo;
+            }
+          }
         }
-        if (r == KB_H_NOTREADY) {
-          queued = true;
-          handle = KB_H_PENDING;
-        } else {
-          handle = r;
-          ++n_memo;
+        ba.handle_out[frag] = handle;
+        if (ba.tl_out) {
+          // KmerIndex::mapPair (KmerIndex.cpp:1622-1693): the first k-mer found by a linear scan is
+          // the first hit of match(); same unitig, same EC set, opposite strands, same block end.
+          uint16_t tl = 0;
+          if (ba.paired && mate == 1 && v_first && v_cur) {
+            const uint32_t a_dist = msave[3 * nt] & 0x7FFFFFFFu;
+            const bool a_strand = (msave[3 * nt] >> 31) != 0;
+            const int a_pos = (int)msave[5 * nt];
+            const int q1 = a_strand ? (int)a_dist - a_pos : (int)a_dist + k + a_pos;
+            const int q2 = f_strand ? (int)f_dist - f_pos : (int)f_dist + k + f_pos;
+            if (msave[0] == f_unitig && msave[2 * nt] == f_ec && (a_strand != f_strand) && msave[4 * nt] == f_ub) {
+              const int d = q1 > q2 ? q1 - q2 : q2 - q1;
+              if (d > 0 && d < 1000) tl = (uint16_t)d;
+            }
+          }
+          ba.tl_out[frag] = tl;
+        }
+        // per-handle accounting, aggregated over the lanes finalised in this round
+        const unsigned grp = __match_any_sync(fin, handle);
+        const uint32_t fmin = __reduce_min_sync(grp, frag);
+        if (handle >= 0 && lane == (unsigned)(__ffs(grp) - 1)) {
+          atomicAdd(&dd.count[handle], (uint32_t)__popc(grp));
+          atomicMin(&dd.first[handle], (unsigned long long)(ba.frag_base + fmin));
+        }
+        st = S_EMPTY;
+      }
+      __syncwarp();
+      // ---- refill: the idle lanes take the next fragments of the warp's chunk and copy their packed
+      //      reads (pack_kernel output) into shared memory with 256-bit loads
+      {
+        const bool is_idle = (idle >> lane) & 1u;
+        const uint32_t rank = __popc(idle & ((1u << lane) - 1));
+        const uint32_t avail = end - next;
+        if (is_idle && rank < avail) {
+          const uint32_t fidx = next + rank;
+          int l0 = 0;
+          for (int mt = 0; mt < n_mates; ++mt) {
+            const uint32_t ridx = ba.paired ? 2 * fidx + mt : fidx;
+            int len = ba.off ? (int)(ba.off[ridx + 1] - ba.off[ridx]) : (int)ba.fixed_len;
+            if (len > nb * 32) len = nb * 32;   // cannot happen: the host sizes nb from the longest read
+            if (mt == 0) l0 = len; else len1 = len;
+            const uint32_t* src = ba.packed + (size_t)ridx * ba.pstride;
+            uint64_t* dbw = s_bw + (size_t)mt * nbw * nt;
+            uint64_t* div = s_iv + (size_t)mt * niw * nt;
+            for (int c = 0; c < n_chunks; ++c) {
+              uint32_t v[8];
+              ld256_nc(src + c * 8, v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                // 32 bytes = 4 u64 of the packed stream [nb base words | nb 32-bit masks | padding]
+                const int g2 = c * 4 + i;
+                const uint64_t q = (uint64_t)v[2 * i] | ((uint64_t)v[2 * i + 1] << 32);
+                if (g2 < nb) dbw[g2 * nt] = q;
+                else if (2 * (g2 - nb) < nb) div[(g2 - nb) * nt] = q;
+              }
+            }
+          }
+          frag = fidx;
+          mate = 0;
+          n_e = 0;
+          overflow = false;
+          v_cur = s_cur = v_first = s_first = false;
+          rv.bw = s_bw;
+          rv.iv = s_iv;
+          rv.len = l0;
+          p = rv.next_valid(0);
+          st = S_MAIN;
+          need_prep = true;
+          if (p < 0) {   // no k-mer in the first mate
+            st = S_FIN;
+            if (n_mates == 2) {
+              mate = 1;
+              rv.bw = s_bw + (size_t)nbw * nt;
+              rv.iv = s_iv + (size_t)niw * nt;
+              rv.len = len1;
+              p = rv.next_valid(0);
+              if (p >= 0) st = S_MAIN;
+            }
+          }
+        }
+        const uint32_t n_idle = __popc(idle);
+        next += n_idle < avail ? n_idle : avail;
+      }
+      continue;
+    }
+    // ------------------------------------------------------------------ one lookup per active lane
+    if (st <= S_BACKOFF) {
+      if (need_prep) {
+        const int pq = (st == S_JUMP) ? p2 : ((st == S_MIDDLE) ? p3 : p);
+        const uint64_t fwd = rv.kmer(pq);
+        const uint64_t rc = kb_revcomp(fwd, k);
+        is_canon = fwd < rc;
+        canon = is_canon ? fwd : rc;
+        slot = kb_mix64(canon) & ix.mask;
+        need_prep = false;
+        ++n_probes;
+      }
+      uint32_t v[8];
+      ld256_nc(ix.slots + slot, v);
+      ++n_visits;
+      const uint64_t key = (uint64_t)v[0] | ((uint64_t)v[1] << 32);
+      if (key != canon && key != KB_EMPTY_KEY) {
+        slot = (slot + 1) & ix.mask;              // linear probing: one more iteration
+      } else {
+        const bool f = key == canon;
+        // hit fields: v[2] unitig, v[3] blk, v[4] ec (set handle), v[5] dist|flag, v[6] lb, v[7] ub
+        const uint32_t r_unitig = v[2], r_ec = v[4];
+        const bool r_strand = (is_canon == ((v[5] >> 31) != 0));
+        const int l = rv.len;
+        bool push = false, end_mate = false, to_backoff = false;
+        int nv_from = -1;      // >= 0: continue with p = next_valid(nv_from) in MAIN (or BACKOFF)
+        if (st == S_MAIN) {
+          if (!f) {
+            nv_from = p + 1;
+          } else {
+            push = true;
+            const int r_dist = (int)(v[5] & 0x7FFFFFFFu);
+            const int off = r_dist - (int)v[6], blen = (int)(v[7] - v[6]);
+            dist = r_strand ? (blen - 1 - off) : off;                       // 1780-1788
+            if (dist >= 2) {
+              np = (p + dist >= l - k) ? (l - k) : (p + dist);              // 1793-1798
+              p2 = rv.next_valid(np);                                       // kit2 += nextPos-pos (adv 0: p itself)
+              if (p2 < 0) {
+                end_mate = true;                                            // 1882-1886
+              } else {
+                hu = r_unitig; he = r_ec;
+                st = S_JUMP;
+                need_prep = true;
+              }
+            } else {
+              nv_from = p + 1;
+            }
+          }
+        } else if (st == S_JUMP) {
+          const bool found2 = !f || (hu == r_unitig && he == r_ec);         // 1807-1815
+          const int found2pos = !f ? p : p + dist;
+          if (found2) {
+            if (found2pos >= l - k) end_mate = true;                        // "fake position", break (1819-1822)
+            else nv_from = p2 + 1;                                          // kit = kit2; ++kit
+          } else {
+            h2u = r_unitig; h2e = r_ec;
+            if (dist > 4) {
+              const int middlePos = (p + np) / 2;
+              p3 = rv.next_valid(middlePos);                                // kit3 += middlePos-pos
+              if (p3 >= 0) { st = S_MIDDLE; need_prep = true; }
+              else to_backoff = true;
+            } else {
+              to_backoff = true;
+            }
+          }
+        } else if (st == S_MIDDLE) {
+          const bool foundMiddle = f && ((hu == r_unitig && he == r_ec) || (h2u == r_unitig && h2e == r_ec));
+          if (foundMiddle) {
+            push = true;
+            if (np >= l - k) end_mate = true;                               // 1867
+            else nv_from = p2 + 1;                                          // kit = kit2; ++kit
+          } else {
+            to_backoff = true;
+          }
+        } else {   // S_BACKOFF: the single probe of the back-off loop
+          push = f;
+          nv_from = p + 1;
+        }
+        if (push) {
+          if (!v_cur) {
+            v_cur = true;
+            f_unitig = r_unitig; f_blk = v[3]; f_ec = r_ec; f_dist = v[5] & 0x7FFFFFFFu; f_ub = v[7];
+            f_pos = p;   // only a MAIN hit can be the first hit of a read
+            f_strand = r_strand;
+          }
+          if (r_ec != ba.empty_ec) {               // "Don't intersect empty EC", MinCollector.cpp:468-469
+            s_cur = true;
+            bool dup = false;
+            for (int i = 0; i < n_e; ++i) dup |= (elist[i * nt] == r_ec);
+            if (!dup) {
+              if (n_e == KB_MAX_E) overflow = true;
+              else { elist[n_e * nt] = r_ec; ++n_e; }
+            }
+          }
+        }
+        if (to_backoff) nv_from = p + 1;           // ++kit; backOff = true
+        if (nv_from >= 0) {
+          p = rv.next_valid(nv_from);
+          if (p < 0) end_mate = true;
+          else { st = to_backoff ? S_BACKOFF : S_MAIN; need_prep = true; }
+        }
+        if (end_mate) {
+          st = S_FIN;
+          if (mate + 1 < n_mates) {
+            // keep the first mate's flags and first hit, move on to the second mate
+            v_first = v_cur; s_first = s_cur;
+            msave[0] = f_unitig; msave[nt] = f_blk; msave[2 * nt] = f_ec;
+            msave[3 * nt] = f_dist | (f_strand ? 0x80000000u : 0u); msave[4 * nt] = f_ub; msave[5 * nt] = (uint32_t)f_pos;
+            v_cur = s_cur = false;
+            mate = 1;
+            rv.bw = s_bw + (size_t)nbw * nt;
+            rv.iv = s_iv + (size_t)niw * nt;
+            rv.len = len1;
+            p = rv.next_valid(0);
+            if (p >= 0) { st = S_MAIN; need_prep = true; }
+          }
         }
       }
-    }
-    if (queued) {
-      const uint32_t q = atomicAdd(ba.q_count, 1u);
-      uint32_t* e = ba.q_entries + (size_t)q * KB_Q_STRIDE;
-      const int n = fs.n_e + (ba.strand_mode != 0 ? 2 : 0);
-      e[0] = f;
-      e[1] = (uint32_t)n;
-      for (int i = 0; i < n; ++i) e[2 + i] = fs.elist[i * nt];
-    }
-    ba.handle_out[f] = handle;
-    if (ba.tl_out) {
-      // KmerIndex::mapPair (KmerIndex.cpp:1622-1693): the first k-mer found by a linear scan is the
-      // first hit of match(); same unitig, same EC set, opposite strands, same block end.
-      uint16_t tl = 0;
-      if (ba.paired && m[0].v_nonempty && m[1].v_nonempty) {
-        const int k = ix.k;
-        const int p1 = m[0].f_strand ? (int)m[0].f_dist - m[0].f_pos : (int)m[0].f_dist + k + m[0].f_pos;
-        const int p2 = m[1].f_strand ? (int)m[1].f_dist - m[1].f_pos : (int)m[1].f_dist + k + m[1].f_pos;
-        if (m[0].f_unitig == m[1].f_unitig && m[0].f_ec == m[1].f_ec && (m[0].f_strand != m[1].f_strand) &&
-            m[0].f_ub == m[1].f_ub) {
-          const int d = p1 > p2 ? p1 - p2 : p2 - p1;
-          if (d > 0 && d < 1000) tl = (uint16_t)d;
-        }
-      }
-      ba.tl_out[f] = tl;
     }
   }
-  __syncwarp();
-  account(dd, (active && handle >= 0) ? handle : (int32_t)(-100 - (int)lane), ba.frag_base + f, lane);
   // statistics: probes and slot visits
   for (int o = 16; o > 0; o >>= 1) {
     n_probes += __shfl_xor_sync(0xFFFFFFFFu, n_probes, o);
@@ -456,13 +588,14 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
 
     if (handle == KB_H_NOTREADY) {
       // 2. intersection of the n_e sets: lanes own elements of the smallest one
+      // the tuple holds set handles: dslots[h] = offset | len << 32 | tag << 56
       int sm = 0;
-      uint32_t sm_len = ix.ec_off[w[0] + 1] - ix.ec_off[w[0]];
+      uint32_t sm_len = (uint32_t)((dd.dslots[w[0]] >> 32) & 0xFFFFFFu);
       for (int j = 1; j < n_e; ++j) {
-        const uint32_t len = ix.ec_off[w[j] + 1] - ix.ec_off[w[j]];
+        const uint32_t len = (uint32_t)((dd.dslots[w[j]] >> 32) & 0xFFFFFFu);
         if (len < sm_len) { sm_len = len; sm = j; }
       }
-      const uint32_t* A = pool + ix.ec_off[w[sm]];
+      const uint32_t* A = pool + (uint32_t)dd.dslots[w[sm]];
       uint32_t nres = 0;
       for (uint32_t base = 0; base < sm_len; base += 32) {
         const uint32_t i = base + lane;
@@ -470,8 +603,9 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
         const uint32_t a = alive ? __ldcg(A + i) : 0;
         for (int j = 0; j < n_e; ++j) {
           if (j == sm) continue;
-          const uint32_t* B = pool + ix.ec_off[w[j]];
-          const uint32_t blen = ix.ec_off[w[j] + 1] - ix.ec_off[w[j]];
+          const unsigned long long bw_ = dd.dslots[w[j]];
+          const uint32_t* B = pool + (uint32_t)bw_;
+          const uint32_t blen = (uint32_t)((bw_ >> 32) & 0xFFFFFFu);
           if (alive) alive = bsearch_contains(B, blen, a, nullptr);
         }
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
@@ -489,9 +623,9 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
           const bool want = (mate == 0) ? (ba.strand_mode == 1) : (ba.strand_mode == 2);
           // EC set of the first-hit block: recover its id from the tuple?  Not possible in general
           // (empty sets are not in the tuple), so the block's set is looked up via blk_ec.
-          const uint32_t be = ix.blk_ec[blk];
-          const uint32_t* B = pool + ix.ec_off[be];
-          const uint32_t blen = ix.ec_off[be + 1] - ix.ec_off[be];
+          const unsigned long long bword = dd.dslots[ix.blk_ec[blk]];   // blk_ec holds set handles
+          const uint32_t* B = pool + (uint32_t)bword;
+          const uint32_t blen = (uint32_t)((bword >> 32) & 0xFFFFFFu);
           const uint8_t* sb = ix.strand + ix.blk_strand_off[blk];
           // u &= ec ; vtmp = strand-compatible subset
           uint32_t n_u = 0, n_v = 0;
@@ -585,8 +719,8 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
           uint64_t s = kb_mix64(key) & dd.m2_mask;
           uint64_t visited = 0;
           for (;;) {
-            const unsigned long long old = atomicCAS(&dd.m2_key[s], ~0ULL, key);
-            if (old == ~0ULL || old == key) { atomicExch(&dd.m2_val[s], handle); break; }
+            const unsigned long long old = atomicCAS(&dd.m2[s].key, ~0ULL, key);
+            if (old == ~0ULL || old == key) { atomicExch(&dd.m2[s].val, handle); break; }
             s = (s + 1) & dd.m2_mask;
             if (++visited > dd.m2_mask) { atomicOr(dd.error, KB_DEVERR_MEMO_FULL); break; }
           }
@@ -655,8 +789,26 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
                         int tpb, cudaStream_t st, cudaEvent_t* ev) {
   if (ba.n_frag == 0) return;
   cudaMemsetAsync(ba.q_count, 0, sizeof(uint32_t), st);
-  const size_t smem = (size_t)tpb * ((size_t)(ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 2) * 4);
-  const unsigned blocks = (ba.n_frag + tpb - 1) / tpb;
+  // persistent grid: as many blocks as fit on the device at once
+  const size_t smem = (size_t)tpb * ((size_t)2 * (ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 8) * 4);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel, tpb, smem);
+  if (per_sm < 1) per_sm = 1;
+  unsigned blocks = (unsigned)(sms * per_sm);
+  const unsigned need = (ba.n_frag + tpb - 1) / tpb;   // never more lanes than fragments
+  if (blocks > need) blocks = need;
+  {
+    const uint32_t n_reads = ba.paired ? 2 * ba.n_frag : ba.n_frag;
+    const uint64_t total = (uint64_t)n_reads * ba.nb;
+    pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ba, n_reads, const_cast<uint32_t*>(ba.packed));
+  }
   if (ev) cudaEventRecord(ev[0], st);
   match_kernel<<<blocks, tpb, smem, st>>>(ix, dd, ba);
   if (ev) cudaEventRecord(ev[1], st);

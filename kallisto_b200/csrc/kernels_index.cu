@@ -81,6 +81,14 @@ __global__ void fill_u64_kernel(unsigned long long* p, uint64_t n, unsigned long
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
+__global__ void fill_memo2_kernel(Memo2Entry* p, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    Memo2Entry e;
+    e.key = ~0ULL; e.val = KB_H_NOTREADY; e.pad = 0;
+    p[i] = e;
+  }
+}
 __global__ void fill_i32_kernel(int32_t* p, uint64_t n, int32_t v) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
@@ -97,6 +105,10 @@ __global__ void fill_slots_kernel(KmerSlot* p, uint64_t n) {
 void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st) {
   if (n == 0) return;
   fill_u64_kernel<<<148 * 8, 256, 0, st>>>(p, n, v);
+}
+void launch_fill_memo2(Memo2Entry* p, uint64_t n, cudaStream_t st) {
+  if (n == 0) return;
+  fill_memo2_kernel<<<148 * 8, 256, 0, st>>>(p, n);
 }
 void launch_fill_i32(int32_t* p, uint64_t n, int32_t v, cudaStream_t st) {
   if (n == 0) return;
