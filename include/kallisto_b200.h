@@ -90,7 +90,7 @@ int kb_quant_sync(kb_quant* q);
 int kb_quant_set_stream(kb_quant* q, void* cuda_stream);
 /* Per-kernel device time measured with CUDA events on the launching stream (for the roofline). */
 typedef struct kb_kernel_timings {
-  double match_ms, resolve_ms, em_ms;
+  double match_ms, resolve_ms, em_ms, em_prep_ms;
   uint64_t match_launches, resolve_launches;
 } kb_kernel_timings;
 int kb_quant_enable_timing(kb_quant* q, int on);

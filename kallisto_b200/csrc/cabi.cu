@@ -164,6 +164,7 @@ int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out) {
     out->match_launches = t.match_launches;
     out->resolve_launches = t.resolve_launches;
     out->em_ms = q->q->last_em_seconds * 1e3;
+    out->em_prep_ms = q->q->last_prep_seconds * 1e3;
   });
 }
 
@@ -223,7 +224,12 @@ int kb_em_run(kb_quant* q, double fld_mean, double fld_sd, double* est_counts_ou
               int32_t* rounds_out, double* seconds_out) {
   if (!q) return fail(KB_ERR_INVALID, "kb_em_run: null argument");
   return guarded([&] {
-    em_common(q, q->q->finalize_ecs(), fld_mean, fld_sd, est_counts_out, eff_lens_out, rounds_out, seconds_out);
+    const auto fl = q->q->mean_fl_trunc(fld_mean, fld_sd);
+    kb::EmResult r = q->q->run_em_device(fl);
+    if (est_counts_out) memcpy(est_counts_out, r.alpha.data(), r.alpha.size() * sizeof(double));
+    if (eff_lens_out) memcpy(eff_lens_out, r.eff_lens.data(), r.eff_lens.size() * sizeof(double));
+    if (rounds_out) *rounds_out = r.rounds;
+    if (seconds_out) *seconds_out = r.seconds;
   });
 }
 

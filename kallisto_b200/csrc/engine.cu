@@ -174,7 +174,18 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
 // ------------------------------------------------------------------------------------------
 // Quant
 // ------------------------------------------------------------------------------------------
-Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(1000, 0) {
+struct EmWs {   // grow-only device workspace of run_em_device
+  DBuf<uint32_t> used, scal, idx_in, order, handle, count, len, multi_len, is_multi, ec_off, m_off, multi_index;
+  DBuf<unsigned long long> key_in, key_out;
+  DBuf<uint8_t> tmp;
+  DBuf<uint32_t> ec_tid, multi_ec, m_rowoff, m_tid, m_row, m_iota, sortk, sortv, t_deg, t_off, t_midx;
+  DBuf<double> m_w, t_w, eff, alpha, norm;
+  DBuf<int32_t> t_single;
+  DBuf<int> emi;
+  DBuf<unsigned int> chcount;
+};
+
+Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(1000, 0), emws_(new EmWs()) {
   if (const char* s = getenv("KB_REFILL_MIN")) opt_.refill_min = std::max(1, std::min(32, atoi(s)));   // tuning knob
   KB_CK(cudaSetDevice(ix_.device));
   KB_CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
@@ -234,6 +245,7 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
 }
 
 Quant::~Quant() {
+  delete emws_;
   if (h_off_pinned_) cudaFreeHost(h_off_pinned_);
   for (auto ev : events_) cudaEventDestroy(ev);
   if (stream_ && own_stream_) cudaStreamDestroy(stream_);
@@ -549,8 +561,8 @@ struct EmDevice {
   DBuf<uint32_t> multi_ec, m_off, m_tid, t_off, t_midx, counts;
   DBuf<double> m_w, t_w, alpha, norm;
   DBuf<int32_t> t_single;
-  DBuf<int> rounds, state;
-  DBuf<unsigned int> chcount, barrier;
+  DBuf<int> rounds, state, fstate;
+  DBuf<unsigned int> chcount;
 };
 
 void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, EmProblem& p, cudaStream_t st) {
@@ -567,15 +579,15 @@ void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, 
   d.alpha.alloc((size_t)nb * T);
   d.norm.alloc(std::max<size_t>(1, (size_t)nb * nm));
   d.rounds.alloc(nb); d.rounds.zero(st);
-  d.state.alloc(nb); d.state.zero(st);
+  d.state.alloc((size_t)nb * 2); d.state.zero(st);
+  d.fstate.alloc(nb); d.fstate.zero(st);
   d.chcount.alloc((size_t)nb * 2); d.chcount.zero(st);
-  d.barrier.alloc(4); d.barrier.zero(st);
   p = EmProblem();
   p.n_ec = n_ec; p.n_targets = T; p.n_multi = (uint32_t)nm;
   p.multi_ec = d.multi_ec.p; p.m_off = d.m_off.p; p.m_tid = d.m_tid.p; p.m_w = d.m_w.p;
   p.t_off = d.t_off.p; p.t_midx = d.t_midx.p; p.t_w = d.t_w.p; p.t_single = d.t_single.p;
   p.nb = nb; p.counts = d.counts.p; p.alpha = d.alpha.p; p.norm = d.norm.p;
-  p.rounds = d.rounds.p; p.state = d.state.p; p.chcount = d.chcount.p; p.barrier = d.barrier.p;
+  p.rounds = d.rounds.p; p.state = d.state.p; p.chcount = d.chcount.p; p.fstate = d.fstate.p;
 }
 
 void em_fetch(const EmProblem& p, EmDevice& d, int nb, uint32_t T, std::vector<double>& alpha, std::vector<int>& rounds,
@@ -585,7 +597,7 @@ void em_fetch(const EmProblem& p, EmDevice& d, int nb, uint32_t T, std::vector<d
   std::vector<int> state(nb);
   d.alpha.download(alpha.data(), alpha.size(), 0, st);
   d.rounds.download(rounds.data(), nb, 0, st);
-  d.state.download(state.data(), nb, 0, st);
+  d.fstate.download(state.data(), nb, 0, st);
   KB_CK(cudaStreamSynchronize(st));
   for (int b = 0; b < nb; ++b)
     if (state[b] == 3)   // stop detected on the last allowed iteration: zero small alphas (EMAlgorithm.h:213-216)
@@ -627,6 +639,131 @@ EmResult Quant::run_em(const EcTable& ecs, const std::vector<double>& fl_trunc, 
   r.rounds = rounds[0];
   r.eff_lens = h.eff;
   return r;
+}
+
+// The whole tail of `kallisto quant` without the EC table ever visiting the host: EC ids by first
+// occurrence, CSR/CSC + weights on the device (kernels_emprep.cu), then em_kernel.
+EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter, int min_rounds) {
+  KB_CK(cudaSetDevice(ix_.device));
+  check_device_errors();
+  const FlatIndex& f = ix_.flat;
+  const uint32_t T = f.num_targets();
+  cudaStream_t st = stream_;
+  EmWs& w = *emws_;
+  // effective lengths (T values, host arithmetic identical to calc_eff_lens)
+  EmResult res;
+  res.eff_lens.resize(T);
+  {
+    const double marginal = fl_trunc[999];
+    for (uint32_t t = 0; t < T; ++t) {
+      const double mean = f.target_len[t] >= 1000 ? marginal : fl_trunc[f.target_len[t]];
+      const double len = static_cast<double>(f.target_len[t]);
+      double e = len - mean + 1;
+      if (e < 1.0) e = len;
+      res.eff_lens[t] = e;
+    }
+  }
+  cudaEvent_t e0, e1, e2;
+  KB_CK(cudaEventCreate(&e0));
+  KB_CK(cudaEventCreate(&e1));
+  KB_CK(cudaEventCreate(&e2));
+  KB_CK(cudaEventRecord(e0, st));
+  // ---- phase 1: used handles, sorted by first occurrence; lengths and offsets
+  if (w.used.n < ix_.dict_cap) w.used.alloc(ix_.dict_cap);
+  if (w.scal.n < 8) w.scal.alloc(8);
+  launch_collect_used(dd_, w.used.p, w.scal.p, st);
+  uint32_t n = 0;
+  w.scal.download(&n, 1, 0, st);
+  KB_CK(cudaStreamSynchronize(st));
+  res.alpha.assign(T, 0.0);
+  if (n == 0) {
+    res.rounds = 0;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return res;
+  }
+  const size_t n1 = (size_t)n + 1;
+  auto grow32 = [](DBuf<uint32_t>& b, size_t need) { if (b.n < need) b.alloc(need + need / 4); };
+  auto growd = [](DBuf<double>& b, size_t need) { if (b.n < need) b.alloc(need + need / 4); };
+  if (w.key_in.n < n1) { w.key_in.alloc(n1 + n1 / 4); w.key_out.alloc(n1 + n1 / 4); }
+  grow32(w.idx_in, n1); grow32(w.order, n1); grow32(w.handle, n1); grow32(w.count, n1); grow32(w.len, n1);
+  grow32(w.multi_len, n1); grow32(w.is_multi, n1); grow32(w.ec_off, n1); grow32(w.m_off, n1); grow32(w.multi_index, n1);
+  const uint32_t nnz_guess = std::max<uint32_t>(n * 4, 1u << 20);
+  size_t tmp_need = emprep_sort_bytes(n + 1, std::max<uint32_t>(nnz_guess, T + 1));
+  if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
+  // the scans run over n + 1 items: the extra item must be zero
+  KB_CK(cudaMemsetAsync(w.len.p + n, 0, 4, st));
+  KB_CK(cudaMemsetAsync(w.multi_len.p + n, 0, 4, st));
+  KB_CK(cudaMemsetAsync(w.is_multi.p + n, 0, 4, st));
+  emprep_sort_by_first(dd_, w.used.p, n, w.key_in.p, w.key_out.p, w.idx_in.p, w.order.p, w.tmp.p, w.tmp.n, st);
+  EmPrep ep{};
+  ep.n_ec = n; ep.n_targets = T;
+  ep.handle = w.handle.p; ep.count = w.count.p; ep.len = w.len.p; ep.ec_off = w.ec_off.p; ep.m_off = w.m_off.p;
+  ep.multi_index = w.multi_index.p;
+  emprep_meta(dd_, w.used.p, w.order.p, n, ep, w.multi_len.p, w.is_multi.p, w.tmp.p, w.tmp.n, st);
+  uint32_t tot[3] = {0, 0, 0};
+  w.ec_off.download(&tot[0], 1, n, st);
+  w.m_off.download(&tot[1], 1, n, st);
+  w.multi_index.download(&tot[2], 1, n, st);
+  KB_CK(cudaStreamSynchronize(st));
+  const uint32_t nnz_all = tot[0], nnz = tot[1], n_multi = tot[2];
+  // ---- phase 2: EC table, CSR, weights, CSC
+  tmp_need = emprep_sort_bytes(n + 1, std::max<uint32_t>(nnz, T + 1));
+  if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
+  grow32(w.ec_tid, std::max<uint32_t>(1, nnz_all)); grow32(w.multi_ec, (size_t)n_multi + 1); grow32(w.m_rowoff, (size_t)n_multi + 2);
+  const size_t nz = std::max<uint32_t>(1, nnz);
+  grow32(w.m_tid, nz); grow32(w.m_row, nz); grow32(w.m_iota, nz); grow32(w.sortk, nz); grow32(w.sortv, nz); grow32(w.t_midx, nz);
+  growd(w.m_w, nz); growd(w.t_w, nz);
+  grow32(w.t_deg, (size_t)T + 1); grow32(w.t_off, (size_t)T + 1);
+  if (w.t_single.n < T) w.t_single.alloc(T);
+  growd(w.eff, T); growd(w.alpha, T); growd(w.norm, (size_t)n_multi + 1);
+  KB_CK(cudaMemsetAsync(w.t_deg.p, 0, ((size_t)T + 1) * 4, st));
+  launch_fill_i32(w.t_single.p, T, -1, st);
+  KB_CK(cudaMemsetAsync(w.m_rowoff.p, 0, 4, st));   // n_multi == 0: offsets [0]
+  w.eff.upload(res.eff_lens.data(), T, st);
+  ep.n_multi = n_multi;
+  ep.ec_tid = w.ec_tid.p; ep.multi_ec = w.multi_ec.p; ep.m_rowoff = w.m_rowoff.p; ep.m_tid = w.m_tid.p; ep.m_w = w.m_w.p;
+  ep.m_row = w.m_row.p; ep.m_iota = w.m_iota.p; ep.t_deg = w.t_deg.p; ep.t_off = w.t_off.p; ep.t_midx = w.t_midx.p;
+  ep.t_w = w.t_w.p; ep.t_single = w.t_single.p; ep.eff = w.eff.p;
+  emprep_fill(dd_, ep, nnz, w.sortk.p, w.sortv.p, w.tmp.p, w.tmp.n, (unsigned long long*)w.key_in.p, st);
+  KB_CK(cudaGetLastError());
+  // ---- EM
+  if (w.emi.n < 8) w.emi.alloc(8);
+  if (w.chcount.n < 2) w.chcount.alloc(2);
+  w.emi.zero(st);
+  w.chcount.zero(st);
+  std::vector<double> a0(T, 1.0 / T);   // uniform start (EMAlgorithm.h:38)
+  w.alpha.upload(a0.data(), T, st);
+  EmProblem p{};
+  p.n_ec = n; p.n_targets = T; p.n_multi = n_multi;
+  p.multi_ec = w.multi_ec.p; p.m_off = w.m_rowoff.p; p.m_tid = w.m_tid.p; p.m_w = w.m_w.p;
+  p.t_off = w.t_off.p; p.t_midx = w.t_midx.p; p.t_w = w.t_w.p; p.t_single = w.t_single.p;
+  p.nb = 1; p.counts = w.count.p; p.alpha = w.alpha.p; p.norm = w.norm.p;
+  p.rounds = w.emi.p; p.state = w.emi.p + 1; p.fstate = w.emi.p + 3; p.chcount = w.chcount.p;
+  p.max_iter = max_iter; p.min_rounds = min_rounds;
+  KB_CK(cudaEventRecord(e1, st));
+  launch_em(p, 256, st);
+  KB_CK(cudaGetLastError());
+  KB_CK(cudaEventRecord(e2, st));
+  int emi[4] = {0, 0, 0, 0};
+  unsigned long long s2[2] = {0, 0};
+  w.alpha.download(res.alpha.data(), T, 0, st);
+  w.emi.download(emi, 4, 0, st);
+  w.key_in.download(s2, 2, 0, st);
+  KB_CK(cudaStreamSynchronize(st));
+  if (emi[3] == 3)
+    for (uint32_t t = 0; t < T; ++t)
+      if (res.alpha[t] < 1e-7 / 10.0) res.alpha[t] = 0.0;
+  float ms_prep = 0, ms_em = 0;
+  KB_CK(cudaEventElapsedTime(&ms_prep, e0, e1));
+  KB_CK(cudaEventElapsedTime(&ms_em, e1, e2));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  res.rounds = emi[0];
+  res.seconds = ms_em * 1e-3;
+  last_em_seconds = res.seconds;
+  last_prep_seconds = ms_prep * 1e-3;
+  dev_stats_valid_ = true;
+  dev_n_ecs_ = n; dev_nnz_ = nnz_all; dev_pseudoaligned_ = s2[0]; dev_unique_ = s2[1];
+  return res;
 }
 
 std::vector<int> Quant::run_bootstrap(const EcTable& ecs, const std::vector<double>& fl_trunc, uint64_t seed, int B,

@@ -96,6 +96,8 @@ struct Stats {
   uint64_t n_probes = 0, n_slot_visits = 0, n_resolved = 0, n_memo_hits = 0;
 };
 
+struct EmWs;
+
 class Quant {
  public:
   Quant(Index& ix, const QuantOptions& opt);
@@ -122,6 +124,8 @@ class Quant {
   // Effective lengths from the fragment-length distribution (or a given mean/sd), then the EM.
   std::vector<double> mean_fl_trunc(double fld_mean, double fld_sd) const;
   EmResult run_em(const EcTable& ecs, const std::vector<double>& fl_trunc, int max_iter = 10000, int min_rounds = 50);
+  // Same result, EC table built and kept on the device (the `quant` fast path).
+  EmResult run_em_device(const std::vector<double>& fl_trunc, int max_iter = 10000, int min_rounds = 50);
   // B bootstrap EMs (Bootstrap::run_em): alpha_out is B x n_targets.  Returns rounds per bootstrap.
   std::vector<int> run_bootstrap(const EcTable& ecs, const std::vector<double>& fl_trunc, uint64_t seed, int B,
                                  std::vector<double>& alpha_out, std::vector<uint32_t>* samples_out = nullptr);
@@ -136,7 +140,10 @@ class Quant {
   Index& index() { return ix_; }
   const QuantOptions& options() const { return opt_; }
   cudaStream_t stream() const { return stream_; }
-  double last_em_seconds = 0;
+  double last_em_seconds = 0, last_prep_seconds = 0;
+  // filled by run_em_device
+  bool dev_stats_valid_ = false;
+  uint64_t dev_n_ecs_ = 0, dev_nnz_ = 0, dev_pseudoaligned_ = 0, dev_unique_ = 0;
 
  private:
   void run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
@@ -172,6 +179,7 @@ class Quant {
   std::vector<uint16_t> h_tl_;
   EcTable ecs_;
   bool ecs_valid_ = false;
+  struct EmWs* emws_ = nullptr;
 };
 
 }  // namespace kb

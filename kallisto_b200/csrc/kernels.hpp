@@ -97,13 +97,48 @@ struct EmProblem {
   double* alpha;                // nb x n_targets (in/out)
   double* norm;                 // nb x n_multi scratch: counts/denom or 0
   int* rounds;                  // nb: iterations run (the reference's "ran for i rounds")
-  int* state;                   // nb: 0 running, 1 final round pending, 2 done
+  int* state;                   // 2 x nb (double-buffered by iteration parity): 0 running, 1 final round, >= 2 done
+  int* fstate;                  // nb: final state (2 finished, 3 finished + host must zero small alphas)
   unsigned int* chcount;        // nb x 2 (double-buffered) change counters
-  unsigned int* barrier;        // grid barrier words
   int max_iter, min_rounds;
 };
 int em_max_blocks(int threads_per_block);
 void launch_em(const EmProblem& p, int threads_per_block, cudaStream_t st);
+
+// Device-side EM problem construction (kernels_emprep.cu)
+struct EmPrep {
+  uint32_t n_ec, n_multi, n_targets;
+  // per EC (id = order of first occurrence); arrays of n_ec + 1 where a scan total is stored
+  uint32_t* handle;
+  uint32_t* count;
+  uint32_t* len;           // n_ec + 1
+  uint32_t* ec_off;        // n_ec + 1: offsets of the EC table
+  uint32_t* m_off;         // n_ec + 1: offsets into the multi-EC entry arrays (0-length for singletons)
+  uint32_t* multi_index;   // n_ec + 1: row index among the multi-transcript ECs
+  uint32_t* ec_tid;        // EC table entries
+  // multi-transcript ECs, CSR
+  uint32_t* multi_ec;      // n_multi
+  uint32_t* m_rowoff;      // n_multi + 1
+  uint32_t* m_tid;
+  double* m_w;
+  uint32_t* m_row;         // entry -> row
+  uint32_t* m_iota;        // entry -> entry (values for the stable sort)
+  // CSC
+  uint32_t* t_deg;         // n_targets + 1 (zeroed by the caller)
+  uint32_t* t_off;         // n_targets + 1
+  uint32_t* t_midx;
+  double* t_w;
+  int32_t* t_single;       // n_targets (filled with -1 by the caller)
+  const double* eff;       // n_targets
+};
+size_t emprep_sort_bytes(uint32_t n_used, uint32_t nnz_max);
+void emprep_sort_by_first(const DevDict& dd, const uint32_t* used, uint32_t n_used, unsigned long long* key_in,
+                          unsigned long long* key_out, uint32_t* idx_in, uint32_t* order_out, void* tmp, size_t tmp_bytes,
+                          cudaStream_t st);
+void emprep_meta(const DevDict& dd, const uint32_t* used, const uint32_t* order, uint32_t n, const EmPrep& p,
+                 uint32_t* multi_len, uint32_t* is_multi, void* tmp, size_t tmp_bytes, cudaStream_t st);
+void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, uint32_t* sort_keys_out, uint32_t* sort_vals_out,
+                 void* tmp, size_t tmp_bytes, unsigned long long* stats2, cudaStream_t st);
 
 struct ResampleArgs {
   const double* cp;          // n_ec cumulative probabilities (discrete_distribution::_M_cp)

@@ -28,6 +28,7 @@ constexpr double kTolerance = 4.9406564584124654e-324;   // std::numeric_limits<
 
 __global__ void __launch_bounds__(256) em_kernel(EmProblem p) {
   cg::grid_group grid = cg::this_grid();
+  extern __shared__ int s_state[];    // per problem: 0 running, 1 final round, >= 2 finished
   const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
   const unsigned lane = threadIdx.x & 31;
@@ -35,11 +36,38 @@ __global__ void __launch_bounds__(256) em_kernel(EmProblem p) {
   const uint64_t nB = (uint64_t)p.nb * p.n_targets;
   const double zero_below = kAlphaLimit / 10.0;
 
-  for (int it = 0; it < p.max_iter; ++it) {
+  for (int it = 0;; ++it) {
+    // ---------------- state machine per problem (:202-221), evaluated redundantly by every block
+    // from the change counters of the iteration that just finished (two grid syncs per iteration)
+    for (int b = threadIdx.x; b < p.nb; b += blockDim.x) {
+      int st = 0;
+      if (it > 0) {
+        const int i = it - 1;                                       // the iteration that just ran
+        st = p.state[(i & 1) * p.nb + b];
+        if (st < 2) {
+          const unsigned ch = p.chcount[2 * b + (i & 1)];
+          if (st == 1) { st = 2; p.rounds[b] = i; }                 // if (finalRound) break;
+          else if (ch == 0 && i > p.min_rounds) st = 1;             // stopEM -> finalRound
+          if (st < 2 && i + 1 == p.max_iter) {
+            // loop runs out: i == n_iter.  If the stop was detected on the very last iteration the
+            // reference still zeroes the small alphas (:213-216); the host does that for state 3.
+            p.rounds[b] = p.max_iter;
+            st = (st == 1) ? 3 : 2;
+          }
+          if (st >= 2) p.fstate[b] = st;
+        }
+      }
+      p.state[(it & 1) * p.nb + b] = st;    // every block writes the same value
+      s_state[b] = st;
+    }
+    __syncthreads();
+    bool mine_done = true;
+    for (int b = threadIdx.x; b < p.nb; b += blockDim.x) mine_done = mine_done && s_state[b] >= 2;
+    if (__syncthreads_and(mine_done)) break;
     // ---------------- pass A: denominators ----------------
     for (uint64_t i = gtid; i < nA; i += gstride) {
       const uint32_t b = (uint32_t)(i / p.n_multi), r = (uint32_t)(i % p.n_multi);
-      const int st = p.state[b];
+      const int st = s_state[b];
       if (st >= 2) continue;
       const uint32_t c = p.counts[(size_t)b * p.n_ec + p.multi_ec[r]];
       double nrm = 0.0;
@@ -56,21 +84,19 @@ __global__ void __launch_bounds__(256) em_kernel(EmProblem p) {
       }
       p.norm[(size_t)b * p.n_multi + r] = nrm;
     }
-    // "all problems finished" flag, double-buffered by iteration parity so that the reset below
-    // can never overtake a slow thread still reading the previous iteration's verdict.
-    int* done_flag = reinterpret_cast<int*>(p.barrier) + (it & 1);
-    if (gtid == 0) *done_flag = 1;
     grid.sync();
+    // the other parity of the change counters was consumed by every block before the sync above
+    if (blockIdx.x == 0)
+      for (int b = threadIdx.x; b < p.nb; b += blockDim.x) p.chcount[2 * b + ((it + 1) & 1)] = 0;
     // ---------------- pass B: numerators, convergence test, alpha <- next ----------------
     for (uint64_t i0 = gtid - lane; i0 < nB; i0 += gstride) {
       const uint64_t i = i0 + lane;
       bool changed = false;
       uint32_t b = 0;
-      int st = 2;
       if (i < nB) {
         b = (uint32_t)(i / p.n_targets);
         const uint32_t t = (uint32_t)(i % p.n_targets);
-        st = p.state[b];
+        const int st = s_state[b];
         if (st < 2) {
           double* al = p.alpha + (size_t)b * p.n_targets;
           double a = al[t];
@@ -96,26 +122,6 @@ __global__ void __launch_bounds__(256) em_kernel(EmProblem p) {
       }
     }
     grid.sync();
-    // ---------------- state machine per problem (:202-221) ----------------
-    for (uint64_t b = gtid; b < (uint64_t)p.nb; b += gstride) {
-      int st = p.state[b];
-      if (st < 2) {
-        const unsigned ch = p.chcount[2 * b + (it & 1)];
-        p.chcount[2 * b + (it & 1)] = 0;
-        if (st == 1) { st = 2; p.rounds[b] = it; }                      // if (finalRound) break;
-        else if (ch == 0 && it > p.min_rounds) st = 1;                  // stopEM -> finalRound
-        if (st < 2 && it + 1 == p.max_iter) {
-          // loop runs out: i == n_iter.  If the stop was detected on the very last iteration the
-          // reference still zeroes the small alphas (:213-216); the host does that for state 3.
-          p.rounds[b] = p.max_iter;
-          st = (st == 1) ? 3 : 2;
-        }
-        p.state[b] = st;
-        if (st < 2) *done_flag = 0;
-      }
-    }
-    grid.sync();
-    if (*reinterpret_cast<volatile int*>(done_flag)) break;
   }
 }
 
@@ -123,7 +129,7 @@ int em_max_blocks(int tpb) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel, tpb, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel, tpb, 4096);
   return sms * per_sm;
 }
 
@@ -135,7 +141,7 @@ void launch_em(const EmProblem& p, int tpb, cudaStream_t st) {
   if (blocks < 1) blocks = 1;
   EmProblem pp = p;
   void* args[] = {&pp};
-  cudaLaunchCooperativeKernel((void*)em_kernel, dim3(blocks), dim3(tpb), args, 0, st);
+  cudaLaunchCooperativeKernel((void*)em_kernel, dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);
 }
 
 // ---------------------------------------------------------------------------------------------
