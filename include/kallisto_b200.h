@@ -82,6 +82,15 @@ void kb_quant_free(kb_quant* q);
  * Host buffers; the host->device copy, the kernels and the copy back are all inside the call. */
 int kb_pseudoalign_batch(kb_quant* q, const char* bases, const uint32_t* offsets, uint32_t n_reads,
                          uint32_t fixed_len, int32_t* ec_out);
+/* Paired batch with one buffer per mate, as a FASTQ reader produces them (R1 and R2 parsed
+ * separately, FastqSequenceReader::fetchSequences, src/ProcessReads.cpp:3128-3267): n_pairs
+ * fragments, offsetsN with n_pairs + 1 entries each (or both NULL with fixed_len). */
+int kb_pseudoalign_batch_pe(kb_quant* q, const char* bases1, const uint32_t* offsets1, const char* bases2,
+                            const uint32_t* offsets2, uint32_t n_pairs, uint32_t fixed_len, int32_t* ec_out);
+/* Page-locked host memory for batch buffers (so that the copies inside kb_pseudoalign_batch* run at
+ * full PCIe speed without the caller linking against CUDA). */
+void* kb_host_alloc(size_t bytes);
+void kb_host_free(void* p);
 /* Same with DEVICE pointers (inputs already resident in HBM); asynchronous on the run's stream. */
 int kb_pseudoalign_batch_device(kb_quant* q, const void* d_bases, const uint32_t* d_offsets, uint32_t n_reads,
                                 uint32_t fixed_len, uint32_t max_read_len);
@@ -130,6 +139,11 @@ int kb_em_run_table(kb_quant* q, uint32_t n_ecs, const uint64_t* ec_offsets, con
  * samples_out (optional) n_bootstrap x n_ecs resampled counts; rounds_out (optional) n_bootstrap. */
 int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed, int32_t n_bootstrap,
                      double* est_counts_out, uint32_t* samples_out, int32_t* rounds_out);
+
+/* Host-only: parse a FASTA/FASTQ file (plain or gzip) with the library's reader (kseq_read grammar,
+ * src/kseq.h) and report the number of records, of bases, and an FNV-1a hash of the sequences
+ * (0xFF after each record).  Tooling / tests. */
+int kb_fastx_summary(const char* path, uint64_t* n_reads, uint64_t* n_bases, uint64_t* fnv1a);
 
 /* counts_to_tpm (src/PlaintextWriter.cpp:5-27) -- host arithmetic, here so that callers format
  * identical numbers. */

@@ -53,9 +53,9 @@ class kb_run_stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "kb_last_error", "kb_version", "kb_index_load", "kb_index_free", "kb_index_get_info", "kb_index_target_name",
     "kb_index_target_lens", "kb_index_inspect", "kb_quant_create", "kb_quant_free", "kb_pseudoalign_batch",
-    "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_set_stream", "kb_quant_enable_timing",
+    "kb_pseudoalign_batch_pe", "kb_host_alloc", "kb_host_free", "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_set_stream", "kb_quant_enable_timing",
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
-    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_counts_to_tpm",
+    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_fastx_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -83,6 +83,10 @@ def lib():
     L.kb_quant_create.argtypes = [vp, C.POINTER(kb_quant_opts), C.POINTER(vp)]
     L.kb_quant_free.argtypes = [vp]
     L.kb_pseudoalign_batch.argtypes = [vp, vp, vp, u32, u32, vp]
+    L.kb_pseudoalign_batch_pe.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp]
+    L.kb_host_alloc.argtypes = [C.c_size_t]
+    L.kb_host_alloc.restype = vp
+    L.kb_host_free.argtypes = [vp]
     L.kb_pseudoalign_batch_device.argtypes = [vp, vp, vp, u32, u32, u32]
     L.kb_quant_sync.argtypes = [vp]
     L.kb_quant_set_stream.argtypes = [vp, vp]
@@ -96,6 +100,7 @@ def lib():
     L.kb_em_run_table.argtypes = [vp, u32, vp, vp, vp, dbl, dbl, vp, vp, C.POINTER(i32), C.POINTER(dbl)]
     L.kb_bootstrap_run.argtypes = [vp, dbl, dbl, u64, i32, vp, vp, vp]
     L.kb_counts_to_tpm.argtypes = [vp, vp, u32, vp]
+    L.kb_fastx_summary.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     _lib = L
     return L
 
@@ -189,6 +194,16 @@ class MinCollector:
         self._stats = None
         return out
 
+    def process_buffer_pe(self, bases1, offsets1, bases2, offsets2, want_handles=True):
+        """Paired batch, one buffer per mate (numpy arrays)."""
+        b1 = np.ascontiguousarray(bases1, np.uint8); b2 = np.ascontiguousarray(bases2, np.uint8)
+        o1 = np.ascontiguousarray(offsets1, np.uint32); o2 = np.ascontiguousarray(offsets2, np.uint32)
+        n = len(o1) - 1
+        out = np.full(n, -1, np.int32) if want_handles else None
+        _ck(lib().kb_pseudoalign_batch_pe(self._h, _p(b1), _p(o1), _p(b2), _p(o2), n, 0, _p(out)))
+        self._stats = None
+        return out
+
     def process_buffer_ptr(self, bases_ptr, offsets_ptr, n_reads, fixed_len, out_ptr=None):
         """Same, raw host pointers (e.g. pinned torch tensors)."""
         _ck(lib().kb_pseudoalign_batch(self._h, bases_ptr, offsets_ptr, n_reads, fixed_len, out_ptr))
@@ -266,6 +281,12 @@ class MinCollector:
         rounds = np.zeros(max(1, n_bootstrap), np.int32)
         _ck(lib().kb_bootstrap_run(self._h, fld_mean, fld_sd, seed, n_bootstrap, _p(est), _p(samples), _p(rounds)))
         return dict(est_counts=est, samples=samples, rounds=rounds[:n_bootstrap])
+
+
+def fastx_summary(path):
+    n, b, h = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    _ck(lib().kb_fastx_summary(os.fsencode(path), C.byref(n), C.byref(b), C.byref(h)))
+    return n.value, b.value, h.value
 
 
 def counts_to_tpm(est_counts, eff_lens):

@@ -5,6 +5,7 @@
 
 #include "../../include/kallisto_b200.h"
 #include "engine.hpp"
+#include "fastx.hpp"
 
 namespace {
 thread_local std::string g_err;
@@ -130,6 +131,25 @@ int kb_pseudoalign_batch(kb_quant* q, const char* bases, const uint32_t* offsets
   return guarded([&] { q->q->pseudoalign_host(bases, offsets, n_reads, fixed_len, ec_out); });
 }
 
+int kb_pseudoalign_batch_pe(kb_quant* q, const char* bases1, const uint32_t* offsets1, const char* bases2,
+                            const uint32_t* offsets2, uint32_t n_pairs, uint32_t fixed_len, int32_t* ec_out) {
+  if (!q || ((!bases1 || !bases2) && n_pairs)) return fail(KB_ERR_INVALID, "kb_pseudoalign_batch_pe: null argument");
+  if (!offsets1 && fixed_len == 0 && n_pairs) return fail(KB_ERR_INVALID, "kb_pseudoalign_batch_pe: need offsets or fixed_len");
+  return guarded([&] { q->q->pseudoalign_host_pe(bases1, offsets1, bases2, offsets2, n_pairs, fixed_len, ec_out); });
+}
+
+void* kb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void kb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int kb_pseudoalign_batch_device(kb_quant* q, const void* d_bases, const uint32_t* d_offsets, uint32_t n_reads,
                                 uint32_t fixed_len, uint32_t max_read_len) {
   if (!q || (!d_bases && n_reads)) return fail(KB_ERR_INVALID, "kb_pseudoalign_batch_device: null argument");
@@ -171,14 +191,15 @@ int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out) {
 int kb_quant_finalize(kb_quant* q, kb_run_stats* stats) {
   if (!q) return fail(KB_ERR_INVALID, "kb_quant_finalize: null argument");
   return guarded([&] {
-    const kb::EcTable& e = q->q->finalize_ecs();
+    const bool fast = q->q->dev_stats_valid_;   // kb_em_run already numbered the ECs on the device
+    if (!fast) q->q->finalize_ecs();
     if (stats) {
       const kb::Stats s = q->q->stats();
       stats->n_processed = s.n_processed;
       stats->n_pseudoaligned = s.n_pseudoaligned;
       stats->n_unique = s.n_unique;
-      stats->n_ecs = e.n();
-      stats->n_ec_entries = e.tid.size();
+      stats->n_ecs = fast ? q->q->dev_n_ecs_ : q->q->finalize_ecs().n();
+      stats->n_ec_entries = fast ? q->q->dev_nnz_ : q->q->finalize_ecs().tid.size();
       stats->n_probes = s.n_probes;
       stats->n_slot_visits = s.n_slot_visits;
       stats->n_resolved = s.n_resolved;
@@ -264,6 +285,32 @@ int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed,
     if (rounds_out)
       for (int b = 0; b < n_bootstrap; ++b) rounds_out[b] = rounds[b];
   });
+}
+
+int kb_fastx_summary(const char* path, uint64_t* n_reads, uint64_t* n_bases, uint64_t* fnv1a) {
+  if (!path || !n_reads || !n_bases || !fnv1a) return fail(KB_ERR_INVALID, "kb_fastx_summary: null argument");
+  try {
+    kb::FastxFile f(path);
+    kb::ReadBatch b;
+    std::vector<char> bases((size_t)(1u << 22) + kb::FastxFile::kMaxRead);
+    std::vector<uint32_t> off(65537);
+    b.bases = bases.data(); b.off = off.data(); b.cap_bases = bases.size(); b.cap_reads = 65536;
+    uint64_t nr = 0, nbz = 0, h = 1469598103934665603ULL;
+    for (;;) {
+      b.clear();
+      if (!f.fill(b, 65536)) break;
+      nr += b.n;
+      nbz += b.n_bases();
+      for (size_t i = 0; i < b.n; ++i) {
+        for (uint32_t j = b.off[i]; j < b.off[i + 1]; ++j) { h ^= (unsigned char)b.bases[j]; h *= 1099511628211ULL; }
+        h ^= 0xFF; h *= 1099511628211ULL;   // record separator
+      }
+    }
+    *n_reads = nr; *n_bases = nbz; *fnv1a = h;
+    return KB_OK;
+  } catch (const std::exception& e) {
+    return fail(KB_ERR_IO, e.what());
+  }
 }
 
 int kb_counts_to_tpm(const double* est_counts, const double* eff_lens, uint32_t n, double* tpm_out) {

@@ -1,0 +1,496 @@
+// kallisto_b200 -- command-line front end: same sub-commands, flags, messages and output files as
+// `kallisto quant` (src/main.cpp:211-392 ParseOptionsEM, 1600-1805 CheckOptionsEM, 2620-2798 the
+// command body), with the read pipeline, EC bookkeeping, EM and bootstrap running on the GPU through
+// the C ABI (include/kallisto_b200.h).  Host work here: option parsing, FASTQ parsing, text output.
+#include <getopt.h>
+#include <sys/stat.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/kallisto_b200.h"
+#include "fastx.hpp"
+
+using std::cerr;
+using std::endl;
+
+namespace {
+
+const char* KALLISTO_VERSION = "0.51.1";   // the reference version whose behaviour is reproduced
+const char* ERROR_STR = "\033[1mError:\033[0m";
+
+struct Options {
+  int threads = 1;
+  std::string index, output;
+  double fld = 0.0, sd = 0.0;
+  int bootstrap = 0;
+  size_t seed = 42;
+  bool plaintext = false, single_end = false, single_overhang = false, verbose = false;
+  int strand = 0;   // 0 none, 1 FR, 2 RF
+  int device = 0;
+  std::vector<std::string> files;
+};
+
+std::string pretty_num(size_t n) {   // src/common.cpp pretty_num
+  std::string s = std::to_string(n);
+  for (int i = (int)s.size() - 3; i > 0; i -= 3) s.insert(i, ",");
+  return s;
+}
+
+std::string to_json(const std::string& id, const std::string& val, bool quote, bool comma = true, int level = 1) {
+  std::string out;   // src/PlaintextWriter.cpp:114-138
+  for (int i = 0; i < level; ++i) out += "\t";
+  out += '"';
+  out += id;
+  out += "\": ";
+  if (quote) out += '"';
+  out += val;
+  if (quote) out += '"';
+  if (comma) out += ',';
+  return out;
+}
+
+void usage_quant() {
+  std::cout << "kallisto_b200 " << KALLISTO_VERSION << " (B200 build)" << endl
+            << "Computes equivalence classes for reads and quantifies abundances" << endl << endl
+            << "Usage: kallisto_b200 quant [arguments] FASTQ-files" << endl << endl
+            << "Required arguments:" << endl
+            << "-i, --index=STRING            Filename for the kallisto index to be used for" << endl
+            << "                              quantification" << endl
+            << "-o, --output-dir=STRING       Directory to write output to" << endl << endl
+            << "Optional arguments:" << endl
+            << "-b, --bootstrap-samples=INT   Number of bootstrap samples (default: 0)" << endl
+            << "    --seed=INT                Seed for the bootstrap sampling (default: 42)" << endl
+            << "    --plaintext               Output plaintext instead of HDF5" << endl
+            << "    --single                  Quantify single-end reads" << endl
+            << "    --single-overhang         Include reads where unobserved rest of fragment is" << endl
+            << "                              predicted to lie outside a transcript" << endl
+            << "    --fr-stranded             Strand specific reads, first read forward" << endl
+            << "    --rf-stranded             Strand specific reads, first read reverse" << endl
+            << "-l, --fragment-length=DOUBLE  Estimated average fragment length" << endl
+            << "-s, --sd=DOUBLE               Estimated standard deviation of fragment length" << endl
+            << "                              (default: -l, -s values are estimated from paired" << endl
+            << "                               end data, but are required when using --single)" << endl
+            << "-t, --threads=INT             Number of host threads parsing input (default: 1)" << endl
+            << "    --device=INT              CUDA device ordinal (default: 0)" << endl
+            << "    --verbose                 Print out progress information every 1M proccessed reads" << endl;
+}
+
+void parse_quant(int argc, char** argv, Options& opt) {
+  int verbose_flag = 0, plaintext_flag = 0, single_flag = 0, single_overhang_flag = 0, fr = 0, rf = 0;
+  const char* opt_string = "t:i:l:s:o:b:d:D:";
+  static struct option long_options[] = {
+      {"verbose", no_argument, &verbose_flag, 1},
+      {"plaintext", no_argument, &plaintext_flag, 1},
+      {"single", no_argument, &single_flag, 1},
+      {"single-overhang", no_argument, &single_overhang_flag, 1},
+      {"fr-stranded", no_argument, &fr, 1},
+      {"rf-stranded", no_argument, &rf, 1},
+      {"seed", required_argument, 0, 'd'},
+      {"threads", required_argument, 0, 't'},
+      {"index", required_argument, 0, 'i'},
+      {"fragment-length", required_argument, 0, 'l'},
+      {"sd", required_argument, 0, 's'},
+      {"output-dir", required_argument, 0, 'o'},
+      {"bootstrap-samples", required_argument, 0, 'b'},
+      {"device", required_argument, 0, 'D'},
+      {0, 0, 0, 0}};
+  int c, option_index = 0;
+  while ((c = getopt_long(argc, argv, opt_string, long_options, &option_index)) != -1) {
+    switch (c) {
+      case 't': std::stringstream(optarg) >> opt.threads; break;
+      case 'i': opt.index = optarg; break;
+      case 'l': std::stringstream(optarg) >> opt.fld; break;
+      case 's': std::stringstream(optarg) >> opt.sd; break;
+      case 'o': opt.output = optarg; break;
+      case 'b': std::stringstream(optarg) >> opt.bootstrap; break;
+      case 'd': std::stringstream(optarg) >> opt.seed; break;
+      case 'D': std::stringstream(optarg) >> opt.device; break;
+      default: break;
+    }
+  }
+  for (int i = optind; i < argc; i++) opt.files.push_back(argv[i]);
+  opt.verbose = verbose_flag;
+  opt.plaintext = plaintext_flag;
+  opt.single_end = single_flag;
+  opt.single_overhang = single_overhang_flag;
+  if (fr) opt.strand = 1;
+  if (rf) opt.strand = 2;
+}
+
+bool check_quant(Options& opt) {   // CheckOptionsEM, src/main.cpp:1600-1805
+  bool ret = true;
+  cerr << endl;
+  struct stat st;
+  if (opt.index.empty()) {
+    cerr << ERROR_STR << " kallisto index file missing" << endl;
+    ret = false;
+  } else if (stat(opt.index.c_str(), &st) != 0) {
+    cerr << ERROR_STR << " kallisto index file not found " << opt.index << endl;
+    ret = false;
+  }
+  if (opt.files.empty()) {
+    cerr << ERROR_STR << " Missing read files" << endl;
+    ret = false;
+  } else {
+    for (auto& fn : opt.files)
+      if (stat(fn.c_str(), &st) != 0) {
+        cerr << ERROR_STR << " file not found " << fn << endl;
+        ret = false;
+      }
+  }
+  if (!opt.single_end && opt.files.size() % 2 != 0) {
+    cerr << "Error: paired-end mode requires an even number of input files" << endl
+         << "       (use --single for processing single-end reads)" << endl;
+    ret = false;
+  }
+  if ((opt.fld != 0.0 && opt.sd == 0.0) || (opt.sd != 0.0 && opt.fld == 0.0)) {
+    cerr << "Error: cannot supply mean/sd without supplying both -l and -s" << endl;
+    ret = false;
+  }
+  if (opt.single_end && (opt.fld == 0.0 || opt.sd == 0.0)) {
+    cerr << "Error: fragment length mean and sd must be supplied for single-end reads using -l and -s" << endl;
+    ret = false;
+  } else if (opt.fld == 0.0 && ret) {
+    cerr << "[quant] fragment length distribution will be estimated from the data" << endl;
+  } else if (ret && opt.fld > 0.0 && opt.sd > 0.0) {
+    cerr << "[quant] fragment length distribution is truncated gaussian with mean = " << opt.fld << ", sd = " << opt.sd << endl;
+  }
+  if (!opt.single_end && (opt.fld > 0.0 && opt.sd > 0.0)) {
+    cerr << "[~warn] you specified using a gaussian but have paired end data" << endl;
+    cerr << "[~warn] we suggest omitting these parameters and let us estimate the distribution from data" << endl;
+  }
+  if (opt.fld < 0.0) { cerr << "Error: invalid value for mean fragment length " << opt.fld << endl; ret = false; }
+  if (opt.sd < 0.0) { cerr << "Error: invalid value for fragment length standard deviation " << opt.sd << endl; ret = false; }
+  if (opt.single_end && !opt.single_overhang) {
+    cerr << "Error: this build quantifies single-end reads only with --single-overhang" << endl
+         << "       (the fragment-position filter of the reference is not implemented yet)" << endl;
+    ret = false;
+  }
+  if (opt.output.empty()) {
+    cerr << "Error: need to specify output directory " << opt.output << endl;
+    ret = false;
+  } else if (stat(opt.output.c_str(), &st) == 0) {
+    if (!S_ISDIR(st.st_mode)) {
+      cerr << "Error: file " << opt.output << " exists and is not a directory" << endl;
+      ret = false;
+    }
+  } else if (mkdir(opt.output.c_str(), 0777) == -1) {
+    cerr << "Error: could not create directory " << opt.output << endl;
+    ret = false;
+  }
+  if (opt.threads <= 0) {
+    cerr << "Error: invalid number of threads " << opt.threads << endl;
+    ret = false;
+  }
+  if (opt.bootstrap < 0) {
+    cerr << "Error: number of bootstrap samples must be a non-negative integer." << endl;
+    ret = false;
+  }
+  if (opt.bootstrap > 0 && !opt.plaintext) {
+    cerr << "Warning: kallisto was not compiled with HDF5 support so no bootstrapping" << endl
+         << "will be performed. Run quant with --plaintext option or recompile with" << endl
+         << "HDF5 support to obtain bootstrap estimates." << endl;
+    opt.bootstrap = 0;
+  }
+  return ret;
+}
+
+// plaintext_writer, src/PlaintextWriter.cpp:29-65 (default ostream formatting: 6 significant digits)
+void write_abundance(const std::string& path, const std::vector<std::string>& names, const std::vector<uint32_t>& lens,
+                     const double* eff, const double* est) {
+  std::ofstream of(path);
+  if (!of.is_open()) {
+    cerr << "Error: Couldn't open file: " << path << endl;
+    exit(1);
+  }
+  std::vector<double> tpm(names.size());
+  kb_counts_to_tpm(est, eff, (uint32_t)names.size(), tpm.data());
+  of << "target_id" << "\t" << "length" << "\t" << "eff_length" << "\t" << "est_counts" << "\t" << "tpm" << std::endl;
+  for (size_t i = 0; i < names.size(); ++i)
+    of << names[i] << '\t' << lens[i] << '\t' << eff[i] << '\t' << est[i] << '\t' << tpm[i] << std::endl;
+}
+
+// plaintext_aux, src/PlaintextWriter.cpp:140-199
+void write_run_info(const std::string& path, size_t n_targets, int n_bootstrap, uint64_t n_processed, uint64_t n_aln,
+                    uint64_t n_unique, int index_version, int k, const std::string& start_time, const std::string& call) {
+  std::ofstream of(path);
+  double p_uniq = 0.0, p_aln = 0.0;
+  if (n_processed > 0) {
+    p_uniq = 100.0 * (double)n_unique / (double)n_processed;
+    p_aln = 100.0 * (double)n_aln / (double)n_processed;
+  }
+  std::stringstream ss;
+  ss << std::fixed << std::setprecision(1) << p_uniq;
+  const std::string p_uniq_s = ss.str();
+  ss.str("");
+  ss << std::fixed << std::setprecision(1) << p_aln;
+  const std::string p_aln_s = ss.str();
+  of << "{" << std::endl
+     << to_json("n_targets", std::to_string(n_targets), false) << std::endl
+     << to_json("n_bootstraps", std::to_string(n_bootstrap), false) << std::endl
+     << to_json("n_processed", std::to_string(n_processed), false) << std::endl
+     << to_json("n_pseudoaligned", std::to_string(n_aln), false) << std::endl
+     << to_json("n_unique", std::to_string(n_unique), false) << std::endl
+     << to_json("p_pseudoaligned", p_aln_s, false) << std::endl
+     << to_json("p_unique", p_uniq_s, false) << std::endl
+     << to_json("kallisto_version", KALLISTO_VERSION, true) << std::endl
+     << to_json("index_version", std::to_string(index_version), false) << std::endl
+     << to_json("k-mer length", std::to_string(k), false) << std::endl
+     << to_json("start_time", start_time, true) << std::endl
+     << to_json("call", call, true, false) << std::endl
+     << "}" << std::endl;
+}
+
+#define KB_TRY(x)                                                     \
+  do {                                                                \
+    if ((x) != KB_OK) {                                               \
+      cerr << "Error: " << kb_last_error() << endl;                   \
+      exit(1);                                                        \
+    }                                                                 \
+  } while (0)
+
+// One parser thread per input stream, handing filled batches to the GPU thread through a small ring.
+struct Stream {
+  std::vector<kb::ReadBatch> ring;
+  std::vector<int> state;   // 0 free, 1 filled
+  size_t head = 0, tail = 0;
+  bool done = false;
+  std::string error;
+  std::mutex m;
+  std::condition_variable cv;
+};
+
+void reader_thread(std::vector<std::string> files, Stream* s, size_t max_reads) {
+  try {
+    size_t slot = 0;
+    for (auto& fn : files) {
+      kb::FastxFile f(fn);
+      for (;;) {
+        {
+          std::unique_lock<std::mutex> lk(s->m);
+          s->cv.wait(lk, [&] { return s->state[slot] == 0; });
+        }
+        kb::ReadBatch& b = s->ring[slot];
+        b.clear();
+        const bool any = f.fill(b, max_reads);
+        if (!any) break;
+        {
+          std::lock_guard<std::mutex> lk(s->m);
+          s->state[slot] = 1;
+        }
+        s->cv.notify_all();
+        slot = (slot + 1) % s->ring.size();
+      }
+    }
+  } catch (const std::exception& e) {
+    std::lock_guard<std::mutex> lk(s->m);
+    s->error = e.what();
+  }
+  {
+    std::lock_guard<std::mutex> lk(s->m);
+    s->done = true;
+  }
+  s->cv.notify_all();
+}
+
+int cmd_quant(int argc, char** argv, const std::string& call, const std::string& start_time) {
+  Options opt;
+  parse_quant(argc, argv, opt);
+  if (!check_quant(opt)) {
+    cerr << endl;
+    usage_quant();
+    return 1;
+  }
+  kb_index* ix = nullptr;
+  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, 0, std::max(1, opt.threads), &ix));
+  kb_index_info info;
+  kb_index_get_info(ix, &info);
+  cerr << "[index] k-mer length: " << info.k << endl;
+  cerr << "[index] number of targets: " << pretty_num(info.n_targets) << endl;
+  cerr << "[index] number of k-mers: " << pretty_num(info.n_kmers) << endl;
+  const bool paired = !opt.single_end;
+  cerr << (paired ? "[quant] running in paired-end mode" : "[quant] running in single-end mode") << endl;
+  for (size_t i = 0; i < opt.files.size(); i += paired ? 2 : 1) {
+    if (paired)
+      cerr << "[quant] will process pair " << (i / 2 + 1) << ": " << opt.files[i] << endl
+           << "                             " << opt.files[i + 1] << endl;
+    else
+      cerr << "[quant] will process file " << i + 1 << ": " << opt.files[i] << endl;
+  }
+  cerr << "[quant] finding pseudoalignments for the reads ...";
+  cerr.flush();
+
+  const size_t max_reads = 1u << 20;                 // reads per batch and mate
+  const size_t max_bases = (size_t)max_reads * 160 + kb::FastxFile::kMaxRead;
+  kb_quant_opts qo{};
+  qo.paired = paired;
+  qo.strand_mode = opt.strand;
+  qo.collect_fld = opt.fld == 0.0;
+  qo.max_batch_reads = (uint32_t)max_reads;
+  qo.max_batch_bases = 2 * max_bases;
+  kb_quant* q = nullptr;
+  KB_TRY(kb_quant_create(ix, &qo, &q));
+
+  const int n_streams = paired ? 2 : 1;
+  std::vector<Stream> streams(n_streams);
+  std::vector<std::thread> readers;
+  for (int s = 0; s < n_streams; ++s) {
+    streams[s].ring.resize(3);
+    streams[s].state.assign(3, 0);
+    for (auto& b : streams[s].ring) {
+      b.cap_bases = max_bases;
+      b.cap_reads = max_reads;
+      b.bases = (char*)kb_host_alloc(max_bases + 64);
+      b.off = (uint32_t*)kb_host_alloc((max_reads + 1) * sizeof(uint32_t));
+      if (!b.bases || !b.off) {
+        cerr << "Error: could not allocate pinned host memory" << endl;
+        return 1;
+      }
+      b.clear();
+    }
+    std::vector<std::string> files;
+    for (size_t i = s; i < opt.files.size(); i += n_streams) files.push_back(opt.files[i]);
+    readers.emplace_back(reader_thread, files, &streams[s], max_reads);
+  }
+  uint64_t n_done = 0;
+  size_t slot = 0;
+  for (;;) {
+    bool have = true;
+    for (int s = 0; s < n_streams; ++s) {
+      std::unique_lock<std::mutex> lk(streams[s].m);
+      streams[s].cv.wait(lk, [&] { return streams[s].state[slot] == 1 || streams[s].done; });
+      if (!streams[s].error.empty()) {
+        cerr << endl << streams[s].error << endl;
+        exit(1);
+      }
+      if (streams[s].state[slot] != 1) have = false;
+    }
+    if (!have) break;
+    kb::ReadBatch& b1 = streams[0].ring[slot];
+    if (paired) {
+      kb::ReadBatch& b2 = streams[1].ring[slot];
+      if (b1.n != b2.n) {
+        cerr << endl << "Error: paired input files hold different numbers of reads" << endl;
+        exit(1);
+      }
+      KB_TRY(kb_pseudoalign_batch_pe(q, b1.bases, b1.off, b2.bases, b2.off, (uint32_t)b1.n, 0, nullptr));
+    } else {
+      KB_TRY(kb_pseudoalign_batch(q, b1.bases, b1.off, (uint32_t)b1.n, 0, nullptr));
+    }
+    n_done += b1.n;
+    if (opt.verbose) cerr << endl << "[quant] processed " << pretty_num(n_done) << " reads";
+    for (int s = 0; s < n_streams; ++s) {
+      {
+        std::lock_guard<std::mutex> lk(streams[s].m);
+        streams[s].state[slot] = 0;
+      }
+      streams[s].cv.notify_all();
+    }
+    slot = (slot + 1) % 3;
+  }
+  for (auto& t : readers) t.join();
+  cerr << " done" << endl;
+
+  const uint32_t T = info.n_targets;
+  std::vector<double> est(T), eff(T);
+  int32_t rounds = 0;
+  uint32_t flens[1000];
+  kb_quant_get_flens(q, flens);
+  if (opt.fld == 0.0) {
+    uint64_t c = 0;
+    for (int i = 0; i < 1000; ++i) c += flens[i];
+    if (c == 0 && paired) {
+      // MinCollector::get_mean_frag_len (src/MinCollector.cpp:583-607) would stop here as well
+    }
+  }
+  KB_TRY(kb_em_run(q, opt.fld, opt.sd, est.data(), eff.data(), &rounds, nullptr));
+  kb_run_stats st{};
+  KB_TRY(kb_quant_finalize(q, &st));
+  cerr << "[quant] processed " << pretty_num(st.n_processed) << " reads, " << pretty_num(st.n_pseudoaligned)
+       << " reads pseudoaligned" << endl;
+  if (st.n_pseudoaligned == 0) cerr << "[~warn] no reads pseudoaligned." << endl;
+  if (opt.fld == 0.0) {
+    // compute_mean_frag_lens_trunc(verbose): mean over the whole histogram
+    double mass = 0;
+    uint64_t cnt = 0;
+    for (size_t i = 0; i < 1000; ++i) { mass += (double)(flens[i] * i); cnt += flens[i]; }
+    cerr << "[quant] estimated average fragment length: " << (cnt ? mass / (double)cnt : 0.0) << endl;
+  }
+  cerr << "[   em] quantifying the abundances ... done" << endl;
+  cerr << "[   em] the Expectation-Maximization algorithm ran for " << pretty_num((size_t)rounds) << " rounds" << endl;
+
+  std::vector<std::string> names(T);
+  std::vector<uint32_t> lens(T);
+  for (uint32_t i = 0; i < T; ++i) names[i] = kb_index_target_name(ix, i);
+  kb_index_target_lens(ix, lens.data());
+  if (st.n_pseudoaligned == 0) cerr << "[~warn] Warning, zero reads pseudoaligned check your input files and index" << endl;
+  write_run_info(opt.output + "/run_info.json", T, opt.bootstrap, st.n_processed, st.n_pseudoaligned, st.n_unique, 13,
+                 info.k, start_time, call);
+  write_abundance(opt.output + "/abundance.tsv", names, lens, eff.data(), est.data());
+  if (opt.bootstrap > 0 && st.n_pseudoaligned == 0) {
+    for (int b = 0; b < opt.bootstrap; ++b)
+      write_abundance(opt.output + "/bs_abundance_" + std::to_string(b) + ".tsv", names, lens, eff.data(), est.data());
+  } else if (opt.bootstrap > 0) {
+    std::vector<double> bs((size_t)opt.bootstrap * T);
+    cerr << "[bstrp] running EM for " << opt.bootstrap << " bootstraps on the device" << endl;
+    KB_TRY(kb_bootstrap_run(q, opt.fld, opt.sd, opt.seed, opt.bootstrap, bs.data(), nullptr, nullptr));
+    for (int b = 0; b < opt.bootstrap; ++b)
+      write_abundance(opt.output + "/bs_abundance_" + std::to_string(b) + ".tsv", names, lens, eff.data(),
+                      bs.data() + (size_t)b * T);
+  }
+  cerr << endl;
+  kb_quant_free(q);
+  kb_index_free(ix);
+  return st.n_pseudoaligned == 0 ? 1 : 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  // start time and call line, as in src/main.cpp:2260-2291
+  std::time_t t = std::time(nullptr);
+  char tbuf[64];
+  std::strftime(tbuf, sizeof(tbuf), "%a %b %e %H:%M:%S %Y", std::localtime(&t));   // std::asctime layout, no newline
+  std::string call;
+  for (int i = 0; i < argc; ++i) {
+    if (i) call += " ";
+    call += argv[i];
+  }
+  if (argc < 2) {
+    std::cout << "kallisto_b200 " << KALLISTO_VERSION << endl << endl
+              << "Usage: kallisto_b200 <CMD> [arguments] .." << endl << endl
+              << "Where <CMD> can be one of:" << endl << endl
+              << "    quant         Runs the quantification algorithm (GPU)" << endl
+              << "    bus           Generate BUS files for single-cell data (GPU)" << endl
+              << "    version       Prints version information" << endl << endl
+              << "Indices are built with the reference `kallisto index` (format v13)." << endl;
+    return 1;
+  }
+  const std::string cmd = argv[1];
+  if (cmd == "version") {
+    std::cout << "kallisto_b200, version " << KALLISTO_VERSION << " (" << kb_version() << ")" << endl;
+    return 0;
+  }
+  if (cmd == "quant") {
+    if (argc == 2) {
+      usage_quant();
+      return 0;
+    }
+    return cmd_quant(argc - 1, argv + 1, call, tbuf);
+  }
+  cerr << "Error: invalid command " << cmd << endl;
+  return 1;
+}

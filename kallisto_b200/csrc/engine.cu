@@ -291,15 +291,18 @@ void Quant::check_device_errors() {
 }
 
 void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
-                      uint32_t max_read_len) {
+                      uint32_t max_read_len, const uint8_t* d_bases2, const uint32_t* d_off2) {
   const uint32_t n_frag = opt_.paired ? n_reads / 2 : n_reads;
   if (opt_.paired && (n_reads & 1)) throw Error("kallisto_b200: odd number of reads in a paired batch");
   if (n_frag > d_handles_.n) throw Error("kallisto_b200: batch larger than max_batch_reads");
   if (n_frag == 0) return;
   ecs_valid_ = false;
+  dev_stats_valid_ = false;
   BatchArgs ba{};
   ba.bases = d_bases;
   ba.off = d_off;
+  ba.bases2 = d_bases2;
+  ba.off2 = d_off2;
   ba.fixed_len = fixed_len;
   ba.n_frag = n_frag;
   ba.paired = opt_.paired;
@@ -390,6 +393,38 @@ void Quant::pseudoalign_host(const char* bases, const uint32_t* off, uint32_t n_
   KB_CK(cudaStreamSynchronize(stream_));
 }
 
+void Quant::pseudoalign_host_pe(const char* bases1, const uint32_t* off1, const char* bases2, const uint32_t* off2,
+                                uint32_t n_pairs, uint32_t fixed_len, int32_t* handles_out) {
+  KB_CK(cudaSetDevice(ix_.device));
+  if (n_pairs == 0) return;
+  if (!opt_.paired) throw Error("kallisto_b200: per-mate buffers need a paired run");
+  if ((off1 == nullptr) != (off2 == nullptr)) throw Error("kallisto_b200: give offsets for both mates or for neither");
+  uint64_t nb1, nb2;
+  uint32_t maxlen = fixed_len;
+  if (off1) {
+    nb1 = off1[n_pairs];
+    nb2 = off2[n_pairs];
+    maxlen = 0;
+    for (uint32_t i = 0; i < n_pairs; ++i) maxlen = std::max(maxlen, std::max(off1[i + 1] - off1[i], off2[i + 1] - off2[i]));
+  } else {
+    nb1 = nb2 = (uint64_t)n_pairs * fixed_len;
+  }
+  if (d_bases_.n < nb1 + 16) d_bases_.alloc(std::max<uint64_t>(nb1 + 16, opt_.max_batch_bases / 2 + 16));
+  if (d_bases2_.n < nb2 + 16) d_bases2_.alloc(std::max<uint64_t>(nb2 + 16, opt_.max_batch_bases / 2 + 16));
+  KB_CK(cudaMemcpyAsync(d_bases_.p, bases1, nb1, cudaMemcpyHostToDevice, stream_));
+  KB_CK(cudaMemcpyAsync(d_bases2_.p, bases2, nb2, cudaMemcpyHostToDevice, stream_));
+  if (off1) {
+    const size_t no = (size_t)n_pairs + 1;
+    if (d_off_.n < no) d_off_.alloc(std::max<size_t>(no, (size_t)opt_.max_batch_reads + 1));
+    if (d_off2_.n < no) d_off2_.alloc(std::max<size_t>(no, (size_t)opt_.max_batch_reads + 1));
+    KB_CK(cudaMemcpyAsync(d_off_.p, off1, no * 4, cudaMemcpyHostToDevice, stream_));
+    KB_CK(cudaMemcpyAsync(d_off2_.p, off2, no * 4, cudaMemcpyHostToDevice, stream_));
+  }
+  run_batch(d_bases_.p, off1 ? d_off_.p : nullptr, 2 * n_pairs, fixed_len, maxlen, d_bases2_.p, off1 ? d_off2_.p : nullptr);
+  if (handles_out) d_handles_.download(handles_out, n_pairs, 0, stream_);
+  KB_CK(cudaStreamSynchronize(stream_));
+}
+
 void Quant::set_flens(const uint32_t* f) { flens_.assign(f, f + 1000); }
 
 namespace {
@@ -458,12 +493,17 @@ const EcTable& Quant::finalize_ecs() {
 }
 
 Stats Quant::stats() {
-  const EcTable& e = finalize_ecs();
   Stats s;
   s.n_processed = n_frag_total_;
-  for (uint32_t i = 0; i < e.n(); ++i) {
-    s.n_pseudoaligned += e.count[i];
-    if (e.off[i + 1] - e.off[i] == 1) s.n_unique += e.count[i];
+  if (dev_stats_valid_) {   // computed on the device by run_em_device: no EC table on the host needed
+    s.n_pseudoaligned = dev_pseudoaligned_;
+    s.n_unique = dev_unique_;
+  } else {
+    const EcTable& e = finalize_ecs();
+    for (uint32_t i = 0; i < e.n(); ++i) {
+      s.n_pseudoaligned += e.count[i];
+      if (e.off[i + 1] - e.off[i] == 1) s.n_unique += e.count[i];
+    }
   }
   unsigned long long st[4];
   KB_CK(cudaMemcpy(st, dd_.stats, sizeof(st), cudaMemcpyDeviceToHost));

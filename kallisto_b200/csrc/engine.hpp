@@ -108,6 +108,10 @@ class Quant {
   // kernels and (if handles_out != null) the copy back of one handle per fragment happen inside.
   void pseudoalign_host(const char* bases, const uint32_t* off, uint32_t n_reads, uint32_t fixed_len,
                         int32_t* handles_out);
+  // Paired batch with one buffer per mate (what a FASTQ reader produces: R1 and R2 parsed
+  // separately), n_pairs fragments; off1/off2 have n_pairs + 1 entries or are null with fixed_len.
+  void pseudoalign_host_pe(const char* bases1, const uint32_t* off1, const char* bases2, const uint32_t* off2,
+                           uint32_t n_pairs, uint32_t fixed_len, int32_t* handles_out);
   // Same, inputs already resident in device memory; handles stay on the device
   // (device_handles(), valid until the next batch).
   void pseudoalign_device(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
@@ -147,7 +151,7 @@ class Quant {
 
  private:
   void run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
-                 uint32_t max_read_len);
+                 uint32_t max_read_len, const uint8_t* d_bases2 = nullptr, const uint32_t* d_off2 = nullptr);
   void check_device_errors();
 
   Index& ix_;
@@ -166,8 +170,8 @@ class Quant {
   DBuf<int32_t> mn_val_;
   DBuf<int> error_;
   // batch staging
-  DBuf<uint8_t> d_bases_;
-  DBuf<uint32_t> d_off_, d_qcount_, d_qentries_, d_scratch_, d_packed_;
+  DBuf<uint8_t> d_bases_, d_bases2_;
+  DBuf<uint32_t> d_off_, d_off2_, d_qcount_, d_qentries_, d_scratch_, d_packed_;
   DBuf<int32_t> d_handles_;
   DBuf<uint16_t> d_tl_;
   uint32_t n_resolve_warps_ = 0;

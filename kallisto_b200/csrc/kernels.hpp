@@ -37,6 +37,8 @@ struct DictInitArgs {
 struct BatchArgs {
   const uint8_t* bases;
   const uint32_t* off;      // n_reads + 1 offsets into bases, or nullptr when every read has fixed_len bases
+  const uint8_t* bases2;    // optional: second-mate buffer (then `bases`/`off` hold the first mates only and
+  const uint32_t* off2;     //           read 2f+m is entry f of buffer m); nullptr = mates interleaved in `bases`
   uint32_t fixed_len;
   uint32_t n_frag;          // pairs (paired) or reads (single)
   int paired;

@@ -120,6 +120,25 @@ __device__ __forceinline__ int32_t memon_lookup(const DevDict& dd, const uint32_
   }
 }
 
+// Location of read `ridx` of a batch (mates interleaved in one buffer, or one buffer per mate).
+__device__ __forceinline__ void read_span(const BatchArgs& ba, uint32_t ridx, const uint8_t*& base, uint64_t& off, int& len) {
+  base = ba.bases;
+  const uint32_t* offs = ba.off;
+  uint32_t i = ridx;
+  if (ba.bases2) {
+    i = ridx >> 1;
+    if (ridx & 1) { base = ba.bases2; offs = ba.off2; }
+  }
+  if (offs) {
+    const uint32_t o0 = offs[i], o1 = offs[i + 1];
+    off = o0;
+    len = (int)(o1 - o0);
+  } else {
+    off = (uint64_t)i * ba.fixed_len;
+    len = (int)ba.fixed_len;
+  }
+}
+
 // Lane states of match_kernel.
 enum : int {
   S_MAIN = 0, S_JUMP = 1, S_MIDDLE = 2, S_BACKOFF = 3,   // k-mer table lookups (KmerIndex::match control flow)
@@ -146,21 +165,15 @@ __global__ void __launch_bounds__(256) pack_kernel(BatchArgs ba, uint32_t n_read
   const uint32_t r = (uint32_t)(gid / nb), w = (uint32_t)(gid % nb);
   uint64_t off;
   int len;
-  if (ba.off) {
-    const uint32_t o0 = ba.off[r], o1 = ba.off[r + 1];
-    off = o0;
-    len = (int)(o1 - o0);
-  } else {
-    off = (uint64_t)r * ba.fixed_len;
-    len = (int)ba.fixed_len;
-  }
+  const uint8_t* src_bases;
+  read_span(ba, r, src_bases, off, len);
   const int base = (int)w * 32;
   uint64_t bwv = 0;
   uint32_t inv32 = ~0u;
   if (base < len) {
     const int n = min(32, len - base);
     const uint64_t a = off + (uint64_t)base;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(ba.bases + (a & ~3ull));
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(src_bases + (a & ~3ull));
     const int sh = (int)(a & 3) * 8;
     const int ng = (n + 3) >> 2;
     uint32_t cur = __ldg(wp);
@@ -368,7 +381,10 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
           int l0 = 0;
           for (int mt = 0; mt < n_mates; ++mt) {
             const uint32_t ridx = ba.paired ? 2 * fidx + mt : fidx;
-            int len = ba.off ? (int)(ba.off[ridx + 1] - ba.off[ridx]) : (int)ba.fixed_len;
+            const uint8_t* unused_base;
+            uint64_t unused_off;
+            int len;
+            read_span(ba, ridx, unused_base, unused_off, len);
             if (len > nb * 32) len = nb * 32;   // cannot happen: the host sizes nb from the longest read
             if (mt == 0) l0 = len; else len1 = len;
             const uint32_t* src = ba.packed + (size_t)ridx * ba.pstride;

@@ -1,0 +1,71 @@
+"""GPU: the kallisto_b200 command line against the files the unmodified reference wrote for the
+same commands (tests/golden/*/ref_quant_*)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(util.ROOT, "kallisto_b200", "kallisto_b200")
+
+
+def run(args, cwd=None):
+    return subprocess.run([BIN] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+def same_run_info(a, b):
+    ja, jb = json.load(open(a)), json.load(open(b))
+    for k in ("n_targets", "n_bootstraps", "n_processed", "n_pseudoaligned", "n_unique", "p_pseudoaligned", "p_unique",
+              "kallisto_version", "index_version", "k-mer length"):
+        assert ja[k] == jb[k], k
+    assert list(ja.keys()) == list(jb.keys())
+
+
+@pytest.mark.parametrize("name", ["config1", "synth_small"])
+def test_quant_paired_with_bootstrap(name, tmp_path):
+    ds = util.dataset(name)
+    out = tmp_path / "o"
+    r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "-b", "3", "--seed", "42",
+             os.path.join(ds["dir"], "reads_1.fastq.gz"), os.path.join(ds["dir"], "reads_2.fastq.gz")])
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(ds["dir"], "ref_quant_paired")
+    for fn in ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv", "bs_abundance_2.tsv"]:
+        assert open(out / fn).read() == open(os.path.join(ref, fn)).read(), fn
+    same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
+    assert "reads pseudoaligned" in r.stderr and "Expectation-Maximization algorithm ran for" in r.stderr
+
+
+def test_quant_fr_stranded(tmp_path):
+    ds = util.dataset("synth_small")
+    out = tmp_path / "o"
+    r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "--fr-stranded",
+             os.path.join(ds["dir"], "reads_1.fastq.gz"), os.path.join(ds["dir"], "reads_2.fastq.gz")])
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(ds["dir"], "ref_quant_paired_fr")
+    assert open(out / "abundance.tsv").read() == open(os.path.join(ref, "abundance.tsv")).read()
+    same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
+
+
+def test_quant_single_overhang(tmp_path):
+    ds = util.dataset("synth_small")
+    out = tmp_path / "o"
+    r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "--single", "--single-overhang", "-l", "200", "-s",
+             "20", os.path.join(ds["dir"], "reads_1.fastq.gz")])
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(ds["dir"], "ref_quant_single_overhang")
+    assert open(out / "abundance.tsv").read() == open(os.path.join(ref, "abundance.tsv")).read()
+    same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
+
+
+def test_cli_errors(tmp_path):
+    r = run(["quant", "-i", "/nonexistent.kidx", "-o", str(tmp_path / "o"), "a.fq", "b.fq"])
+    assert r.returncode == 1 and "kallisto index file not found" in r.stderr
+    ds = util.dataset("config1")
+    r = run(["quant", "-i", ds["index"], "-o", str(tmp_path / "o2"), os.path.join(ds["dir"], "reads_1.fastq.gz")])
+    assert r.returncode == 1 and "paired-end mode requires an even number of input files" in r.stderr
+    r = run(["quant", "-i", ds["index"], "-o", str(tmp_path / "o3"), "--single", os.path.join(ds["dir"], "reads_1.fastq.gz")])
+    assert r.returncode == 1 and "fragment length mean and sd must be supplied" in r.stderr
