@@ -140,6 +140,34 @@ int kb_em_run_table(kb_quant* q, uint32_t n_ecs, const uint64_t* ec_offsets, con
 int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed, int32_t n_bootstrap,
                      double* est_counts_out, uint32_t* samples_out, int32_t* rounds_out);
 
+/* ---- `kallisto bus`: replaces BUSProcessor::processBuffer (src/ProcessReads.cpp:1380-1832) + the
+ * record writing / EC id assignment of MasterProcessor::update (:603-624) ------------------------ */
+typedef struct kb_bus_substr { int32_t fileno, start, stop; } kb_bus_substr;   /* BUSOptionSubstr, src/common.h:29-36 */
+typedef struct kb_bus_opts {
+  int32_t nfiles;                 /* files per read set (technology), <= 4 */
+  int32_t n_bc;  kb_bus_substr bc[4];    /* n_bc == 0: no barcode (fake barcode of 16 A) */
+  int32_t n_umi; kb_bus_substr umi[4];
+  kb_bus_substr seq;              /* the read that is pseudoaligned; stop must be 0 (to the end of the read) */
+  int32_t strand_mode;            /* 0 unstranded, 1 --fr-stranded (default of the 10x technologies), 2 --rf-stranded */
+  int32_t num;                    /* --num: flags = read number */
+  uint32_t max_batch_sets;        /* 0 = default */
+  uint64_t max_batch_bases;
+} kb_bus_opts;
+typedef struct kb_bus_record {    /* BUSData, src/BUSData.h:30-38: 32 bytes, as written to output.bus */
+  uint64_t barcode, umi;
+  int32_t ec;
+  uint32_t count, flags, pad;
+} kb_bus_record;
+int kb_bus_create(kb_index* ix, const kb_bus_opts* opts, kb_quant** out);
+/* One batch of read sets: bases[f] / offsets[f] (n_sets + 1 entries) for each file f of the technology.
+ * records_out (capacity n_sets) receives one record per pseudoaligned set, in read order, with final
+ * EC ids (order of first occurrence = the ids of the reference with -t 1). */
+int kb_bus_batch(kb_quant* q, const char* const* bases, const uint32_t* const* offsets, uint32_t n_sets,
+                 kb_bus_record* records_out, uint32_t* n_records_out);
+/* Observed barcode / UMI length histograms (33 bins), for the header of output.bus
+ * (src/main.cpp:2470-2508). */
+int kb_bus_lengths(kb_quant* q, uint32_t* bc_hist, uint32_t* umi_hist);
+
 /* Host-only: parse a FASTA/FASTQ file (plain or gzip) with the library's reader (kseq_read grammar,
  * src/kseq.h) and report the number of records, of bases, and an FNV-1a hash of the sequences
  * (0xFF after each record).  Tooling / tests. */

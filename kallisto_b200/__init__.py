@@ -43,6 +43,37 @@ class kb_kernel_timings(C.Structure):
                 ("match_launches", C.c_uint64), ("resolve_launches", C.c_uint64)]
 
 
+class kb_bus_substr(C.Structure):
+    _fields_ = [("fileno", C.c_int32), ("start", C.c_int32), ("stop", C.c_int32)]
+
+
+class kb_bus_opts(C.Structure):
+    _fields_ = [("nfiles", C.c_int32), ("n_bc", C.c_int32), ("bc", kb_bus_substr * 4), ("n_umi", C.c_int32),
+                ("umi", kb_bus_substr * 4), ("seq", kb_bus_substr), ("strand_mode", C.c_int32), ("num", C.c_int32),
+                ("max_batch_sets", C.c_uint32), ("max_batch_bases", C.c_uint64)]
+
+
+BUS_RECORD_DTYPE = np.dtype([("barcode", "<u8"), ("umi", "<u8"), ("ec", "<i4"), ("count", "<u4"), ("flags", "<u4"),
+                             ("pad", "<u4")])
+
+# technology table of `kallisto bus -x` (src/main.cpp:1283-1437): (nfiles, bc pieces, umi pieces, seq, default strand)
+TECHNOLOGIES = {
+    "10XV1": (3, [(0, 0, 14)], [(1, 0, 10)], (2, 0, 0), 1),
+    "10XV2": (2, [(0, 0, 16)], [(0, 16, 26)], (1, 0, 0), 1),
+    "10XV3": (2, [(0, 0, 16)], [(0, 16, 28)], (1, 0, 0), 1),
+    "VISIUM": (2, [(0, 0, 16)], [(0, 16, 28)], (1, 0, 0), 1),
+    "SURECELL": (2, [(0, 0, 6), (0, 21, 27), (0, 42, 48)], [(0, 51, 59)], (1, 0, 0), 1),
+    "DROPSEQ": (2, [(0, 0, 12)], [(0, 12, 20)], (1, 0, 0), 0),
+    "INDROPSV1": (2, [(0, 0, 11), (0, 30, 38)], [(0, 42, 48)], (1, 0, 0), 0),
+    "INDROPSV2": (2, [(1, 0, 11), (1, 30, 38)], [(1, 42, 48)], (0, 0, 0), 0),
+    "INDROPSV3": (3, [(0, 0, 8), (1, 0, 8)], [(1, 8, 14)], (2, 0, 0), 0),
+    "CELSEQ": (2, [(0, 0, 8)], [(0, 8, 12)], (1, 0, 0), 1),
+    "CELSEQ2": (2, [(0, 6, 12)], [(0, 0, 6)], (1, 0, 0), 1),
+    "SPLIT-SEQ": (2, [(1, 10, 18), (1, 48, 56), (1, 78, 86)], [(1, 0, 10)], (0, 0, 0), 1),
+    "SCRBSEQ": (2, [(0, 0, 6)], [(0, 6, 16)], (1, 0, 0), 0),
+}
+
+
 class kb_run_stats(C.Structure):
     _fields_ = [("n_processed", C.c_uint64), ("n_pseudoaligned", C.c_uint64), ("n_unique", C.c_uint64),
                 ("n_ecs", C.c_uint64), ("n_ec_entries", C.c_uint64), ("n_probes", C.c_uint64),
@@ -55,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "kb_index_target_lens", "kb_index_inspect", "kb_quant_create", "kb_quant_free", "kb_pseudoalign_batch",
     "kb_pseudoalign_batch_pe", "kb_host_alloc", "kb_host_free", "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_set_stream", "kb_quant_enable_timing",
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
-    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_fastx_summary", "kb_counts_to_tpm",
+    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_bus_create", "kb_bus_batch", "kb_bus_lengths", "kb_fastx_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -100,6 +131,9 @@ def lib():
     L.kb_em_run_table.argtypes = [vp, u32, vp, vp, vp, dbl, dbl, vp, vp, C.POINTER(i32), C.POINTER(dbl)]
     L.kb_bootstrap_run.argtypes = [vp, dbl, dbl, u64, i32, vp, vp, vp]
     L.kb_counts_to_tpm.argtypes = [vp, vp, u32, vp]
+    L.kb_bus_create.argtypes = [vp, C.POINTER(kb_bus_opts), C.POINTER(vp)]
+    L.kb_bus_batch.argtypes = [vp, vp, vp, u32, vp, C.POINTER(u32)]
+    L.kb_bus_lengths.argtypes = [vp, vp, vp]
     L.kb_fastx_summary.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     _lib = L
     return L
@@ -281,6 +315,50 @@ class MinCollector:
         rounds = np.zeros(max(1, n_bootstrap), np.int32)
         _ck(lib().kb_bootstrap_run(self._h, fld_mean, fld_sd, seed, n_bootstrap, _p(est), _p(samples), _p(rounds)))
         return dict(est_counts=est, samples=samples, rounds=rounds[:n_bootstrap])
+
+
+class BUSProcessor(MinCollector):
+    """`kallisto bus` run (BUSProcessor::processBuffer + the BUS part of MasterProcessor::update)."""
+
+    def __init__(self, index, technology, strand="default", num=False, max_batch_sets=0):
+        self.index = index
+        self.paired = False
+        nfiles, bc, umi, seq, dstrand = TECHNOLOGIES[technology.upper()] if isinstance(technology, str) else technology
+        o = kb_bus_opts()
+        o.nfiles = nfiles
+        o.n_bc = len(bc)
+        for i, t in enumerate(bc):
+            o.bc[i] = kb_bus_substr(*t)
+        o.n_umi = len(umi)
+        for i, t in enumerate(umi):
+            o.umi[i] = kb_bus_substr(*t)
+        o.seq = kb_bus_substr(*seq)
+        o.strand_mode = dstrand if strand == "default" else {None: 0, "unstranded": 0, "fr": 1, "rf": 2}[strand]
+        o.num = int(num)
+        o.max_batch_sets = max_batch_sets
+        self.nfiles = nfiles
+        self._h = C.c_void_p()
+        _ck(lib().kb_bus_create(index._h, C.byref(o), C.byref(self._h)))
+        self._stats = None
+
+    def process_sets(self, files):
+        """files: list of (bases uint8, offsets uint32) per file of the technology -> structured record array."""
+        assert len(files) == self.nfiles
+        bs = [np.ascontiguousarray(b, np.uint8) for b, _ in files]
+        os_ = [np.ascontiguousarray(o, np.uint32) for _, o in files]
+        n = len(os_[0]) - 1
+        bp = (C.c_void_p * self.nfiles)(*[b.ctypes.data for b in bs])
+        op = (C.c_void_p * self.nfiles)(*[o.ctypes.data for o in os_])
+        rec = np.zeros(max(1, n), BUS_RECORD_DTYPE)
+        nrec = C.c_uint32(0)
+        _ck(lib().kb_bus_batch(self._h, bp, op, n, _p(rec), C.byref(nrec)))
+        self._stats = None
+        return rec[: nrec.value]
+
+    def lengths(self):
+        b, u = np.zeros(33, np.uint32), np.zeros(33, np.uint32)
+        _ck(lib().kb_bus_lengths(self._h, _p(b), _p(u)))
+        return b, u
 
 
 def fastx_summary(path):

@@ -287,6 +287,53 @@ int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed,
   });
 }
 
+int kb_bus_create(kb_index* ix, const kb_bus_opts* o, kb_quant** out) {
+  if (!ix || !o || !out) return fail(KB_ERR_INVALID, "kb_bus_create: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    if (o->nfiles < 1 || o->nfiles > 4 || o->n_bc < 0 || o->n_bc > 4 || o->n_umi < 1 || o->n_umi > 4)
+      throw std::invalid_argument("kb_bus_create: unsupported technology layout");
+    if (o->seq.stop != 0 || o->seq.fileno < 0 || o->seq.fileno >= o->nfiles || o->seq.start < 0)
+      throw std::invalid_argument("kb_bus_create: the sequence must run to the end of its read (stop == 0)");
+    kb::QuantOptions q;
+    q.paired = 0;
+    q.strand_mode = o->strand_mode;
+    q.collect_fld = 0;
+    q.bus = true;
+    if (o->max_batch_sets) q.max_batch_reads = o->max_batch_sets;
+    if (o->max_batch_bases) q.max_batch_bases = o->max_batch_bases;
+    kb::BusSpec& s = q.bus_spec;
+    s.nfiles = o->nfiles;
+    s.n_bc = o->n_bc;
+    s.n_umi = o->n_umi;
+    auto chk = [&](const kb_bus_substr& x) {
+      if (x.fileno < 0 || x.fileno >= o->nfiles || x.start < 0 || x.stop < 0)
+        throw std::invalid_argument("kb_bus_create: bad barcode/UMI location");
+    };
+    for (int i = 0; i < o->n_bc; ++i) { chk(o->bc[i]); s.bc_f[i] = o->bc[i].fileno; s.bc_a[i] = o->bc[i].start; s.bc_b[i] = o->bc[i].stop; }
+    for (int i = 0; i < o->n_umi; ++i) { chk(o->umi[i]); s.umi_f[i] = o->umi[i].fileno; s.umi_a[i] = o->umi[i].start; s.umi_b[i] = o->umi[i].stop; }
+    s.seq_file = o->seq.fileno;
+    s.seq_start = o->seq.start;
+    s.num_flag = o->num;
+    kb_quant* h = new kb_quant();
+    h->owner = ix;
+    h->q.reset(new kb::Quant(*ix->ix, q));
+    *out = h;
+  });
+}
+
+int kb_bus_batch(kb_quant* q, const char* const* bases, const uint32_t* const* offsets, uint32_t n_sets,
+                 kb_bus_record* records_out, uint32_t* n_records_out) {
+  if (!q || !bases || !offsets || (!records_out && n_sets)) return fail(KB_ERR_INVALID, "kb_bus_batch: null argument");
+  static_assert(sizeof(kb_bus_record) == sizeof(kb::BusRecord), "record layout");
+  return guarded([&] { q->q->bus_batch_host(bases, offsets, n_sets, (kb::BusRecord*)records_out, n_records_out); });
+}
+
+int kb_bus_lengths(kb_quant* q, uint32_t* bc_hist, uint32_t* umi_hist) {
+  if (!q || !bc_hist || !umi_hist) return fail(KB_ERR_INVALID, "kb_bus_lengths: null argument");
+  return guarded([&] { q->q->bus_lengths(bc_hist, umi_hist); });
+}
+
 int kb_fastx_summary(const char* path, uint64_t* n_reads, uint64_t* n_bases, uint64_t* fnv1a) {
   if (!path || !n_reads || !n_bases || !fnv1a) return fail(KB_ERR_INVALID, "kb_fastx_summary: null argument");
   try {

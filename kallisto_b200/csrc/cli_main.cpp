@@ -457,6 +457,318 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   return st.n_pseudoaligned == 0 ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// kallisto bus (src/main.cpp:541-776 ParseOptionsBus, 923-1526 CheckOptionsBus, 2336-2617 body)
+// ------------------------------------------------------------------------------------------------
+struct Tech {
+  const char* name;
+  int nfiles;
+  std::vector<kb_bus_substr> bc, umi;
+  kb_bus_substr seq;
+  int strand;   // default strand of the technology: 0 none, 1 FR
+};
+
+const std::vector<Tech>& tech_table() {   // src/main.cpp:1283-1437 (technologies with one cDNA read, no tag sequence)
+  static const std::vector<Tech> t = {
+      {"10XV1", 3, {{0, 0, 14}}, {{1, 0, 10}}, {2, 0, 0}, 1},
+      {"10XV2", 2, {{0, 0, 16}}, {{0, 16, 26}}, {1, 0, 0}, 1},
+      {"10XV3", 2, {{0, 0, 16}}, {{0, 16, 28}}, {1, 0, 0}, 1},
+      {"VISIUM", 2, {{0, 0, 16}}, {{0, 16, 28}}, {1, 0, 0}, 1},
+      {"SURECELL", 2, {{0, 0, 6}, {0, 21, 27}, {0, 42, 48}}, {{0, 51, 59}}, {1, 0, 0}, 1},
+      {"DROPSEQ", 2, {{0, 0, 12}}, {{0, 12, 20}}, {1, 0, 0}, 0},
+      {"INDROPSV1", 2, {{0, 0, 11}, {0, 30, 38}}, {{0, 42, 48}}, {1, 0, 0}, 0},
+      {"INDROPSV2", 2, {{1, 0, 11}, {1, 30, 38}}, {{1, 42, 48}}, {0, 0, 0}, 0},
+      {"INDROPSV3", 3, {{0, 0, 8}, {1, 0, 8}}, {{1, 8, 14}}, {2, 0, 0}, 0},
+      {"CELSEQ", 2, {{0, 0, 8}}, {{0, 8, 12}}, {1, 0, 0}, 1},
+      {"CELSEQ2", 2, {{0, 6, 12}}, {{0, 0, 6}}, {1, 0, 0}, 1},
+      {"SPLIT-SEQ", 2, {{1, 10, 18}, {1, 48, 56}, {1, 78, 86}}, {{1, 0, 10}}, {0, 0, 0}, 1},
+      {"SCRBSEQ", 2, {{0, 0, 6}}, {{0, 6, 16}}, {1, 0, 0}, 0},
+  };
+  return t;
+}
+
+bool parse_triplets(const std::string& s, std::vector<kb_bus_substr>& out) {
+  std::vector<int> v;
+  std::stringstream ss(s);
+  std::string tok;
+  while (std::getline(ss, tok, ',')) {
+    try { v.push_back(std::stoi(tok)); } catch (...) { return false; }
+  }
+  if (v.empty() || v.size() % 3) return false;
+  for (size_t i = 0; i < v.size(); i += 3) out.push_back(kb_bus_substr{v[i], v[i + 1], v[i + 2]});
+  return true;
+}
+
+void usage_bus() {
+  std::cout << "kallisto_b200 " << KALLISTO_VERSION << " (B200 build)" << endl
+            << "Generates BUS files for single-cell sequencing" << endl << endl
+            << "Usage: kallisto_b200 bus [arguments] FASTQ-files" << endl << endl
+            << "Required arguments:" << endl
+            << "-i, --index=STRING            Filename for the kallisto index to be used for" << endl
+            << "                              pseudoalignment" << endl
+            << "-o, --output-dir=STRING       Directory to write output to" << endl
+            << "-x, --technology=STRING       Single-cell technology used (10xv1, 10xv2, 10xv3, visium, surecell," << endl
+            << "                              dropseq, indropsv1/2/3, celseq, celseq2, split-seq, scrbseq) or a" << endl
+            << "                              custom bc:umi:seq string of file,start,stop triplets" << endl << endl
+            << "Optional arguments:" << endl
+            << "-t, --threads=INT             Number of host threads (default: 1)" << endl
+            << "-n, --num                     Output number of read in flag column" << endl
+            << "    --fr-stranded / --rf-stranded / --unstranded   Strand specificity" << endl
+            << "    --device=INT              CUDA device ordinal (default: 0)" << endl;
+}
+
+int cmd_bus(int argc, char** argv, const std::string& call, const std::string& start_time) {
+  Options opt;
+  std::string technology;
+  int num_flag = 0, fr = 0, rf = 0, unstranded = 0, verbose_flag = 0;
+  const char* opt_string = "i:o:x:t:nD:";
+  static struct option long_options[] = {{"verbose", no_argument, &verbose_flag, 1},
+                                         {"num", no_argument, 0, 'n'},
+                                         {"fr-stranded", no_argument, &fr, 1},
+                                         {"rf-stranded", no_argument, &rf, 1},
+                                         {"unstranded", no_argument, &unstranded, 1},
+                                         {"index", required_argument, 0, 'i'},
+                                         {"output-dir", required_argument, 0, 'o'},
+                                         {"technology", required_argument, 0, 'x'},
+                                         {"threads", required_argument, 0, 't'},
+                                         {"device", required_argument, 0, 'D'},
+                                         {0, 0, 0, 0}};
+  int c, oi = 0;
+  while ((c = getopt_long(argc, argv, opt_string, long_options, &oi)) != -1) {
+    switch (c) {
+      case 'i': opt.index = optarg; break;
+      case 'o': opt.output = optarg; break;
+      case 'x': technology = optarg; break;
+      case 't': std::stringstream(optarg) >> opt.threads; break;
+      case 'n': num_flag = 1; break;
+      case 'D': std::stringstream(optarg) >> opt.device; break;
+      default: break;
+    }
+  }
+  for (int i = optind; i < argc; i++) opt.files.push_back(argv[i]);
+  // ---- CheckOptionsBus
+  bool ret = true;
+  struct stat stt;
+  cerr << endl;
+  if (opt.index.empty()) { cerr << ERROR_STR << " kallisto index file missing" << endl; ret = false; }
+  else if (stat(opt.index.c_str(), &stt) != 0) { cerr << ERROR_STR << " kallisto index file not found " << opt.index << endl; ret = false; }
+  if (opt.threads <= 0) { cerr << "Error: invalid number of threads " << opt.threads << endl; ret = false; }
+  if (opt.files.empty()) { cerr << ERROR_STR << " Missing read files" << endl; ret = false; }
+  for (auto& fn : opt.files)
+    if (stat(fn.c_str(), &stt) != 0) { cerr << ERROR_STR << " file not found " << fn << endl; ret = false; }
+  kb_bus_opts bo{};
+  int tech_strand = 0;
+  if (technology.empty()) {
+    cerr << "Error: need to specify technology to use" << endl;
+    ret = false;
+  } else {
+    std::string up = technology;
+    for (auto& ch : up) ch = (char)toupper(ch);
+    const Tech* found = nullptr;
+    for (auto& t : tech_table())
+      if (up == t.name) found = &t;
+    std::vector<kb_bus_substr> bc, umi, seq;
+    if (found) {
+      bo.nfiles = found->nfiles;
+      bc = found->bc; umi = found->umi; seq = {found->seq};
+      tech_strand = found->strand;
+    } else if (technology.find(':') != std::string::npos) {
+      std::vector<std::string> parts;
+      std::stringstream ss(technology);
+      std::string part;
+      while (std::getline(ss, part, ':')) parts.push_back(part);
+      if (parts.size() != 3 || !parse_triplets(parts[0], bc) || !parse_triplets(parts[1], umi) || !parse_triplets(parts[2], seq)) {
+        cerr << "Error: could not parse technology string " << technology << endl;
+        ret = false;
+      } else {
+        int nf = 0;
+        for (auto* v : {&bc, &umi, &seq}) for (auto& x : *v) nf = std::max(nf, x.fileno + 1);
+        bo.nfiles = nf;
+        if (bc.size() == 1 && bc[0].fileno == -1) bc.clear();   // no barcode
+      }
+    } else {
+      cerr << "Error: technology " << technology << " is not supported by this build" << endl;
+      ret = false;
+    }
+    if (ret) {
+      if (seq.size() != 1 || seq[0].stop != 0 || bc.size() > 4 || umi.empty() || umi.size() > 4 || bo.nfiles > 4) {
+        cerr << "Error: this build handles technologies with one sequence read running to the end of its file" << endl;
+        ret = false;
+      } else {
+        bo.n_bc = (int)bc.size();
+        for (size_t i = 0; i < bc.size(); ++i) bo.bc[i] = bc[i];
+        bo.n_umi = (int)umi.size();
+        for (size_t i = 0; i < umi.size(); ++i) bo.umi[i] = umi[i];
+        bo.seq = seq[0];
+      }
+    }
+  }
+  if (ret && opt.files.size() % bo.nfiles != 0) {
+    cerr << "Error: Number of files (" << opt.files.size() << ") does not match number of input files required by "
+         << "technology " << technology << " (" << bo.nfiles << ")" << endl;
+    ret = false;
+  }
+  int strand = 0;
+  if (fr) strand = 1;
+  else if (rf) strand = 2;
+  else if (unstranded) strand = 0;
+  else if (ret) {
+    strand = tech_strand;
+    if (strand == 1) cerr << "[bus] Note: Strand option was not specified; setting it to --fr-stranded for specified technology" << endl;
+    else cerr << "[bus] Note: Strand option was not specified; setting it to --unstranded for specified technology" << endl;
+  }
+  if (opt.output.empty()) { cerr << "Error: need to specify output directory " << opt.output << endl; ret = false; }
+  else if (stat(opt.output.c_str(), &stt) == 0) {
+    if (!S_ISDIR(stt.st_mode)) { cerr << "Error: file " << opt.output << " exists and is not a directory" << endl; ret = false; }
+  } else if (ret && mkdir(opt.output.c_str(), 0777) == -1) { cerr << "Error: could not create directory " << opt.output << endl; ret = false; }
+  if (!ret) {
+    usage_bus();
+    return 1;
+  }
+  kb_index* ix = nullptr;
+  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, 0, std::max(1, opt.threads), &ix));
+  kb_index_info info;
+  kb_index_get_info(ix, &info);
+  cerr << "[index] k-mer length: " << info.k << endl;
+  cerr << "[index] number of targets: " << pretty_num(info.n_targets) << endl;
+  cerr << "[index] number of k-mers: " << pretty_num(info.n_kmers) << endl;
+  cerr << "[quant] will process sample 1: ";
+  for (size_t i = 0; i < opt.files.size(); ++i) cerr << (i ? "\n                               " : "") << opt.files[i];
+  cerr << endl << "[quant] finding pseudoalignments for the reads ...";
+  cerr.flush();
+
+  const size_t max_reads = 1u << 20;
+  const size_t max_bases = (size_t)max_reads * 160 + kb::FastxFile::kMaxRead;
+  bo.strand_mode = strand;
+  bo.num = num_flag;
+  bo.max_batch_sets = (uint32_t)max_reads;
+  bo.max_batch_bases = 2 * max_bases;
+  kb_quant* q = nullptr;
+  KB_TRY(kb_bus_create(ix, &bo, &q));
+  auto spec_len = [](const kb_bus_substr* v, int n) {   // BUSOptions::getBCLength / getUMILength
+    int r = 0;
+    for (int i = 0; i < n; ++i) {
+      if (v[i].start < 0 || v[i].stop == 0) return 0;
+      r += v[i].stop - v[i].start;
+    }
+    return r;
+  };
+  uint32_t bclen = (uint32_t)spec_len(bo.bc, bo.n_bc), umilen = (uint32_t)spec_len(bo.umi, bo.n_umi);
+  const uint32_t hdr_bclen = bo.n_bc == 0 ? 16u : bclen;
+  const std::string busfile = opt.output + "/output.bus";
+  std::ofstream busf(busfile, std::ios::out | std::ios::binary);
+  {   // writeBUSHeader, src/BUSTools.cpp:5-14
+    const uint32_t version = 1;
+    busf.write("BUS\0", 4);
+    busf.write((const char*)&version, 4);
+    busf.write((const char*)&hdr_bclen, 4);
+    busf.write((const char*)&umilen, 4);
+    const std::string text = "BUS file produced by kallisto";
+    const uint32_t tl = (uint32_t)text.size();
+    busf.write((const char*)&tl, 4);
+    busf.write(text.c_str(), tl);
+  }
+  const int n_streams = bo.nfiles;
+  std::vector<Stream> streams(n_streams);
+  std::vector<std::thread> readers;
+  for (int s2 = 0; s2 < n_streams; ++s2) {
+    streams[s2].ring.resize(3);
+    streams[s2].state.assign(3, 0);
+    for (auto& b : streams[s2].ring) {
+      b.cap_bases = max_bases;
+      b.cap_reads = max_reads;
+      b.bases = (char*)kb_host_alloc(max_bases + 64);
+      b.off = (uint32_t*)kb_host_alloc((max_reads + 1) * sizeof(uint32_t));
+      if (!b.bases || !b.off) { cerr << "Error: could not allocate pinned host memory" << endl; return 1; }
+      b.clear();
+    }
+    std::vector<std::string> files;
+    for (size_t i = s2; i < opt.files.size(); i += n_streams) files.push_back(opt.files[i]);
+    readers.emplace_back(reader_thread, files, &streams[s2], max_reads);
+  }
+  std::vector<kb_bus_record> recs(max_reads);
+  size_t slot = 0;
+  for (;;) {
+    bool have = true;
+    for (int s2 = 0; s2 < n_streams; ++s2) {
+      std::unique_lock<std::mutex> lk(streams[s2].m);
+      streams[s2].cv.wait(lk, [&] { return streams[s2].state[slot] == 1 || streams[s2].done; });
+      if (!streams[s2].error.empty()) { cerr << endl << streams[s2].error << endl; exit(1); }
+      if (streams[s2].state[slot] != 1) have = false;
+    }
+    if (!have) break;
+    const char* bp[4] = {nullptr, nullptr, nullptr, nullptr};
+    const uint32_t* op[4] = {nullptr, nullptr, nullptr, nullptr};
+    const size_t n = streams[0].ring[slot].n;
+    for (int s2 = 0; s2 < n_streams; ++s2) {
+      if (streams[s2].ring[slot].n != n) { cerr << endl << "Error: input files hold different numbers of reads" << endl; exit(1); }
+      bp[s2] = streams[s2].ring[slot].bases;
+      op[s2] = streams[s2].ring[slot].off;
+    }
+    uint32_t nrec = 0;
+    KB_TRY(kb_bus_batch(q, bp, op, (uint32_t)n, recs.data(), &nrec));
+    busf.write((const char*)recs.data(), (std::streamsize)nrec * sizeof(kb_bus_record));
+    for (int s2 = 0; s2 < n_streams; ++s2) {
+      { std::lock_guard<std::mutex> lk(streams[s2].m); streams[s2].state[slot] = 0; }
+      streams[s2].cv.notify_all();
+    }
+    slot = (slot + 1) % 3;
+  }
+  for (auto& t : readers) t.join();
+  busf.close();
+  cerr << " done" << endl;
+  // barcode / UMI lengths of the header when the technology does not fix them (src/main.cpp:2470-2508)
+  {
+    uint32_t bh[33], uh[33];
+    KB_TRY(kb_bus_lengths(q, bh, uh));
+    uint32_t bl = 0, ul = 0;
+    for (uint32_t i = 0; i <= 32; ++i) {
+      if (bh[i] > bh[bl]) bl = i;
+      if (uh[i] > uh[ul]) ul = i;
+    }
+    bool write = false;
+    uint32_t wb = hdr_bclen, wu = umilen;
+    if (bclen == 0 && bo.n_bc > 0) { if (bl > 0) { write = true; } wb = bl; }
+    if (bclen == 0 && bo.n_bc == 0) { if (bl > 0) write = true; wb = bl; }
+    if (umilen == 0) { if (ul > 0) write = true; wu = ul; }
+    if (write) {
+      std::FILE* fp = std::fopen(busfile.c_str(), "r+b");
+      if (fp) {
+        std::fseek(fp, 8, SEEK_SET);
+        std::fwrite(&wb, 4, 1, fp);
+        std::fwrite(&wu, 4, 1, fp);
+        std::fclose(fp);
+      }
+    }
+  }
+  kb_run_stats st{};
+  KB_TRY(kb_quant_finalize(q, &st));
+  cerr << "[quant] processed " << pretty_num(st.n_processed) << " reads, " << pretty_num(st.n_pseudoaligned)
+       << " reads pseudoaligned" << endl;
+  if (st.n_pseudoaligned == 0) cerr << "[~warn] no reads pseudoaligned." << endl;
+  {   // writeECList, src/PlaintextWriter.cpp:235-266
+    std::vector<uint64_t> eo(st.n_ecs + 1);
+    std::vector<uint32_t> et(std::max<uint64_t>(1, st.n_ec_entries)), ec(std::max<uint64_t>(1, st.n_ecs));
+    KB_TRY(kb_quant_ec_table(q, eo.data(), et.data(), ec.data(), nullptr));
+    std::ofstream ecof(opt.output + "/matrix.ec");
+    for (uint64_t i = 0; i < st.n_ecs; ++i) {
+      ecof << i << "\t";
+      for (uint64_t j = eo[i]; j < eo[i + 1]; ++j) ecof << (j > eo[i] ? "," : "") << et[j];
+      ecof << "\n";
+    }
+  }
+  {
+    std::ofstream tf(opt.output + "/transcripts.txt");
+    for (uint32_t i = 0; i < info.n_targets; ++i) tf << kb_index_target_name(ix, i) << "\n";
+  }
+  write_run_info(opt.output + "/run_info.json", info.n_targets, 0, st.n_processed, st.n_pseudoaligned, st.n_unique, 13, info.k,
+                 start_time, call);
+  cerr << endl;
+  kb_quant_free(q);
+  kb_index_free(ix);
+  return st.n_pseudoaligned == 0 ? 1 : 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -490,6 +802,13 @@ int main(int argc, char** argv) {
       return 0;
     }
     return cmd_quant(argc - 1, argv + 1, call, tbuf);
+  }
+  if (cmd == "bus") {
+    if (argc == 2) {
+      usage_bus();
+      return 0;
+    }
+    return cmd_bus(argc - 1, argv + 1, call, tbuf);
   }
   cerr << "Error: invalid command " << cmd << endl;
   return 1;

@@ -324,6 +324,8 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.packed = d_packed_.p;
   ba.empty_ec = ix_.empty_ec;
   ba.refill_min = opt_.refill_min;
+  ba.skip = cur_skip_;
+  ba.start = cur_start_;
   ResolveArgs ra{};
   ra.scratch = d_scratch_.p;
   ra.scratch_stride = (uint32_t)(d_scratch_.n / n_resolve_warps_);
@@ -425,6 +427,82 @@ void Quant::pseudoalign_host_pe(const char* bases1, const uint32_t* off1, const 
   KB_CK(cudaStreamSynchronize(stream_));
 }
 
+void Quant::bus_batch_host(const char* const* bases, const uint32_t* const* offs, uint32_t n_sets, BusRecord* records_out,
+                           uint32_t* n_records_out) {
+  KB_CK(cudaSetDevice(ix_.device));
+  if (!opt_.bus) throw Error("kallisto_b200: not a bus run");
+  if (n_records_out) *n_records_out = 0;
+  if (n_sets == 0) return;
+  const BusSpec& sp = opt_.bus_spec;
+  cudaStream_t st = stream_;
+  BusArgs a{};
+  for (int k = 0; k < sp.nfiles; ++k) {
+    if (!bases[k] || !offs[k]) throw Error("kallisto_b200: bus batch needs bases and offsets for every file of the technology");
+    const uint64_t nbz = offs[k][n_sets];
+    if (bus_b_[k].n < nbz + 16) bus_b_[k].alloc(std::max<uint64_t>(nbz + 16, opt_.max_batch_bases / 2 + 16));
+    if (bus_o_[k].n < (size_t)n_sets + 1) bus_o_[k].alloc(std::max<size_t>((size_t)n_sets + 1, (size_t)opt_.max_batch_reads + 1));
+    KB_CK(cudaMemcpyAsync(bus_b_[k].p, bases[k], nbz, cudaMemcpyHostToDevice, st));
+    KB_CK(cudaMemcpyAsync(bus_o_[k].p, offs[k], ((size_t)n_sets + 1) * 4, cudaMemcpyHostToDevice, st));
+    a.bases[k] = bus_b_[k].p;
+    a.off[k] = bus_o_[k].p;
+  }
+  const size_t n1 = (size_t)n_sets + 1;
+  auto grow = [&](auto& b, size_t need) { if (b.n < need) b.alloc(std::max<size_t>(need, (size_t)opt_.max_batch_reads + 1)); };
+  grow(bus_bc_, n1); grow(bus_umi_, n1); grow(bus_flags_, n1); grow(bus_skip_, n1);
+  grow(bus_isnew_, n1); grow(bus_newrank_, n1); grow(bus_ismapped_, n1); grow(bus_rank_, n1); grow(bus_rec_, n1);
+  if (bus_hist_.n < 66) { bus_hist_.alloc(66); bus_hist_.zero(st); }
+  if (bus_nvalid_.n < 1) bus_nvalid_.alloc(1);
+  if (bus_idof_.n < ix_.dict_cap) { bus_idof_.alloc(ix_.dict_cap); launch_fill_i32(bus_idof_.p, ix_.dict_cap, -1, st); }
+  const size_t tb = bus_scan_bytes(n_sets);
+  if (bus_tmp_.n < tb) bus_tmp_.alloc(std::max(tb, bus_scan_bytes(opt_.max_batch_reads)));
+  bus_nvalid_.zero(st);
+  a.n_sets = n_sets;
+  a.set_base = n_frag_total_;
+  a.spec = sp;
+  a.barcode = (uint64_t*)bus_bc_.p; a.umi = (uint64_t*)bus_umi_.p; a.flags = bus_flags_.p; a.skip = bus_skip_.p;
+  a.bc_hist = bus_hist_.p; a.umi_hist = bus_hist_.p + 33; a.n_valid = bus_nvalid_.p;
+  launch_bus_fields(a, st);
+  KB_CK(cudaGetLastError());
+  // the cDNA read: single-read pseudoalignment with the strand filter of the technology
+  uint32_t maxlen = 0;
+  const uint32_t* so = offs[sp.seq_file];
+  for (uint32_t i = 0; i < n_sets; ++i) maxlen = std::max(maxlen, so[i + 1] - so[i]);
+  maxlen = maxlen > (uint32_t)sp.seq_start ? maxlen - sp.seq_start : 1;
+  const uint64_t base = n_frag_total_;
+  cur_skip_ = bus_skip_.p;
+  cur_start_ = (uint32_t)sp.seq_start;
+  run_batch(bus_b_[sp.seq_file].p, bus_o_[sp.seq_file].p, n_sets, 0, maxlen);
+  cur_skip_ = nullptr;
+  cur_start_ = 0;
+  launch_bus_records(dd_, d_handles_.p, n_sets, base, bus_next_id_, bus_idof_.p, bus_isnew_.p, bus_newrank_.p,
+                     bus_ismapped_.p, bus_rank_.p, (const uint64_t*)bus_bc_.p, (const uint64_t*)bus_umi_.p, bus_flags_.p,
+                     bus_rec_.p, bus_tmp_.p, bus_tmp_.n, st);
+  KB_CK(cudaGetLastError());
+  uint32_t n_new = 0, n_rec = 0;
+  unsigned long long n_valid = 0;
+  bus_newrank_.download(&n_new, 1, n_sets, st);
+  bus_rank_.download(&n_rec, 1, n_sets, st);
+  bus_nvalid_.download(&n_valid, 1, 0, st);
+  KB_CK(cudaStreamSynchronize(st));
+  if (n_rec && records_out) {
+    bus_rec_.download(records_out, n_rec, 0, st);
+    KB_CK(cudaStreamSynchronize(st));
+  }
+  bus_next_id_ += n_new;
+  bus_valid_total_ += n_valid;
+  if (n_records_out) *n_records_out = n_rec;
+}
+
+void Quant::bus_lengths(uint32_t* bc_hist, uint32_t* umi_hist) {
+  uint32_t h[66] = {0};
+  if (bus_hist_.n >= 66) {
+    bus_hist_.download(h, 66, 0, stream_);
+    KB_CK(cudaStreamSynchronize(stream_));
+  }
+  memcpy(bc_hist, h, 33 * 4);
+  memcpy(umi_hist, h + 33, 33 * 4);
+}
+
 void Quant::set_flens(const uint32_t* f) { flens_.assign(f, f + 1000); }
 
 namespace {
@@ -494,7 +572,7 @@ const EcTable& Quant::finalize_ecs() {
 
 Stats Quant::stats() {
   Stats s;
-  s.n_processed = n_frag_total_;
+  s.n_processed = n_frag_total_;   // bus: read sets with a bad barcode/UMI are skipped but still counted as processed (ProcessReads.cpp:1372)
   if (dev_stats_valid_) {   // computed on the device by run_em_device: no EC table on the host needed
     s.n_pseudoaligned = dev_pseudoaligned_;
     s.n_unique = dev_unique_;
@@ -883,5 +961,6 @@ template struct DBuf<unsigned long long>;
 template struct DBuf<double>;
 template struct DBuf<KmerSlot>;
 template struct DBuf<Memo2Entry>;
+template struct DBuf<BusRecord>;
 
 }  // namespace kb

@@ -72,6 +72,8 @@ struct QuantOptions {
   uint32_t max_batch_reads = 1u << 22;     // staging capacity (reads per batch)
   uint64_t max_batch_bases = 1ull << 29;   // staging capacity (bases per batch)
   int threads_per_block = 256;
+  bool bus = false;        // `kallisto bus` run: records instead of (only) counts
+  BusSpec bus_spec{};
   int refill_min = 16;     // match_kernel: finished lanes per warp that trigger a finalise + refill round
 };
 
@@ -112,6 +114,11 @@ class Quant {
   // separately), n_pairs fragments; off1/off2 have n_pairs + 1 entries or are null with fixed_len.
   void pseudoalign_host_pe(const char* bases1, const uint32_t* off1, const char* bases2, const uint32_t* off2,
                            uint32_t n_pairs, uint32_t fixed_len, int32_t* handles_out);
+  // `kallisto bus`: one batch of read sets (bases[k]/offs[k] = file k of the technology, n_sets + 1
+  // offsets each).  Writes the BUS records of the pseudoaligned sets, in read order, EC ids final.
+  void bus_batch_host(const char* const* bases, const uint32_t* const* offs, uint32_t n_sets, BusRecord* records_out,
+                      uint32_t* n_records_out);
+  void bus_lengths(uint32_t* bc_hist, uint32_t* umi_hist);
   // Same, inputs already resident in device memory; handles stay on the device
   // (device_handles(), valid until the next batch).
   void pseudoalign_device(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
@@ -184,6 +191,17 @@ class Quant {
   EcTable ecs_;
   bool ecs_valid_ = false;
   struct EmWs* emws_ = nullptr;
+  // bus mode
+  DBuf<uint8_t> bus_b_[4], bus_skip_;
+  DBuf<uint32_t> bus_o_[4], bus_flags_, bus_hist_, bus_isnew_, bus_newrank_, bus_ismapped_, bus_rank_;
+  DBuf<unsigned long long> bus_bc_, bus_umi_, bus_nvalid_;
+  DBuf<int32_t> bus_idof_;
+  DBuf<BusRecord> bus_rec_;
+  DBuf<uint8_t> bus_tmp_;
+  uint32_t bus_next_id_ = 0;
+  uint64_t bus_valid_total_ = 0;
+  const uint8_t* cur_skip_ = nullptr;
+  uint32_t cur_start_ = 0;
 };
 
 }  // namespace kb

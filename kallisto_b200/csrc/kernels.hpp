@@ -54,6 +54,8 @@ struct BatchArgs {
   uint32_t pstride;         // 32-bit words per packed read (multiple of 8 = 32 bytes)
   uint32_t empty_ec;        // handle of the empty index EC set, or 0xFFFFFFFF
   int refill_min;           // finished lanes of a warp that trigger a finalise + refill round
+  const uint8_t* skip;      // optional per fragment: 1 = treat as having no sequence (bus: bad barcode/UMI)
+  uint32_t start;           // first base of every read that is matched (bus: BUSOptionSubstr.start of the sequence)
 };
 static constexpr int KB_Q_STRIDE = 2 + KB_MAX_E + 2;
 
@@ -141,6 +143,41 @@ void emprep_meta(const DevDict& dd, const uint32_t* used, const uint32_t* order,
                  uint32_t* multi_len, uint32_t* is_multi, void* tmp, size_t tmp_bytes, cudaStream_t st);
 void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, uint32_t* sort_keys_out, uint32_t* sort_vals_out,
                  void* tmp, size_t tmp_bytes, unsigned long long* stats2, cudaStream_t st);
+
+// ---- BUS (kernels_bus.cu) ----
+struct BusRecord {      // BUSData, src/BUSData.h:30-38
+  uint64_t barcode, umi;
+  int32_t ec;
+  uint32_t count, flags, pad;
+};
+struct BusSpec {        // BUSOptions (src/common.h:38-91): where barcode / UMI / sequence sit in the files of a read set
+  int nfiles;
+  int n_bc, n_umi;
+  int bc_f[4], bc_a[4], bc_b[4];
+  int umi_f[4], umi_a[4], umi_b[4];
+  int seq_file, seq_start;
+  int num_flag;         // --num: flags = read number
+};
+struct BusArgs {
+  const uint8_t* bases[4];
+  const uint32_t* off[4];
+  uint32_t n_sets;
+  uint64_t set_base;
+  BusSpec spec;
+  uint64_t* barcode;
+  uint64_t* umi;
+  uint32_t* flags;
+  uint8_t* skip;
+  uint32_t* bc_hist;    // 33 bins
+  uint32_t* umi_hist;   // 33 bins
+  unsigned long long* n_valid;
+};
+size_t bus_scan_bytes(uint32_t n);
+void launch_bus_fields(const BusArgs& a, cudaStream_t st);
+void launch_bus_records(const DevDict& dd, const int32_t* handle, uint32_t n, uint64_t base, uint32_t next_id,
+                        int32_t* id_of, uint32_t* is_new, uint32_t* new_rank, uint32_t* is_mapped, uint32_t* rank,
+                        const uint64_t* barcode, const uint64_t* umi, const uint32_t* flags, BusRecord* out, void* tmp,
+                        size_t tmp_bytes, cudaStream_t st);
 
 struct ResampleArgs {
   const double* cp;          // n_ec cumulative probabilities (discrete_distribution::_M_cp)

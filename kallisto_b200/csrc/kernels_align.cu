@@ -137,6 +137,12 @@ __device__ __forceinline__ void read_span(const BatchArgs& ba, uint32_t ridx, co
     off = (uint64_t)i * ba.fixed_len;
     len = (int)ba.fixed_len;
   }
+  if (ba.start) {
+    off += ba.start;
+    len -= (int)ba.start;
+    if (len < 0) len = 0;
+  }
+  if (ba.skip && ba.skip[ba.paired ? (ridx >> 1) : ridx]) len = 0;
 }
 
 // Lane states of match_kernel.

@@ -69,3 +69,28 @@ def test_cli_errors(tmp_path):
     assert r.returncode == 1 and "paired-end mode requires an even number of input files" in r.stderr
     r = run(["quant", "-i", ds["index"], "-o", str(tmp_path / "o3"), "--single", os.path.join(ds["dir"], "reads_1.fastq.gz")])
     assert r.returncode == 1 and "fragment length mean and sd must be supplied" in r.stderr
+
+
+@pytest.mark.parametrize("tag,args", [("10xv2", ["-x", "10xv2"]), ("10xv2_num", ["-x", "10xv2", "--num"]),
+                                      ("10xv2", ["-x", "0,0,16:0,16,26:1,0,0", "--fr-stranded"])])
+def test_bus_command(tag, args, tmp_path):
+    d = os.path.join(util.GOLDEN, "bus10x")
+    out = tmp_path / "o"
+    r = run(["bus", "-i", os.path.join(util.GOLDEN, "config1", "transcripts.kidx"), "-o", str(out)] + args +
+            [os.path.join(d, "sc_reads_1.fastq.gz"), os.path.join(d, "sc_reads_2.fastq.gz")])
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(d, "ref_" + tag)
+    for fn in ("output.bus", "matrix.ec", "transcripts.txt"):
+        assert open(out / fn, "rb").read() == open(os.path.join(ref, fn), "rb").read(), fn
+    same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
+
+
+def test_bus_nothing_aligned_exits_1(tmp_path):
+    d = os.path.join(util.GOLDEN, "bus10x")
+    out = tmp_path / "o"
+    r = run(["bus", "-i", os.path.join(util.GOLDEN, "config1", "transcripts.kidx"), "-o", str(out), "-x", "10xv3",
+             "--unstranded", os.path.join(d, "sc_reads_1.fastq.gz"), os.path.join(d, "sc_reads_2.fastq.gz")])
+    assert r.returncode == 1
+    ref = os.path.join(d, "ref_10xv3_unstranded")
+    assert open(out / "output.bus", "rb").read() == open(os.path.join(ref, "output.bus"), "rb").read()
+    same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
