@@ -258,7 +258,9 @@ def main():
         torch.cuda.synchronize()
 
     def new_run():
-        mc = K200.MinCollector(index, paired=True, max_batch_reads=P, max_batch_bases=P * 2 * READ_LEN + 64)
+        # the fragment-length distribution comes from the first slice of the input (rank 0), like -t 1
+        mc = K200.MinCollector(index, paired=True, collect_fld=(rank == 0), max_batch_reads=P,
+                               max_batch_bases=P * 2 * READ_LEN + 64)
         mc.set_stream(stream.cuda_stream)
         return mc
 
@@ -281,7 +283,11 @@ def main():
     for s in range(W, W + K):
         mc.process_buffer_device(d_batches[s].data_ptr(), None, n_reads, READ_LEN)
     ev1.record(stream)
-    em = mc.run_em()        # finalises the EC table (D2H of the used sets), builds CSR/CSC, runs the EM kernel
+    if world > 1:
+        # the one exchange step: EC tables all-gathered over NCCL, merged by content on rank 0's GPU
+        from kallisto_b200 import multigpu
+        multigpu.merge_on_rank0(mc, K * P, dev)
+    em = mc.run_em() if rank == 0 else None   # EC ids, CSR/CSC and the EM kernel on the device (rank 0 only)
     ev2.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -301,7 +307,9 @@ def main():
     t0 = time.perf_counter()
     for s in range(W, W + K):
         mc2.process_buffer_ptr(h_batches[s].data_ptr(), None, n_reads, READ_LEN, None)
-    em2 = mc2.run_em()
+    if world > 1:
+        multigpu.merge_on_rank0(mc2, K * P, dev)
+    em2 = mc2.run_em() if rank == 0 else None
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
@@ -328,7 +336,7 @@ def main():
                 "bytes_per_pair": bytes_per_pair, "probes_per_pair": probes_per_pair,
                 "slot_visits_per_pair": visits_per_pair, "ms_per_launch": match_ms_per_launch,
                 "resolve_ms_per_launch": tm["resolve_ms"] / max(1, tm["resolve_launches"]), "em_ms": tm["em_ms"],
-                "em_rounds": em["rounds"]}
+                "em_rounds": em["rounds"] if em else None}
     prof = os.path.join(ROOT, "profiles", "match_kernel_traffic.json")
     if os.path.exists(prof):
         try:

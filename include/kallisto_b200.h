@@ -123,6 +123,18 @@ int kb_quant_ec_table(kb_quant* q, uint64_t* ec_offsets /* n_ecs+1 */, uint32_t*
 int kb_quant_get_flens(kb_quant* q, uint32_t* flens_out);
 int kb_quant_set_flens(kb_quant* q, const uint32_t* flens_in);
 
+/* ---- multi-GPU: reads are sharded across ranks (one kb_quant per GPU, index replicated); before the
+ * single EM the per-rank equivalence classes are merged by CONTENT on one rank -- the multi-rank
+ * form of MasterProcessor::update's merge under writer_lock (src/ProcessReads.cpp:424-483).
+ * export: number this rank's ECs and copy them into caller-provided DEVICE buffers (which the caller
+ * moves with NCCL): off[n_sets+1], tids[n_entries], counts[n_sets], first[n_sets] (fragment index of
+ * first occurrence).  import: fold such a table into this run's dictionary; first_offset orders the
+ * ranks' fragment indices (rank r: r << 40), n_processed adds the other rank's fragment count. */
+int kb_quant_export_prepare(kb_quant* q, uint32_t* n_sets, uint32_t* n_entries);
+int kb_quant_export_device(kb_quant* q, uint32_t* d_off, uint32_t* d_tids, uint32_t* d_counts, uint64_t* d_first);
+int kb_quant_import_device(kb_quant* q, uint32_t n_sets, const uint32_t* d_off, const uint32_t* d_tids,
+                           const uint32_t* d_counts, const uint64_t* d_first, uint64_t first_offset, uint64_t n_processed);
+
 /* Replaces compute_mean_frag_lens_trunc / init_mean_fl_trunc + get_frag_len_means + calc_eff_lens +
  * calc_weights + EMAlgorithm::run(10000, 50) (src/MinCollector.cpp:629-651, src/weights.cpp,
  * src/EMAlgorithm.h:95-221).  fld_mean == 0 uses the estimated distribution, otherwise the

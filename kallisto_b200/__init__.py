@@ -86,7 +86,7 @@ EXPORTED_SYMBOLS = [
     "kb_index_target_lens", "kb_index_inspect", "kb_quant_create", "kb_quant_free", "kb_pseudoalign_batch",
     "kb_pseudoalign_batch_pe", "kb_host_alloc", "kb_host_free", "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_set_stream", "kb_quant_enable_timing",
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
-    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_bus_create", "kb_bus_batch", "kb_bus_lengths", "kb_fastx_summary", "kb_counts_to_tpm",
+    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device", "kb_bus_create", "kb_bus_batch", "kb_bus_lengths", "kb_fastx_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -131,6 +131,9 @@ def lib():
     L.kb_em_run_table.argtypes = [vp, u32, vp, vp, vp, dbl, dbl, vp, vp, C.POINTER(i32), C.POINTER(dbl)]
     L.kb_bootstrap_run.argtypes = [vp, dbl, dbl, u64, i32, vp, vp, vp]
     L.kb_counts_to_tpm.argtypes = [vp, vp, u32, vp]
+    L.kb_quant_export_prepare.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    L.kb_quant_export_device.argtypes = [vp, vp, vp, vp, vp]
+    L.kb_quant_import_device.argtypes = [vp, u32, vp, vp, vp, vp, u64, u64]
     L.kb_bus_create.argtypes = [vp, C.POINTER(kb_bus_opts), C.POINTER(vp)]
     L.kb_bus_batch.argtypes = [vp, vp, vp, u32, vp, C.POINTER(u32)]
     L.kb_bus_lengths.argtypes = [vp, vp, vp]
@@ -290,6 +293,20 @@ class MinCollector:
         f = np.ascontiguousarray(f, np.uint32)
         assert len(f) == 1000
         _ck(lib().kb_quant_set_flens(self._h, _p(f)))
+
+    # -- multi-GPU exchange (device pointers; see kallisto_b200/multigpu.py) -----------------------
+    def export_prepare(self):
+        n, m = C.c_uint32(0), C.c_uint32(0)
+        _ck(lib().kb_quant_export_prepare(self._h, C.byref(n), C.byref(m)))
+        return n.value, m.value
+
+    def export_device(self, off_ptr, tids_ptr, counts_ptr, first_ptr):
+        _ck(lib().kb_quant_export_device(self._h, off_ptr, tids_ptr, counts_ptr, first_ptr))
+
+    def import_device(self, n_sets, off_ptr, tids_ptr, counts_ptr, first_ptr, first_offset, n_processed):
+        _ck(lib().kb_quant_import_device(self._h, n_sets, off_ptr, tids_ptr, counts_ptr, first_ptr, first_offset,
+                                         n_processed))
+        self._stats = None
 
     # -- EMAlgorithm::run / Bootstrap::run_em --------------------------------------------------
     def run_em(self, fld_mean=0.0, fld_sd=0.0, table=None):

@@ -287,6 +287,23 @@ int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed,
   });
 }
 
+int kb_quant_export_prepare(kb_quant* q, uint32_t* n_sets, uint32_t* n_entries) {
+  if (!q || !n_sets || !n_entries) return fail(KB_ERR_INVALID, "kb_quant_export_prepare: null argument");
+  return guarded([&] { q->q->export_prepare(n_sets, n_entries); });
+}
+int kb_quant_export_device(kb_quant* q, uint32_t* d_off, uint32_t* d_tids, uint32_t* d_counts, uint64_t* d_first) {
+  if (!q || !d_off || !d_tids || !d_counts || !d_first) return fail(KB_ERR_INVALID, "kb_quant_export_device: null argument");
+  return guarded([&] { q->q->export_copy(d_off, d_tids, d_counts, (unsigned long long*)d_first); });
+}
+int kb_quant_import_device(kb_quant* q, uint32_t n_sets, const uint32_t* d_off, const uint32_t* d_tids, const uint32_t* d_counts,
+                           const uint64_t* d_first, uint64_t first_offset, uint64_t n_processed) {
+  if (!q || (n_sets && (!d_off || !d_tids || !d_counts || !d_first))) return fail(KB_ERR_INVALID, "kb_quant_import_device: null argument");
+  return guarded([&] {
+    q->q->import_sets_device(n_sets, d_off, d_tids, d_counts, (const unsigned long long*)d_first, first_offset);
+    q->q->add_processed(n_processed);
+  });
+}
+
 int kb_bus_create(kb_index* ix, const kb_bus_opts* o, kb_quant** out) {
   if (!ix || !o || !out) return fail(KB_ERR_INVALID, "kb_bus_create: null argument");
   *out = nullptr;

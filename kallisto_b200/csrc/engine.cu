@@ -884,6 +884,72 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   return res;
 }
 
+void Quant::export_prepare(uint32_t* n_sets, uint32_t* n_entries) {
+  KB_CK(cudaSetDevice(ix_.device));
+  check_device_errors();
+  cudaStream_t st = stream_;
+  EmWs& w = *emws_;
+  if (w.used.n < ix_.dict_cap) w.used.alloc(ix_.dict_cap);
+  if (w.scal.n < 8) w.scal.alloc(8);
+  launch_collect_used(dd_, w.used.p, w.scal.p, st);
+  uint32_t n = 0;
+  w.scal.download(&n, 1, 0, st);
+  KB_CK(cudaStreamSynchronize(st));
+  exp_n_ = n;
+  exp_nnz_ = 0;
+  if (n) {
+    const size_t n1 = (size_t)n + 1;
+    auto grow32 = [](DBuf<uint32_t>& b, size_t need) { if (b.n < need) b.alloc(need + need / 4); };
+    if (w.key_in.n < n1) { w.key_in.alloc(n1 + n1 / 4); w.key_out.alloc(n1 + n1 / 4); }
+    grow32(w.idx_in, n1); grow32(w.order, n1); grow32(w.handle, n1); grow32(w.count, n1); grow32(w.len, n1);
+    grow32(w.multi_len, n1); grow32(w.is_multi, n1); grow32(w.ec_off, n1); grow32(w.m_off, n1); grow32(w.multi_index, n1);
+    const size_t tmp_need = emprep_sort_bytes(n + 1, 1u << 20);
+    if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
+    KB_CK(cudaMemsetAsync(w.len.p + n, 0, 4, st));
+    KB_CK(cudaMemsetAsync(w.multi_len.p + n, 0, 4, st));
+    KB_CK(cudaMemsetAsync(w.is_multi.p + n, 0, 4, st));
+    emprep_sort_by_first(dd_, w.used.p, n, w.key_in.p, w.key_out.p, w.idx_in.p, w.order.p, w.tmp.p, w.tmp.n, st);
+    EmPrep ep{};
+    ep.n_ec = n; ep.n_targets = ix_.flat.num_targets();
+    ep.handle = w.handle.p; ep.count = w.count.p; ep.len = w.len.p; ep.ec_off = w.ec_off.p; ep.m_off = w.m_off.p;
+    ep.multi_index = w.multi_index.p;
+    emprep_meta(dd_, w.used.p, w.order.p, n, ep, w.multi_len.p, w.is_multi.p, w.tmp.p, w.tmp.n, st);
+    w.ec_off.download(&exp_nnz_, 1, n, st);
+    KB_CK(cudaStreamSynchronize(st));
+    grow32(w.ec_tid, std::max<uint32_t>(1, exp_nnz_));
+    ep.ec_tid = w.ec_tid.p;
+    emprep_fill_table(dd_, ep, st);
+    KB_CK(cudaGetLastError());
+  }
+  *n_sets = exp_n_;
+  *n_entries = exp_nnz_;
+}
+
+void Quant::export_copy(uint32_t* d_off, uint32_t* d_tids, uint32_t* d_counts, unsigned long long* d_first) {
+  KB_CK(cudaSetDevice(ix_.device));
+  EmWs& w = *emws_;
+  cudaStream_t st = stream_;
+  if (exp_n_) {
+    KB_CK(cudaMemcpyAsync(d_off, w.ec_off.p, ((size_t)exp_n_ + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    KB_CK(cudaMemcpyAsync(d_tids, w.ec_tid.p, (size_t)exp_nnz_ * 4, cudaMemcpyDeviceToDevice, st));
+    KB_CK(cudaMemcpyAsync(d_counts, w.count.p, (size_t)exp_n_ * 4, cudaMemcpyDeviceToDevice, st));
+    KB_CK(cudaMemcpyAsync(d_first, w.key_out.p, (size_t)exp_n_ * 8, cudaMemcpyDeviceToDevice, st));
+  } else {
+    KB_CK(cudaMemsetAsync(d_off, 0, 4, st));
+  }
+  KB_CK(cudaStreamSynchronize(st));
+}
+
+void Quant::import_sets_device(uint32_t n_sets, const uint32_t* d_off, const uint32_t* d_tids, const uint32_t* d_counts,
+                               const unsigned long long* d_first, unsigned long long first_offset) {
+  KB_CK(cudaSetDevice(ix_.device));
+  ecs_valid_ = false;
+  dev_stats_valid_ = false;
+  launch_import_sets(dd_, n_sets, d_off, d_tids, d_counts, d_first, first_offset, stream_);
+  KB_CK(cudaGetLastError());
+  KB_CK(cudaStreamSynchronize(stream_));
+}
+
 std::vector<int> Quant::run_bootstrap(const EcTable& ecs, const std::vector<double>& fl_trunc, uint64_t seed, int B,
                                       std::vector<double>& alpha_out, std::vector<uint32_t>* samples_out) {
   KB_CK(cudaSetDevice(ix_.device));

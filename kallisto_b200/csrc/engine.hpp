@@ -141,6 +141,16 @@ class Quant {
   std::vector<int> run_bootstrap(const EcTable& ecs, const std::vector<double>& fl_trunc, uint64_t seed, int B,
                                  std::vector<double>& alpha_out, std::vector<uint32_t>* samples_out = nullptr);
 
+  // ---- multi-GPU: ship this rank's equivalence classes to another rank / fold another rank's in ----
+  // export_prepare numbers the ECs (first occurrence) and lays the table out on the device; returns
+  // {n_sets, n_entries}.  export_copy then fills caller-provided DEVICE buffers (e.g. torch tensors
+  // about to go through NCCL): off[n_sets+1], tids[n_entries], counts[n_sets], first[n_sets].
+  void export_prepare(uint32_t* n_sets, uint32_t* n_entries);
+  void export_copy(uint32_t* d_off, uint32_t* d_tids, uint32_t* d_counts, unsigned long long* d_first);
+  void import_sets_device(uint32_t n_sets, const uint32_t* d_off, const uint32_t* d_tids, const uint32_t* d_counts,
+                          const unsigned long long* d_first, unsigned long long first_offset);
+  void add_processed(uint64_t n) { n_frag_total_ += n; }
+
   // Run on a caller-provided stream (e.g. the framework's current stream) instead of the run's own.
   void set_stream(cudaStream_t st);
   // Per-kernel device time, measured with CUDA events on the launching stream.
@@ -198,6 +208,7 @@ class Quant {
   DBuf<int32_t> bus_idof_;
   DBuf<BusRecord> bus_rec_;
   DBuf<uint8_t> bus_tmp_;
+  uint32_t exp_n_ = 0, exp_nnz_ = 0;
   uint32_t bus_next_id_ = 0;
   uint64_t bus_valid_total_ = 0;
   const uint8_t* cur_skip_ = nullptr;

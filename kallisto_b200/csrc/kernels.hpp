@@ -77,6 +77,8 @@ void launch_dict_init(const DictInitArgs& a, cudaStream_t st);
 void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& ba, const ResolveArgs& ra,
                         int threads_per_block, cudaStream_t st, cudaEvent_t* ev = nullptr);
 void launch_fld_finalize(const DevDict& dd, const BatchArgs& ba, cudaStream_t st);
+void launch_import_sets(const DevDict& dd, uint32_t n_sets, const uint32_t* off, const uint32_t* tids, const uint32_t* counts,
+                        const unsigned long long* first, unsigned long long first_offset, cudaStream_t st);
 // Compact the handles with count > 0: used[0..*n_used)
 void launch_collect_used(const DevDict& dd, uint32_t* used, uint32_t* n_used, cudaStream_t st);
 
@@ -141,6 +143,7 @@ void emprep_sort_by_first(const DevDict& dd, const uint32_t* used, uint32_t n_us
                           cudaStream_t st);
 void emprep_meta(const DevDict& dd, const uint32_t* used, const uint32_t* order, uint32_t n, const EmPrep& p,
                  uint32_t* multi_len, uint32_t* is_multi, void* tmp, size_t tmp_bytes, cudaStream_t st);
+void emprep_fill_table(const DevDict& dd, const EmPrep& p, cudaStream_t st);
 void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, uint32_t* sort_keys_out, uint32_t* sort_vals_out,
                  void* tmp, size_t tmp_bytes, unsigned long long* stats2, cudaStream_t st);
 

@@ -583,6 +583,56 @@ __device__ __forceinline__ bool bsearch_contains(const uint32_t* s, uint32_t n, 
   return lo < n && __ldcg(s + lo) == v;
 }
 
+// Warp-cooperative lookup-or-insert of a sorted transcript-id list in the content-addressed set
+// dictionary (ecmapinv semantics: equal sets share one handle).  `src` may be shared or global memory
+// readable by all lanes.  Returns the handle, or KB_H_UNMAPPED after flagging an error.
+__device__ __forceinline__ int32_t dict_insert_warp(const DevDict& dd, const uint32_t* src, uint32_t nres, unsigned lane) {
+  uint64_t sum = 0;
+  for (uint32_t i = lane; i < nres; i += 32) sum += kb_mix64((uint64_t)src[i] + 0x9E3779B97F4A7C15ULL);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  const uint64_t hsh = kb_mix64(sum ^ nres);
+  const unsigned long long tag = hsh >> 56;
+  uint64_t s = hsh & dd.dmask;
+  unsigned long long my_word = ~0ULL;   // pool space is allocated lazily
+  uint64_t visited = 0;
+  for (;;) {
+    unsigned long long word = 0;
+    if (lane == 0) word = ld_acquire_u64(&dd.dslots[s]);
+    word = __shfl_sync(0xFFFFFFFFu, word, 0);
+    if (word == ~0ULL) {
+      if (my_word == ~0ULL) {
+        unsigned long long off = 0;
+        if (lane == 0) off = atomicAdd(dd.pool_top, (unsigned long long)nres);
+        off = __shfl_sync(0xFFFFFFFFu, off, 0);
+        if (off + nres > dd.pool_cap || off + nres > 0xFFFFFFFFULL) {
+          if (lane == 0) atomicOr(dd.error, KB_DEVERR_POOL_FULL);
+          return KB_H_UNMAPPED;
+        }
+        for (uint32_t i = lane; i < nres; i += 32) dd.pool[off + i] = src[i];
+        __threadfence();
+        __syncwarp();
+        my_word = off | ((unsigned long long)nres << 32) | (tag << 56);
+      }
+      unsigned long long old = 0;
+      if (lane == 0) old = atomicCAS(&dd.dslots[s], ~0ULL, my_word);
+      old = __shfl_sync(0xFFFFFFFFu, old, 0);
+      if (old == ~0ULL) return (int32_t)s;
+      word = old;   // somebody else took the slot: compare against theirs
+    }
+    if ((word >> 56) == tag && ((word >> 32) & 0xFFFFFFu) == nres) {
+      const uint32_t* S = dd.pool + (uint32_t)word;
+      bool eq = true;
+      for (uint32_t i = lane; i < nres; i += 32) eq = eq && (__ldcg(S + i) == src[i]);
+      if (__all_sync(0xFFFFFFFFu, eq)) return (int32_t)s;
+    }
+    s = (s + 1) & dd.dmask;
+    if (++visited > dd.dmask) {
+      if (lane == 0) atomicOr(dd.error, KB_DEVERR_DICT_FULL);
+      return KB_H_UNMAPPED;
+    }
+  }
+}
+
 }  // namespace
 
 // One warp per queued fragment.
@@ -684,56 +734,7 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
         }
       }
       // 4. set -> handle through the content-addressed dictionary
-      if (nres == 0) {
-        handle = KB_H_UNMAPPED;
-      } else {
-        uint64_t sum = 0;
-        for (uint32_t i = lane; i < nres; i += 32) sum += kb_mix64((uint64_t)scratch[i] + 0x9E3779B97F4A7C15ULL);
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-        const uint64_t hsh = kb_mix64(sum ^ nres);
-        const unsigned long long tag = hsh >> 56;
-        uint64_t s = hsh & dd.dmask;
-        unsigned long long my_word = ~0ULL;   // allocated lazily
-        uint64_t visited = 0;
-        for (;;) {
-          unsigned long long word = 0;
-          if (lane == 0) word = ld_acquire_u64(&dd.dslots[s]);
-          word = __shfl_sync(0xFFFFFFFFu, word, 0);
-          if (word == ~0ULL) {
-            if (my_word == ~0ULL) {
-              unsigned long long off = 0;
-              if (lane == 0) off = atomicAdd(dd.pool_top, (unsigned long long)nres);
-              off = __shfl_sync(0xFFFFFFFFu, off, 0);
-              if (off + nres > dd.pool_cap || off + nres > 0xFFFFFFFFULL) {
-                if (lane == 0) atomicOr(dd.error, KB_DEVERR_POOL_FULL);
-                handle = KB_H_UNMAPPED;
-                break;
-              }
-              for (uint32_t i = lane; i < nres; i += 32) dd.pool[off + i] = scratch[i];
-              __threadfence();
-              __syncwarp();
-              my_word = off | ((unsigned long long)nres << 32) | (tag << 56);
-            }
-            unsigned long long old = 0;
-            if (lane == 0) old = atomicCAS(&dd.dslots[s], ~0ULL, my_word);
-            old = __shfl_sync(0xFFFFFFFFu, old, 0);
-            if (old == ~0ULL) { handle = (int32_t)s; break; }
-            word = old;   // somebody else took the slot: compare against theirs
-          }
-          if ((word >> 56) == tag && ((word >> 32) & 0xFFFFFFu) == nres) {
-            const uint32_t* S = pool + (uint32_t)word;
-            bool eq = true;
-            for (uint32_t i = lane; i < nres; i += 32) eq = eq && (__ldcg(S + i) == scratch[i]);
-            if (__all_sync(0xFFFFFFFFu, eq)) { handle = (int32_t)s; break; }
-          }
-          s = (s + 1) & dd.dmask;
-          if (++visited > dd.dmask) {
-            if (lane == 0) atomicOr(dd.error, KB_DEVERR_DICT_FULL);
-            handle = KB_H_UNMAPPED;
-            break;
-          }
-        }
-      }
+      handle = nres == 0 ? KB_H_UNMAPPED : dict_insert_warp(dd, scratch, nres, lane);
       // 5. publish tuple -> handle
       if (lane == 0) {
         if (use_m2) {
@@ -836,6 +837,33 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
   if (ev) cudaEventRecord(ev[1], st);
   resolve_kernel<<<(ra.n_warps * 32 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra);
   if (ev) cudaEventRecord(ev[2], st);
+}
+
+// Multi-GPU merge: equivalence classes exported by another rank (CSR of transcript ids, counts, first
+// fragment index) are folded into this rank's dictionary -- the content-keyed reduction that replaces
+// a dense all-reduce, since EC ids are discovered independently on every rank.  One warp per set.
+__global__ void __launch_bounds__(128) import_sets_kernel(DevDict dd, uint32_t n_sets, const uint32_t* off, const uint32_t* tids,
+                                                         const uint32_t* counts, const unsigned long long* first,
+                                                         unsigned long long first_offset) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t s = w; s < n_sets; s += nw) {
+    const uint32_t o0 = off[s], n = off[s + 1] - o0;
+    if (n == 0) continue;
+    const int32_t h = dict_insert_warp(dd, tids + o0, n, lane);
+    if (lane == 0 && h >= 0) {
+      atomicAdd(&dd.count[h], counts[s]);
+      atomicMin(&dd.first[h], first[s] + first_offset);
+    }
+    __syncwarp();
+  }
+}
+
+void launch_import_sets(const DevDict& dd, uint32_t n_sets, const uint32_t* off, const uint32_t* tids, const uint32_t* counts,
+                        const unsigned long long* first, unsigned long long first_offset, cudaStream_t st) {
+  if (n_sets == 0) return;
+  import_sets_kernel<<<148 * 8, 128, 0, st>>>(dd, n_sets, off, tids, counts, first, first_offset);
 }
 
 void launch_fld_finalize(const DevDict& dd, const BatchArgs& ba, cudaStream_t st) {

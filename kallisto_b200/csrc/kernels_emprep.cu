@@ -71,6 +71,16 @@ __global__ void ec_fill_kernel(DevDict dd, EmPrep p) {
   }
 }
 
+// EC table only (export to other ranks): one warp per EC copies its transcript ids
+__global__ void ec_table_kernel(DevDict dd, EmPrep p) {
+  const uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (e >= p.n_ec) return;
+  const uint32_t* src = dd.pool + (uint32_t)dd.dslots[p.handle[e]];
+  const uint32_t l = p.len[e], eo = p.ec_off[e];
+  for (uint32_t j = lane; j < l; j += 32) p.ec_tid[eo + j] = src[j];
+}
+
 // CSC entries in (transcript, EC id) order from the stable sort of (tid, entry index)
 __global__ void csc_fill_kernel(EmPrep p, const uint32_t* sorted_entry, uint32_t nnz) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,6 +134,12 @@ void emprep_meta(const DevDict& dd, const uint32_t* used, const uint32_t* order,
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, p.len, p.ec_off, (int)n + 1, st);
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, multi_len, p.m_off, (int)n + 1, st);
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, is_multi, p.multi_index, (int)n + 1, st);
+}
+
+void emprep_fill_table(const DevDict& dd, const EmPrep& p, cudaStream_t st) {
+  if (p.n_ec == 0) return;
+  const uint64_t threads = (uint64_t)p.n_ec * 32;
+  ec_table_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dd, p);
 }
 
 void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, uint32_t* sort_keys_out, uint32_t* sort_vals_out,
