@@ -45,9 +45,27 @@ def log(*a):
 # workload: index + transcriptome (cached under bench_data/, rebuilt with the reference if absent)
 # ---------------------------------------------------------------------------------------------
 def workload(genes):
+    import fcntl
     os.makedirs(DATA, exist_ok=True)
     idx = os.path.join(DATA, "g%d.kidx" % genes)
     txf = os.path.join(DATA, "g%d.tx.npz" % genes)
+    with open(os.path.join(DATA, ".lock"), "w") as lockf:   # ranks of one node: one builds, the others wait
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            _build_workload(genes, idx, txf)
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
+    z = np.load(txf)
+    packed, lens = z["packed"], z["lens"]
+    concat = np.empty(len(packed) * 4, np.uint8)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    for j in range(4):
+        concat[j::4] = lut[(packed >> (2 * j)) & 3]
+    concat = concat[: int(lens.sum())]
+    return idx, concat, lens
+
+
+def _build_workload(genes, idx, txf):
     if not (os.path.exists(idx) and os.path.exists(txf)):
         from oracle import oracle as O
         log("building workload for %d genes (one-off, cached in bench_data/)" % genes)
@@ -70,14 +88,6 @@ def workload(genes):
                 O.ref_run(["index", "-t", str(min(32, os.cpu_count() or 8)), "-i", idx + ".tmp", fa])
             os.replace(idx + ".tmp", idx)
         log("workload built in %.0f s" % (time.time() - t0))
-    z = np.load(txf)
-    packed, lens = z["packed"], z["lens"]
-    concat = np.empty(len(packed) * 4, np.uint8)
-    lut = np.frombuffer(b"ACGT", np.uint8)
-    for j in range(4):
-        concat[j::4] = lut[(packed >> (2 * j)) & 3]
-    concat = concat[: int(lens.sum())]
-    return idx, concat, lens
 
 
 class ClockSampler:
@@ -268,7 +278,10 @@ def main():
     mc = new_run()
     for s in range(W):
         mc.process_buffer_device(d_batches[s].data_ptr(), None, n_reads, READ_LEN)
-    if W:
+    if world > 1:
+        from kallisto_b200 import multigpu
+        multigpu.merge_on_rank0(mc, W * P, dev)    # also brings the NCCL communicator up before the timed region
+    if W and rank == 0:
         mc.run_em()
     mc.close()
 
@@ -285,7 +298,6 @@ def main():
     ev1.record(stream)
     if world > 1:
         # the one exchange step: EC tables all-gathered over NCCL, merged by content on rank 0's GPU
-        from kallisto_b200 import multigpu
         multigpu.merge_on_rank0(mc, K * P, dev)
     em = mc.run_em() if rank == 0 else None   # EC ids, CSR/CSC and the EM kernel on the device (rank 0 only)
     ev2.record(stream)
@@ -323,8 +335,8 @@ def main():
     e2e_value = total_pairs / t_e2e
 
     # ---- roofline of the dominant kernel (match_kernel) ----
-    probes_per_pair = st["n_probes"] / max(1, st["n_processed"])
-    visits_per_pair = st["n_slot_visits"] / max(1, st["n_processed"])
+    probes_per_pair = st["n_probes"] / max(1, K * P)          # this rank's own fragments
+    visits_per_pair = st["n_slot_visits"] / max(1, K * P)
     # algorithmic bytes per pair: read bases + one 32-byte sector per executed probe +
     # the per-pair result; EC-list bytes are only touched by the (rare) resolve kernel
     bytes_per_pair = 2 * READ_LEN + probes_per_pair * 32 + 16
@@ -344,6 +356,10 @@ def main():
         except Exception:
             pass
 
+    if world > 1:
+        # every rank leaves the process group together (a rank that exits early can stall the others' teardown)
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     cpu = None
@@ -377,8 +393,6 @@ def main():
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
