@@ -45,38 +45,38 @@ def main():
                 out.append("| %s | %s | %s |" % (w, row[i], unit[i]))
     src = run(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"])
     rows = list(csv.reader(io.StringIO(src)))
-    # find the header row of the correlated view
-    h = None
-    for i, r in enumerate(rows):
+    # sections: "Function Name",<kernel> ... header row ... (source line rows followed by their SASS rows)
+    per = {}
+    cur, H = None, None
+    for r in rows:
+        if len(r) >= 2 and r[0] == "Function Name":
+            cur = r[1].split("(")[0]
+            H = None
+            continue
         if "Instructions Executed" in r and "Source" in r:
-            h = i
-            break
-    if h is not None:
-        H = rows[h]
-        ci, cs, csm = H.index("Instructions Executed"), H.index("Source"), H.index("# Samples")
-        lines = []
-        tot_i = tot_s = 0
-        for r in rows[h + 1:]:
-            if len(r) <= max(ci, cs, csm):
-                continue
-            try:
-                n, s = int(r[ci]), int(r[csm])
-            except ValueError:
-                continue
-            lines.append((r[0], r[cs], n, s))
-        # the cuda,sass view lists source lines followed by their SASS; keep rows whose first column is a line number
-        src_lines = [(a, b, n, s) for a, b, n, s in lines if a.isdigit()]
-        use = src_lines if src_lines else lines
+            H = r
+            ci, cs, csm = H.index("Instructions Executed"), H.index("Source"), H.index("# Samples")
+            continue
+        if cur is None or H is None or len(r) <= max(ci, cs, csm) or not r[0].isdigit():
+            continue
+        try:
+            n, smp = int(r[ci]), int(r[csm])
+        except ValueError:
+            continue
+        per.setdefault(cur, []).append((r[0], r[cs], n, smp))
+    for fn, use in per.items():
         tot_i = sum(x[2] for x in use) or 1
         tot_s = sum(x[3] for x in use) or 1
-        out.append("\n### hottest lines by executed warp instructions")
+        if tot_i < 1000:
+            continue
+        out.append("\n### %s: hottest source lines by executed warp instructions" % fn)
         out.append("| line | % inst | % stall samples | source |\n|---|---|---|---|")
-        for a, b, n, s in sorted(use, key=lambda x: -x[2])[:25]:
-            out.append("| %s | %.1f | %.1f | `%s` |" % (a, 100.0 * n / tot_i, 100.0 * s / tot_s, b.strip()[:110]))
-        out.append("\n### hottest lines by stall samples")
+        for a_, b_, n, smp in sorted(use, key=lambda x: -x[2])[:16]:
+            out.append("| %s | %.1f | %.1f | `%s` |" % (a_, 100.0 * n / tot_i, 100.0 * smp / tot_s, b_.strip()[:110]))
+        out.append("\n### %s: hottest source lines by stall samples" % fn)
         out.append("| line | % inst | % stall samples | source |\n|---|---|---|---|")
-        for a, b, n, s in sorted(use, key=lambda x: -x[3])[:15]:
-            out.append("| %s | %.1f | %.1f | `%s` |" % (a, 100.0 * n / tot_i, 100.0 * s / tot_s, b.strip()[:110]))
+        for a_, b_, n, smp in sorted(use, key=lambda x: -x[3])[:8]:
+            out.append("| %s | %.1f | %.1f | `%s` |" % (a_, 100.0 * n / tot_i, 100.0 * smp / tot_s, b_.strip()[:110]))
     text = "\n".join(out) + "\n"
     if len(sys.argv) > 2:
         open(sys.argv[2], "w").write(text)
