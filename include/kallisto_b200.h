@@ -65,6 +65,9 @@ typedef struct kb_quant_opts {
   int32_t collect_fld;       /* 1: estimate the fragment-length distribution from the first 10000 unique pairs */
   uint32_t max_batch_reads;  /* largest batch (reads) that will be submitted; 0 = default (4 Mi) */
   uint64_t max_batch_bases;  /* largest batch (bases); 0 = default (512 Mi) */
+  int32_t single_overhang;   /* --single-overhang: skip the fragment-position filter (ProcessReads.cpp:1095-1136) */
+  double fld_mean;           /* -l (0 = not given); with !single_overhang the filter runs for single-end reads and for
+                                pairs with one mate mapped, and needs an index loaded with load_positions = 1 */
 } kb_quant_opts;
 int kb_quant_create(kb_index* ix, const kb_quant_opts* opts, kb_quant** out);
 void kb_quant_free(kb_quant* q);

@@ -35,7 +35,8 @@ class kb_index_info(C.Structure):
 
 class kb_quant_opts(C.Structure):
     _fields_ = [("paired", C.c_int32), ("strand_mode", C.c_int32), ("collect_fld", C.c_int32),
-                ("max_batch_reads", C.c_uint32), ("max_batch_bases", C.c_uint64)]
+                ("max_batch_reads", C.c_uint32), ("max_batch_bases", C.c_uint64), ("single_overhang", C.c_int32),
+                ("fld_mean", C.c_double)]
 
 
 class kb_kernel_timings(C.Structure):
@@ -192,7 +193,8 @@ class MinCollector:
     Stands in for MinCollector + MasterProcessor/ReadProcessor (src/ProcessReads.cpp) followed by
     EMAlgorithm / Bootstrap."""
 
-    def __init__(self, index, paired=True, strand=None, collect_fld=True, max_batch_reads=0, max_batch_bases=0):
+    def __init__(self, index, paired=True, strand=None, collect_fld=True, max_batch_reads=0, max_batch_bases=0,
+                 single_overhang=True, fld_mean=0.0):
         self.index = index
         self.paired = bool(paired)
         o = kb_quant_opts()
@@ -201,6 +203,8 @@ class MinCollector:
         o.collect_fld = int(collect_fld)
         o.max_batch_reads = max_batch_reads
         o.max_batch_bases = max_batch_bases
+        o.single_overhang = int(single_overhang)
+        o.fld_mean = fld_mean
         self._h = C.c_void_p()
         _ck(lib().kb_quant_create(index._h, C.byref(o), C.byref(self._h)))
         self._stats = None

@@ -111,6 +111,8 @@ int kb_quant_create(kb_index* ix, const kb_quant_opts* opts, kb_quant** out) {
       o.paired = opts->paired;
       o.strand_mode = opts->strand_mode;
       o.collect_fld = opts->collect_fld;
+      // ProcessReads.cpp:1095: !single_overhang && tc.has_mean_fl  (has_mean_fl <=> -l given, MinCollector.h:37-41)
+      if (!opts->single_overhang && opts->fld_mean > 0.0) o.fp_fl = (int)opts->fld_mean;
       if (opts->max_batch_reads) o.max_batch_reads = opts->max_batch_reads;
       if (opts->max_batch_bases) o.max_batch_bases = opts->max_batch_bases;
     }

@@ -174,11 +174,6 @@ bool check_quant(Options& opt) {   // CheckOptionsEM, src/main.cpp:1600-1805
   }
   if (opt.fld < 0.0) { cerr << "Error: invalid value for mean fragment length " << opt.fld << endl; ret = false; }
   if (opt.sd < 0.0) { cerr << "Error: invalid value for fragment length standard deviation " << opt.sd << endl; ret = false; }
-  if (opt.single_end && !opt.single_overhang) {
-    cerr << "Error: this build quantifies single-end reads only with --single-overhang" << endl
-         << "       (the fragment-position filter of the reference is not implemented yet)" << endl;
-    ret = false;
-  }
   if (opt.output.empty()) {
     cerr << "Error: need to specify output directory " << opt.output << endl;
     ret = false;
@@ -315,7 +310,9 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     return 1;
   }
   kb_index* ix = nullptr;
-  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, 0, std::max(1, opt.threads), &ix));
+  // positions are needed only by the fragment-position filter (KmerIndex.h:78: load_positional_info)
+  const int need_positions = (!opt.single_overhang && opt.fld > 0.0) ? 1 : 0;
+  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, need_positions, std::max(1, opt.threads), &ix));
   kb_index_info info;
   kb_index_get_info(ix, &info);
   cerr << "[index] k-mer length: " << info.k << endl;
@@ -339,6 +336,8 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   qo.paired = paired;
   qo.strand_mode = opt.strand;
   qo.collect_fld = opt.fld == 0.0;
+  qo.single_overhang = opt.single_overhang;
+  qo.fld_mean = opt.fld;
   qo.max_batch_reads = (uint32_t)max_reads;
   qo.max_batch_bases = 2 * max_bases;
   kb_quant* q = nullptr;

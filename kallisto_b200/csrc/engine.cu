@@ -93,6 +93,17 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   ix->blk_strand_off.upload(f.blk_strand_off.data(), f.blk_strand_off.size(), st);
   ix->strand.alloc(std::max<size_t>(1, f.strand.size()));
   ix->strand.upload(f.strand.data(), f.strand.size(), st);
+  if (f.has_positions) {
+    ix->fp_info.alloc(std::max<size_t>(1, f.fp_info.size() / 4));
+    if (!f.fp_info.empty())
+      KB_CK(cudaMemcpyAsync(ix->fp_info.p, f.fp_info.data(), f.fp_info.size() * 4, cudaMemcpyHostToDevice, st));
+    std::vector<uint32_t> busize(f.blk_lb.size());
+    for (uint32_t u = 0; u < f.n_unitigs(); ++u)
+      for (uint64_t b = f.blk_off[u]; b < f.blk_off[u + 1]; ++b) busize[b] = f.ulen[u];
+    ix->blk_usize.upload(busize.data(), busize.size(), st);
+    ix->target_len.upload(f.target_len.data(), f.target_len.size(), st);
+    KB_CK(cudaStreamSynchronize(st));
+  }
   for (uint32_t e = 0; e < f.n_ec(); ++e) {
     const uint32_t len = (uint32_t)(f.ec_off[e + 1] - f.ec_off[e]);
     if (len == 0) ix->empty_ec = e;
@@ -167,6 +178,9 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   d.blk_ec = ix->blk_ec.p;
   d.blk_strand_off = ix->blk_strand_off.p;
   d.strand = ix->strand.p;
+  d.fp_info = f.has_positions ? ix->fp_info.p : nullptr;
+  d.blk_usize = f.has_positions ? ix->blk_usize.p : nullptr;
+  d.target_len = f.has_positions ? ix->target_len.p : nullptr;
   ix->build_seconds = now_s() - t1;
   return ix;
 }
@@ -186,9 +200,16 @@ struct EmWs {   // grow-only device workspace of run_em_device
 };
 
 Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(1000, 0), emws_(new EmWs()) {
+  if (opt_.fp_fl >= 0 && !ix_.flat.has_positions)
+    throw Error("kallisto_b200: the fragment-position filter needs an index loaded with positions (load_positions = 1)");
   if (const char* s = getenv("KB_REFILL_MIN")) opt_.refill_min = std::max(1, std::min(32, atoi(s)));   // tuning knob
   KB_CK(cudaSetDevice(ix_.device));
   KB_CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  KB_CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    KB_CK(cudaEventCreateWithFlags(&ev_copied_[i], cudaEventDisableTiming));
+    KB_CK(cudaEventCreateWithFlags(&ev_done_[i], cudaEventDisableTiming));
+  }
   cudaStream_t st = stream_;
   const uint64_t nE = ix_.flat.n_ec();
   // pools and tables of this run
@@ -238,7 +259,7 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
   // resolve-kernel scratch: 2 x max_set_len words per warp, at most ~1 GiB in total
   const uint64_t stride = std::max<uint64_t>(64, 2ull * ix_.max_set_len);
   uint64_t warps = (1ull << 28) / stride;
-  warps = std::min<uint64_t>(148 * 16, std::max<uint64_t>(64, warps));
+  warps = std::min<uint64_t>(148 * 32, std::max<uint64_t>(64, warps));   // the kernel is latency-bound: fill the SMs
   n_resolve_warps_ = (uint32_t)(warps / 4 * 4);
   d_scratch_.alloc((size_t)n_resolve_warps_ * stride);
   KB_CK(cudaStreamSynchronize(st));
@@ -248,6 +269,11 @@ Quant::~Quant() {
   delete emws_;
   if (h_off_pinned_) cudaFreeHost(h_off_pinned_);
   for (auto ev : events_) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) {
+    if (ev_copied_[i]) cudaEventDestroy(ev_copied_[i]);
+    if (ev_done_[i]) cudaEventDestroy(ev_done_[i]);
+  }
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (stream_ && own_stream_) cudaStreamDestroy(stream_);
 }
 
@@ -325,6 +351,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.empty_ec = ix_.empty_ec;
   ba.refill_min = opt_.refill_min;
   ba.skip = cur_skip_;
+  ba.fp_fl = opt_.fp_fl;
   ba.start = cur_start_;
   ResolveArgs ra{};
   ra.scratch = d_scratch_.p;
@@ -381,18 +408,30 @@ void Quant::pseudoalign_host(const char* bases, const uint32_t* off, uint32_t n_
   } else {
     n_bases = (uint64_t)n_reads * fixed_len;
   }
-  if (d_bases_.n < n_bases + 16) d_bases_.alloc(std::max<uint64_t>(n_bases + 16, opt_.max_batch_bases));
-  KB_CK(cudaMemcpyAsync(d_bases_.p, bases, n_bases, cudaMemcpyHostToDevice, stream_));
+  // stage into buffer `s`; the copy runs on its own stream so that it overlaps the previous batch's kernels
+  const int s = stage_idx_;
+  stage_idx_ ^= 1;
+  DBuf<uint8_t>& db = stage_b_[s][0];
+  DBuf<uint32_t>& dofs = stage_o_[s][0];
+  KB_CK(cudaStreamWaitEvent(copy_stream_, ev_done_[s], 0));      // kernels that last read this buffer
+  if (db.n < n_bases + 16) { KB_CK(cudaStreamSynchronize(stream_)); db.alloc(std::max<uint64_t>(n_bases + 16, opt_.max_batch_bases)); }
+  KB_CK(cudaMemcpyAsync(db.p, bases, n_bases, cudaMemcpyHostToDevice, copy_stream_));
   if (off) {
-    if (d_off_.n < (size_t)n_reads + 1) d_off_.alloc(std::max<size_t>((size_t)n_reads + 1, (size_t)opt_.max_batch_reads * 2 + 1));
-    KB_CK(cudaMemcpyAsync(d_off_.p, off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, stream_));
+    if (dofs.n < (size_t)n_reads + 1) { KB_CK(cudaStreamSynchronize(stream_)); dofs.alloc(std::max<size_t>((size_t)n_reads + 1, (size_t)opt_.max_batch_reads * 2 + 1)); }
+    KB_CK(cudaMemcpyAsync(dofs.p, off, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, copy_stream_));
   }
-  run_batch(d_bases_.p, off ? d_off_.p : nullptr, n_reads, fixed_len, maxlen);
+  KB_CK(cudaEventRecord(ev_copied_[s], copy_stream_));
+  KB_CK(cudaStreamWaitEvent(stream_, ev_copied_[s], 0));
+  run_batch(db.p, off ? dofs.p : nullptr, n_reads, fixed_len, maxlen);
+  KB_CK(cudaEventRecord(ev_done_[s], stream_));
   if (handles_out) {
     const uint32_t n_frag = opt_.paired ? n_reads / 2 : n_reads;
     d_handles_.download(handles_out, n_frag, 0, stream_);
+    KB_CK(cudaStreamSynchronize(stream_));
+  } else {
+    // the caller may reuse its buffers once the copy is done; the kernels keep running
+    KB_CK(cudaEventSynchronize(ev_copied_[s]));
   }
-  KB_CK(cudaStreamSynchronize(stream_));
 }
 
 void Quant::pseudoalign_host_pe(const char* bases1, const uint32_t* off1, const char* bases2, const uint32_t* off2,
@@ -411,20 +450,34 @@ void Quant::pseudoalign_host_pe(const char* bases1, const uint32_t* off1, const 
   } else {
     nb1 = nb2 = (uint64_t)n_pairs * fixed_len;
   }
-  if (d_bases_.n < nb1 + 16) d_bases_.alloc(std::max<uint64_t>(nb1 + 16, opt_.max_batch_bases / 2 + 16));
-  if (d_bases2_.n < nb2 + 16) d_bases2_.alloc(std::max<uint64_t>(nb2 + 16, opt_.max_batch_bases / 2 + 16));
-  KB_CK(cudaMemcpyAsync(d_bases_.p, bases1, nb1, cudaMemcpyHostToDevice, stream_));
-  KB_CK(cudaMemcpyAsync(d_bases2_.p, bases2, nb2, cudaMemcpyHostToDevice, stream_));
+  const int s = stage_idx_;
+  stage_idx_ ^= 1;
+  DBuf<uint8_t>& b1 = stage_b_[s][0];
+  DBuf<uint8_t>& b2 = stage_b_[s][1];
+  DBuf<uint32_t>& o1 = stage_o_[s][0];
+  DBuf<uint32_t>& o2 = stage_o_[s][1];
+  KB_CK(cudaStreamWaitEvent(copy_stream_, ev_done_[s], 0));
+  if (b1.n < nb1 + 16) { KB_CK(cudaStreamSynchronize(stream_)); b1.alloc(std::max<uint64_t>(nb1 + 16, opt_.max_batch_bases / 2 + 16)); }
+  if (b2.n < nb2 + 16) { KB_CK(cudaStreamSynchronize(stream_)); b2.alloc(std::max<uint64_t>(nb2 + 16, opt_.max_batch_bases / 2 + 16)); }
+  KB_CK(cudaMemcpyAsync(b1.p, bases1, nb1, cudaMemcpyHostToDevice, copy_stream_));
+  KB_CK(cudaMemcpyAsync(b2.p, bases2, nb2, cudaMemcpyHostToDevice, copy_stream_));
   if (off1) {
     const size_t no = (size_t)n_pairs + 1;
-    if (d_off_.n < no) d_off_.alloc(std::max<size_t>(no, (size_t)opt_.max_batch_reads + 1));
-    if (d_off2_.n < no) d_off2_.alloc(std::max<size_t>(no, (size_t)opt_.max_batch_reads + 1));
-    KB_CK(cudaMemcpyAsync(d_off_.p, off1, no * 4, cudaMemcpyHostToDevice, stream_));
-    KB_CK(cudaMemcpyAsync(d_off2_.p, off2, no * 4, cudaMemcpyHostToDevice, stream_));
+    if (o1.n < no) { KB_CK(cudaStreamSynchronize(stream_)); o1.alloc(std::max<size_t>(no, (size_t)opt_.max_batch_reads + 1)); }
+    if (o2.n < no) { KB_CK(cudaStreamSynchronize(stream_)); o2.alloc(std::max<size_t>(no, (size_t)opt_.max_batch_reads + 1)); }
+    KB_CK(cudaMemcpyAsync(o1.p, off1, no * 4, cudaMemcpyHostToDevice, copy_stream_));
+    KB_CK(cudaMemcpyAsync(o2.p, off2, no * 4, cudaMemcpyHostToDevice, copy_stream_));
   }
-  run_batch(d_bases_.p, off1 ? d_off_.p : nullptr, 2 * n_pairs, fixed_len, maxlen, d_bases2_.p, off1 ? d_off2_.p : nullptr);
-  if (handles_out) d_handles_.download(handles_out, n_pairs, 0, stream_);
-  KB_CK(cudaStreamSynchronize(stream_));
+  KB_CK(cudaEventRecord(ev_copied_[s], copy_stream_));
+  KB_CK(cudaStreamWaitEvent(stream_, ev_copied_[s], 0));
+  run_batch(b1.p, off1 ? o1.p : nullptr, 2 * n_pairs, fixed_len, maxlen, b2.p, off1 ? o2.p : nullptr);
+  KB_CK(cudaEventRecord(ev_done_[s], stream_));
+  if (handles_out) {
+    d_handles_.download(handles_out, n_pairs, 0, stream_);
+    KB_CK(cudaStreamSynchronize(stream_));
+  } else {
+    KB_CK(cudaEventSynchronize(ev_copied_[s]));
+  }
 }
 
 void Quant::bus_batch_host(const char* const* bases, const uint32_t* const* offs, uint32_t n_sets, BusRecord* records_out,
@@ -625,6 +678,10 @@ std::vector<double> Quant::mean_fl_trunc(double fld_mean, double fld_sd) const {
 }
 
 namespace {
+int em_tpb() {
+  if (const char* s = getenv("KB_EM_TPB")) return std::max(32, std::min(1024, atoi(s)));   // tuning knob
+  return 256;
+}
 struct EmHost {
   std::vector<uint32_t> multi_ec, m_off, m_tid, t_off, t_midx;
   std::vector<double> m_w, t_w, eff;
@@ -859,7 +916,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   p.rounds = w.emi.p; p.state = w.emi.p + 1; p.fstate = w.emi.p + 3; p.chcount = w.chcount.p;
   p.max_iter = max_iter; p.min_rounds = min_rounds;
   KB_CK(cudaEventRecord(e1, st));
-  launch_em(p, 256, st);
+  launch_em(p, em_tpb(), st);
   KB_CK(cudaGetLastError());
   KB_CK(cudaEventRecord(e2, st));
   int emi[4] = {0, 0, 0, 0};
@@ -1028,5 +1085,6 @@ template struct DBuf<double>;
 template struct DBuf<KmerSlot>;
 template struct DBuf<Memo2Entry>;
 template struct DBuf<BusRecord>;
+template struct DBuf<uint4>;
 
 }  // namespace kb

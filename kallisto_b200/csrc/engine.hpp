@@ -63,6 +63,8 @@ class Index {
   DBuf<uint32_t> blk_ec;
   DBuf<uint64_t> blk_strand_off;
   DBuf<uint8_t> strand;
+  DBuf<uint4> fp_info;            // only when loaded with positions
+  DBuf<uint32_t> blk_usize, target_len;
 };
 
 struct QuantOptions {
@@ -72,6 +74,7 @@ struct QuantOptions {
   uint32_t max_batch_reads = 1u << 22;     // staging capacity (reads per batch)
   uint64_t max_batch_bases = 1ull << 29;   // staging capacity (bases per batch)
   int threads_per_block = 256;
+  int fp_fl = -1;          // >= 0: fragment-position filter with this mean fragment length (!single_overhang && -l given)
   bool bus = false;        // `kallisto bus` run: records instead of (only) counts
   BusSpec bus_spec{};
   int refill_min = 16;     // match_kernel: finished lanes per warp that trigger a finalise + refill round
@@ -188,6 +191,12 @@ class Quant {
   DBuf<int> error_;
   // batch staging
   DBuf<uint8_t> d_bases_, d_bases2_;
+  // double-buffered input staging: the H2D copy of batch i+1 overlaps the kernels of batch i
+  DBuf<uint8_t> stage_b_[2][2];
+  DBuf<uint32_t> stage_o_[2][2];
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_done_[2] = {nullptr, nullptr};
+  int stage_idx_ = 0;
   DBuf<uint32_t> d_off_, d_off2_, d_qcount_, d_qentries_, d_scratch_, d_packed_;
   DBuf<int32_t> d_handles_;
   DBuf<uint16_t> d_tl_;

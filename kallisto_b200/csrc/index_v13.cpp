@@ -450,6 +450,59 @@ void load_index_v13(const std::string& path, FlatIndex& fi, bool load_positions,
     }
   }
   chunks.clear();
+  if (load_positions) {
+    // findPosition constants.  `holds(b, tr)` = tr is a member of block b's EC.
+    fi.fp_info.assign((size_t)total_members * 4, 0);
+    for (uint32_t u = 0; u < nU; ++u) {
+      const uint64_t b0 = fi.blk_off[u], b1 = fi.blk_off[u + 1];
+      auto holds = [&](uint64_t b, uint32_t tr) {
+        const uint64_t e = fi.blk_ec[b];
+        const uint32_t* s = fi.ec_tid.data() + fi.ec_off[e];
+        const uint32_t* t = s + (fi.ec_off[e + 1] - fi.ec_off[e]);
+        return std::binary_search(s, t, tr);
+      };
+      for (uint64_t b = b0; b < b1; ++b) {
+        const uint64_t e = fi.blk_ec[b];
+        const uint64_t n = fi.ec_off[e + 1] - fi.ec_off[e];
+        for (uint64_t m = 0; m < n; ++m) {
+          const uint32_t tr = fi.ec_tid[fi.ec_off[e] + m];
+          const uint64_t slot = fi.blk_strand_off[b] + m;
+          uint32_t* out = fi.fp_info.data() + slot * 4;
+          const uint32_t rawmin = fi.pos_val[fi.pos_off[slot]];   // sorted ascending: the minimum
+          out[0] = rawmin;
+          // case I: only when trpos == 0
+          uint32_t pad = 0;
+          if ((rawmin & 0x7FFFFFFFu) == 0) {
+            uint64_t cur = b;
+            for (uint64_t i = b; i-- > b0;) {
+              if (!holds(i, tr)) { pad = fi.blk_lb[cur]; break; }
+              cur = i;
+            }
+          }
+          out[1] = pad;
+          // case III
+          uint32_t left3 = 0;
+          for (uint64_t i = b; i-- > b0;) {
+            if (!holds(i, tr)) { left3 = fi.blk_ub[i]; break; }
+          }
+          out[2] = left3;
+          // cases II / IV: over all blocks of the unitig
+          uint32_t left = 0, right = 0, unmapped = 0;
+          bool found = false;
+          for (uint64_t i = b0; i < b1; ++i) {
+            const bool hs = holds(i, tr);
+            if (!hs && found) {
+              if (unmapped == 0) left = fi.blk_lb[i];
+              right = fi.blk_ub[i];
+              unmapped += fi.blk_ub[i] - fi.blk_lb[i];
+            }
+            if (hs) found = true;
+          }
+          out[3] = right - left;
+        }
+      }
+    }
+  }
 
   // 4-6. targets (KmerIndex.cpp:1470-1519)
   int32_t num_trans = c.get<int32_t>();

@@ -45,6 +45,14 @@ struct FlatIndex {
   std::vector<uint64_t> pos_off;        // strand.size() + 1
   std::vector<uint32_t> pos_val;
 
+  // Per (block, member), when load_positions: the read-independent part of KmerIndex::findPosition
+  // (src/KmerIndex.cpp:2188-2292), 4 words each, same slots as `strand`:
+  //   [0] smallest stored position of the transcript in this block (pos | antisense << 31)
+  //   [1] case I   padding   (lb of the first block of the run of blocks holding tr that ends here, if pos == 0)
+  //   [2] case III left_one  (ub of the nearest earlier block that does not hold tr, else 0)
+  //   [3] case II/IV right_one - left_one over the blocks not holding tr after the first that does
+  std::vector<uint32_t> fp_info;
+
   // Transcript sets de-duplicated by content (SparseVector::operator== compares only the
   // Roaring of transcript ids, src/SparseVector.tcc:391-394).
   std::vector<uint64_t> ec_off;         // n_ec + 1

@@ -47,6 +47,11 @@ struct DevIndex {
   const uint32_t* blk_ec;    // per block: set handle of its EC (strand filter)
   const uint64_t* blk_strand_off;  // per block offset into strand bytes (stranded modes)
   const uint8_t* strand;
+  // single-end fragment-position filter (findPosition): per (block, member) constants, unitig length per
+  // block, target lengths; null unless the index was loaded with positions
+  const uint4* fp_info;
+  const uint32_t* blk_usize;
+  const uint32_t* target_len;
 };
 
 struct __align__(16) Memo2Entry {

@@ -55,9 +55,10 @@ struct BatchArgs {
   uint32_t empty_ec;        // handle of the empty index EC set, or 0xFFFFFFFF
   int refill_min;           // finished lanes of a warp that trigger a finalise + refill round
   const uint8_t* skip;      // optional per fragment: 1 = treat as having no sequence (bus: bad barcode/UMI)
+  int fp_fl;                // >= 0: apply the fragment-position filter of ProcessReads.cpp:1095-1136 with this mean fragment length
   uint32_t start;           // first base of every read that is matched (bus: BUSOptionSubstr.start of the sequence)
 };
-static constexpr int KB_Q_STRIDE = 2 + KB_MAX_E + 2;
+static constexpr int KB_Q_STRIDE = 2 + KB_MAX_E + 6;   // frag, n|flags, handles, 2 strand words, 4 position-filter words
 
 struct ResolveArgs {
   uint32_t* scratch;        // per warp: scratch_stride entries

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
   uint64_t* s_bw = smem + tid;                               // [mate][nbw]
   uint64_t* s_iv = smem + (size_t)2 * nbw * nt + tid;        // [mate][niw]
   uint32_t* elist = reinterpret_cast<uint32_t*>(smem + (size_t)2 * (nbw + niw) * nt) + tid;
-  uint32_t* msave = elist + (size_t)(KB_MAX_E + 2) * nt;
+  uint32_t* msave = elist + (size_t)(KB_MAX_E + 6) * nt;
   for (int mt = 0; mt < 2; ++mt) {   // words the packed reads never overwrite
     s_bw[(mt * nbw + nb) * nt] = 0;
     for (int w = (nb + 1) / 2; w < niw; ++w) s_iv[(mt * niw + w) * nt] = ~0ULL;
@@ -310,14 +310,17 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
             while (j >= 0 && elist[j * nt] > x) { elist[(j + 1) * nt] = elist[j * nt]; --j; }
             elist[(j + 1) * nt] = x;
           }
+          // single-end reads / pairs with one mate mapped, known mean fragment length: the transcripts
+          // whose ends the fragment would overhang are filtered per fragment (ProcessReads.cpp:1095-1136)
+          const bool want_fp = ba.fp_fl >= 0 && (!ba.paired || !v0 || !v1);
           if (overflow) {
             atomicOr(dd.error, KB_DEVERR_E_OVERFLOW);
-          } else if (ba.strand_mode == 0 && n_e == 1) {
+          } else if (ba.strand_mode == 0 && n_e == 1 && !want_fp) {
             handle = (int32_t)elist[0];            // a single EC set: its handle is stored in the slot
           } else {
             int n = n_e;
             int32_t r;
-            if (ba.strand_mode == 0 && n_e == 2) {
+            if (ba.strand_mode == 0 && n_e == 2 && !want_fp) {
               r = memo2_lookup(dd, elist[0], elist[nt]);
             } else {
               if (ba.strand_mode != 0) {
@@ -333,14 +336,25 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
                 elist[(n + 1) * nt] = w1;
                 n += 2;
               }
-              r = memon_lookup(dd, elist, n, nt);
+              if (want_fp) {
+                // first hit of the mapped mate: block, orientation, read position, offset in the unitig
+                const bool use_first = (mate == 1) && !v_cur;     // second mate empty: the first mate's hit
+                elist[n * nt] = use_first ? msave[nt] : f_blk;
+                elist[(n + 1) * nt] = use_first ? (msave[3 * nt] >> 31) : (f_strand ? 1u : 0u);
+                elist[(n + 2) * nt] = use_first ? msave[5 * nt] : (uint32_t)f_pos;
+                elist[(n + 3) * nt] = use_first ? (msave[3 * nt] & 0x7FFFFFFFu) : f_dist;
+                n += 4;
+                r = KB_H_NOTREADY;                      // depends on the read itself: never memoised
+              } else {
+                r = memon_lookup(dd, elist, n, nt);
+              }
             }
             if (r == KB_H_NOTREADY) {
               handle = KB_H_PENDING;
               const uint32_t q = atomicAdd(ba.q_count, 1u);
               uint32_t* e = ba.q_entries + (size_t)q * KB_Q_STRIDE;
               e[0] = frag;
-              e[1] = (uint32_t)n;
+              e[1] = (uint32_t)n | (want_fp ? 0x80000000u : 0u);
               for (int i = 0; i < n; ++i) e[2 + i] = elist[i * nt];
             } else {
               handle = r;
@@ -647,15 +661,16 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
   for (uint32_t q = warp; q < nq; q += ra.n_warps) {
     const uint32_t* e = ba.q_entries + (size_t)q * KB_Q_STRIDE;
     const uint32_t f = e[0];
-    const int n = (int)e[1];
+    const bool has_fp = (e[1] >> 31) != 0;
+    const int n = (int)(e[1] & 0xFFFFu);
     const uint32_t* w = e + 2;
     const bool stranded = ba.strand_mode != 0;
-    const int n_e = stranded ? n - 2 : n;
-    const bool use_m2 = (!stranded && n_e == 2);
+    const int n_e = n - (stranded ? 2 : 0) - (has_fp ? 4 : 0);
+    const bool use_m2 = (!stranded && !has_fp && n_e == 2);
 
     // 1. has somebody else resolved the same tuple in the meantime?
     int32_t handle = KB_H_NOTREADY;
-    if (lane == 0) handle = use_m2 ? memo2_lookup(dd, w[0], w[1]) : memon_lookup(dd, w, n, 1);
+    if (lane == 0 && !has_fp) handle = use_m2 ? memo2_lookup(dd, w[0], w[1]) : memon_lookup(dd, w, n, 1);
     handle = __shfl_sync(0xFFFFFFFFu, handle, 0);
 
     if (handle == KB_H_NOTREADY) {
@@ -685,6 +700,53 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
         nres += __popc(bal);
       }
       __syncwarp();
+      // 2b. fragment-position filter (ProcessReads.cpp:1095-1136 with KmerIndex::findPosition,
+      //     KmerIndex.cpp:2188-2292): keep the transcripts the fragment fits into
+      if (has_fp && nres > 0) {
+        const uint32_t* fw = w + n - 4;
+        const uint32_t blk = fw[0];
+        const bool csense = fw[1] != 0;
+        const long long pp = (long long)fw[2], udist = (long long)fw[3];
+        const long long usize = (long long)ix.blk_usize[blk], kk = (long long)ix.k, fl = (long long)ba.fp_fl;
+        const unsigned long long bword = dd.dslots[ix.blk_ec[blk]];
+        const uint32_t* B = pool + (uint32_t)bword;
+        const uint32_t blen = (uint32_t)((bword >> 32) & 0xFFFFFFu);
+        const uint4* info = ix.fp_info + ix.blk_strand_off[blk];
+        uint32_t n_v = 0;
+        for (uint32_t base = 0; base < nres; base += 32) {
+          const uint32_t i = base + lane;
+          bool keep = false;
+          const uint32_t tr = i < nres ? scratch[i] : 0;
+          if (i < nres) {
+            uint32_t rank = 0;
+            if (bsearch_contains(B, blen, tr, &rank)) {
+              const uint4 c = info[rank];
+              const long long trpos = (long long)(c.x & 0x7FFFFFFFu);
+              const bool trsense = (c.x >> 31) == 0;
+              long long x;
+              bool s;
+              if (trsense) {
+                if (csense) { x = trpos - pp + udist + 1 - (long long)c.y; s = true; }           // case I
+                else { x = trpos + pp + kk + udist - (long long)c.z; s = false; }                // case III
+              } else {
+                if (csense) { x = trpos - udist + usize - (long long)c.w + pp; s = false; }      // case IV
+                else { x = trpos + usize - udist - (long long)c.w - kk + 1 - pp; s = true; }     // case II
+              }
+              const int xi = (int)x;
+              keep = (s && xi + (int)fl <= (int)ix.target_len[tr]) || (!s && xi - (int)fl >= 0);
+            }
+          }
+          const unsigned bv = __ballot_sync(0xFFFFFFFFu, keep);
+          if (keep) scratch[ra.scratch_stride / 2 + n_v + __popc(bv & ((1u << lane) - 1))] = tr;
+          n_v += __popc(bv);
+        }
+        __syncwarp();
+        if (n_v < nres) {
+          for (uint32_t i = lane; i < n_v; i += 32) scratch[i] = scratch[ra.scratch_stride / 2 + i];
+          nres = n_v;
+        }
+        __syncwarp();
+      }
       // 3. doStrandSpecificity (ProcessReads.cpp:61-124), first mate then second mate
       if (stranded) {
         for (int mate = 0; mate < 2 && nres > 0; ++mate) {
@@ -735,8 +797,8 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
       }
       // 4. set -> handle through the content-addressed dictionary
       handle = nres == 0 ? KB_H_UNMAPPED : dict_insert_warp(dd, scratch, nres, lane);
-      // 5. publish tuple -> handle
-      if (lane == 0) {
+      // 5. publish tuple -> handle (not for position-filtered fragments: the result depends on the read)
+      if (lane == 0 && !has_fp) {
         if (use_m2) {
           const unsigned long long key = ((unsigned long long)w[0] << 32) | w[1];
           uint64_t s = kb_mix64(key) & dd.m2_mask;
@@ -813,7 +875,7 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
   if (ba.n_frag == 0) return;
   cudaMemsetAsync(ba.q_count, 0, sizeof(uint32_t), st);
   // persistent grid: as many blocks as fit on the device at once
-  const size_t smem = (size_t)tpb * ((size_t)2 * (ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 8) * 4);
+  const size_t smem = (size_t)tpb * ((size_t)2 * (ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 12) * 4);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;

@@ -11,6 +11,8 @@
 // bit-identical to the CPU result, iteration count included.  A batch dimension runs the B
 // bootstrap EMs of Bootstrap::run_em (src/Bootstrap.cpp:4-13) concurrently over the same structure.
 #include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
 
 #include "kb_device.cuh"
 #include "kernels.hpp"
@@ -26,7 +28,8 @@ constexpr double kAlphaChange = 1e-2;         // :103
 constexpr double kTolerance = 4.9406564584124654e-324;   // std::numeric_limits<double>::denorm_min()
 }
 
-__global__ void __launch_bounds__(256) em_kernel(EmProblem p) {
+template <int TPB>
+__global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4))) em_kernel(EmProblem p) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ int s_state[];    // per problem: 0 running, 1 final round, >= 2 finished
   const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,19 +132,24 @@ int em_max_blocks(int tpb) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel, tpb, 4096);
+  if (tpb >= 1024) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel<1024>, 1024, 4096);
+  else if (tpb >= 512) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel<512>, 512, 4096);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel<256>, 256, 4096);
   return sms * per_sm;
 }
 
-void launch_em(const EmProblem& p, int tpb, cudaStream_t st) {
+void launch_em(const EmProblem& p, int tpb_req, cudaStream_t st) {
+  const int tpb = tpb_req >= 1024 ? 1024 : (tpb_req >= 512 ? 512 : 256);
   const int maxb = em_max_blocks(tpb);
   const uint64_t work = (uint64_t)p.nb * (p.n_multi > p.n_targets ? p.n_multi : p.n_targets);
   int blocks = (int)((work + tpb - 1) / tpb);
   if (blocks > maxb) blocks = maxb;
+  if (const char* s = getenv("KB_EM_BLOCKS")) { const int v = atoi(s); if (v > 0) blocks = std::min(maxb, v); }   // tuning knob
   if (blocks < 1) blocks = 1;
   EmProblem pp = p;
   void* args[] = {&pp};
-  cudaLaunchCooperativeKernel((void*)em_kernel, dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);
+  void* fn = tpb == 1024 ? (void*)em_kernel<1024> : (tpb == 512 ? (void*)em_kernel<512> : (void*)em_kernel<256>);
+  cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);
 }
 
 // ---------------------------------------------------------------------------------------------

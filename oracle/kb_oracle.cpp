@@ -538,6 +538,71 @@ void doStrandSpecificity(const OIndex& ix, TidSet& u, int strand, const HitVec& 
   }
 }
 
+// KmerIndex::findPosition, src/KmerIndex.cpp:2188-2292, restated literally on the flat block list
+// (ecs = leading blocks, get_mc_contig = block bounds).  Returns {position, sense}.
+std::pair<int, bool> findPosition(const OIndex& ix, uint32_t tr, const Um& um, int p) {
+  const int k = ix.k;
+  const bool csense = um.strand;
+  const Unitig& un = ix.unitigs[um.unitig];
+  const std::vector<Block>& B = un.blocks;
+  const int64_t um_size = (int64_t)un.seq.size();
+  int cur = um.block;                                   // ecs.size()-1
+  const Block& v_ec = B[cur];
+  const size_t rank = std::lower_bound(v_ec.tids.begin(), v_ec.tids.end(), tr) - v_ec.tids.begin();
+  const uint32_t rawpos = v_ec.pos[rank].front();       // v_ec.get(tr, true).minimum()
+  const int trpos = (int)(rawpos & 0x7FFFFFFF);
+  const bool trsense = (rawpos == (uint32_t)trpos);
+  auto contains = [&](int i) { return std::binary_search(B[i].tids.begin(), B[i].tids.end(), tr); };
+  std::pair<int, bool> ret;
+  if (trsense) {
+    if (csense) {
+      size_t padding = 0;
+      if (trpos == 0) {
+        int mc = cur;                                   // block whose bounds `mc` holds
+        for (int i = cur - 1; i >= 0; i--) {
+          if (!contains(i)) { padding = B[mc].lb; break; }
+          mc = mc - 1;                                  // get_mc_contig(mc.first-1): the previous block
+        }
+      }
+      ret = {(int)(static_cast<int64_t>(trpos) - p + static_cast<int64_t>(um.dist) + 1 - (int64_t)padding), csense};   // Case I
+    } else {
+      const int64_t initial = B[cur].ub;
+      int right_one = 0, left_one = 0;
+      int mc = cur;
+      for (int i = cur; i >= 0; i--) {
+        if (i == cur) right_one = B[mc].ub;
+        if (!contains(i)) { left_one = B[mc].ub; break; }
+        else if (i == 0) left_one = 0;
+        mc = mc > 0 ? mc - 1 : (int)B.size() - 1;       // below 0: "returns the right-most block"
+      }
+      const int64_t padding = -(left_one + right_one - um_size + k - 1);
+      ret = {(int)(trpos + p + k - (um_size - k - um.dist) + initial - 1 + padding), csense};   // Case III
+    }
+  } else {
+    int left_one = 0, right_one = 0, unmapped_len = 0;
+    bool found_first_mapped = false;
+    for (size_t i = 0; i < B.size(); i++) {             // get_leading_vals(-1): every block
+      if (!contains((int)i) && found_first_mapped) {
+        if (unmapped_len == 0) left_one = B[i].lb;
+        right_one = B[i].ub;
+        unmapped_len += (B[i].ub - B[i].lb);
+      }
+      if (contains((int)i)) found_first_mapped = true;
+    }
+    if (csense) {
+      int64_t start = 0;
+      start -= right_one - left_one;
+      start += um_size - k;
+      ret = {(int)(trpos + (static_cast<int64_t>(-((int64_t)um.dist - start))) + k + p), !csense};   // Case IV
+    } else {
+      unmapped_len = right_one - left_one;
+      const int64_t padding = um_size - um.dist - (unmapped_len) - k + 1;
+      ret = {(int)(trpos + padding - p), !csense};      // case II
+    }
+  }
+  return ret;
+}
+
 // KmerIndex::mapPair, src/KmerIndex.cpp:1622-1693
 int mapPair(const OIndex& ix, const char* s1, const char* s2, uint64_t* n_find) {
   const int k = ix.k;
@@ -576,6 +641,7 @@ int mapPair(const OIndex& ix, const char* s1, const char* s2, uint64_t* n_find) 
 struct ORun {
   OIndex* ix;
   int paired, strand;   // strand: 0 none, 1 FR, 2 RF
+  int fp_fl = -1;       // >= 0: !single_overhang && has_mean_fl, with (int) mean fragment length
   std::map<TidSet, int32_t> ecmapinv;       // EC set -> id (ids = insertion order, as with the ankerl map)
   std::vector<TidSet> ecs;
   std::vector<uint32_t> counts;
@@ -620,6 +686,7 @@ void* oracle_run_create(void* ix, int paired, int strand) {
   return r;
 }
 void oracle_run_free(void* r) { delete (ORun*)r; }
+void oracle_run_set_fp(void* r, int fl) { ((ORun*)r)->fp_fl = fl; }
 
 // One batch, reads given like kb_pseudoalign_batch.  ec_out: EC id per fragment (ids final: -t 1
 // assigns them in first-occurrence order) or -1.  collect_fld mirrors opt.fld == 0.
@@ -651,6 +718,22 @@ void oracle_pseudoalign_batch(void* run, const char* bases, const uint32_t* off,
     if (paired) match(ix, s2.c_str(), (int)s2.size(), v2, !paired, &R.n_find);
     intersectKmers(ix, v1, v2, u);
     u = intersect(u, ix.onlist);                                        // :1072
+    if (R.fp_fl >= 0 && !u.empty() && (!paired || v1.empty() || v2.empty())) {   // :1095-1136
+      TidSet vtmp;
+      const int fl = R.fp_fl;
+      int p = -1;
+      Um um;
+      if (!v1.empty()) { auto res = findFirstMappingKmer(v1); um = res.first; p = res.second; }
+      if (!v2.empty()) { auto res = findFirstMappingKmer(v2); um = res.first; p = res.second; }
+      for (uint32_t tr : u) {
+        auto x = findPosition(ix, tr, um, p);
+        bool add = false;
+        if (x.second && x.first + fl <= (int)ix.target_len[tr]) add = true;
+        if (!x.second && x.first - fl >= 0) add = true;
+        if (add) vtmp.push_back(tr);
+      }
+      if (vtmp.size() < u.size()) u = vtmp;
+    }
     if (R.strand != 0 && !u.empty()) doStrandSpecificity(ix, u, R.strand, v1, v2);   // :1138-1145
     int32_t ec = -1;
     if (!u.empty()) {

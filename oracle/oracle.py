@@ -49,6 +49,7 @@ def lib():
         L.oracle_run_create.restype = C.c_void_p
         L.oracle_run_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_run_free.argtypes = [C.c_void_p]
+        L.oracle_run_set_fp.argtypes = [C.c_void_p, C.c_int]
         L.oracle_pseudoalign_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                                C.c_void_p]
         L.oracle_n_ecs.argtypes = [C.c_void_p]
@@ -99,11 +100,14 @@ class OracleIndex:
 class OracleRun:
     """ReadProcessor::processBuffer + MasterProcessor::update, -t 1 semantics."""
 
-    def __init__(self, index, paired=True, strand=0, collect_fld=True):
+    def __init__(self, index, paired=True, strand=0, collect_fld=True, fp_fl=-1):
+        """fp_fl >= 0: the fragment-position filter of ProcessReads.cpp:1095-1136 ((int) of the -l value)."""
         self.index = index
         self.paired = paired
         self.collect_fld = collect_fld
         self.h = lib().oracle_run_create(index.h, int(paired), int(strand))
+        if fp_fl >= 0:
+            lib().oracle_run_set_fp(self.h, int(fp_fl))
 
     def __del__(self):
         if getattr(self, "h", None):

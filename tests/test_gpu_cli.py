@@ -94,3 +94,33 @@ def test_bus_nothing_aligned_exits_1(tmp_path):
     ref = os.path.join(d, "ref_10xv3_unstranded")
     assert open(out / "output.bus", "rb").read() == open(os.path.join(ref, "output.bus"), "rb").read()
     same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
+
+
+def _functest_cases():
+    d = os.path.join(util.GOLDEN, "functests")
+    return d, json.load(open(os.path.join(d, "cases.json")))
+
+
+@pytest.mark.parametrize("case", _functest_cases()[1], ids=lambda c: c["name"])
+def test_reference_functests_md5(case, tmp_path):
+    """The quant cases of the reference's own func_tests/runtests.sh:265-304, run through the
+    kallisto_b200 command line: abundance.tsv must have the md5 that script pins."""
+    import hashlib
+    d, _ = _functest_cases()
+    out = tmp_path / "o"
+    r = run(["quant", "-o", str(out), "-i", os.path.join(d, case["index"])] + case["args"] +
+            [os.path.join(d, f) for f in case["files"]])
+    assert r.returncode == 0, r.stderr
+    assert hashlib.md5(open(out / "abundance.tsv", "rb").read()).hexdigest() == case["md5"]
+    same_run_info(out / "run_info.json", os.path.join(d, case["name"], "run_info.json"))
+
+
+def test_quant_single_with_position_filter(tmp_path):
+    ds = util.dataset("synth_small")
+    out = tmp_path / "o"
+    r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "--single", "-l", "200", "-s", "20",
+             os.path.join(ds["dir"], "reads_1.fastq.gz")])
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(ds["dir"], "ref_quant_single")
+    assert open(out / "abundance.tsv").read() == open(os.path.join(ref, "abundance.tsv")).read()
+    same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))

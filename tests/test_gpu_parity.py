@@ -141,3 +141,33 @@ def test_fixed_length_path_equals_offsets_path(indices):
     h2 = mc2.process_buffer(bases, None, fixed_len=100)
     np.testing.assert_array_equal(h1, h2)
     mc1.close(); mc2.close()
+
+
+@pytest.mark.parametrize("mode", ["single", "single_fr", "paired_with_l"])
+def test_fragment_position_filter_per_fragment(mode):
+    """findPosition filter (ProcessReads.cpp:1095-1136): per-fragment ECs against the oracle's literal
+    restatement (itself pinned on the reference's single-end abundance.tsv and functests md5s)."""
+    ds = util.dataset("synth_small")
+    ix = K.KmerIndex(ds["index"], device=0, load_positions=True)
+    paired = mode == "paired_with_l"
+    strand = 1 if mode == "single_fr" else 0
+    mc = K.MinCollector(ix, paired=paired, strand=strand, collect_fld=False, single_overhang=False, fld_mean=200.0)
+    bases, off = util.batch(ds, paired)
+    h = mc.process_buffer(bases, off)
+    eo, et, ec, eh = mc.ec_table()
+    o_ix = O.OracleIndex(ds["index"])
+    o_run = O.OracleRun(o_ix, paired, strand, False, fp_fl=200)
+    ofrag = o_run.pseudoalign(bases, off)
+    oo, ot, oc = o_run.ec_table()
+    np.testing.assert_array_equal(util.handles_to_ids(h, eh), ofrag)
+    assert util.ec_sets(eo, et) == util.ec_sets(oo, ot)
+    np.testing.assert_array_equal(ec, oc)
+    mc.close(); ix.close()
+
+
+def test_position_filter_needs_positions():
+    ds = util.dataset("synth_small")
+    ix = K.KmerIndex(ds["index"], device=0, load_positions=False)
+    with pytest.raises(K.KallistoB200Error):
+        K.MinCollector(ix, paired=False, single_overhang=False, fld_mean=200.0)
+    ix.close()

@@ -83,3 +83,58 @@ def test_single_overhang_quant_matches_reference():
     txt = O.abundance_tsv(ix.target_names, ix.target_lens, eff, alpha, O.tpm(alpha, eff))
     ref = open(os.path.join(ds["dir"], "ref_quant_single_overhang", "abundance.tsv")).read()
     assert txt == ref
+
+
+def test_single_end_with_position_filter_matches_reference():
+    """--single -l 200 -s 20 (no --single-overhang): KmerIndex::findPosition filter."""
+    import json
+    ds = util.dataset("synth_small")
+    ix = O.OracleIndex(ds["index"])
+    run = O.OracleRun(ix, False, 0, False, fp_fl=200)
+    bases, off = util.batch(ds, False)
+    frag = run.pseudoalign(bases, off)
+    eo, et, ec = run.ec_table()
+    info = json.load(open(os.path.join(ds["dir"], "ref_quant_single", "run_info.json")))
+    assert int(ec.sum()) == info["n_pseudoaligned"]
+    assert int(sum(c for c, a, b in zip(ec, eo[:-1], eo[1:]) if b - a == 1)) == info["n_unique"]
+    # the filter must actually do something on this data set
+    plain = O.OracleRun(ix, False, 0, False)
+    assert not np.array_equal(plain.pseudoalign(bases, off), frag) or plain.ec_table()[2].sum() != ec.sum()
+    fl = O.mean_fl_trunc(np.zeros(1000, np.uint32), 200.0, 20.0)
+    eff = O.eff_lens(ix.target_lens, fl)
+    alpha, _ = O.em(eo, et, ec, eff, ix.n_targets)
+    txt = O.abundance_tsv(ix.target_names, ix.target_lens, eff, alpha, O.tpm(alpha, eff))
+    assert txt == open(os.path.join(ds["dir"], "ref_quant_single", "abundance.tsv")).read()
+
+
+def _functest_cases():
+    import json
+    d = os.path.join(util.GOLDEN, "functests")
+    return d, json.load(open(os.path.join(d, "cases.json")))
+
+
+@pytest.mark.parametrize("case", _functest_cases()[1], ids=lambda c: c["name"])
+def test_functests_md5_goldens(case):
+    """The quant cases of the reference's own func_tests/runtests.sh:265-304 (toy k=5/7/11 indices,
+    N bases, lowercase, poly-A clipping, strandedness, the findPosition filter): the oracle must
+    reproduce the md5 the script pins for abundance.tsv."""
+    d, _ = _functest_cases()
+    ix = O.OracleIndex(os.path.join(d, case["index"]))
+    single = "--single" in case["args"]
+    strand = 1 if "--fr-stranded" in case["args"] else (2 if "--rf-stranded" in case["args"] else 0)
+    files = [os.path.join(d, f) for f in case["files"]]
+    if single:
+        run = O.OracleRun(ix, False, strand, False, fp_fl=5)
+        for f in files:
+            run.pseudoalign(*O.to_batch(O.read_fastq(f)))
+        fl = O.mean_fl_trunc(np.zeros(1000, np.uint32), 5.0, 2.0)
+    else:
+        run = O.OracleRun(ix, True, strand, True)
+        for i in range(0, len(files), 2):
+            run.pseudoalign(*O.to_batch(O.read_fastq(files[i]), O.read_fastq(files[i + 1])))
+        fl = O.mean_fl_trunc(run.flens())
+    eo, et, ec = run.ec_table()
+    eff = O.eff_lens(ix.target_lens, fl)
+    alpha, _ = O.em(eo, et, ec, eff, ix.n_targets)
+    txt = O.abundance_tsv(ix.target_names, ix.target_lens, eff, alpha, O.tpm(alpha, eff))
+    assert hashlib.md5(txt.encode()).hexdigest() == case["md5"]
