@@ -50,10 +50,21 @@ template <class T> void DBuf<T>::zero(cudaStream_t st) {
   if (n) KB_CK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
 }
 
+struct EmWs {   // grow-only device workspace of run_em_device
+  DBuf<uint32_t> used, scal, idx_in, order, handle, count, len, multi_len, is_multi, ec_off, m_off, multi_index;
+  DBuf<unsigned long long> key_in, key_out;
+  DBuf<uint8_t> tmp;
+  DBuf<uint32_t> ec_tid, multi_ec, m_rowoff, m_tid, m_row, m_iota, sortk, sortv, t_deg, t_off, t_midx;
+  DBuf<double> m_w, t_w, eff, alpha, norm;
+  DBuf<int32_t> t_single;
+  DBuf<int> emi;
+  DBuf<unsigned int> chcount;
+};
+
 // ------------------------------------------------------------------------------------------
 // Index
 // ------------------------------------------------------------------------------------------
-Index::~Index() {}
+Index::~Index() { delete shared_emws; }
 
 std::unique_ptr<Index> Index::load(const std::string& path, int device, bool load_positions, int threads) {
   int ndev = 0;
@@ -188,18 +199,17 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
 // ------------------------------------------------------------------------------------------
 // Quant
 // ------------------------------------------------------------------------------------------
-struct EmWs {   // grow-only device workspace of run_em_device
-  DBuf<uint32_t> used, scal, idx_in, order, handle, count, len, multi_len, is_multi, ec_off, m_off, multi_index;
-  DBuf<unsigned long long> key_in, key_out;
-  DBuf<uint8_t> tmp;
-  DBuf<uint32_t> ec_tid, multi_ec, m_rowoff, m_tid, m_row, m_iota, sortk, sortv, t_deg, t_off, t_midx;
-  DBuf<double> m_w, t_w, eff, alpha, norm;
-  DBuf<int32_t> t_single;
-  DBuf<int> emi;
-  DBuf<unsigned int> chcount;
-};
-
-Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(1000, 0), emws_(new EmWs()) {
+Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(1000, 0) {
+  if (!ix_.ws_in_use) {   // borrow the index's work buffers
+    ix_.ws_in_use = true;
+    if (!ix_.shared_emws) ix_.shared_emws = new EmWs();
+    bws_ = &ix_.shared_bws;
+    emws_ = ix_.shared_emws;
+  } else {
+    own_ws_ = true;
+    bws_ = new BatchWs();
+    emws_ = new EmWs();
+  }
   if (opt_.fp_fl >= 0 && !ix_.flat.has_positions)
     throw Error("kallisto_b200: the fragment-position filter needs an index loaded with positions (load_positions = 1)");
   if (const char* s = getenv("KB_REFILL_MIN")) opt_.refill_min = std::max(1, std::min(32, atoi(s)));   // tuning knob
@@ -252,21 +262,23 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
 
   // batch staging
   const uint32_t max_frag = opt_.max_batch_reads;
-  d_handles_.alloc(max_frag);
-  d_tl_.alloc(max_frag);
-  d_qcount_.alloc(1);
-  d_qentries_.alloc((size_t)max_frag * KB_Q_STRIDE);
+  if (bws_->d_handles.n < max_frag) bws_->d_handles.alloc(max_frag);
+  if (bws_->d_tl.n < max_frag) bws_->d_tl.alloc(max_frag);
+  if (bws_->d_qcount.n < 1) bws_->d_qcount.alloc(1);
+  if (bws_->d_qentries.n < (size_t)max_frag * KB_Q_STRIDE) bws_->d_qentries.alloc((size_t)max_frag * KB_Q_STRIDE);
   // resolve-kernel scratch: 2 x max_set_len words per warp, at most ~1 GiB in total
   const uint64_t stride = std::max<uint64_t>(64, 2ull * ix_.max_set_len);
   uint64_t warps = (1ull << 28) / stride;
   warps = std::min<uint64_t>(148 * 32, std::max<uint64_t>(64, warps));   // the kernel is latency-bound: fill the SMs
   n_resolve_warps_ = (uint32_t)(warps / 4 * 4);
-  d_scratch_.alloc((size_t)n_resolve_warps_ * stride);
+  if (bws_->d_scratch.n < (size_t)n_resolve_warps_ * stride) bws_->d_scratch.alloc((size_t)n_resolve_warps_ * stride);
+  scratch_stride_ = (uint32_t)stride;
   KB_CK(cudaStreamSynchronize(st));
 }
 
 Quant::~Quant() {
-  delete emws_;
+  if (stream_) cudaStreamSynchronize(stream_);
+  if (own_ws_) { delete emws_; delete bws_; } else { ix_.ws_in_use = false; }
   if (h_off_pinned_) cudaFreeHost(h_off_pinned_);
   for (auto ev : events_) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) {
@@ -320,7 +332,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
                       uint32_t max_read_len, const uint8_t* d_bases2, const uint32_t* d_off2) {
   const uint32_t n_frag = opt_.paired ? n_reads / 2 : n_reads;
   if (opt_.paired && (n_reads & 1)) throw Error("kallisto_b200: odd number of reads in a paired batch");
-  if (n_frag > d_handles_.n) throw Error("kallisto_b200: batch larger than max_batch_reads");
+  if (n_frag > bws_->d_handles.n) throw Error("kallisto_b200: batch larger than max_batch_reads");
   if (n_frag == 0) return;
   ecs_valid_ = false;
   dev_stats_valid_ = false;
@@ -334,28 +346,28 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.paired = opt_.paired;
   ba.strand_mode = opt_.strand_mode;
   ba.frag_base = n_frag_total_;
-  ba.handle_out = d_handles_.p;
+  ba.handle_out = bws_->d_handles.p;
   const bool want_fld = opt_.paired && opt_.collect_fld && tlencount_ < 10000;   // ProcessReads.cpp:981-1017
-  ba.tl_out = want_fld ? d_tl_.p : nullptr;
-  ba.q_count = d_qcount_.p;
-  ba.q_entries = d_qentries_.p;
+  ba.tl_out = want_fld ? bws_->d_tl.p : nullptr;
+  ba.q_count = bws_->d_qcount.p;
+  ba.q_entries = bws_->d_qentries.p;
   ba.nb = std::max<uint32_t>(1, (max_read_len + 31) / 32);
   ba.bwords = ba.nb + 1;
   ba.iwords = ba.bwords / 2 + 1;
   ba.pstride = (3 * ba.nb + 7) & ~7u;
   {
     const size_t need = (size_t)n_reads * ba.pstride;
-    if (d_packed_.n < need) d_packed_.alloc(std::max(need, (size_t)opt_.max_batch_reads * 2 * 16));
+    if (bws_->d_packed.n < need) bws_->d_packed.alloc(std::max(need, (size_t)opt_.max_batch_reads * 2 * 16));
   }
-  ba.packed = d_packed_.p;
+  ba.packed = bws_->d_packed.p;
   ba.empty_ec = ix_.empty_ec;
   ba.refill_min = opt_.refill_min;
   ba.skip = cur_skip_;
   ba.fp_fl = opt_.fp_fl;
   ba.start = cur_start_;
   ResolveArgs ra{};
-  ra.scratch = d_scratch_.p;
-  ra.scratch_stride = (uint32_t)(d_scratch_.n / n_resolve_warps_);
+  ra.scratch = bws_->d_scratch.p;
+  ra.scratch_stride = scratch_stride_;
   ra.n_warps = n_resolve_warps_;
 
   int tpb = opt_.threads_per_block;
@@ -374,7 +386,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   if (want_fld) {
     launch_fld_finalize(dd_, ba, stream_);
     h_tl_.resize(n_frag);
-    d_tl_.download(h_tl_.data(), n_frag, 0, stream_);
+    bws_->d_tl.download(h_tl_.data(), n_frag, 0, stream_);
     KB_CK(cudaStreamSynchronize(stream_));
     // first (10000 - tlencount) qualifying fragments of this batch, in read order
     int goal = 10000 - (int)tlencount_;
@@ -411,8 +423,8 @@ void Quant::pseudoalign_host(const char* bases, const uint32_t* off, uint32_t n_
   // stage into buffer `s`; the copy runs on its own stream so that it overlaps the previous batch's kernels
   const int s = stage_idx_;
   stage_idx_ ^= 1;
-  DBuf<uint8_t>& db = stage_b_[s][0];
-  DBuf<uint32_t>& dofs = stage_o_[s][0];
+  DBuf<uint8_t>& db = bws_->stage_b[s][0];
+  DBuf<uint32_t>& dofs = bws_->stage_o[s][0];
   KB_CK(cudaStreamWaitEvent(copy_stream_, ev_done_[s], 0));      // kernels that last read this buffer
   if (db.n < n_bases + 16) { KB_CK(cudaStreamSynchronize(stream_)); db.alloc(std::max<uint64_t>(n_bases + 16, opt_.max_batch_bases)); }
   KB_CK(cudaMemcpyAsync(db.p, bases, n_bases, cudaMemcpyHostToDevice, copy_stream_));
@@ -426,7 +438,7 @@ void Quant::pseudoalign_host(const char* bases, const uint32_t* off, uint32_t n_
   KB_CK(cudaEventRecord(ev_done_[s], stream_));
   if (handles_out) {
     const uint32_t n_frag = opt_.paired ? n_reads / 2 : n_reads;
-    d_handles_.download(handles_out, n_frag, 0, stream_);
+    bws_->d_handles.download(handles_out, n_frag, 0, stream_);
     KB_CK(cudaStreamSynchronize(stream_));
   } else {
     // the caller may reuse its buffers once the copy is done; the kernels keep running
@@ -452,10 +464,10 @@ void Quant::pseudoalign_host_pe(const char* bases1, const uint32_t* off1, const 
   }
   const int s = stage_idx_;
   stage_idx_ ^= 1;
-  DBuf<uint8_t>& b1 = stage_b_[s][0];
-  DBuf<uint8_t>& b2 = stage_b_[s][1];
-  DBuf<uint32_t>& o1 = stage_o_[s][0];
-  DBuf<uint32_t>& o2 = stage_o_[s][1];
+  DBuf<uint8_t>& b1 = bws_->stage_b[s][0];
+  DBuf<uint8_t>& b2 = bws_->stage_b[s][1];
+  DBuf<uint32_t>& o1 = bws_->stage_o[s][0];
+  DBuf<uint32_t>& o2 = bws_->stage_o[s][1];
   KB_CK(cudaStreamWaitEvent(copy_stream_, ev_done_[s], 0));
   if (b1.n < nb1 + 16) { KB_CK(cudaStreamSynchronize(stream_)); b1.alloc(std::max<uint64_t>(nb1 + 16, opt_.max_batch_bases / 2 + 16)); }
   if (b2.n < nb2 + 16) { KB_CK(cudaStreamSynchronize(stream_)); b2.alloc(std::max<uint64_t>(nb2 + 16, opt_.max_batch_bases / 2 + 16)); }
@@ -473,7 +485,7 @@ void Quant::pseudoalign_host_pe(const char* bases1, const uint32_t* off1, const 
   run_batch(b1.p, off1 ? o1.p : nullptr, 2 * n_pairs, fixed_len, maxlen, b2.p, off1 ? o2.p : nullptr);
   KB_CK(cudaEventRecord(ev_done_[s], stream_));
   if (handles_out) {
-    d_handles_.download(handles_out, n_pairs, 0, stream_);
+    bws_->d_handles.download(handles_out, n_pairs, 0, stream_);
     KB_CK(cudaStreamSynchronize(stream_));
   } else {
     KB_CK(cudaEventSynchronize(ev_copied_[s]));
@@ -527,7 +539,7 @@ void Quant::bus_batch_host(const char* const* bases, const uint32_t* const* offs
   run_batch(bus_b_[sp.seq_file].p, bus_o_[sp.seq_file].p, n_sets, 0, maxlen);
   cur_skip_ = nullptr;
   cur_start_ = 0;
-  launch_bus_records(dd_, d_handles_.p, n_sets, base, bus_next_id_, bus_idof_.p, bus_isnew_.p, bus_newrank_.p,
+  launch_bus_records(dd_, bws_->d_handles.p, n_sets, base, bus_next_id_, bus_idof_.p, bus_isnew_.p, bus_newrank_.p,
                      bus_ismapped_.p, bus_rank_.p, (const uint64_t*)bus_bc_.p, (const uint64_t*)bus_umi_.p, bus_flags_.p,
                      bus_rec_.p, bus_tmp_.p, bus_tmp_.n, st);
   KB_CK(cudaGetLastError());

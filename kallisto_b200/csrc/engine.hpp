@@ -39,6 +39,18 @@ struct DBuf {
   void zero(cudaStream_t st = 0);
 };
 
+// Grow-only device work buffers.  They belong to the Index and are lent to one run at a time, so that
+// consecutive runs on the same index (the normal case) do not pay cudaMalloc again; a second run
+// created while the first is still alive gets private ones.
+struct EmWs;
+struct BatchWs {
+  DBuf<uint8_t> stage_b[2][2];      // double-buffered input staging: H2D of batch i+1 overlaps the kernels of batch i
+  DBuf<uint32_t> stage_o[2][2];
+  DBuf<uint32_t> d_qcount, d_qentries, d_scratch, d_packed;
+  DBuf<int32_t> d_handles;
+  DBuf<uint16_t> d_tl;
+};
+
 class Index {
  public:
   static std::unique_ptr<Index> load(const std::string& path, int device, bool load_positions, int threads);
@@ -63,6 +75,9 @@ class Index {
   DBuf<uint32_t> blk_ec;
   DBuf<uint64_t> blk_strand_off;
   DBuf<uint8_t> strand;
+  BatchWs shared_bws;
+  EmWs* shared_emws = nullptr;
+  bool ws_in_use = false;
   DBuf<uint4> fp_info;            // only when loaded with positions
   DBuf<uint32_t> blk_usize, target_len;
 };
@@ -101,8 +116,6 @@ struct Stats {
   uint64_t n_probes = 0, n_slot_visits = 0, n_resolved = 0, n_memo_hits = 0;
 };
 
-struct EmWs;
-
 class Quant {
  public:
   Quant(Index& ix, const QuantOptions& opt);
@@ -126,7 +139,7 @@ class Quant {
   // (device_handles(), valid until the next batch).
   void pseudoalign_device(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
                           uint32_t max_read_len);
-  const int32_t* device_handles() const { return d_handles_.p; }
+  const int32_t* device_handles() const { return bws_->d_handles.p; }
   void sync();
 
   // MasterProcessor tail flush + EC id assignment.
@@ -190,17 +203,12 @@ class Quant {
   DBuf<int32_t> mn_val_;
   DBuf<int> error_;
   // batch staging
-  DBuf<uint8_t> d_bases_, d_bases2_;
-  // double-buffered input staging: the H2D copy of batch i+1 overlaps the kernels of batch i
-  DBuf<uint8_t> stage_b_[2][2];
-  DBuf<uint32_t> stage_o_[2][2];
+  BatchWs* bws_ = nullptr;
+  bool own_ws_ = false;
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_done_[2] = {nullptr, nullptr};
   int stage_idx_ = 0;
-  DBuf<uint32_t> d_off_, d_off2_, d_qcount_, d_qentries_, d_scratch_, d_packed_;
-  DBuf<int32_t> d_handles_;
-  DBuf<uint16_t> d_tl_;
-  uint32_t n_resolve_warps_ = 0;
+  uint32_t n_resolve_warps_ = 0, scratch_stride_ = 0;
   uint32_t* h_off_pinned_ = nullptr;
   // host-side run state
   uint64_t n_frag_total_ = 0;
