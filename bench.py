@@ -311,6 +311,14 @@ def main():
     t_total_ms, t_align_ms = float(tt[0]), float(tt[1])
     st = mc.finalize()
     tm = mc.timings()
+    if os.environ.get("KB_BENCH_ROWSTATS") and rank == 0:     # shape of the EM problem (diagnostics only)
+        eo, et, ec, _ = mc.ec_table()
+        ln = np.diff(eo.astype(np.int64))
+        deg = np.bincount(et[np.repeat(ln > 1, ln)], minlength=index.num_trans)
+        q = [50, 90, 99, 99.9, 100]
+        log("EM rows: multi ECs %d entries %d; EC size pct%s = %s; transcript degree pct = %s" % (
+            int((ln > 1).sum()), int(ln[ln > 1].sum()), q, np.percentile(ln[ln > 1], q).tolist(),
+            np.percentile(deg, q).tolist()))
     mc.close()
 
     # ---- e2e: pinned host buffers through the C ABI, H2D inside, est_counts back on the host ----

@@ -72,7 +72,9 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
     throw Error("kallisto_b200: no CUDA device available (this build has no CPU path)");
   if (device < 0 || device >= ndev) throw Error("kallisto_b200: invalid CUDA device ordinal");
   KB_CK(cudaSetDevice(device));
-  if (const char* s = getenv("KB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s));   // experiment knob
+  if (const char* s = getenv("KB_L2_FETCH")) {   // experiment knob
+    if (atoi(s) > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s)) != cudaSuccess) cudaGetLastError();
+  }
 
   std::unique_ptr<Index> ix(new Index());
   ix->device = device;

@@ -45,6 +45,29 @@ __device__ __forceinline__ void ld256_nc(const void* p, uint32_t (&w)[8]) {
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                : "l"(p));
 }
+// The k-mer table probe: one random 32-byte sector out of a multi-GB table, never reused.
+#ifndef KB_PROBE_LD
+#define KB_PROBE_LD 0
+#endif
+__device__ __forceinline__ void ld256_probe(const void* p, uint32_t (&w)[8]) {
+#if KB_PROBE_LD == 0
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif KB_PROBE_LD == 1
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif KB_PROBE_LD == 2
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif KB_PROBE_LD == 3
+  asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%8]; ld.global.nc.v4.b32 {%4,%5,%6,%7}, [%8+16];"
+#elif KB_PROBE_LD == 4
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif KB_PROBE_LD == 5
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif KB_PROBE_LD == 6
+  asm volatile("ld.global.cg.v4.b32 {%0,%1,%2,%3}, [%8]; ld.global.cg.v4.b32 {%4,%5,%6,%7}, [%8+16];"
+#endif
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
 // Same for memory other blocks may be writing during the kernel (memo tables): L2-coherent.
 __device__ __forceinline__ void ld256_cg(const void* p, uint32_t (&w)[8]) {
   asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -464,7 +487,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
         ++n_probes;
       }
       uint32_t v[8];
-      ld256_nc(ix.slots + slot, v);
+      ld256_probe(ix.slots + slot, v);
       ++n_visits;
       const uint64_t key = (uint64_t)v[0] | ((uint64_t)v[1] << 32);
       if (key != canon && key != KB_EMPTY_KEY) {
