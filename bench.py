@@ -142,6 +142,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def random_sector_peak(table_bytes):
+    """Hardware ceiling for the probe pattern of match_kernel: independent random 32-byte sector reads over a
+    table of this size (tools/randbench.cu, run live, a few seconds)."""
+    exe = os.path.join(ROOT, "tools", "randbench")
+    if not os.path.exists(exe):
+        return None
+    gib = max(1, int(round(table_bytes / 2.0 ** 30)))
+    gib = 1 << (gib.bit_length() - 1)          # the benchmark rounds down to a power of two anyway
+    try:
+        out = subprocess.run([exe, str(gib)], capture_output=True, text=True, timeout=120).stdout
+        rows = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+        best = max(rows, key=lambda r: r["gsectors_per_s"])
+        return {"gsectors_per_s": best["gsectors_per_s"], "gb_per_s": best["gb_per_s_32B"], "table_gib": best["table_gib"],
+                "source": "tools/randbench (live): independent random 32-byte sector reads, 1536 threads/SM x 4 in flight"}
+    except Exception as e:
+        log("randbench failed: %r" % e)
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -357,6 +376,13 @@ def main():
                 "slot_visits_per_pair": visits_per_pair, "ms_per_launch": match_ms_per_launch,
                 "resolve_ms_per_launch": tm["resolve_ms"] / max(1, tm["resolve_launches"]), "em_ms": tm["em_ms"],
                 "em_rounds": em["rounds"] if em else None}
+    if world == 1 and not os.environ.get("KB_BENCH_NO_RANDBENCH"):
+        rs = random_sector_peak(index.info["table_slots"] * 32)
+        if rs:
+            sectors_per_s = visits_per_pair * P / (match_ms_per_launch * 1e-3) / 1e9
+            roofline["random_sector_peak"] = rs
+            roofline["sectors_per_s_achieved"] = sectors_per_s
+            roofline["frac_random"] = sectors_per_s / rs["gsectors_per_s"]
     prof = os.path.join(ROOT, "profiles", "match_kernel_traffic.json")
     if os.path.exists(prof):
         try:

@@ -72,8 +72,14 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
     throw Error("kallisto_b200: no CUDA device available (this build has no CPU path)");
   if (device < 0 || device >= ndev) throw Error("kallisto_b200: invalid CUDA device ordinal");
   KB_CK(cudaSetDevice(device));
-  if (const char* s = getenv("KB_L2_FETCH")) {   // experiment knob
-    if (atoi(s) > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(s)) != cudaSuccess) cudaGetLastError();
+  {
+    // The k-mer table probes touch one random 32-byte sector each.  With the default L2 fetch granularity
+    // every miss pulls 64-128 bytes from HBM (ncu: 5.2 GB per 2 M pairs against 1.5 GB algorithmic); with
+    // 32 bytes the DRAM traffic equals the algorithmic bytes (1.85 GB) at the same probe rate -- the rate is
+    // bounded by the random-sector throughput of the L2-miss path (tools/randbench), not by bytes.
+    size_t gran = 32;
+    if (const char* s = getenv("KB_L2_FETCH")) gran = (size_t)atoi(s);    // 0: leave the device default
+    if (gran > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError();
   }
 
   std::unique_ptr<Index> ix(new Index());
@@ -373,7 +379,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ra.n_warps = n_resolve_warps_;
 
   int tpb = opt_.threads_per_block;
-  const size_t per_thread = (size_t)2 * (ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 8) * 4;
+  const size_t per_thread = (size_t)4 * (KB_MAX_E + 3 + 4 * ba.nb);   // match_kernel's shared memory per lane
   while (tpb > 32 && per_thread * tpb > 200 * 1024) tpb >>= 1;
   if (per_thread * tpb > 200 * 1024) throw Error("kallisto_b200: read too long for the short-read kernel");
   cudaEvent_t* ev = nullptr;

@@ -21,7 +21,7 @@
 #include "kernels.hpp"
 
 #ifndef KB_MATCH_MIN_BLOCKS
-#define KB_MATCH_MIN_BLOCKS 3
+#define KB_MATCH_MIN_BLOCKS 4
 #endif
 
 namespace kb {
@@ -76,31 +76,38 @@ __device__ __forceinline__ void ld256_cg(const void* p, uint32_t (&w)[8]) {
                : "memory");
 }
 
-// Per-lane view of the read being matched: 2-bit bases and an invalid-base mask in shared memory,
-// word w of lane t at [w * stride + t] (bank-conflict free).
+// Per-lane view of the read being matched: 2-bit bases in shared memory as 32-bit words (base i in
+// bits 30-2*(i&15) of word i>>4), word w of lane t at [w * stride + t] (bank-conflict free).
+// Bases other than A/C/G/T are rare, so the lane keeps only a flag in a register; a read that has
+// one consults the invalid-base masks of its packed form in global memory (bit i&31 of word i>>5;
+// positions past the end of the read are marked invalid there as well).
 struct ReadView {
-  const uint64_t* bw;   // base words: base i in bits 62-2*(i&31) of word i>>5
-  const uint64_t* iv;   // invalid mask: bit (i&63) of word i>>6
+  const uint32_t* bw;
+  const uint32_t* gmask;
+  int n_mask;
   int stride;
   int len;
   int k;
+  bool has_invalid;
 
   __device__ __forceinline__ uint64_t kmer(int p) const {
-    const int w = p >> 5, s = (p & 31) * 2;
-    const uint64_t hi = bw[w * stride];
-    uint64_t x = hi << s;
-    if (s) x |= bw[(w + 1) * stride] >> (64 - s);
+    const int w = p >> 4, s = (p & 15) * 2;
+    uint64_t x = (uint64_t)bw[w * stride] << 32;
+    if (s + 2 * k > 32) x |= bw[(w + 1) * stride];
+    x <<= s;
+    if (s + 2 * k > 64) x |= (uint64_t)(bw[(w + 2) * stride] >> (32 - s));   // s > 0 here: 2k <= 62
     return x >> (64 - 2 * k);
   }
   // first start position >= p whose k-window holds only A/C/G/T, or -1
   // (KmerIterator::operator++ / operator+=, ext/bifrost/src/KmerIterator.cpp:6-63)
   __device__ __forceinline__ int next_valid(int p) const {
+    if (!has_invalid) return p <= len - k ? p : -1;
     const uint64_t wmask = (1ULL << k) - 1;
     while (p <= len - k) {
-      const int w = p >> 6, s = p & 63;
-      uint64_t x = iv[w * stride] >> s;
-      if (s) x |= iv[(w + 1) * stride] << (64 - s);
-      x &= wmask;
+      const int w = p >> 5, s = p & 31;
+      const uint64_t lo = __ldg(gmask + w);
+      const uint64_t hi = (w + 1 < n_mask) ? __ldg(gmask + w + 1) : 0xFFFFFFFFu;
+      const uint64_t x = (((hi << 32) | lo) >> s) & wmask;      // s + k <= 63
       if (x == 0) return p;
       p += 64 - __clzll((long long)x);
     }
@@ -264,21 +271,19 @@ __global__ void __launch_bounds__(256) pack_kernel(BatchArgs ba, uint32_t n_read
 // set and are dropped.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevIndex ix, DevDict dd, BatchArgs ba) {
-  extern __shared__ uint64_t smem[];
+  extern __shared__ uint32_t smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const unsigned lane = tid & 31;
-  const int nb = (int)ba.nb, nbw = nb + 1, niw = nbw / 2 + 1;
+  const int nb = (int)ba.nb, nw = 2 * nb;
   const int k = ix.k;
-  // shared memory per lane: two reads (base words, invalid words), the tuple of EC-set handles,
-  // 6 words of first-mate information
-  uint64_t* s_bw = smem + tid;                               // [mate][nbw]
-  uint64_t* s_iv = smem + (size_t)2 * nbw * nt + tid;        // [mate][niw]
-  uint32_t* elist = reinterpret_cast<uint32_t*>(smem + (size_t)2 * (nbw + niw) * nt) + tid;
-  uint32_t* msave = elist + (size_t)(KB_MAX_E + 6) * nt;
-  for (int mt = 0; mt < 2; ++mt) {   // words the packed reads never overwrite
-    s_bw[(mt * nbw + nb) * nt] = 0;
-    for (int w = (nb + 1) / 2; w < niw; ++w) s_iv[(mt * niw + w) * nt] = ~0ULL;
-  }
+  // shared memory per lane (32-bit words, word w of lane t at [w * nt + t]): the tuple of EC-set
+  // handles, 3 words of first-mate information, the 2-bit bases of both mates.  When a fragment is
+  // finalised the handle tuple may grow by up to 6 words over the two regions that follow it; their
+  // contents are in registers by then.
+  uint32_t* elist = smem + tid;                                  // [KB_MAX_E]
+  uint32_t* msave = elist + (size_t)KB_MAX_E * nt;               // [3]: block, offset | strand << 31, read position
+  uint32_t* s_bw = msave + (size_t)3 * nt;                       // [mate][nw]
+  static_assert(KB_MAX_E + 6 <= KB_MAX_E + 3 + 4, "tuple extension must fit in the words that follow the handle list");
 
   // contiguous chunk of fragments owned by this warp
   const uint32_t n_warps = (gridDim.x * nt) >> 5;
@@ -299,8 +304,9 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
   bool overflow = false, need_prep = false;
   // first hit of the mate being matched (findFirstMappingKmer / mapPair) and hit flags of both mates
   bool v_cur = false, s_cur = false, v_first = false, s_first = false, f_strand = false;
-  uint32_t f_unitig = 0, f_blk = 0, f_ec = 0, f_dist = 0, f_ub = 0;
+  uint32_t f_blk = 0, f_dist = 0;
   int f_pos = 0;
+  unsigned inv_flags = 0;    // bit m: mate m holds a base other than A/C/G/T
   uint64_t canon = 0, slot = 0;
   bool is_canon = false;
   uint32_t n_probes = 0, n_visits = 0, n_memo = 0;
@@ -309,7 +315,16 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
   rv.k = k;
   rv.len = 0;
   rv.bw = s_bw;
-  rv.iv = s_iv;
+  rv.gmask = nullptr;
+  rv.n_mask = nb;
+  rv.has_invalid = false;
+  // point the view at mate `mt` of the lane's fragment
+  auto set_mate = [&](int mt, int len_mt) {
+    rv.bw = s_bw + (size_t)mt * nw * nt;
+    rv.len = len_mt;
+    rv.has_invalid = ((inv_flags >> mt) & 1u) != 0;
+    rv.gmask = ba.packed + (size_t)(ba.paired ? 2 * frag + mt : frag) * ba.pstride + nw;
+  };
 
   for (;;) {
     // ------------------------------------------------------------------ service round
@@ -322,6 +337,8 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
         // ---- MinCollector::intersectKmers, net effect (MinCollector.cpp:160-218) ----
         bool v0 = v_cur, s0 = s_cur, v1 = false, s1 = false;
         if (mate == 1) { v0 = v_first; s0 = s_first; v1 = v_cur; s1 = s_cur; }
+        // first hit of the first mate (written at the mate switch), before the tuple may grow over it
+        const uint32_t m_blk = msave[0], m_ds = msave[nt], m_pos = msave[2 * nt];
         bool mapped = v0 || v1;
         if ((v0 && !s0) || (v1 && !s1)) mapped = false;
         if (mapped && n_e == 0) mapped = false;
@@ -350,7 +367,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
                 // the strand filter depends on the first hit of each mate: (block, orientation)
                 uint32_t w0, w1 = 0xFFFFFFFFu;
                 if (mate == 1) {
-                  w0 = v_first ? (msave[nt] * 2u + (msave[3 * nt] >> 31)) : 0xFFFFFFFFu;
+                  w0 = v_first ? (m_blk * 2u + (m_ds >> 31)) : 0xFFFFFFFFu;
                   w1 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
                 } else {
                   w0 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
@@ -362,10 +379,10 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
               if (want_fp) {
                 // first hit of the mapped mate: block, orientation, read position, offset in the unitig
                 const bool use_first = (mate == 1) && !v_cur;     // second mate empty: the first mate's hit
-                elist[n * nt] = use_first ? msave[nt] : f_blk;
-                elist[(n + 1) * nt] = use_first ? (msave[3 * nt] >> 31) : (f_strand ? 1u : 0u);
-                elist[(n + 2) * nt] = use_first ? msave[5 * nt] : (uint32_t)f_pos;
-                elist[(n + 3) * nt] = use_first ? (msave[3 * nt] & 0x7FFFFFFFu) : f_dist;
+                elist[n * nt] = use_first ? m_blk : f_blk;
+                elist[(n + 1) * nt] = use_first ? (m_ds >> 31) : (f_strand ? 1u : 0u);
+                elist[(n + 2) * nt] = use_first ? m_pos : (uint32_t)f_pos;
+                elist[(n + 3) * nt] = use_first ? (m_ds & 0x7FFFFFFFu) : f_dist;
                 n += 4;
                 r = KB_H_NOTREADY;                      // depends on the read itself: never memoised
               } else {
@@ -388,15 +405,16 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
         ba.handle_out[frag] = handle;
         if (ba.tl_out) {
           // KmerIndex::mapPair (KmerIndex.cpp:1622-1693): the first k-mer found by a linear scan is
-          // the first hit of match(); same unitig, same EC set, opposite strands, same block end.
+          // the first hit of match(); same unitig, same EC set, opposite strands, same block end --
+          // i.e. the same EC block of the index (blocks tile their unitig and carry one EC set).
           uint16_t tl = 0;
           if (ba.paired && mate == 1 && v_first && v_cur) {
-            const uint32_t a_dist = msave[3 * nt] & 0x7FFFFFFFu;
-            const bool a_strand = (msave[3 * nt] >> 31) != 0;
-            const int a_pos = (int)msave[5 * nt];
+            const uint32_t a_dist = m_ds & 0x7FFFFFFFu;
+            const bool a_strand = (m_ds >> 31) != 0;
+            const int a_pos = (int)m_pos;
             const int q1 = a_strand ? (int)a_dist - a_pos : (int)a_dist + k + a_pos;
             const int q2 = f_strand ? (int)f_dist - f_pos : (int)f_dist + k + f_pos;
-            if (msave[0] == f_unitig && msave[2 * nt] == f_ec && (a_strand != f_strand) && msave[4 * nt] == f_ub) {
+            if (m_blk == f_blk && (a_strand != f_strand)) {
               const int d = q1 > q2 ? q1 - q2 : q2 - q1;
               if (d > 0 && d < 1000) tl = (uint16_t)d;
             }
@@ -422,6 +440,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
         if (is_idle && rank < avail) {
           const uint32_t fidx = next + rank;
           int l0 = 0;
+          unsigned inv = 0;
           for (int mt = 0; mt < n_mates; ++mt) {
             const uint32_t ridx = ba.paired ? 2 * fidx + mt : fidx;
             const uint8_t* unused_base;
@@ -431,29 +450,34 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
             if (len > nb * 32) len = nb * 32;   // cannot happen: the host sizes nb from the longest read
             if (mt == 0) l0 = len; else len1 = len;
             const uint32_t* src = ba.packed + (size_t)ridx * ba.pstride;
-            uint64_t* dbw = s_bw + (size_t)mt * nbw * nt;
-            uint64_t* div = s_iv + (size_t)mt * niw * nt;
+            uint32_t* dbw = s_bw + (size_t)mt * nw * nt;
+            uint32_t bad = 0;
             for (int c = 0; c < n_chunks; ++c) {
               uint32_t v[8];
               ld256_nc(src + c * 8, v);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                // 32 bytes = 4 u64 of the packed stream [nb base words | nb 32-bit masks | padding]
-                const int g2 = c * 4 + i;
-                const uint64_t q = (uint64_t)v[2 * i] | ((uint64_t)v[2 * i + 1] << 32);
-                if (g2 < nb) dbw[g2 * nt] = q;
-                else if (2 * (g2 - nb) < nb) div[(g2 - nb) * nt] = q;
+              for (int i = 0; i < 8; ++i) {
+                // packed stream: nb 64-bit base words (little-endian halves: the high half holds the
+                // first 16 bases), then nb 32-bit invalid masks, then padding
+                const int g = c * 8 + i;
+                if (g < nw) {
+                  dbw[(g ^ 1) * nt] = v[i];
+                } else if (g < nw + nb) {
+                  const int first = (g - nw) * 32;           // mask of bases [first, first + 32)
+                  const uint32_t in_read = len >= first + 32 ? 0xFFFFFFFFu : (len > first ? ((1u << (len - first)) - 1u) : 0u);
+                  bad |= v[i] & in_read;
+                }
               }
             }
+            if (bad) inv |= 1u << mt;
           }
           frag = fidx;
           mate = 0;
           n_e = 0;
           overflow = false;
           v_cur = s_cur = v_first = s_first = false;
-          rv.bw = s_bw;
-          rv.iv = s_iv;
-          rv.len = l0;
+          inv_flags = inv;
+          set_mate(0, l0);
           p = rv.next_valid(0);
           st = S_MAIN;
           need_prep = true;
@@ -461,9 +485,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
             st = S_FIN;
             if (n_mates == 2) {
               mate = 1;
-              rv.bw = s_bw + (size_t)nbw * nt;
-              rv.iv = s_iv + (size_t)niw * nt;
-              rv.len = len1;
+              set_mate(1, len1);
               p = rv.next_valid(0);
               if (p >= 0) st = S_MAIN;
             }
@@ -555,7 +577,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
         if (push) {
           if (!v_cur) {
             v_cur = true;
-            f_unitig = r_unitig; f_blk = v[3]; f_ec = r_ec; f_dist = v[5] & 0x7FFFFFFFu; f_ub = v[7];
+            f_blk = v[3]; f_dist = v[5] & 0x7FFFFFFFu;
             f_pos = p;   // only a MAIN hit can be the first hit of a read
             f_strand = r_strand;
           }
@@ -580,13 +602,10 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
           if (mate + 1 < n_mates) {
             // keep the first mate's flags and first hit, move on to the second mate
             v_first = v_cur; s_first = s_cur;
-            msave[0] = f_unitig; msave[nt] = f_blk; msave[2 * nt] = f_ec;
-            msave[3 * nt] = f_dist | (f_strand ? 0x80000000u : 0u); msave[4 * nt] = f_ub; msave[5 * nt] = (uint32_t)f_pos;
+            msave[0] = f_blk; msave[nt] = f_dist | (f_strand ? 0x80000000u : 0u); msave[2 * nt] = (uint32_t)f_pos;
             v_cur = s_cur = false;
             mate = 1;
-            rv.bw = s_bw + (size_t)nbw * nt;
-            rv.iv = s_iv + (size_t)niw * nt;
-            rv.len = len1;
+            set_mate(1, len1);
             p = rv.next_valid(0);
             if (p >= 0) { st = S_MAIN; need_prep = true; }
           }
@@ -898,7 +917,7 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
   if (ba.n_frag == 0) return;
   cudaMemsetAsync(ba.q_count, 0, sizeof(uint32_t), st);
   // persistent grid: as many blocks as fit on the device at once
-  const size_t smem = (size_t)tpb * ((size_t)2 * (ba.bwords + ba.iwords) * 8 + (KB_MAX_E + 12) * 4);
+  const size_t smem = (size_t)tpb * 4 * ((size_t)KB_MAX_E + 3 + 4 * ba.nb);   // per lane: handle tuple, first-mate words, 2 x 2nb base words
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;

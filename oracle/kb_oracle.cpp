@@ -334,6 +334,10 @@ struct KIt {
 
 typedef std::vector<std::pair<Um, int>> HitVec;
 
+// diagnostics: lookups of match() by kind -- 0 main hit, 1 main miss, 2 jump landing exactly where the
+// read would be if it followed the unitig, 3 jump on an absent k-mer, 4 other jumps, 5 middle, 6 back-off
+static uint64_t g_kind[8];
+
 // KmerIndex::match, src/KmerIndex.cpp:1698-1940 (default flags; no D-list)
 void match(const OIndex& ix, const char* s, int l, HitVec& v, bool partial, uint64_t* n_find) {
   const int k = ix.k;
@@ -359,6 +363,7 @@ void match(const OIndex& ix, const char* s, int l, HitVec& v, bool partial, uint
     ++*n_find;
     const Um um = find(ix, kit.km);
     const int pos = kit.p;
+    ++g_kind[um.isEmpty ? 1 : 0];
     if (!um.isEmpty) {
       if (partial && !and_partial(um)) { v.clear(); return; }
       v.push_back({um, kit.p});
@@ -375,6 +380,12 @@ void match(const OIndex& ix, const char* s, int l, HitVec& v, bool partial, uint
         if (!kit2.invalid) {
           ++*n_find;
           const Um um2 = find(ix, kit2.km);
+          {
+            const long expect = forward ? (long)um.dist + (kit2.p - pos) : (long)um.dist - (kit2.p - pos);
+            if (um2.isEmpty) ++g_kind[3];
+            else if (um2.unitig == um.unitig && (long)um2.dist == expect && um2.strand == um.strand) ++g_kind[2];
+            else ++g_kind[4];
+          }
           bool found2 = false;
           int found2pos = pos + dist;
           if (um2.isEmpty) {
@@ -401,6 +412,7 @@ void match(const OIndex& ix, const char* s, int l, HitVec& v, bool partial, uint
               kit3.add(middlePos - pos);
               if (!kit3.invalid) {
                 ++*n_find;
+                ++g_kind[5];
                 const Um um3 = find(ix, kit3.km);
                 if (!um3.isEmpty) {
                   if (same_unitig_ec(ix, um, um3)) {
@@ -433,6 +445,7 @@ void match(const OIndex& ix, const char* s, int l, HitVec& v, bool partial, uint
       for (int j = 0; !kit.invalid; kit.inc(), ++j) {
         if (j == 0) {
           ++*n_find;
+          ++g_kind[6];
           const Um um4 = find(ix, kit.km);
           if (!um4.isEmpty) {
             if (partial && !and_partial(um4)) { v.clear(); return; }
@@ -768,6 +781,7 @@ uint64_t oracle_n_ec_entries(void* run) {
   return n;
 }
 uint64_t oracle_n_find(void* run) { return ((ORun*)run)->n_find; }
+void oracle_kind_counts(uint64_t* out) { for (int i = 0; i < 8; ++i) out[i] = g_kind[i]; }
 void oracle_ec_table(void* run, uint64_t* off, uint32_t* tids, uint32_t* counts) {
   ORun& R = *(ORun*)run;
   uint64_t o = 0;
