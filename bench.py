@@ -142,6 +142,45 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cli_run(idx, concat, lens, n_pairs, device):
+    """File to file: `kallisto_b200 quant` (the drop-in CLI, csrc/cli_main.cpp) on plain FASTQ in /dev/shm --
+    the same measurement the reference arm gets (start-up + index load of a one-pair run subtracted)."""
+    exe = os.path.join(ROOT, "kallisto_b200", "kallisto_b200")
+    if not os.path.exists(exe):
+        return None
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    sim = benchdata.TorchSimulator(concat, lens, device, read_len=READ_LEN)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else DATA
+    with tempfile.TemporaryDirectory(dir=shm) as td:
+        f1, f2 = os.path.join(td, "s_1.fq"), os.path.join(td, "s_2.fq")
+        chunk = 1000000
+        with open(f1, "wb") as a, open(f2, "wb") as b:
+            pass
+        for c0 in range(0, n_pairs, chunk):
+            reads = sim.pairs(min(chunk, n_pairs - c0), seed=5000 + c0).cpu().numpy()
+            benchdata.write_fastq_fast(f1, reads[:, 0], 1, append=True)
+            benchdata.write_fastq_fast(f2, reads[:, 1], 2, append=True)
+        t1, t2 = os.path.join(td, "t_1.fq"), os.path.join(td, "t_2.fq")
+        benchdata.write_fastq_fast(t1, reads[:1, 0], 1)
+        benchdata.write_fastq_fast(t2, reads[:1, 1], 2)
+
+        def run(files):
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "quant", "-i", idx, "-o", os.path.join(td, "out"), "--plaintext", "-t", str(threads)] + files,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise RuntimeError("kallisto_b200 quant failed: " + r.stderr[-300:])
+            return dt
+        t_load = run([t1, t2])
+        t_total = min(run([f1, f2]) for _ in range(2))
+    return {"value": n_pairs / max(1e-9, t_total - t_load), "unit": "pairs/s", "pairs": n_pairs, "threads": threads,
+            "seconds_total": round(t_total, 3), "seconds_startup_and_index_load": round(t_load, 3),
+            "what": "kallisto_b200 quant --plaintext -t %d on plain FASTQ in /dev/shm -> abundance.tsv, wall clock, minus a "
+                    "one-pair run (start-up + index load)" % threads}
+
+
 def random_sector_peak(table_bytes):
     """Hardware ceiling for the probe pattern of match_kernel: independent random 32-byte sector reads over a
     table of this size (tools/randbench.cu, run live, a few seconds)."""
@@ -426,6 +465,13 @@ def main():
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if world == 1 and not os.environ.get("KB_BENCH_NO_CLI"):
+        try:
+            c = cli_run(idx, concat, lens, int(os.environ.get("KB_BENCH_CLI_PAIRS", "8000000")), dev)
+            if c:
+                line["cli"] = c
+        except Exception as e:
+            line["cli"] = {"value": None, "error": repr(e)[:300]}
     print(json.dumps(line), flush=True)
     return 0
 

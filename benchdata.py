@@ -203,12 +203,12 @@ class TorchSimulator:
         return out
 
 
-def write_fastq_fast(path, reads, tag):
+def write_fastq_fast(path, reads, tag, append=False):
     """Vectorised FASTQ writer: fixed-width names @r%09d/<tag>, constant quality 'I'."""
     n, L = reads.shape
     name_w = 1 + 1 + 9 + 2   # '@' 'r' digits '/' tag
     row = name_w + 1 + L + 1 + 2 + L + 1
-    with open(path, "wb") as f:
+    with open(path, "ab" if append else "wb") as f:
         CH = 500000
         for c0 in range(0, n, CH):
             c1 = min(n, c0 + CH)

@@ -187,6 +187,12 @@ int kb_bus_lengths(kb_quant* q, uint32_t* bc_hist, uint32_t* umi_hist);
  * src/kseq.h) and report the number of records, of bases, and an FNV-1a hash of the sequences
  * (0xFF after each record).  Tooling / tests. */
 int kb_fastx_summary(const char* path, uint64_t* n_reads, uint64_t* n_bases, uint64_t* fnv1a);
+/* Same through the command-line front end's ingest path: with threads > 1 a plain (uncompressed) regular
+ * file is mapped and parsed by `threads` host threads (csrc/fastx.hpp: segment starts are guessed, then
+ * proven by the parse of the preceding segment), otherwise the sequential zlib reader is used.  The
+ * result is the sequential parse in every case (replaces the serial fetchSequences + kseq_read under
+ * reader_lock, src/ProcessReads.cpp:945,3128-3267). */
+int kb_fastx_summary_mt(const char* path, int threads, uint64_t* n_reads, uint64_t* n_bases, uint64_t* fnv1a);
 
 /* counts_to_tpm (src/PlaintextWriter.cpp:5-27) -- host arithmetic, here so that callers format
  * identical numbers. */

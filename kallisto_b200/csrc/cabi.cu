@@ -354,9 +354,13 @@ int kb_bus_lengths(kb_quant* q, uint32_t* bc_hist, uint32_t* umi_hist) {
 }
 
 int kb_fastx_summary(const char* path, uint64_t* n_reads, uint64_t* n_bases, uint64_t* fnv1a) {
+  return kb_fastx_summary_mt(path, 1, n_reads, n_bases, fnv1a);
+}
+
+int kb_fastx_summary_mt(const char* path, int threads, uint64_t* n_reads, uint64_t* n_bases, uint64_t* fnv1a) {
   if (!path || !n_reads || !n_bases || !fnv1a) return fail(KB_ERR_INVALID, "kb_fastx_summary: null argument");
   try {
-    kb::FastxFile f(path);
+    kb::FastxReader f(path, threads);
     kb::ReadBatch b;
     std::vector<char> bases((size_t)(1u << 22) + kb::FastxFile::kMaxRead);
     std::vector<uint32_t> off(65537);

@@ -268,11 +268,11 @@ struct Stream {
   std::condition_variable cv;
 };
 
-void reader_thread(std::vector<std::string> files, Stream* s, size_t max_reads) {
+void reader_thread(std::vector<std::string> files, Stream* s, size_t max_reads, int parse_threads) {
   try {
     size_t slot = 0;
     for (auto& fn : files) {
-      kb::FastxFile f(fn);
+      kb::FastxReader f(fn, parse_threads);   // plain files: mapped and parsed by parse_threads threads
       for (;;) {
         {
           std::unique_lock<std::mutex> lk(s->m);
@@ -300,6 +300,63 @@ void reader_thread(std::vector<std::string> files, Stream* s, size_t max_reads) 
   }
   s->cv.notify_all();
 }
+
+// Lock-step consumer of the parser streams.  The streams cut their batches independently (by read count
+// or by bytes, whichever fills first), so a round hands out the reads that are available in EVERY stream
+// and leaves the rest of a longer batch for the next round.
+class LockStep {
+ public:
+  explicit LockStep(std::vector<Stream>& s) : st_(s), cur_(s.size(), 0), used_(s.size(), 0) {}
+
+  // false at the end of the input
+  bool next(size_t& n, const char** bases, const uint32_t** off) {
+    size_t with_data = 0;
+    n = (size_t)-1;
+    for (size_t i = 0; i < st_.size(); ++i) {
+      Stream& s = st_[i];
+      std::unique_lock<std::mutex> lk(s.m);
+      s.cv.wait(lk, [&] { return s.state[cur_[i]] == 1 || s.done; });
+      if (!s.error.empty()) {
+        cerr << endl << s.error << endl;
+        exit(1);
+      }
+      if (s.state[cur_[i]] != 1) continue;
+      ++with_data;
+      const kb::ReadBatch& b = s.ring[cur_[i]];
+      n = std::min(n, b.n - used_[i]);
+      bases[i] = b.bases;
+      off[i] = b.off + used_[i];          // offsets are absolute positions in `bases`
+    }
+    if (with_data == 0) return false;
+    if (with_data != st_.size()) {
+      cerr << endl << "Error: input files hold different numbers of reads" << endl;
+      exit(1);
+    }
+    n_ = n;
+    return true;
+  }
+  // the reads of the last round have been consumed
+  void release() {
+    for (size_t i = 0; i < st_.size(); ++i) {
+      Stream& s = st_[i];
+      used_[i] += n_;
+      if (used_[i] == s.ring[cur_[i]].n) {
+        {
+          std::lock_guard<std::mutex> lk(s.m);
+          s.state[cur_[i]] = 0;
+        }
+        s.cv.notify_all();
+        cur_[i] = (cur_[i] + 1) % s.ring.size();
+        used_[i] = 0;
+      }
+    }
+  }
+
+ private:
+  std::vector<Stream>& st_;
+  std::vector<size_t> cur_, used_;
+  size_t n_ = 0;
+};
 
 int cmd_quant(int argc, char** argv, const std::string& call, const std::string& start_time) {
   Options opt;
@@ -362,43 +419,21 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     }
     std::vector<std::string> files;
     for (size_t i = s; i < opt.files.size(); i += n_streams) files.push_back(opt.files[i]);
-    readers.emplace_back(reader_thread, files, &streams[s], max_reads);
+    readers.emplace_back(reader_thread, files, &streams[s], max_reads, std::max(1, opt.threads / n_streams));
   }
   uint64_t n_done = 0;
-  size_t slot = 0;
-  for (;;) {
-    bool have = true;
-    for (int s = 0; s < n_streams; ++s) {
-      std::unique_lock<std::mutex> lk(streams[s].m);
-      streams[s].cv.wait(lk, [&] { return streams[s].state[slot] == 1 || streams[s].done; });
-      if (!streams[s].error.empty()) {
-        cerr << endl << streams[s].error << endl;
-        exit(1);
-      }
-      if (streams[s].state[slot] != 1) have = false;
+  {
+    LockStep ls(streams);
+    const char* bp[2] = {nullptr, nullptr};
+    const uint32_t* op[2] = {nullptr, nullptr};
+    size_t n = 0;
+    while (ls.next(n, bp, op)) {
+      if (paired) KB_TRY(kb_pseudoalign_batch_pe(q, bp[0], op[0], bp[1], op[1], (uint32_t)n, 0, nullptr));
+      else KB_TRY(kb_pseudoalign_batch(q, bp[0], op[0], (uint32_t)n, 0, nullptr));
+      n_done += n;
+      if (opt.verbose) cerr << endl << "[quant] processed " << pretty_num(n_done) << " reads";
+      ls.release();
     }
-    if (!have) break;
-    kb::ReadBatch& b1 = streams[0].ring[slot];
-    if (paired) {
-      kb::ReadBatch& b2 = streams[1].ring[slot];
-      if (b1.n != b2.n) {
-        cerr << endl << "Error: paired input files hold different numbers of reads" << endl;
-        exit(1);
-      }
-      KB_TRY(kb_pseudoalign_batch_pe(q, b1.bases, b1.off, b2.bases, b2.off, (uint32_t)b1.n, 0, nullptr));
-    } else {
-      KB_TRY(kb_pseudoalign_batch(q, b1.bases, b1.off, (uint32_t)b1.n, 0, nullptr));
-    }
-    n_done += b1.n;
-    if (opt.verbose) cerr << endl << "[quant] processed " << pretty_num(n_done) << " reads";
-    for (int s = 0; s < n_streams; ++s) {
-      {
-        std::lock_guard<std::mutex> lk(streams[s].m);
-        streams[s].state[slot] = 0;
-      }
-      streams[s].cv.notify_all();
-    }
-    slot = (slot + 1) % 3;
   }
   for (auto& t : readers) t.join();
   cerr << " done" << endl;
@@ -683,35 +718,20 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     }
     std::vector<std::string> files;
     for (size_t i = s2; i < opt.files.size(); i += n_streams) files.push_back(opt.files[i]);
-    readers.emplace_back(reader_thread, files, &streams[s2], max_reads);
+    readers.emplace_back(reader_thread, files, &streams[s2], max_reads, std::max(1, opt.threads / n_streams));
   }
   std::vector<kb_bus_record> recs(max_reads);
-  size_t slot = 0;
-  for (;;) {
-    bool have = true;
-    for (int s2 = 0; s2 < n_streams; ++s2) {
-      std::unique_lock<std::mutex> lk(streams[s2].m);
-      streams[s2].cv.wait(lk, [&] { return streams[s2].state[slot] == 1 || streams[s2].done; });
-      if (!streams[s2].error.empty()) { cerr << endl << streams[s2].error << endl; exit(1); }
-      if (streams[s2].state[slot] != 1) have = false;
-    }
-    if (!have) break;
+  {
+    LockStep ls(streams);
     const char* bp[4] = {nullptr, nullptr, nullptr, nullptr};
     const uint32_t* op[4] = {nullptr, nullptr, nullptr, nullptr};
-    const size_t n = streams[0].ring[slot].n;
-    for (int s2 = 0; s2 < n_streams; ++s2) {
-      if (streams[s2].ring[slot].n != n) { cerr << endl << "Error: input files hold different numbers of reads" << endl; exit(1); }
-      bp[s2] = streams[s2].ring[slot].bases;
-      op[s2] = streams[s2].ring[slot].off;
+    size_t n = 0;
+    while (ls.next(n, bp, op)) {
+      uint32_t nrec = 0;
+      KB_TRY(kb_bus_batch(q, bp, op, (uint32_t)n, recs.data(), &nrec));
+      busf.write((const char*)recs.data(), (std::streamsize)nrec * sizeof(kb_bus_record));
+      ls.release();
     }
-    uint32_t nrec = 0;
-    KB_TRY(kb_bus_batch(q, bp, op, (uint32_t)n, recs.data(), &nrec));
-    busf.write((const char*)recs.data(), (std::streamsize)nrec * sizeof(kb_bus_record));
-    for (int s2 = 0; s2 < n_streams; ++s2) {
-      { std::lock_guard<std::mutex> lk(streams[s2].m); streams[s2].state[slot] = 0; }
-      streams[s2].cv.notify_all();
-    }
-    slot = (slot + 1) % 3;
   }
   for (auto& t : readers) t.join();
   busf.close();

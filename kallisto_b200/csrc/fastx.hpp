@@ -4,11 +4,28 @@
 // or '+'; for '+', a quality string at least as long as the sequence (possibly over several lines).
 // Sequences are appended to a caller-owned batch (concatenated bases + offsets), the layout
 // kb_pseudoalign_batch* takes; names and qualities are skipped (quant/bus never use them).
+//
+// ParallelFastx is the ingest path for plain (uncompressed) files: the file is mapped, cut into byte
+// segments, and the segments are parsed concurrently with the same grammar.  A segment may only start
+// where the sequential parser would start a record; that is not decidable locally (a quality line may
+// begin with '@'), so every start is a guess that is then PROVEN: segment i, which starts at a proven
+// boundary, must stop exactly on the guessed start of segment i+1.  If it does not, the remaining
+// segments of the window are re-parsed sequentially from the proven position -- the result is always
+// the sequential parse.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <future>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -137,6 +154,259 @@ class FastxFile {
   size_t pos_ = 0, end_ = 0;
   bool eof_ = false;
   int last_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Memory-range parser with FastxFile::next's grammar.  parse_range() appends the records whose header
+// character lies in [pos, stop) and returns the position of the first header at or after `stop` (or
+// `size` at the end of the data): the place where the sequential parser would begin its next record.
+struct ParsedSegment {
+  std::vector<char> bases;
+  std::vector<uint32_t> lens;
+  size_t end_pos = 0;
+};
+
+inline size_t parse_range(const char* d, size_t size, size_t pos, size_t stop, ParsedSegment& out) {
+  auto skip_line = [&](size_t p) -> size_t {   // position after the next '\n' (or size)
+    const char* nl = (const char*)memchr(d + p, '\n', size - p);
+    return nl ? (size_t)(nl - d) + 1 : size;
+  };
+  for (;;) {
+    // header search: anything up to the next '>' or '@' is skipped, like kseq_read
+    while (pos < size && d[pos] != '>' && d[pos] != '@') ++pos;
+    if (pos >= size) return size;
+    if (pos >= stop) return pos;
+    pos = skip_line(pos + 1);                                   // name / comment
+    const size_t first = out.bases.size();
+    while (pos < size) {
+      const char c = d[pos];
+      if (c == '>' || c == '+' || c == '@') break;
+      if (c == '\n') { ++pos; continue; }
+      const char* nl = (const char*)memchr(d + pos, '\n', size - pos);
+      size_t e = nl ? (size_t)(nl - d) : size;
+      const size_t next = nl ? e + 1 : size;
+      if (e > pos + 1 && d[e - 1] == '\r') --e;   // FastxFile keeps the first character of a line whatever it is
+      out.bases.insert(out.bases.end(), d + pos, d + e);
+      pos = next;
+    }
+    const size_t len = out.bases.size() - first;
+    if (len > FastxFile::kMaxRead) throw std::runtime_error("Error: sequence too long");
+    if (pos < size && d[pos] == '+') {
+      pos = skip_line(pos + 1);                                 // rest of the '+' line
+      size_t q = 0;
+      for (;;) {                                                // at least one line, like kseq_read
+        if (pos >= size) break;
+        const char* nl = (const char*)memchr(d + pos, '\n', size - pos);
+        size_t e = nl ? (size_t)(nl - d) : size;
+        const bool got = nl != nullptr;
+        const size_t next = nl ? e + 1 : size;
+        // FastxFile counts the characters of the line without a trailing '\r' only when it copies them;
+        // for discarded lines it counts every character before the '\n'
+        q += e - pos;
+        pos = next;
+        if (!got || q >= len) break;
+      }
+    }
+    out.lens.push_back((uint32_t)len);
+  }
+}
+
+class ParallelFastx {
+ public:
+  // threads >= 2.  Throws if the file cannot be mapped; is_plain_regular() tells whether to try.
+  ParallelFastx(const std::string& path, int threads) : path_(path), threads_(threads < 1 ? 1 : threads) {
+    fd_ = ::open(path.c_str(), O_RDONLY);
+    if (fd_ < 0) throw std::runtime_error("Error: could not open file " + path);
+    struct stat st;
+    if (fstat(fd_, &st) != 0) { ::close(fd_); throw std::runtime_error("Error: could not stat file " + path); }
+    size_ = (size_t)st.st_size;
+    if (size_ > 0) {
+      void* m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+      if (m == MAP_FAILED) { ::close(fd_); throw std::runtime_error("Error: could not map file " + path); }
+      data_ = (const char*)m;
+      madvise((void*)data_, size_, MADV_SEQUENTIAL);
+    }
+    window_ = (size_t)64 << 20;
+    if (const char* s = getenv("KB_FASTX_WINDOW")) { const long long v = atoll(s); if (v > 0) window_ = (size_t)v; }   // tests
+    window_ *= (size_t)threads_;
+    launch_next();
+  }
+  ~ParallelFastx() {
+    if (pending_.valid()) pending_.wait();
+    if (data_) munmap((void*)data_, size_);
+    if (fd_ >= 0) ::close(fd_);
+  }
+  ParallelFastx(const ParallelFastx&) = delete;
+  ParallelFastx& operator=(const ParallelFastx&) = delete;
+
+  // plain (not gzip) regular file?
+  static bool is_plain_regular(const std::string& path) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return false;
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    unsigned char m[2] = {0, 0};
+    const size_t n = fread(m, 1, 2, f);
+    fclose(f);
+    return !(n == 2 && m[0] == 0x1f && m[1] == 0x8b);
+  }
+
+  // same contract as FastxFile::fill
+  bool fill(ReadBatch& b, size_t max_reads) {
+    size_t added = 0;
+    while (b.n < max_reads && b.n < b.cap_reads) {
+      if (cur_.empty() || seg_ == cur_.size()) {
+        if (!next_window()) break;
+        continue;
+      }
+      ParsedSegment& s = *cur_[seg_];
+      if (rd_ == s.lens.size()) { ++seg_; rd_ = 0; boff_ = 0; continue; }
+      // as many whole reads of this segment as fit
+      size_t take = std::min(s.lens.size() - rd_, std::min(max_reads, b.cap_reads) - b.n);
+      uint32_t o = b.off[b.n];
+      size_t bytes = 0, i = 0;
+      for (; i < take; ++i) {
+        const uint32_t l = s.lens[rd_ + i];
+        if ((size_t)o + bytes + l + FastxFile::kMaxRead > b.cap_bases) break;
+        bytes += l;
+        b.off[b.n + i + 1] = o + (uint32_t)bytes;
+        if (l > b.max_len) b.max_len = l;
+      }
+      if (i == 0) break;                                           // batch full
+      memcpy(b.bases + o, s.bases.data() + boff_, bytes);
+      b.n += i;
+      rd_ += i;
+      boff_ += bytes;
+      added += i;
+      if (i < take) break;                                         // base buffer full
+    }
+    return added > 0;
+  }
+  const std::string& path() const { return path_; }
+
+ private:
+  typedef std::vector<std::unique_ptr<ParsedSegment>> Window;
+
+  // first position >= s that starts a line "@..." whose next-but-one line starts with '+', or npos
+  size_t guess_start(size_t s, size_t limit) const {
+    const char* nl = (const char*)memchr(data_ + s, '\n', size_ - s);
+    size_t p = nl ? (size_t)(nl - data_) + 1 : size_;
+    for (int tries = 0; p < limit && tries < 64; ++tries) {
+      const char* n1 = (const char*)memchr(data_ + p, '\n', size_ - p);
+      if (!n1) return (size_t)-1;
+      const size_t l1 = (size_t)(n1 - data_) + 1;
+      if (data_[p] == '@' && l1 < size_) {
+        const char* n2 = (const char*)memchr(data_ + l1, '\n', size_ - l1);
+        if (n2) {
+          const size_t l2 = (size_t)(n2 - data_) + 1;
+          if (l2 < size_ && data_[l2] == '+') return p;
+        }
+      }
+      p = l1;
+    }
+    return (size_t)-1;
+  }
+
+  Window parse_window(size_t begin, size_t end) {
+    // begin is a proven record boundary; records whose header lies in [begin, end) belong to this window
+    std::vector<size_t> starts(1, begin);
+    const size_t step = std::max<size_t>((end - begin) / (size_t)threads_, 1);
+    for (int t = 1; t < threads_; ++t) {
+      const size_t want = begin + step * (size_t)t;
+      if (want <= starts.back() || want >= end) continue;
+      const size_t g = guess_start(want, end);
+      if (g != (size_t)-1 && g > starts.back() && g < end) starts.push_back(g);
+    }
+    const size_t n = starts.size();
+    Window w(n);
+    std::vector<std::future<void>> fu;
+    for (size_t i = 0; i < n; ++i) {
+      w[i] = take_segment();
+      const size_t a = starts[i], z = i + 1 < n ? starts[i + 1] : end;
+      ParsedSegment* seg = w[i].get();
+      fu.push_back(std::async(std::launch::async, [this, a, z, seg] {
+        seg->bases.reserve((z - a) / 2 + 64);
+        seg->lens.reserve((z - a) / 64 + 16);
+        seg->end_pos = parse_range(data_, size_, a, z, *seg);
+      }));
+    }
+    for (auto& f : fu) f.get();
+    // proof: every segment must stop exactly where the next one started
+    for (size_t i = 0; i + 1 < n; ++i) {
+      if (w[i]->end_pos != starts[i + 1]) {
+        // the guess was not a record boundary: everything after segment i is re-parsed from the proven position
+        for (size_t j = i + 1; j < w.size(); ++j) give_segment(std::move(w[j]));
+        w.resize(i + 1);
+        w.emplace_back(take_segment());
+        w.back()->end_pos = parse_range(data_, size_, w[i]->end_pos, end, *w.back());
+        ++n_fallbacks_;
+        break;
+      }
+    }
+    return w;
+  }
+
+  // parsed-segment buffers are recycled: fresh 100 MB vectors would page-fault under the process-wide mmap lock
+  std::unique_ptr<ParsedSegment> take_segment() {
+    std::lock_guard<std::mutex> lk(pool_m_);
+    if (pool_.empty()) return std::unique_ptr<ParsedSegment>(new ParsedSegment());
+    std::unique_ptr<ParsedSegment> s = std::move(pool_.back());
+    pool_.pop_back();
+    s->bases.clear();
+    s->lens.clear();
+    s->end_pos = 0;
+    return s;
+  }
+  void give_segment(std::unique_ptr<ParsedSegment> s) {
+    std::lock_guard<std::mutex> lk(pool_m_);
+    pool_.push_back(std::move(s));
+  }
+
+  void launch_next() {
+    if (next_begin_ >= size_) return;
+    const size_t begin = next_begin_;
+    const size_t end = std::min(size_, begin + window_);
+    pending_ = std::async(std::launch::async, [this, begin, end] { return parse_window(begin, end); });
+  }
+
+  bool next_window() {
+    for (auto& s : cur_) give_segment(std::move(s));
+    cur_.clear();
+    seg_ = rd_ = boff_ = 0;
+    if (!pending_.valid()) return false;
+    cur_ = pending_.get();
+    next_begin_ = cur_.empty() ? size_ : cur_.back()->end_pos;   // proven: the sequential parser continues here
+    launch_next();
+    return true;
+  }
+
+  std::string path_;
+  int threads_;
+  int fd_ = -1;
+  const char* data_ = nullptr;
+  size_t size_ = 0, window_ = 0, next_begin_ = 0;
+  std::future<Window> pending_;
+  Window cur_;
+  size_t seg_ = 0, rd_ = 0, boff_ = 0;
+  size_t n_fallbacks_ = 0;
+  std::mutex pool_m_;
+  std::vector<std::unique_ptr<ParsedSegment>> pool_;
+};
+
+// Either reader behind one interface: ParallelFastx for plain regular files when more than one parser
+// thread is available, FastxFile (zlib) otherwise.
+class FastxReader {
+ public:
+  FastxReader(const std::string& path, int threads) {
+    if (threads > 1 && ParallelFastx::is_plain_regular(path)) par_.reset(new ParallelFastx(path, threads));
+    else ser_.reset(new FastxFile(path));
+  }
+  bool fill(ReadBatch& b, size_t max_reads) { return par_ ? par_->fill(b, max_reads) : ser_->fill(b, max_reads); }
+  bool parallel() const { return (bool)par_; }
+
+ private:
+  std::unique_ptr<ParallelFastx> par_;
+  std::unique_ptr<FastxFile> ser_;
 };
 
 }  // namespace kb

@@ -63,3 +63,60 @@ def test_formats(tmp_path):
 def test_missing_file():
     with pytest.raises(K.KallistoB200Error):
         K.fastx_summary("/nonexistent.fq")
+
+
+# ---- parallel ingest path (ParallelFastx): always the sequential parse, whatever the segment cuts hit ----
+def _same(path, threads=(2, 3, 8)):
+    want = K.fastx_summary(path, 1)
+    for t in threads:
+        assert K.fastx_summary(path, t) == want, (path, t)
+    return want
+
+
+def test_parallel_matches_sequential(tmp_path, monkeypatch):
+    import random
+    rnd = random.Random(7)
+    recs = []
+    for i in range(3000):
+        L = rnd.choice([0, 1, 5, 30, 50, 75, 100, 151])
+        s = bytes(rnd.choice(b"ACGTNacgt") for _ in range(L))
+        q = bytes(rnd.choice(b"@+>I#5F!") for _ in range(L))     # quality lines that look like headers / separators
+        recs.append((s, q))
+    p = tmp_path / "p.fq"
+    p.write_bytes(b"".join(b"@r%d/1\n%s\n+\n%s\n" % (i, s, q) for i, (s, q) in enumerate(recs)))
+    seqs = [s for s, _ in recs]
+    for window in ("1000", "4096", "65536", "100000000"):        # bytes per thread and window: many cuts ... one
+        monkeypatch.setenv("KB_FASTX_WINDOW", window)
+        n, b, h = _same(str(p))
+        assert n == len(seqs) and b == sum(map(len, seqs)) and h == fnv(seqs)
+
+
+def test_parallel_odd_layouts(tmp_path, monkeypatch):
+    monkeypatch.setenv("KB_FASTX_WINDOW", "64")
+    # multi-line FASTQ: guessed segment starts are frequently wrong and must be rejected by the proof
+    body = b"".join(b"@r%d\nACGTACGTAC\nGGGGG\n+\n@IIIIIIIII\n+IIII\n" % i for i in range(400))
+    p = tmp_path / "ml.fq"
+    p.write_bytes(body)
+    n, b, h = _same(str(p))
+    assert n == 400 and b == 400 * 15
+    # FASTA (no '+' lines at all: no segment start can be guessed, the window is parsed by one thread)
+    p = tmp_path / "x.fa"
+    p.write_bytes(b"".join(b">t%d\nACGTAC\nGT\n" % i for i in range(500)))
+    n, b, h = _same(str(p))
+    assert n == 500 and b == 500 * 8
+    # CRLF, no trailing newline, empty file, garbage before the first header
+    p = tmp_path / "crlf.fq"
+    p.write_bytes(b"".join(b"@r%d\r\nACGTA\r\n+\r\nIIIII\r\n" % i for i in range(300))[:-2])
+    assert _same(str(p))[0] == 300
+    p = tmp_path / "empty.fq"
+    p.write_bytes(b"")
+    assert _same(str(p)) == (0, 0, fnv([]))
+    p = tmp_path / "junk.fq"
+    p.write_bytes(b"junk line\n\n" + b"".join(b"@r%d\nAC\n+\nII\n" % i for i in range(100)))
+    assert _same(str(p))[0] == 100
+
+
+def test_parallel_gz_falls_back_to_zlib(tmp_path):
+    d = util.dataset("config1")
+    f = os.path.join(d["dir"], "reads_1.fastq.gz")
+    assert K.fastx_summary(f, 8) == K.fastx_summary(f, 1)

@@ -124,3 +124,23 @@ def test_quant_single_with_position_filter(tmp_path):
     ref = os.path.join(ds["dir"], "ref_quant_single")
     assert open(out / "abundance.tsv").read() == open(os.path.join(ref, "abundance.tsv")).read()
     same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
+
+
+def test_quant_parallel_ingest_plain_fastq(tmp_path, monkeypatch):
+    """-t 8 on uncompressed files takes the mapped, multi-threaded reader (csrc/fastx.hpp ParallelFastx); tiny
+    windows force many segment cuts and unequal batch cuts between the two files (LockStep rounds)."""
+    import gzip
+    ds = util.dataset("synth_small")
+    files = []
+    for m in (1, 2):
+        p = tmp_path / ("r%d.fq" % m)
+        p.write_bytes(gzip.open(os.path.join(ds["dir"], "reads_%d.fastq.gz" % m)).read())
+        files.append(str(p))
+    monkeypatch.setenv("KB_FASTX_WINDOW", "30000")
+    out = tmp_path / "o"
+    r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "-t", "8", "-b", "2", "--seed", "42"] + files)
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(ds["dir"], "ref_quant_paired")
+    for fn in ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv"]:
+        assert open(out / fn).read() == open(os.path.join(ref, fn)).read(), fn
+    same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
