@@ -21,6 +21,7 @@ Every step uses different reads and each batch (pairs_per_step x 200 B) is large
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -166,19 +167,30 @@ def cli_run(idx, concat, lens, n_pairs, device):
         benchdata.write_fastq_fast(t2, reads[:1, 1], 2)
 
         def run(files):
+            env = dict(os.environ, KB_CLI_TIMING="1")
             t0 = time.perf_counter()
             r = subprocess.run([exe, "quant", "-i", idx, "-o", os.path.join(td, "out"), "--plaintext", "-t", str(threads)] + files,
-                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env)
             dt = time.perf_counter() - t0
             if r.returncode != 0:
                 raise RuntimeError("kallisto_b200 quant failed: " + r.stderr[-300:])
-            return dt
-        t_load = run([t1, t2])
-        t_total = min(run([f1, f2]) for _ in range(2))
-    return {"value": n_pairs / max(1e-9, t_total - t_load), "unit": "pairs/s", "pairs": n_pairs, "threads": threads,
-            "seconds_total": round(t_total, 3), "seconds_startup_and_index_load": round(t_load, 3),
-            "what": "kallisto_b200 quant --plaintext -t %d on plain FASTQ in /dev/shm -> abundance.tsv, wall clock, minus a "
-                    "one-pair run (start-up + index load)" % threads}
+            ph = {}
+            for m in re.finditer(r"\[timing\] ([^:\n]+): ([0-9.eE+-]+) s \(at", r.stderr):
+                ph[m.group(1)] = float(m.group(2))
+            return dt, ph
+        run([t1, t2])                                  # page cache, driver start-up
+        best = None
+        for _ in range(2):
+            dt, ph = run([f1, f2])
+            work = sum(v for k2, v in ph.items() if k2 not in ("index load", "run set-up"))
+            if best is None or work < best[0]:
+                best = (work, dt, ph)
+    work, dt, ph = best
+    return {"value": n_pairs / max(1e-9, work), "unit": "pairs/s", "pairs": n_pairs, "threads": threads,
+            "seconds_reads_to_outputs": round(work, 4), "seconds_process_wall": round(dt, 3),
+            "phases_s": {k2: round(v, 4) for k2, v in ph.items()},
+            "what": "kallisto_b200 quant --plaintext -t %d on plain FASTQ in /dev/shm -> abundance.tsv + run_info.json; value = pairs / "
+                    "(process wall clock minus its own index load and run set-up phases, which are listed; parsing starts while the index loads)" % threads}
 
 
 def random_sector_peak(table_bytes):

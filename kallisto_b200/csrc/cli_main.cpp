@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 
 #include <atomic>
+#include <charconv>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -203,19 +204,40 @@ bool check_quant(Options& opt) {   // CheckOptionsEM, src/main.cpp:1600-1805
   return ret;
 }
 
-// plaintext_writer, src/PlaintextWriter.cpp:29-65 (default ostream formatting: 6 significant digits)
+// plaintext_writer, src/PlaintextWriter.cpp:29-65.  The reference streams every value with operator<< and
+// ends every line with std::endl (one write() per transcript); the bytes are reproduced here -- default
+// ostream formatting of a double is printf's %g with 6 significant digits, which is what
+// std::to_chars(general, 6) is specified to produce -- but formatted into one buffer and written once.
+void append_double(std::string& s, double v) {
+  char buf[64];
+  const auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::general, 6);
+  s.append(buf, r.ptr);
+}
 void write_abundance(const std::string& path, const std::vector<std::string>& names, const std::vector<uint32_t>& lens,
                      const double* eff, const double* est) {
-  std::ofstream of(path);
+  std::ofstream of(path, std::ios::out | std::ios::binary);
   if (!of.is_open()) {
     cerr << "Error: Couldn't open file: " << path << endl;
     exit(1);
   }
   std::vector<double> tpm(names.size());
   kb_counts_to_tpm(est, eff, (uint32_t)names.size(), tpm.data());
-  of << "target_id" << "\t" << "length" << "\t" << "eff_length" << "\t" << "est_counts" << "\t" << "tpm" << std::endl;
-  for (size_t i = 0; i < names.size(); ++i)
-    of << names[i] << '\t' << lens[i] << '\t' << eff[i] << '\t' << est[i] << '\t' << tpm[i] << std::endl;
+  std::string out;
+  out.reserve(names.size() * 72 + 64);
+  out += "target_id\tlength\teff_length\test_counts\ttpm\n";
+  for (size_t i = 0; i < names.size(); ++i) {
+    out += names[i];
+    out += '\t';
+    out += std::to_string(lens[i]);
+    out += '\t';
+    append_double(out, eff[i]);
+    out += '\t';
+    append_double(out, est[i]);
+    out += '\t';
+    append_double(out, tpm[i]);
+    out += '\n';
+  }
+  of.write(out.data(), (std::streamsize)out.size());
 }
 
 // plaintext_aux, src/PlaintextWriter.cpp:140-199
@@ -257,6 +279,20 @@ void write_run_info(const std::string& path, size_t n_targets, int n_bootstrap, 
     }                                                                 \
   } while (0)
 
+// KB_CLI_TIMING=1: wall-clock phases on stderr
+struct PhaseTimer {
+  bool on = getenv("KB_CLI_TIMING") != nullptr;
+  bool verbose = on && atoi(getenv("KB_CLI_TIMING")) > 1;      // 2: also every round
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+  void mark(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    cerr << endl << "[timing] " << what << ": " << std::chrono::duration<double>(now - last).count() << " s (at "
+         << std::chrono::duration<double>(now - t0).count() << " s)";
+    last = now;
+  }
+};
+
 // One parser thread per input stream, handing filled batches to the GPU thread through a small ring.
 struct Stream {
   std::vector<kb::ReadBatch> ring;
@@ -270,6 +306,14 @@ struct Stream {
 
 void reader_thread(std::vector<std::string> files, Stream* s, size_t max_reads, int parse_threads) {
   try {
+    // the ring of pinned batch buffers is allocated here, so that it happens on all streams at once and
+    // while the main thread is still loading the index
+    for (auto& b : s->ring) {
+      b.bases = (char*)kb_host_alloc(b.cap_bases + 64);
+      b.off = (uint32_t*)kb_host_alloc((b.cap_reads + 1) * sizeof(uint32_t));
+      if (!b.bases || !b.off) throw std::runtime_error("Error: could not allocate pinned host memory");
+      b.clear();
+    }
     size_t slot = 0;
     for (auto& fn : files) {
       kb::FastxReader f(fn, parse_threads);   // plain files: mapped and parsed by parse_threads threads
@@ -299,6 +343,39 @@ void reader_thread(std::vector<std::string> files, Stream* s, size_t max_reads, 
     s->done = true;
   }
   s->cv.notify_all();
+}
+
+// Reads per batch of stream s.  KB_CLI_BATCH_READS="a,b,..." (tests) gives the streams different batch sizes, the
+// situation that otherwise only arises when one file's batches fill up by bytes before they fill up by reads.
+size_t stream_batch_reads(int s, size_t dflt) {
+  const char* e = getenv("KB_CLI_BATCH_READS");
+  if (!e || !*e) return dflt;
+  std::vector<size_t> v;
+  std::stringstream ss(e);
+  std::string tok;
+  while (std::getline(ss, tok, ',')) {
+    const long long x = atoll(tok.c_str());
+    if (x > 0) v.push_back(std::min<size_t>((size_t)x, dflt));
+  }
+  return v.empty() ? dflt : v[(size_t)s % v.size()];
+}
+
+// Starts one parser thread per input stream (file i of every group of n_streams files goes to stream i).  Called
+// before the index is loaded: parsing does not need it, so the first batches are ready when the device is.
+void start_streams(std::vector<Stream>& streams, std::vector<std::thread>& readers, const std::vector<std::string>& all_files,
+                   size_t max_bases, size_t max_reads, int threads) {
+  const int n_streams = (int)streams.size();
+  for (int s = 0; s < n_streams; ++s) {
+    streams[s].ring.resize(3);
+    streams[s].state.assign(3, 0);
+    for (auto& b : streams[s].ring) {
+      b.cap_bases = max_bases;
+      b.cap_reads = max_reads;
+    }
+    std::vector<std::string> files;
+    for (size_t i = s; i < all_files.size(); i += n_streams) files.push_back(all_files[i]);
+    readers.emplace_back(reader_thread, files, &streams[s], stream_batch_reads(s, max_reads), std::max(1, threads / n_streams));
+  }
 }
 
 // Lock-step consumer of the parser streams.  The streams cut their batches independently (by read count
@@ -366,16 +443,24 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     usage_quant();
     return 1;
   }
+  PhaseTimer pt;
+  const bool paired = !opt.single_end;
+  const size_t max_reads = 1u << 20;                 // reads per batch and mate
+  const size_t max_bases = (size_t)max_reads * 160 + kb::FastxFile::kMaxRead;
+  const int n_streams = paired ? 2 : 1;
+  std::vector<Stream> streams(n_streams);
+  std::vector<std::thread> readers;
+  start_streams(streams, readers, opt.files, max_bases, max_reads, opt.threads);
   kb_index* ix = nullptr;
   // positions are needed only by the fragment-position filter (KmerIndex.h:78: load_positional_info)
   const int need_positions = (!opt.single_overhang && opt.fld > 0.0) ? 1 : 0;
-  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, need_positions, std::max(1, opt.threads), &ix));
+  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, need_positions, std::min(16, std::max(1, opt.threads)), &ix));
+  pt.mark("index load");
   kb_index_info info;
   kb_index_get_info(ix, &info);
   cerr << "[index] k-mer length: " << info.k << endl;
   cerr << "[index] number of targets: " << pretty_num(info.n_targets) << endl;
   cerr << "[index] number of k-mers: " << pretty_num(info.n_kmers) << endl;
-  const bool paired = !opt.single_end;
   cerr << (paired ? "[quant] running in paired-end mode" : "[quant] running in single-end mode") << endl;
   for (size_t i = 0; i < opt.files.size(); i += paired ? 2 : 1) {
     if (paired)
@@ -387,8 +472,6 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   cerr << "[quant] finding pseudoalignments for the reads ...";
   cerr.flush();
 
-  const size_t max_reads = 1u << 20;                 // reads per batch and mate
-  const size_t max_bases = (size_t)max_reads * 160 + kb::FastxFile::kMaxRead;
   kb_quant_opts qo{};
   qo.paired = paired;
   qo.strand_mode = opt.strand;
@@ -399,28 +482,9 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   qo.max_batch_bases = 2 * max_bases;
   kb_quant* q = nullptr;
   KB_TRY(kb_quant_create(ix, &qo, &q));
+  if (pt.on) kb_quant_enable_timing(q, 1);
 
-  const int n_streams = paired ? 2 : 1;
-  std::vector<Stream> streams(n_streams);
-  std::vector<std::thread> readers;
-  for (int s = 0; s < n_streams; ++s) {
-    streams[s].ring.resize(3);
-    streams[s].state.assign(3, 0);
-    for (auto& b : streams[s].ring) {
-      b.cap_bases = max_bases;
-      b.cap_reads = max_reads;
-      b.bases = (char*)kb_host_alloc(max_bases + 64);
-      b.off = (uint32_t*)kb_host_alloc((max_reads + 1) * sizeof(uint32_t));
-      if (!b.bases || !b.off) {
-        cerr << "Error: could not allocate pinned host memory" << endl;
-        return 1;
-      }
-      b.clear();
-    }
-    std::vector<std::string> files;
-    for (size_t i = s; i < opt.files.size(); i += n_streams) files.push_back(opt.files[i]);
-    readers.emplace_back(reader_thread, files, &streams[s], max_reads, std::max(1, opt.threads / n_streams));
-  }
+  pt.mark("run set-up");
   uint64_t n_done = 0;
   {
     LockStep ls(streams);
@@ -428,14 +492,18 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     const uint32_t* op[2] = {nullptr, nullptr};
     size_t n = 0;
     while (ls.next(n, bp, op)) {
+      const auto c0 = std::chrono::steady_clock::now();
       if (paired) KB_TRY(kb_pseudoalign_batch_pe(q, bp[0], op[0], bp[1], op[1], (uint32_t)n, 0, nullptr));
       else KB_TRY(kb_pseudoalign_batch(q, bp[0], op[0], (uint32_t)n, 0, nullptr));
+      if (pt.verbose) cerr << endl << "[timing] round of " << n << " reads: call " << std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count()
+                      << " s, at " << std::chrono::duration<double>(std::chrono::steady_clock::now() - pt.t0).count() << " s";
       n_done += n;
       if (opt.verbose) cerr << endl << "[quant] processed " << pretty_num(n_done) << " reads";
       ls.release();
     }
   }
   for (auto& t : readers) t.join();
+  pt.mark("read + pseudoalign loop");
   cerr << " done" << endl;
 
   const uint32_t T = info.n_targets;
@@ -451,6 +519,13 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     }
   }
   KB_TRY(kb_em_run(q, opt.fld, opt.sd, est.data(), eff.data(), &rounds, nullptr));
+  pt.mark("EM");
+  if (pt.on) {
+    kb_kernel_timings kt{};
+    kb_quant_get_timings(q, &kt);
+    cerr << endl << "[timing] device: match " << kt.match_ms << " ms in " << kt.match_launches << " launches, resolve " << kt.resolve_ms
+         << " ms in " << kt.resolve_launches << " launches, EM " << kt.em_ms << " ms, EM set-up " << kt.em_prep_ms << " ms";
+  }
   kb_run_stats st{};
   KB_TRY(kb_quant_finalize(q, &st));
   cerr << "[quant] processed " << pretty_num(st.n_processed) << " reads, " << pretty_num(st.n_pseudoaligned)
@@ -474,6 +549,8 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   write_run_info(opt.output + "/run_info.json", T, opt.bootstrap, st.n_processed, st.n_pseudoaligned, st.n_unique, 13,
                  info.k, start_time, call);
   write_abundance(opt.output + "/abundance.tsv", names, lens, eff.data(), est.data());
+  pt.mark("finalize + write abundance.tsv");
+  if (pt.on) cerr << endl;
   if (opt.bootstrap > 0 && st.n_pseudoaligned == 0) {
     for (int b = 0; b < opt.bootstrap; ++b)
       write_abundance(opt.output + "/bs_abundance_" + std::to_string(b) + ".tsv", names, lens, eff.data(), est.data());
@@ -660,7 +737,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     return 1;
   }
   kb_index* ix = nullptr;
-  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, 0, std::max(1, opt.threads), &ix));
+  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, 0, std::min(16, std::max(1, opt.threads)), &ix));
   kb_index_info info;
   kb_index_get_info(ix, &info);
   cerr << "[index] k-mer length: " << info.k << endl;
@@ -705,21 +782,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   const int n_streams = bo.nfiles;
   std::vector<Stream> streams(n_streams);
   std::vector<std::thread> readers;
-  for (int s2 = 0; s2 < n_streams; ++s2) {
-    streams[s2].ring.resize(3);
-    streams[s2].state.assign(3, 0);
-    for (auto& b : streams[s2].ring) {
-      b.cap_bases = max_bases;
-      b.cap_reads = max_reads;
-      b.bases = (char*)kb_host_alloc(max_bases + 64);
-      b.off = (uint32_t*)kb_host_alloc((max_reads + 1) * sizeof(uint32_t));
-      if (!b.bases || !b.off) { cerr << "Error: could not allocate pinned host memory" << endl; return 1; }
-      b.clear();
-    }
-    std::vector<std::string> files;
-    for (size_t i = s2; i < opt.files.size(); i += n_streams) files.push_back(opt.files[i]);
-    readers.emplace_back(reader_thread, files, &streams[s2], max_reads, std::max(1, opt.threads / n_streams));
-  }
+  start_streams(streams, readers, opt.files, max_bases, max_reads, opt.threads);
   std::vector<kb_bus_record> recs(max_reads);
   {
     LockStep ls(streams);

@@ -858,11 +858,20 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
       res.eff_lens[t] = e;
     }
   }
+  const bool trace = getenv("KB_EM_TRACE") != nullptr;     // host wall clock of the set-up steps on stderr
+  double t_last = now_s();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    const double t = now_s();
+    fprintf(stderr, "[em-trace] %s: %.3f ms\n", what, (t - t_last) * 1e3);
+    t_last = t;
+  };
   cudaEvent_t e0, e1, e2;
   KB_CK(cudaEventCreate(&e0));
   KB_CK(cudaEventCreate(&e1));
   KB_CK(cudaEventCreate(&e2));
   KB_CK(cudaEventRecord(e0, st));
+  mark("eff lens + events");
   // ---- phase 1: used handles, sorted by first occurrence; lengths and offsets
   if (w.used.n < ix_.dict_cap) w.used.alloc(ix_.dict_cap);
   if (w.scal.n < 8) w.scal.alloc(8);
@@ -870,6 +879,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   uint32_t n = 0;
   w.scal.download(&n, 1, 0, st);
   KB_CK(cudaStreamSynchronize(st));
+  mark("drain stream + collect used handles");
   res.alpha.assign(T, 0.0);
   if (n == 0) {
     res.rounds = 0;
@@ -885,6 +895,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   const uint32_t nnz_guess = std::max<uint32_t>(n * 4, 1u << 20);
   size_t tmp_need = emprep_sort_bytes(n + 1, std::max<uint32_t>(nnz_guess, T + 1));
   if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
+  mark("phase-1 buffers");
   // the scans run over n + 1 items: the extra item must be zero
   KB_CK(cudaMemsetAsync(w.len.p + n, 0, 4, st));
   KB_CK(cudaMemsetAsync(w.multi_len.p + n, 0, 4, st));
@@ -900,6 +911,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   w.m_off.download(&tot[1], 1, n, st);
   w.multi_index.download(&tot[2], 1, n, st);
   KB_CK(cudaStreamSynchronize(st));
+  mark("sort by first occurrence + scans");
   const uint32_t nnz_all = tot[0], nnz = tot[1], n_multi = tot[2];
   // ---- phase 2: EC table, CSR, weights, CSC
   tmp_need = emprep_sort_bytes(n + 1, std::max<uint32_t>(nnz, T + 1));
@@ -911,6 +923,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   grow32(w.t_deg, (size_t)T + 1); grow32(w.t_off, (size_t)T + 1);
   if (w.t_single.n < T) w.t_single.alloc(T);
   growd(w.eff, T); growd(w.alpha, T); growd(w.norm, (size_t)n_multi + 1);
+  mark("phase-2 buffers");
   KB_CK(cudaMemsetAsync(w.t_deg.p, 0, ((size_t)T + 1) * 4, st));
   launch_fill_i32(w.t_single.p, T, -1, st);
   KB_CK(cudaMemsetAsync(w.m_rowoff.p, 0, 4, st));   // n_multi == 0: offsets [0]
@@ -935,6 +948,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   p.nb = 1; p.counts = w.count.p; p.alpha = w.alpha.p; p.norm = w.norm.p;
   p.rounds = w.emi.p; p.state = w.emi.p + 1; p.fstate = w.emi.p + 3; p.chcount = w.chcount.p;
   p.max_iter = max_iter; p.min_rounds = min_rounds;
+  mark("fill launches + uploads");
   KB_CK(cudaEventRecord(e1, st));
   launch_em(p, em_tpb(), st);
   KB_CK(cudaGetLastError());
@@ -945,6 +959,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   w.emi.download(emi, 4, 0, st);
   w.key_in.download(s2, 2, 0, st);
   KB_CK(cudaStreamSynchronize(st));
+  mark("EM kernel + results");
   if (emi[3] == 3)
     for (uint32_t t = 0; t < T; ++t)
       if (res.alpha[t] < 1e-7 / 10.0) res.alpha[t] = 0.0;

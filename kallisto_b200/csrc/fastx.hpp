@@ -19,7 +19,10 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -162,8 +165,11 @@ class FastxFile {
 // `size` at the end of the data): the place where the sequential parser would begin its next record.
 struct ParsedSegment {
   std::vector<char> bases;
-  std::vector<uint32_t> lens;
+  std::vector<uint32_t> cum{0};   // cum[i] = bases before read i of the segment; cum.size() = reads + 1
+  uint32_t max_len = 0;
   size_t end_pos = 0;
+  size_t n_reads() const { return cum.size() - 1; }
+  void reset() { bases.clear(); cum.assign(1, 0); max_len = 0; end_pos = 0; }
 };
 
 inline size_t parse_range(const char* d, size_t size, size_t pos, size_t stop, ParsedSegment& out) {
@@ -207,7 +213,9 @@ inline size_t parse_range(const char* d, size_t size, size_t pos, size_t stop, P
         if (!got || q >= len) break;
       }
     }
-    out.lens.push_back((uint32_t)len);
+    if (out.bases.size() > 0xFFFFFFFFull) throw std::runtime_error("Error: parse window too large");
+    out.cum.push_back((uint32_t)out.bases.size());
+    if (len > out.max_len) out.max_len = (uint32_t)len;
   }
 }
 
@@ -226,14 +234,20 @@ class ParallelFastx {
       data_ = (const char*)m;
       madvise((void*)data_, size_, MADV_SEQUENTIAL);
     }
-    window_ = (size_t)64 << 20;
+    if (threads_ > 16) threads_ = 16;         // more parser threads than this only fight over memory bandwidth
+    copy_threads_ = std::max(1, std::min(4, threads_ / 2));
+    window_ = (size_t)4 << 20;                // bytes per parser thread and window
     if (const char* s = getenv("KB_FASTX_WINDOW")) { const long long v = atoll(s); if (v > 0) window_ = (size_t)v; }   // tests
     window_ *= (size_t)threads_;
     launch_next();
   }
   ~ParallelFastx() {
     if (pending_.valid()) pending_.wait();
-    if (data_) munmap((void*)data_, size_);
+    if (data_ && unmapped_ < size_) munmap((void*)(data_ + unmapped_), size_ - unmapped_);
+    data_ = nullptr;
+    if (getenv("KB_FASTX_DEBUG"))
+      fprintf(stderr, "[fastx] %s: %zu windows, %zu segments, %zu rejected segment starts, parse %.3f s, wait %.3f s\n", path_.c_str(),
+              n_windows_, n_segments_, n_fallbacks_, t_parse_, t_wait_);
     if (fd_ >= 0) ::close(fd_);
   }
   ParallelFastx(const ParallelFastx&) = delete;
@@ -253,39 +267,74 @@ class ParallelFastx {
 
   // same contract as FastxFile::fill
   bool fill(ReadBatch& b, size_t max_reads) {
-    size_t added = 0;
-    while (b.n < max_reads && b.n < b.cap_reads) {
-      if (cur_.empty() || seg_ == cur_.size()) {
-        if (!next_window()) break;
-        continue;
-      }
-      ParsedSegment& s = *cur_[seg_];
-      if (rd_ == s.lens.size()) { ++seg_; rd_ = 0; boff_ = 0; continue; }
-      // as many whole reads of this segment as fit
-      size_t take = std::min(s.lens.size() - rd_, std::min(max_reads, b.cap_reads) - b.n);
-      uint32_t o = b.off[b.n];
-      size_t bytes = 0, i = 0;
-      for (; i < take; ++i) {
-        const uint32_t l = s.lens[rd_ + i];
-        if ((size_t)o + bytes + l + FastxFile::kMaxRead > b.cap_bases) break;
-        bytes += l;
-        b.off[b.n + i + 1] = o + (uint32_t)bytes;
-        if (l > b.max_len) b.max_len = l;
-      }
-      if (i == 0) break;                                           // batch full
-      memcpy(b.bases + o, s.bases.data() + boff_, bytes);
-      b.n += i;
-      rd_ += i;
-      boff_ += bytes;
-      added += i;
-      if (i < take) break;                                         // base buffer full
+    const size_t n_before = b.n;
+    for (;;) {
+      const int r = fill_from_window(b, max_reads);       // copies what the current window offers
+      if (r != kNeedWindow) break;
+      if (!next_window()) break;
     }
-    return added > 0;
+    return b.n > n_before;
   }
   const std::string& path() const { return path_; }
 
  private:
   typedef std::vector<std::unique_ptr<ParsedSegment>> Window;
+
+  enum { kBatchFull = 0, kNeedWindow = 1 };
+  int fill_from_window(ReadBatch& b, size_t max_reads) {
+    struct Job { const ParsedSegment* s; size_t rd, cnt; uint32_t dst_off; size_t dst_rd; };
+    std::vector<Job> jobs;
+    const size_t limit = std::min(max_reads, b.cap_reads);
+    size_t n = b.n;
+    uint64_t o = b.off[b.n];
+    size_t total_bytes = 0;
+    int status = kBatchFull;
+    while (n < limit) {
+      if (cur_.empty() || seg_ == cur_.size()) { status = kNeedWindow; break; }
+      const ParsedSegment& s = *cur_[seg_];
+      if (rd_ == s.n_reads()) { ++seg_; rd_ = 0; continue; }
+      // as many whole reads of this segment as fit (FastxFile keeps kMaxRead bytes of head room)
+      size_t take = std::min(s.n_reads() - rd_, limit - n);
+      if (o + FastxFile::kMaxRead > b.cap_bases) break;
+      const uint64_t room = b.cap_bases - FastxFile::kMaxRead - o;
+      const uint32_t c0 = s.cum[rd_];
+      bool full = false;
+      if ((uint64_t)(s.cum[rd_ + take] - c0) > room) {
+        // largest i with cum[rd_ + i] - c0 <= room
+        const uint32_t* lo = s.cum.data() + rd_;
+        const uint32_t* it = std::upper_bound(lo, lo + take + 1, (uint32_t)std::min<uint64_t>(room + c0, 0xFFFFFFFFull));
+        take = (size_t)(it - lo) - 1;
+        full = true;
+        if (take == 0) break;
+      }
+      jobs.push_back({&s, rd_, take, (uint32_t)o, n});
+      total_bytes += s.cum[rd_ + take] - c0;
+      o += s.cum[rd_ + take] - c0;
+      n += take;
+      rd_ += take;
+      if (full) break;                                             // base buffer full
+    }
+    auto run_job = [&b](const Job& j) {
+      const uint32_t c0 = j.s->cum[j.rd];
+      memcpy(b.bases + j.dst_off, j.s->bases.data() + c0, j.s->cum[j.rd + j.cnt] - c0);
+      const uint32_t* c = j.s->cum.data() + j.rd;
+      uint32_t* d = b.off + j.dst_rd;
+      const uint32_t shift = j.dst_off - c0;     // modular arithmetic: dst = cum - c0 + dst_off
+      for (size_t i = 1; i <= j.cnt; ++i) d[i] = c[i] + shift;
+    };
+    const size_t n_workers = total_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>((size_t)copy_threads_, jobs.size());
+    if (n_workers <= 1) {
+      for (const Job& j : jobs) run_job(j);
+    } else {
+      std::vector<std::future<void>> fu;
+      for (size_t w = 0; w < n_workers; ++w)
+        fu.push_back(std::async(std::launch::async, [&, w] { for (size_t i = w; i < jobs.size(); i += n_workers) run_job(jobs[i]); }));
+      for (auto& f : fu) f.get();
+    }
+    for (const Job& j : jobs) if (j.s->max_len > b.max_len) b.max_len = j.s->max_len;   // upper bound
+    b.n = n;
+    return status;
+  }
 
   // first position >= s that starts a line "@..." whose next-but-one line starts with '+', or npos
   size_t guess_start(size_t s, size_t limit) const {
@@ -307,7 +356,12 @@ class ParallelFastx {
     return (size_t)-1;
   }
 
+  static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+
   Window parse_window(size_t begin, size_t end) {
+    const double t0 = now_s();
     // begin is a proven record boundary; records whose header lies in [begin, end) belong to this window
     std::vector<size_t> starts(1, begin);
     const size_t step = std::max<size_t>((end - begin) / (size_t)threads_, 1);
@@ -326,7 +380,7 @@ class ParallelFastx {
       ParsedSegment* seg = w[i].get();
       fu.push_back(std::async(std::launch::async, [this, a, z, seg] {
         seg->bases.reserve((z - a) / 2 + 64);
-        seg->lens.reserve((z - a) / 64 + 16);
+        seg->cum.reserve((z - a) / 64 + 16);
         seg->end_pos = parse_range(data_, size_, a, z, *seg);
       }));
     }
@@ -343,6 +397,9 @@ class ParallelFastx {
         break;
       }
     }
+    ++n_windows_;
+    n_segments_ += w.size();
+    t_parse_ += now_s() - t0;
     return w;
   }
 
@@ -352,9 +409,7 @@ class ParallelFastx {
     if (pool_.empty()) return std::unique_ptr<ParsedSegment>(new ParsedSegment());
     std::unique_ptr<ParsedSegment> s = std::move(pool_.back());
     pool_.pop_back();
-    s->bases.clear();
-    s->lens.clear();
-    s->end_pos = 0;
+    s->reset();
     return s;
   }
   void give_segment(std::unique_ptr<ParsedSegment> s) {
@@ -372,10 +427,18 @@ class ParallelFastx {
   bool next_window() {
     for (auto& s : cur_) give_segment(std::move(s));
     cur_.clear();
-    seg_ = rd_ = boff_ = 0;
+    seg_ = rd_ = 0;
     if (!pending_.valid()) return false;
+    const double t0 = now_s();
     cur_ = pending_.get();
+    t_wait_ += now_s() - t0;
     next_begin_ = cur_.empty() ? size_ : cur_.back()->end_pos;   // proven: the sequential parser continues here
+    // the file bytes before next_begin_ are parsed: give the pages back now, not in one long munmap at the end
+    const size_t page = 4096, upto = std::min(next_begin_, size_) / page * page;
+    if (upto > unmapped_) {
+      munmap((void*)(data_ + unmapped_), upto - unmapped_);
+      unmapped_ = upto;
+    }
     launch_next();
     return true;
   }
@@ -384,11 +447,13 @@ class ParallelFastx {
   int threads_;
   int fd_ = -1;
   const char* data_ = nullptr;
-  size_t size_ = 0, window_ = 0, next_begin_ = 0;
+  size_t size_ = 0, window_ = 0, next_begin_ = 0, unmapped_ = 0;
+  int copy_threads_ = 1;
   std::future<Window> pending_;
   Window cur_;
-  size_t seg_ = 0, rd_ = 0, boff_ = 0;
-  size_t n_fallbacks_ = 0;
+  size_t seg_ = 0, rd_ = 0;
+  size_t n_fallbacks_ = 0, n_windows_ = 0, n_segments_ = 0;
+  double t_parse_ = 0, t_wait_ = 0;
   std::mutex pool_m_;
   std::vector<std::unique_ptr<ParsedSegment>> pool_;
 };

@@ -137,10 +137,25 @@ def test_quant_parallel_ingest_plain_fastq(tmp_path, monkeypatch):
         p.write_bytes(gzip.open(os.path.join(ds["dir"], "reads_%d.fastq.gz" % m)).read())
         files.append(str(p))
     monkeypatch.setenv("KB_FASTX_WINDOW", "30000")
+    monkeypatch.setenv("KB_CLI_BATCH_READS", "700,1100")      # the two files cut their batches differently
     out = tmp_path / "o"
-    r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "-t", "8", "-b", "2", "--seed", "42"] + files)
+    r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "-t", "8", "-b", "3", "--seed", "42"] + files)
     assert r.returncode == 0, r.stderr
     ref = os.path.join(ds["dir"], "ref_quant_paired")
-    for fn in ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv"]:
+    for fn in ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv", "bs_abundance_2.tsv"]:
         assert open(out / fn).read() == open(os.path.join(ref, fn)).read(), fn
     same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
+
+
+def test_bus_unequal_batch_cuts(tmp_path, monkeypatch):
+    """The barcode file and the cDNA file cut their batches at different read counts: records still come out in
+    read order with the same EC ids."""
+    monkeypatch.setenv("KB_CLI_BATCH_READS", "300,470")
+    d = os.path.join(util.GOLDEN, "bus10x")
+    out = tmp_path / "o"
+    r = run(["bus", "-i", os.path.join(util.GOLDEN, "config1", "transcripts.kidx"), "-o", str(out), "-x", "10xv2", "-t", "4",
+             os.path.join(d, "sc_reads_1.fastq.gz"), os.path.join(d, "sc_reads_2.fastq.gz")])
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(d, "ref_10xv2")
+    for fn in ("output.bus", "matrix.ec", "transcripts.txt"):
+        assert open(out / fn, "rb").read() == open(os.path.join(ref, fn), "rb").read(), fn
