@@ -154,8 +154,20 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   }
   if (ix->empty_ec != 0xFFFFFFFFu) ix->empty_ec = (uint32_t)ix->h_ec_handle[ix->empty_ec];
 
-  // k-mer table: load factor <= 0.5
-  ix->table_cap = pow2_ge(std::max<uint64_t>(1024, f.n_kmers * 2));
+  // k-mer table.  Every probe costs one random 32-byte sector whatever the table size, and the sector rate of the
+  // L2-miss path is the bound of match_kernel (profiles/README.md), so HBM capacity is traded for shorter probe
+  // sequences: slots >= 4 x k-mers (load 0.14-0.27: 1.14 visits per lookup; human: 34 GB of the 180 GB) when that
+  // leaves three quarters of the free device memory to the run, else 2 x (load <= 0.5; 1.37 visits measured at
+  // 0.27).  KB_TABLE_FACTOR overrides.
+  double factor = 4.0;
+  {
+    size_t free_b = 0, total_b = 0;
+    KB_CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t cap4 = pow2_ge(std::max<uint64_t>(1024, f.n_kmers * 4));
+    if (cap4 * sizeof(KmerSlot) > free_b / 4) factor = 2.0;
+  }
+  if (const char* s = getenv("KB_TABLE_FACTOR")) { const double v = atof(s); if (v >= 1.25 && v <= 64.0) factor = v; }
+  ix->table_cap = pow2_ge(std::max<uint64_t>(1024, (uint64_t)((double)f.n_kmers * factor)));
   ix->slots.alloc(ix->table_cap);
   DBuf<int> err;
   err.alloc(1);
