@@ -286,6 +286,16 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
   if (bws_->d_tl.n < max_frag) bws_->d_tl.alloc(max_frag);
   if (bws_->d_qcount.n < 1) bws_->d_qcount.alloc(1);
   if (bws_->d_qentries.n < (size_t)max_frag * KB_Q_STRIDE) bws_->d_qentries.alloc((size_t)max_frag * KB_Q_STRIDE);
+  // rare path: fragments with more than KB_MAX_E distinct EC sets (spill area per resident lane + wide queue)
+  if (bws_->d_qbig_count.n < 1) bws_->d_qbig_count.alloc(1);
+  if (bws_->d_qbig.n < (size_t)KB_QBIG_CAP * KB_QBIG_STRIDE) bws_->d_qbig.alloc((size_t)KB_QBIG_CAP * KB_QBIG_STRIDE);
+  {
+    int sms = 0, tpsm = 0;
+    KB_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix_.device));
+    KB_CK(cudaDeviceGetAttribute(&tpsm, cudaDevAttrMaxThreadsPerMultiProcessor, ix_.device));
+    const size_t lanes = (size_t)sms * (size_t)tpsm;
+    if (bws_->d_spill.n < lanes * KB_SPILL) bws_->d_spill.alloc(lanes * KB_SPILL);
+  }
   // resolve-kernel scratch: 2 x max_set_len words per warp, at most ~1 GiB in total
   const uint64_t stride = std::max<uint64_t>(64, 2ull * ix_.max_set_len);
   uint64_t warps = (1ull << 28) / stride;
@@ -344,7 +354,7 @@ void Quant::check_device_errors() {
   if (herr & KB_DEVERR_DICT_FULL) m += " set dictionary full;";
   if (herr & KB_DEVERR_MEMO_FULL) m += " memo table full;";
   if (herr & KB_DEVERR_TPOOL_FULL) m += " tuple pool exhausted;";
-  if (herr & KB_DEVERR_E_OVERFLOW) m += " a fragment hit more than 16 distinct EC sets;";
+  if (herr & KB_DEVERR_E_OVERFLOW) m += " a fragment hit more than 128 distinct EC sets, or more than 65536 fragments of a batch hit more than 16;";
   throw Error(m);
 }
 
@@ -371,9 +381,11 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.tl_out = want_fld ? bws_->d_tl.p : nullptr;
   ba.q_count = bws_->d_qcount.p;
   ba.q_entries = bws_->d_qentries.p;
+  ba.spill = bws_->d_spill.p;
+  ba.qbig_count = bws_->d_qbig_count.p;
+  ba.qbig_entries = bws_->d_qbig.p;
+  ba.qbig_cap = KB_QBIG_CAP;
   ba.nb = std::max<uint32_t>(1, (max_read_len + 31) / 32);
-  ba.bwords = ba.nb + 1;
-  ba.iwords = ba.bwords / 2 + 1;
   ba.pstride = (3 * ba.nb + 7) & ~7u;
   {
     const size_t need = (size_t)n_reads * ba.pstride;

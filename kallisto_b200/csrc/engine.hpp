@@ -47,6 +47,7 @@ struct BatchWs {
   DBuf<uint8_t> stage_b[2][2];      // double-buffered input staging: H2D of batch i+1 overlaps the kernels of batch i
   DBuf<uint32_t> stage_o[2][2];
   DBuf<uint32_t> d_qcount, d_qentries, d_scratch, d_packed;
+  DBuf<uint32_t> d_spill, d_qbig_count, d_qbig;   // fragments with more than KB_MAX_E distinct EC sets
   DBuf<int32_t> d_handles;
   DBuf<uint16_t> d_tl;
 };

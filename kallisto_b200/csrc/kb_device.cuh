@@ -87,7 +87,7 @@ enum {
   KB_DEVERR_POOL_FULL = 1,
   KB_DEVERR_DICT_FULL = 2,
   KB_DEVERR_MEMO_FULL = 4,
-  KB_DEVERR_E_OVERFLOW = 8,     // more than KB_MAX_E distinct EC sets on the fast path (handled by slow path)
+  KB_DEVERR_E_OVERFLOW = 8,     // more than KB_MAX_E + KB_SPILL distinct EC sets in one fragment, or wide queue full
   KB_DEVERR_TABLE_DUP = 16,     // duplicate k-mer while building the table (corrupt index)
   KB_DEVERR_TPOOL_FULL = 32,
 };

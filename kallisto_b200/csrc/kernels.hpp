@@ -48,7 +48,10 @@ struct BatchArgs {
   uint16_t* tl_out;         // per fragment fragment-length candidate (mapPair), or nullptr
   uint32_t* q_count;        // resolve queue
   uint32_t* q_entries;      // stride KB_Q_STRIDE
-  uint32_t bwords, iwords;  // shared-memory words per read (2-bit bases / invalid mask)
+  uint32_t* spill;          // KB_SPILL words per resident lane of match_kernel: set handles beyond KB_MAX_E
+  uint32_t* qbig_count;     // wide resolve queue (fragments that hit more than KB_MAX_E distinct EC sets)
+  uint32_t* qbig_entries;   // stride KB_QBIG_STRIDE
+  uint32_t qbig_cap;        // entries
   const uint32_t* packed;   // pack_kernel output: per read, nb 64-bit base words then nb 32-bit invalid masks
   uint32_t nb;              // 32-base words per packed read = ceil(max_read_len / 32)
   uint32_t pstride;         // 32-bit words per packed read (multiple of 8 = 32 bytes)
@@ -59,6 +62,9 @@ struct BatchArgs {
   uint32_t start;           // first base of every read that is matched (bus: BUSOptionSubstr.start of the sequence)
 };
 static constexpr int KB_Q_STRIDE = 2 + KB_MAX_E + 6;   // frag, n|flags, handles, 2 strand words, 4 position-filter words
+static constexpr int KB_SPILL = 112;                   // a fragment may hit KB_MAX_E + KB_SPILL = 128 distinct EC sets
+static constexpr int KB_QBIG_STRIDE = 2 + KB_MAX_E + KB_SPILL + 6;
+static constexpr uint32_t KB_QBIG_CAP = 1u << 16;      // wide-queue entries per batch
 
 struct ResolveArgs {
   uint32_t* scratch;        // per warp: scratch_stride entries

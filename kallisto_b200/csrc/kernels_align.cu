@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
   uint32_t* elist = smem + tid;                                  // [KB_MAX_E]
   uint32_t* msave = elist + (size_t)KB_MAX_E * nt;               // [3]: block, offset | strand << 31, read position
   uint32_t* s_bw = msave + (size_t)3 * nt;                       // [mate][nw]
+  uint32_t* spill = ba.spill + ((size_t)blockIdx.x * nt + tid) * KB_SPILL;   // handles beyond KB_MAX_E (global memory)
   static_assert(KB_MAX_E + 6 <= KB_MAX_E + 3 + 4, "tuple extension must fit in the words that follow the handle list");
 
   // contiguous chunk of fragments owned by this warp
@@ -344,61 +345,88 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
         if (mapped && n_e == 0) mapped = false;
         int32_t handle = KB_H_UNMAPPED;
         if (mapped) {
-          for (int i = 1; i < n_e; ++i) {   // sort the distinct set handles (<= 16 entries)
-            const uint32_t x = elist[i * nt];
-            int j = i - 1;
-            while (j >= 0 && elist[j * nt] > x) { elist[(j + 1) * nt] = elist[j * nt]; --j; }
-            elist[(j + 1) * nt] = x;
-          }
           // single-end reads / pairs with one mate mapped, known mean fragment length: the transcripts
           // whose ends the fragment would overhang are filtered per fragment (ProcessReads.cpp:1095-1136)
           const bool want_fp = ba.fp_fl >= 0 && (!ba.paired || !v0 || !v1);
+          // words that follow the set handles in the tuple: (block, orientation) of each mate's first hit for the
+          // strand filter; block, orientation, read position and unitig offset of the mapped mate's first hit for
+          // the position filter
+          const bool stranded = ba.strand_mode != 0;
+          uint32_t xs0 = 0xFFFFFFFFu, xs1 = 0xFFFFFFFFu;
+          if (stranded) {
+            if (mate == 1) {
+              xs0 = v_first ? (m_blk * 2u + (m_ds >> 31)) : 0xFFFFFFFFu;
+              xs1 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
+            } else {
+              xs0 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
+            }
+          }
+          const bool use_first = (mate == 1) && !v_cur;     // second mate empty: the first mate's hit
+          const uint32_t xf0 = use_first ? m_blk : f_blk;
+          const uint32_t xf1 = use_first ? (m_ds >> 31) : (f_strand ? 1u : 0u);
+          const uint32_t xf2 = use_first ? m_pos : (uint32_t)f_pos;
+          const uint32_t xf3 = use_first ? (m_ds & 0x7FFFFFFFu) : f_dist;
+          const int nx = (stranded ? 2 : 0) + (want_fp ? 4 : 0);
+          // appends the extra words to a tuple stored with stride `st` starting at index `at`
+          auto put_extras = [&](uint32_t* dst, int at, int st) {
+            if (stranded) { dst[at * st] = xs0; dst[(at + 1) * st] = xs1; at += 2; }
+            if (want_fp) { dst[at * st] = xf0; dst[(at + 1) * st] = xf1; dst[(at + 2) * st] = xf2; dst[(at + 3) * st] = xf3; }
+          };
           if (overflow) {
             atomicOr(dd.error, KB_DEVERR_E_OVERFLOW);
-          } else if (ba.strand_mode == 0 && n_e == 1 && !want_fp) {
-            handle = (int32_t)elist[0];            // a single EC set: its handle is stored in the slot
-          } else {
-            int n = n_e;
-            int32_t r;
-            if (ba.strand_mode == 0 && n_e == 2 && !want_fp) {
-              r = memo2_lookup(dd, elist[0], elist[nt]);
-            } else {
-              if (ba.strand_mode != 0) {
-                // the strand filter depends on the first hit of each mate: (block, orientation)
-                uint32_t w0, w1 = 0xFFFFFFFFu;
-                if (mate == 1) {
-                  w0 = v_first ? (m_blk * 2u + (m_ds >> 31)) : 0xFFFFFFFFu;
-                  w1 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
-                } else {
-                  w0 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
-                }
-                elist[n * nt] = w0;
-                elist[(n + 1) * nt] = w1;
-                n += 2;
-              }
-              if (want_fp) {
-                // first hit of the mapped mate: block, orientation, read position, offset in the unitig
-                const bool use_first = (mate == 1) && !v_cur;     // second mate empty: the first mate's hit
-                elist[n * nt] = use_first ? m_blk : f_blk;
-                elist[(n + 1) * nt] = use_first ? (m_ds >> 31) : (f_strand ? 1u : 0u);
-                elist[(n + 2) * nt] = use_first ? m_pos : (uint32_t)f_pos;
-                elist[(n + 3) * nt] = use_first ? (m_ds & 0x7FFFFFFFu) : f_dist;
-                n += 4;
-                r = KB_H_NOTREADY;                      // depends on the read itself: never memoised
-              } else {
-                r = memon_lookup(dd, elist, n, nt);
-              }
+          } else if (n_e > KB_MAX_E) {
+            // ---- rare: more distinct EC sets than the shared-memory tuple holds (reads crossing many short EC
+            //      blocks).  The tail of the list lives in this lane's spill area in global memory; the tuple is
+            //      sorted through an accessor and handed to the resolve kernel through the wide queue, unmemoised.
+            auto E = [&](int i) -> uint32_t { return i < KB_MAX_E ? elist[i * nt] : spill[i - KB_MAX_E]; };
+            auto S = [&](int i, uint32_t x) { if (i < KB_MAX_E) elist[i * nt] = x; else spill[i - KB_MAX_E] = x; };
+            for (int i = 1; i < n_e; ++i) {
+              const uint32_t x = E(i);
+              int j = i - 1;
+              while (j >= 0 && E(j) > x) { S(j + 1, E(j)); --j; }
+              S(j + 1, x);
             }
-            if (r == KB_H_NOTREADY) {
-              handle = KB_H_PENDING;
-              const uint32_t q = atomicAdd(ba.q_count, 1u);
-              uint32_t* e = ba.q_entries + (size_t)q * KB_Q_STRIDE;
-              e[0] = frag;
-              e[1] = (uint32_t)n | (want_fp ? 0x80000000u : 0u);
-              for (int i = 0; i < n; ++i) e[2 + i] = elist[i * nt];
+            const uint32_t q = atomicAdd(ba.qbig_count, 1u);
+            if (q >= ba.qbig_cap) {
+              atomicOr(dd.error, KB_DEVERR_E_OVERFLOW);
             } else {
-              handle = r;
-              ++n_memo;
+              uint32_t* e = ba.qbig_entries + (size_t)q * KB_QBIG_STRIDE;
+              e[0] = frag;
+              e[1] = (uint32_t)(n_e + nx) | (want_fp ? 0x80000000u : 0u) | 0x40000000u;   // bit 30: never memoised
+              for (int i = 0; i < n_e; ++i) e[2 + i] = E(i);
+              put_extras(e + 2, n_e, 1);
+              handle = KB_H_PENDING;
+            }
+          } else {
+            for (int i = 1; i < n_e; ++i) {   // sort the distinct set handles (<= 16 entries)
+              const uint32_t x = elist[i * nt];
+              int j = i - 1;
+              while (j >= 0 && elist[j * nt] > x) { elist[(j + 1) * nt] = elist[j * nt]; --j; }
+              elist[(j + 1) * nt] = x;
+            }
+            if (ba.strand_mode == 0 && n_e == 1 && !want_fp) {
+              handle = (int32_t)elist[0];            // a single EC set: its handle is stored in the slot
+            } else {
+              const int n = n_e + nx;
+              int32_t r;
+              if (ba.strand_mode == 0 && n_e == 2 && !want_fp) {
+                r = memo2_lookup(dd, elist[0], elist[nt]);
+              } else {
+                put_extras(elist, n_e, nt);
+                // position-filtered fragments depend on the read itself: never memoised
+                r = want_fp ? KB_H_NOTREADY : memon_lookup(dd, elist, n, nt);
+              }
+              if (r == KB_H_NOTREADY) {
+                handle = KB_H_PENDING;
+                const uint32_t q = atomicAdd(ba.q_count, 1u);
+                uint32_t* e = ba.q_entries + (size_t)q * KB_Q_STRIDE;
+                e[0] = frag;
+                e[1] = (uint32_t)n | (want_fp ? 0x80000000u : 0u);
+                for (int i = 0; i < n; ++i) e[2 + i] = elist[i * nt];
+              } else {
+                handle = r;
+                ++n_memo;
+              }
             }
           }
         }
@@ -584,10 +612,13 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
           if (r_ec != ba.empty_ec) {               // "Don't intersect empty EC", MinCollector.cpp:468-469
             s_cur = true;
             bool dup = false;
-            for (int i = 0; i < n_e; ++i) dup |= (elist[i * nt] == r_ec);
+            const int n_sh = n_e < KB_MAX_E ? n_e : KB_MAX_E;
+            for (int i = 0; i < n_sh; ++i) dup |= (elist[i * nt] == r_ec);
+            for (int i = KB_MAX_E; i < n_e; ++i) dup |= (spill[i - KB_MAX_E] == r_ec);     // rare: spilled tail
             if (!dup) {
-              if (n_e == KB_MAX_E) overflow = true;
-              else { elist[n_e * nt] = r_ec; ++n_e; }
+              if (n_e < KB_MAX_E) { elist[n_e * nt] = r_ec; ++n_e; }
+              else if (n_e < KB_MAX_E + KB_SPILL) { spill[n_e - KB_MAX_E] = r_ec; ++n_e; }
+              else overflow = true;
             }
           }
         }
@@ -692,27 +723,32 @@ __device__ __forceinline__ int32_t dict_insert_warp(const DevDict& dd, const uin
 }  // namespace
 
 // One warp per queued fragment.
-__global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, BatchArgs ba, ResolveArgs ra) {
+__global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd, BatchArgs ba, ResolveArgs ra) {
   const unsigned lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= ra.n_warps) return;
-  const uint32_t nq = *ba.q_count;
   uint32_t* scratch = ra.scratch + (size_t)warp * ra.scratch_stride;
   const uint32_t* pool = dd.pool;
 
+  // pass 0: the regular queue; pass 1: the wide queue (fragments with more than KB_MAX_E distinct EC sets)
+  for (int pass = 0; pass < 2; ++pass) {
+  const uint32_t nq = pass == 0 ? *ba.q_count : min(*ba.qbig_count, ba.qbig_cap);
+  const uint32_t* entries = pass == 0 ? ba.q_entries : ba.qbig_entries;
+  const size_t stride = pass == 0 ? (size_t)KB_Q_STRIDE : (size_t)KB_QBIG_STRIDE;
   for (uint32_t q = warp; q < nq; q += ra.n_warps) {
-    const uint32_t* e = ba.q_entries + (size_t)q * KB_Q_STRIDE;
+    const uint32_t* e = entries + (size_t)q * stride;
     const uint32_t f = e[0];
     const bool has_fp = (e[1] >> 31) != 0;
+    const bool no_memo = has_fp || ((e[1] >> 30) & 1u) != 0;
     const int n = (int)(e[1] & 0xFFFFu);
     const uint32_t* w = e + 2;
     const bool stranded = ba.strand_mode != 0;
     const int n_e = n - (stranded ? 2 : 0) - (has_fp ? 4 : 0);
-    const bool use_m2 = (!stranded && !has_fp && n_e == 2);
+    const bool use_m2 = (!stranded && !no_memo && n_e == 2);
 
     // 1. has somebody else resolved the same tuple in the meantime?
     int32_t handle = KB_H_NOTREADY;
-    if (lane == 0 && !has_fp) handle = use_m2 ? memo2_lookup(dd, w[0], w[1]) : memon_lookup(dd, w, n, 1);
+    if (lane == 0 && !no_memo) handle = use_m2 ? memo2_lookup(dd, w[0], w[1]) : memon_lookup(dd, w, n, 1);
     handle = __shfl_sync(0xFFFFFFFFu, handle, 0);
 
     if (handle == KB_H_NOTREADY) {
@@ -840,7 +876,7 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
       // 4. set -> handle through the content-addressed dictionary
       handle = nres == 0 ? KB_H_UNMAPPED : dict_insert_warp(dd, scratch, nres, lane);
       // 5. publish tuple -> handle (not for position-filtered fragments: the result depends on the read)
-      if (lane == 0 && !has_fp) {
+      if (lane == 0 && !no_memo) {
         if (use_m2) {
           const unsigned long long key = ((unsigned long long)w[0] << 32) | w[1];
           uint64_t s = kb_mix64(key) & dd.m2_mask;
@@ -892,6 +928,7 @@ __global__ void __launch_bounds__(128) resolve_kernel(DevIndex ix, DevDict dd, B
     }
     __syncwarp();
   }
+  }
 }
 
 // A fragment contributes to the fragment-length distribution only if its EC has a single
@@ -916,6 +953,7 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
                         int tpb, cudaStream_t st, cudaEvent_t* ev) {
   if (ba.n_frag == 0) return;
   cudaMemsetAsync(ba.q_count, 0, sizeof(uint32_t), st);
+  cudaMemsetAsync(ba.qbig_count, 0, sizeof(uint32_t), st);
   // persistent grid: as many blocks as fit on the device at once
   const size_t smem = (size_t)tpb * 4 * ((size_t)KB_MAX_E + 3 + 4 * ba.nb);   // per lane: handle tuple, first-mate words, 2 x 2nb base words
   static int sms = 0;

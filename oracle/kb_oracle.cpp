@@ -335,7 +335,8 @@ struct KIt {
 typedef std::vector<std::pair<Um, int>> HitVec;
 
 // diagnostics: lookups of match() by kind -- 0 main hit, 1 main miss, 2 jump landing exactly where the
-// read would be if it followed the unitig, 3 jump on an absent k-mer, 4 other jumps, 5 middle, 6 back-off
+// read would be if it followed the unitig, 3 jump on an absent k-mer, 4 other jumps, 5 middle, 6 back-off;
+// [7] = largest number of distinct non-empty EC sets hit by one fragment
 static uint64_t g_kind[8];
 
 // KmerIndex::match, src/KmerIndex.cpp:1698-1940 (default flags; no D-list)
@@ -730,6 +731,18 @@ void oracle_pseudoalign_batch(void* run, const char* bases, const uint32_t* off,
     match(ix, s1.c_str(), (int)s1.size(), v1, !paired, &R.n_find);
     if (paired) match(ix, s2.c_str(), (int)s2.size(), v2, !paired, &R.n_find);
     intersectKmers(ix, v1, v2, u);
+    {   // diagnostics: distinct non-empty EC sets hit by the fragment (g_kind[7] = max over the run)
+      std::vector<const TidSet*> seen;
+      for (const HitVec* v : {&v1, &v2})
+        for (const auto& h : *v) {
+          const TidSet& t = blk(ix, h.first).tids;
+          if (t.empty()) continue;
+          bool dup = false;
+          for (const TidSet* s : seen) dup = dup || (*s == t);
+          if (!dup) seen.push_back(&t);
+        }
+      if (seen.size() > g_kind[7]) g_kind[7] = seen.size();
+    }
     u = intersect(u, ix.onlist);                                        // :1072
     if (R.fp_fl >= 0 && !u.empty() && (!paired || v1.empty() || v2.empty())) {   // :1095-1136
       TidSet vtmp;

@@ -25,7 +25,7 @@ def same_run_info(a, b):
     assert list(ja.keys()) == list(jb.keys())
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs"])
 def test_quant_paired_with_bootstrap(name, tmp_path):
     ds = util.dataset(name)
     out = tmp_path / "o"
