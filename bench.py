@@ -381,7 +381,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_total_ms, t_align_ms = float(tt[0]), float(tt[1])
     st = mc.finalize()
-    tm = mc.timings()
+    tm = mc.timings()       # after run_em: includes the EC numbering / CSR / CSC / EM launches
     if os.environ.get("KB_BENCH_ROWSTATS") and rank == 0:     # shape of the EM problem (diagnostics only)
         eo, et, ec, _ = mc.ec_table()
         ln = np.diff(eo.astype(np.int64))
@@ -473,7 +473,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": P * 2 * READ_LEN,
                 "d2h_bytes_per_step": int(index.num_trans * 16 / K), "seconds": t_e2e,
                 "api": "kb_pseudoalign_batch (pinned host bases) x K, kb_em_run"},
-        "gpu_launches": int(tm["match_launches"] + tm["resolve_launches"] + 4),
+        "gpu_launches": int(tm["kernel_launches"]) + (2 if world > 1 else 0),   # counted by the engine; + export/import kernels of the merge
         "roofline": roofline,
     }
     if cpu:

@@ -104,6 +104,8 @@ int kb_quant_set_stream(kb_quant* q, void* cuda_stream);
 typedef struct kb_kernel_timings {
   double match_ms, resolve_ms, em_ms, em_prep_ms;
   uint64_t match_launches, resolve_launches;
+  uint64_t kernel_launches;   /* launches of the library's own kernels by this run so far (pack, match, resolve,
+                                 fld, EC numbering / CSR / CSC construction, EM); CUB sort/scan launches not counted */
 } kb_kernel_timings;
 int kb_quant_enable_timing(kb_quant* q, int on);
 int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out);

@@ -187,6 +187,7 @@ int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out) {
     out->resolve_launches = t.resolve_launches;
     out->em_ms = q->q->last_em_seconds * 1e3;
     out->em_prep_ms = q->q->last_prep_seconds * 1e3;
+    out->kernel_launches = q->q->n_kernel_launches;
   });
 }
 

@@ -415,8 +415,10 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   }
   launch_pseudoalign(ix_.dev, dd_, ba, ra, tpb, stream_, ev);
   KB_CK(cudaGetLastError());
+  n_kernel_launches += 3;          // pack_kernel, match_kernel, resolve_kernel
   if (want_fld) {
     launch_fld_finalize(dd_, ba, stream_);
+    ++n_kernel_launches;
     h_tl_.resize(n_frag);
     bws_->d_tl.download(h_tl_.data(), n_frag, 0, stream_);
     KB_CK(cudaStreamSynchronize(stream_));
@@ -973,6 +975,8 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   p.rounds = w.emi.p; p.state = w.emi.p + 1; p.fstate = w.emi.p + 3; p.chcount = w.chcount.p;
   p.max_iter = max_iter; p.min_rounds = min_rounds;
   mark("fill launches + uploads");
+  // collect_used, gather_used, ec_meta, ec_fill, csc_fill, stats, fill_i32 + em_kernel
+  n_kernel_launches += 7 + 1;
   KB_CK(cudaEventRecord(e1, st));
   launch_em(p, em_tpb(), st);
   KB_CK(cudaGetLastError());

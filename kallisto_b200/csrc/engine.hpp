@@ -179,6 +179,7 @@ class Quant {
   const QuantOptions& options() const { return opt_; }
   cudaStream_t stream() const { return stream_; }
   double last_em_seconds = 0, last_prep_seconds = 0;
+  uint64_t n_kernel_launches = 0;   // launches of this library's own kernels by this run (CUB's are not counted)
   // filled by run_em_device
   bool dev_stats_valid_ = false;
   uint64_t dev_n_ecs_ = 0, dev_nnz_ = 0, dev_pseudoaligned_ = 0, dev_unique_ = 0;

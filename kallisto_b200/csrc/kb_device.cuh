@@ -21,7 +21,6 @@ namespace kb {
 
 static constexpr uint64_t KB_EMPTY_KEY = ~0ULL;
 static constexpr int KB_MAX_E = 16;          // distinct EC sets tracked per fragment on the fast path
-static constexpr int KB_SCAN_W = 4;         // independent k-mer lookups in flight while scanning a stretch of misses
 static constexpr int32_t KB_H_UNMAPPED = -1;
 static constexpr int32_t KB_H_PENDING = -2;  // fragment queued for the resolve kernel
 static constexpr int32_t KB_H_NOTREADY = -3; // memo slot claimed, value not yet published

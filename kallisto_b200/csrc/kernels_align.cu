@@ -68,14 +68,6 @@ __device__ __forceinline__ void ld256_probe(const void* p, uint32_t (&w)[8]) {
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                : "l"(p));
 }
-// Same for memory other blocks may be writing during the kernel (memo tables): L2-coherent.
-__device__ __forceinline__ void ld256_cg(const void* p, uint32_t (&w)[8]) {
-  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-               : "l"(p)
-               : "memory");
-}
-
 // Per-lane view of the read being matched: 2-bit bases in shared memory as 32-bit words (base i in
 // bits 30-2*(i&15) of word i>>4), word w of lane t at [w * stride + t] (bank-conflict free).
 // Bases other than A/C/G/T are rare, so the lane keeps only a flag in a register; a read that has
