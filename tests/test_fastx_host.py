@@ -120,3 +120,42 @@ def test_parallel_gz_falls_back_to_zlib(tmp_path):
     d = util.dataset("config1")
     f = os.path.join(d["dir"], "reads_1.fastq.gz")
     assert K.fastx_summary(f, 8) == K.fastx_summary(f, 1)
+
+
+def test_garbage_input_never_crashes(tmp_path):
+    """Random bytes, records cut mid-way, a truncated gzip stream: both readers finish (with records or an error)."""
+    import random
+    import subprocess
+    import sys
+    rnd = random.Random(11)
+    good = b"".join(b"@r%d\nACGTNACGT%s\n+\nIIIIIIIII%s\n" % (i, b"A" * (i % 7), b"I" * (i % 7)) for i in range(300))
+    cases = {"rand": bytes(rnd.randrange(256) for _ in range(20000)),
+             "ats": b"@" * 5000, "plus": b"@x\n" + b"+\n" * 3000, "nl": b"\n" * 4000,
+             "cut1": good[:len(good) // 2 + 3], "cut2": good[:len(good) - 5], "nul": good.replace(b"A", b"\0", 50)}
+    for i in range(8):
+        b = bytearray(good)
+        for _ in range(20):
+            b[rnd.randrange(len(b))] = rnd.randrange(256)
+        cases["flip%d" % i] = bytes(b)
+    gz = gzip.compress(good)
+    cases["trunc.gz"] = gz[:len(gz) // 2]
+    for name, blob in cases.items():
+        (tmp_path / name).write_bytes(blob)
+    child = ("import sys, os\nsys.path.insert(0, sys.argv[1])\nimport kallisto_b200 as K\n"
+             "os.environ['KB_FASTX_WINDOW'] = '257'\n"
+             "for fn in sorted(os.listdir(sys.argv[2])):\n"
+             "    for t in (1, 4):\n"
+             "        try:\n"
+             "            r = K.fastx_summary(os.path.join(sys.argv[2], fn), t)\n"
+             "            print(fn, t, 'OK', r[0], r[1], r[2], flush=True)\n"
+             "        except K.KallistoB200Error:\n"
+             "            print(fn, t, 'ERR', flush=True)\n")
+    r = subprocess.run([sys.executable, "-c", child, util.ROOT, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, "a reader crashed: rc %d\n%s\n%s" % (r.returncode, r.stdout[-400:], r.stderr[-400:])
+    out = {}
+    for line in r.stdout.splitlines():
+        a = line.split()
+        out.setdefault(a[0], {})[a[1]] = a[2:]
+    assert set(out) == set(cases)
+    for name, res in out.items():
+        assert res["1"] == res["4"], (name, res)          # the parallel reader is the sequential parse, also on garbage
