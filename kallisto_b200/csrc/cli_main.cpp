@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 
 #include <atomic>
+#include <algorithm>
 #include <charconv>
 #include <chrono>
 #include <condition_variable>
@@ -30,7 +31,7 @@ using std::endl;
 namespace {
 
 const char* KALLISTO_VERSION = "0.51.1";   // the reference version whose behaviour is reproduced
-const char* ERROR_STR = "\033[1mError:\033[0m";
+const char* ERROR_STR = "Error:";   // src/main.cpp:29
 
 struct Options {
   int threads = 1;
@@ -669,8 +670,10 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     if (stat(fn.c_str(), &stt) != 0) { cerr << ERROR_STR << " file not found " << fn << endl; ret = false; }
   kb_bus_opts bo{};
   int tech_strand = 0;
+  std::string tech_upper = technology;
+  for (auto& ch : tech_upper) ch = (char)toupper(ch);
   if (technology.empty()) {
-    cerr << "Error: need to specify technology to use" << endl;
+    if (ret) cerr << "Error: the technology must be specified via -x, use \"bulk\" for regular RNA-seq reads" << endl;   // src/main.cpp:1058
     ret = false;
   } else {
     std::string up = technology;
@@ -688,7 +691,12 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
       std::stringstream ss(technology);
       std::string part;
       while (std::getline(ss, part, ':')) parts.push_back(part);
-      if (parts.size() != 3 || !parse_triplets(parts[0], bc) || !parse_triplets(parts[1], umi) || !parse_triplets(parts[2], seq)) {
+      const size_t n_colons = (size_t)std::count(technology.begin(), technology.end(), ':');
+      if (n_colons != 2) {
+        cerr << "Error: technology string must contain two colons (:), " << (n_colons == 1 ? "only one found" : "three found") << ": \""
+             << tech_upper << "\"" << endl;
+        ret = false;
+      } else if (parts.size() != 3 || !parse_triplets(parts[0], bc) || !parse_triplets(parts[1], umi) || !parse_triplets(parts[2], seq)) {
         cerr << "Error: could not parse technology string " << technology << endl;
         ret = false;
       } else {
@@ -698,7 +706,8 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
         if (bc.size() == 1 && bc[0].fileno == -1) bc.clear();   // no barcode
       }
     } else {
-      cerr << "Error: technology " << technology << " is not supported by this build" << endl;
+      // ParseTechnology, src/main.cpp:778-794: anything that is not a known name is read as a bc:umi:seq string
+      cerr << "Error: technology string must contain two colons (:), none found: \"" << tech_upper << "\"" << endl;
       ret = false;
     }
     if (ret) {
@@ -716,7 +725,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   }
   if (ret && opt.files.size() % bo.nfiles != 0) {
     cerr << "Error: Number of files (" << opt.files.size() << ") does not match number of input files required by "
-         << "technology " << technology << " (" << bo.nfiles << ")" << endl;
+         << "technology " << tech_upper << " (" << bo.nfiles << ")" << endl;
     ret = false;
   }
   int strand = 0;
