@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over gloo: the EC-table exchange of kallisto_b200/multigpu.py (the only
+"""CPU, world_size 2 and 4 over gloo: the EC-table exchange of kallisto_b200/multigpu.py (the only
 collective step of the multi-GPU path).  The GPU-side merge kernel is covered by tests/test_gpu_multi.py;
 here the protocol itself (sizes, padding, ordering) is checked against a single-process merge."""
 import os
@@ -71,17 +71,18 @@ def worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_table_exchange_world2():
+@pytest.mark.parametrize("world", [2, 4])
+def test_table_exchange(world):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=180) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, True), (1, True)]
+    assert sorted(res) == [(r, True) for r in range(world)]
