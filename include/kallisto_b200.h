@@ -196,6 +196,11 @@ int kb_fastx_summary(const char* path, uint64_t* n_reads, uint64_t* n_bases, uin
  * reader_lock, src/ProcessReads.cpp:945,3128-3267). */
 int kb_fastx_summary_mt(const char* path, int threads, uint64_t* n_reads, uint64_t* n_bases, uint64_t* fnv1a);
 
+/* Host-only: decompress a gzip file with the command-line front end's decoder (csrc/fast_inflate.hpp, which
+ * stands in for zlib's gzread on the reference's input path, src/common.h:216-225) and report the number of
+ * bytes and their CRC-32.  Tooling / tests: the decoder must produce what zlib produces. */
+int kb_gz_summary(const char* path, uint64_t* n_bytes, uint32_t* crc32_out);
+
 /* counts_to_tpm (src/PlaintextWriter.cpp:5-27) -- host arithmetic, here so that callers format
  * identical numbers. */
 int kb_counts_to_tpm(const double* est_counts, const double* eff_lens, uint32_t n, double* tpm_out);

@@ -87,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "kb_index_target_lens", "kb_index_inspect", "kb_quant_create", "kb_quant_free", "kb_pseudoalign_batch",
     "kb_pseudoalign_batch_pe", "kb_host_alloc", "kb_host_free", "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_set_stream", "kb_quant_enable_timing",
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
-    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device", "kb_bus_create", "kb_bus_batch", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_counts_to_tpm",
+    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device", "kb_bus_create", "kb_bus_batch", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -139,6 +139,7 @@ def lib():
     L.kb_bus_batch.argtypes = [vp, vp, vp, u32, vp, C.POINTER(u32)]
     L.kb_bus_lengths.argtypes = [vp, vp, vp]
     L.kb_fastx_summary.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.kb_gz_summary.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.kb_fastx_summary_mt.argtypes = [C.c_char_p, C.c_int, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     _lib = L
     return L
@@ -388,6 +389,13 @@ def fastx_summary(path, threads=1):
     n, b, h = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
     _ck(lib().kb_fastx_summary_mt(os.fsencode(path), int(threads), C.byref(n), C.byref(b), C.byref(h)))
     return n.value, b.value, h.value
+
+
+def gz_summary(path):
+    """(bytes, crc32) of a gzip file's content through the CLI's own inflate (csrc/fast_inflate.hpp)."""
+    n, c = C.c_uint64(0), C.c_uint32(0)
+    _ck(lib().kb_gz_summary(os.fsencode(path), C.byref(n), C.byref(c)))
+    return n.value, c.value
 
 
 def counts_to_tpm(est_counts, eff_lens):

@@ -384,6 +384,26 @@ int kb_fastx_summary_mt(const char* path, int threads, uint64_t* n_reads, uint64
   }
 }
 
+int kb_gz_summary(const char* path, uint64_t* n_bytes, uint32_t* crc) {
+  if (!path || !n_bytes || !crc) return fail(KB_ERR_INVALID, "kb_gz_summary: null argument");
+  try {
+    kb::FastGz g(path);
+    const char* p = nullptr;
+    size_t n = 0;
+    uint64_t tot = 0;
+    uint32_t c = 0;
+    while (g.next_chunk(p, n)) {
+      tot += n;
+      c = kb::fast_crc32(c, (const uint8_t*)p, n);
+    }
+    *n_bytes = tot;
+    *crc = c;
+    return KB_OK;
+  } catch (const std::exception& e) {
+    return fail(KB_ERR_IO, e.what());
+  }
+}
+
 int kb_counts_to_tpm(const double* est_counts, const double* eff_lens, uint32_t n, double* tpm_out) {
   if (!est_counts || !eff_lens || !tpm_out) return fail(KB_ERR_INVALID, "kb_counts_to_tpm: null argument");
   const double MILLION = 1e6;
