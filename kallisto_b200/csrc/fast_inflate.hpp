@@ -124,7 +124,8 @@ class FastGz {
       in_ = (const uint8_t*)m;
       madvise((void*)in_, size_, MADV_SEQUENTIAL);
     }
-    out_.resize(kHist + kChunk + kSlack);
+    for (auto& b : bufs_) b.resize(kHist + kChunk + kSlack);
+    out_ = bufs_[0].data();
     op_ = rp_ = crc_from_ = floor_ = kHist;
   }
   ~FastGz() {
@@ -144,21 +145,27 @@ class FastGz {
     return n == 3 && m[0] == 0x1f && m[1] == 0x8b && m[2] == 8;
   }
 
-  // Next piece of decompressed data (valid until the next call); false at the end of the file.
+  // Next piece of decompressed data; false at the end of the file.  The decoder rotates through kBufs output
+  // buffers, so a chunk stays valid until kBufs - 1 further calls have been made (GzPrefetch hands chunks to the
+  // parser without copying them).
+  static constexpr int kBufs = 4;
   bool next_chunk(const char*& p, size_t& n) {
     while (rp_ == op_) {
       if (state_ == kEnd) return false;
-      // keep the last 32 KiB as match history, decode the next chunk behind it
+      // the last 32 KiB are the match history of what comes next: carry them to the front of the next buffer
       if (op_ > kHist) {
         flush_crc();
         const size_t delta = op_ - kHist;
-        memmove(out_.data(), out_.data() + delta, kHist);
+        cur_buf_ = (cur_buf_ + 1) % kBufs;
+        uint8_t* next = bufs_[cur_buf_].data();
+        memcpy(next, out_ + delta, kHist);
+        out_ = next;
         op_ = rp_ = crc_from_ = kHist;
         floor_ = floor_ > delta ? floor_ - delta : 0;
       }
       decode(kHist + kChunk);
     }
-    p = (const char*)out_.data() + rp_;
+    p = (const char*)out_ + rp_;
     n = op_ - rp_;
     rp_ = op_;
     return true;
@@ -407,7 +414,7 @@ class FastGz {
   // brings crc_ / isize_ up to date with everything decoded so far
   void flush_crc() {
     if (op_ > crc_from_) {
-      crc_ = fast_crc32((uint32_t)crc_, out_.data() + crc_from_, op_ - crc_from_);
+      crc_ = fast_crc32((uint32_t)crc_, out_ + crc_from_, op_ - crc_from_);
       isize_ += op_ - crc_from_;
       crc_from_ = op_;
     }
@@ -452,7 +459,7 @@ class FastGz {
           if (room == 0) return;
           const size_t n = stored_left_ < room ? stored_left_ : room;
           if (ip_ + n > size_) bad("truncated stored block");
-          memcpy(out_.data() + op_, in_ + ip_, n);
+          memcpy(out_ + op_, in_ + ip_, n);
           ip_ += n;
           op_ += n;
           stored_left_ -= n;
@@ -471,7 +478,7 @@ class FastGz {
   // true when the end-of-block symbol was consumed; false when the output limit was reached first.
   // The bit reader lives in locals here (the members would be reloaded around every store through `out`).
   bool huffman(size_t limit) {
-    uint8_t* const out = out_.data();
+    uint8_t* const out = out_;
     size_t op = op_;
     const uint32_t* const lit = lit_.data();
     const uint32_t* const dst = dist_.data();
@@ -663,7 +670,9 @@ class FastGz {
   size_t size_ = 0, ip_ = 0;
   uint64_t bitbuf_ = 0;
   int bitcnt_ = 0;
-  std::vector<uint8_t> out_;
+  std::vector<uint8_t> bufs_[kBufs];
+  int cur_buf_ = 0;
+  uint8_t* out_ = nullptr;
   size_t op_ = 0, rp_ = 0, crc_from_ = 0;
   size_t floor_ = 0;     // oldest position in out_ a match may reference
   State state_ = kMemberHeader;

@@ -49,10 +49,12 @@ struct ReadBatch {
   size_t n_bases() const { return off ? off[n] : 0; }
 };
 
-// Decompression of a regular .gz file on its own thread (csrc/fast_inflate.hpp), a few chunks ahead of the parser.
+// Decompression of a regular .gz file on its own thread (csrc/fast_inflate.hpp), up to two chunks ahead of the
+// parser.  Chunks are handed over by pointer: the decoder rotates through FastGz::kBufs buffers and a slot of the
+// ring is reserved BEFORE a chunk is decoded, so a buffer is only reused after the parser has released it.
 class GzPrefetch {
  public:
-  explicit GzPrefetch(const std::string& path) : gz_(path), slots_(3) {
+  explicit GzPrefetch(const std::string& path) : gz_(path) {
     th_ = std::thread([this] { run(); });
   }
   ~GzPrefetch() {
@@ -69,39 +71,43 @@ class GzPrefetch {
   // next piece of decompressed data, valid until the next call; false at the end; rethrows decoder errors
   bool next_chunk(const char*& p, size_t& n) {
     std::unique_lock<std::mutex> lk(m_);
-    if (held_) {                       // give the previous slot back
-      slots_[tail_].full = false;
-      tail_ = (tail_ + 1) % slots_.size();
+    if (held_) {                       // give the previous chunk back
+      --outstanding_;
+      tail_ = (tail_ + 1) % kRing;
       held_ = false;
       cv_.notify_all();
     }
-    cv_.wait(lk, [&] { return slots_[tail_].full || done_; });
-    if (!slots_[tail_].full) {
+    cv_.wait(lk, [&] { return ready_ > 0 || done_; });
+    if (ready_ == 0) {
       if (err_) std::rethrow_exception(err_);
       return false;
     }
-    p = slots_[tail_].data.data();
-    n = slots_[tail_].data.size();
+    p = ring_[tail_].p;
+    n = ring_[tail_].n;
+    --ready_;
     held_ = true;
     return true;
   }
 
  private:
-  struct Slot { std::vector<char> data; bool full = false; };
+  static constexpr size_t kRing = FastGz::kBufs - 1;     // chunks decoded and not yet released
+  struct Slot { const char* p; size_t n; };
   void run() {
     try {
-      const char* p;
-      size_t n;
-      while (gz_.next_chunk(p, n)) {
-        std::unique_lock<std::mutex> lk(m_);
-        cv_.wait(lk, [&] { return !slots_[head_].full || stop_; });
-        if (stop_) return;
-        Slot& s = slots_[head_];
-        lk.unlock();
-        s.data.assign(p, p + n);       // the decoder reuses its buffer: copy out (memcpy speed)
-        lk.lock();
-        s.full = true;
-        head_ = (head_ + 1) % slots_.size();
+      for (;;) {
+        {
+          std::unique_lock<std::mutex> lk(m_);
+          cv_.wait(lk, [&] { return outstanding_ < kRing || stop_; });
+          if (stop_) return;
+          ++outstanding_;              // reserve before decoding: the buffer about to be written is free
+        }
+        const char* p = nullptr;
+        size_t n = 0;
+        if (!gz_.next_chunk(p, n)) break;
+        std::lock_guard<std::mutex> lk(m_);
+        ring_[head_] = Slot{p, n};
+        head_ = (head_ + 1) % kRing;
+        ++ready_;
         cv_.notify_all();
       }
     } catch (...) {
@@ -113,8 +119,8 @@ class GzPrefetch {
     cv_.notify_all();
   }
   FastGz gz_;
-  std::vector<Slot> slots_;
-  size_t head_ = 0, tail_ = 0;
+  Slot ring_[kRing];
+  size_t head_ = 0, tail_ = 0, ready_ = 0, outstanding_ = 0;
   bool held_ = false, done_ = false, stop_ = false;
   std::exception_ptr err_;
   std::mutex m_;
