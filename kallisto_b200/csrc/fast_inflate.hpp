@@ -505,79 +505,106 @@ class FastGz {
   } while (0)
     // ---- fast loop: at least 8 input bytes ahead, so every refill leaves >= 56 valid bits and no availability
     //      checks are needed (longest chain: 15 + 5 + 15 + 13 = 48 bits for a match, 3 x 11 for the literal run)
-    while (op < limit && ip <= in_fast_end) {
-      {
-        uint64_t w_;
-        memcpy(&w_, in + ip, 8);
-        bb |= w_ << bc;
-        ip += (size_t)((63 - bc) >> 3);
-        bc |= 56;
-      }
+    // The table entry of the NEXT symbol is looked up as soon as its index bits are known (a refill only adds
+    // bits above the ones already counted), so its L1 latency overlaps the stores of the current symbol.
+#define KB_FAST_REFILL()                       \
+  do {                                         \
+    uint64_t w_;                               \
+    memcpy(&w_, in + ip, 8);                   \
+    bb |= w_ << bc;                            \
+    ip += (size_t)((63 - bc) >> 3);            \
+    bc |= 56;                                  \
+  } while (0)
+    if (op < limit && ip <= in_fast_end) {
+      KB_FAST_REFILL();
       uint32_t e = lit[bb & lmask];
-      if (e & kSub) {
-        bb >>= (e & 0xFF);
-        bc -= (int)(e & 0xFF);
-        e = lit[(e >> 16) + (uint32_t)(bb & ((1u << ((e >> 11) & 31)) - 1))];
-      }
-      int cl = (int)(e & 0xFF);
-      if (cl == 0) { err = "invalid literal/length code"; break; }
-      bb >>= cl;
-      bc -= cl;
-      if (e & kLit) {
-        out[op] = (uint8_t)(e >> 16);
-        out[op + 1] = (uint8_t)(e >> 24);
-        op += 1 + ((e >> 11) & 1);
-        e = lit[bb & lmask];
-        cl = (int)(e & 0xFF);
-        if ((e & (kLit | kSub)) == kLit) {           // primary literal entries have 1 <= cl <= 11
-          bb >>= cl;
-          bc -= cl;
+      for (;;) {
+        // invariant: e = lit[bb & lmask] for the current bit position, bc >= 48 valid bits
+        if (e & kSub) {
+          bb >>= (e & 0xFF);
+          bc -= (int)(e & 0xFF);
+          e = lit[(e >> 16) + (uint32_t)(bb & ((1u << ((e >> 11) & 31)) - 1))];
+        }
+        int cl = (int)(e & 0xFF);
+        if (cl == 0) { err = "invalid literal/length code"; break; }
+        bb >>= cl;
+        bc -= cl;
+        if (e & kLit) {
+          uint32_t e2 = lit[bb & lmask];
           out[op] = (uint8_t)(e >> 16);
           out[op + 1] = (uint8_t)(e >> 24);
           op += 1 + ((e >> 11) & 1);
-          e = lit[bb & lmask];
-          cl = (int)(e & 0xFF);
-          if ((e & (kLit | kSub)) == kLit) {
+          if ((e2 & (kLit | kSub)) == kLit) {           // primary literal entries have 1 <= cl <= 11
+            cl = (int)(e2 & 0xFF);
             bb >>= cl;
             bc -= cl;
-            out[op] = (uint8_t)(e >> 16);
-            out[op + 1] = (uint8_t)(e >> 24);
-            op += 1 + ((e >> 11) & 1);
+            e = lit[bb & lmask];
+            out[op] = (uint8_t)(e2 >> 16);
+            out[op + 1] = (uint8_t)(e2 >> 24);
+            op += 1 + ((e2 >> 11) & 1);
+            if ((e & (kLit | kSub)) == kLit) {
+              cl = (int)(e & 0xFF);
+              bb >>= cl;
+              bc -= cl;
+              out[op] = (uint8_t)(e >> 16);
+              out[op + 1] = (uint8_t)(e >> 24);
+              op += 1 + ((e >> 11) & 1);
+              if (!(op < limit && ip <= in_fast_end)) break;
+              KB_FAST_REFILL();
+              e = lit[bb & lmask];
+              continue;
+            }
+          } else {
+            e = e2;
           }
+          // e is the entry at the current position (bc >= 56 - 15 - 11 - 11 = 19 >= 11 index bits): top up and go on
+          if (!(op < limit && ip <= in_fast_end)) break;
+          KB_FAST_REFILL();
+          continue;
         }
-        continue;
-      }
-      if (e & kEob) { eob = true; break; }
-      const int leb = (int)((e >> 11) & 31);
-      uint32_t len = (e >> 16) + (uint32_t)(bb & ((1u << leb) - 1));
-      bb >>= leb;
-      bc -= leb;
-      uint32_t d = dst[bb & dmask];
-      if (d & kSub) {
-        bb >>= (d & 0xFF);
-        bc -= (int)(d & 0xFF);
-        d = dst[(d >> 16) + (uint32_t)(bb & ((1u << ((d >> 11) & 31)) - 1))];
-      }
-      const int dl = (int)(d & 0xFF);
-      if (dl == 0) { err = "invalid distance code"; break; }
-      const int deb = (int)((d >> 11) & 31);
-      bb >>= dl;
-      const uint32_t distance = (d >> 16) + (uint32_t)(bb & ((1u << deb) - 1));
-      bb >>= deb;
-      bc -= dl + deb;
-      if (distance > op - floor) { err = "distance too far back"; break; }
-      const uint8_t* src = out + op - distance;
-      uint8_t* dp = out + op;
-      op += len;
-      if (distance >= 8) {
-        const uint8_t* const end = dp + len;
-        do { memcpy(dp, src, 8); dp += 8; src += 8; } while (dp < end);
-      } else if (distance == 1) {
-        memset(dp, *src, len);
-      } else {
-        while (len--) *dp++ = *src++;
+        if (e & kEob) { eob = true; break; }
+        const int leb = (int)((e >> 11) & 31);
+        uint32_t len = (e >> 16) + (uint32_t)(bb & ((1u << leb) - 1));
+        bb >>= leb;
+        bc -= leb;
+        uint32_t d = dst[bb & dmask];
+        if (d & kSub) {
+          bb >>= (d & 0xFF);
+          bc -= (int)(d & 0xFF);
+          d = dst[(d >> 16) + (uint32_t)(bb & ((1u << ((d >> 11) & 31)) - 1))];
+        }
+        const int dl = (int)(d & 0xFF);
+        if (dl == 0) { err = "invalid distance code"; break; }
+        const int deb = (int)((d >> 11) & 31);
+        bb >>= dl;
+        const uint32_t distance = (d >> 16) + (uint32_t)(bb & ((1u << deb) - 1));
+        bb >>= deb;
+        bc -= dl + deb;
+        if (distance > op - floor) { err = "distance too far back"; break; }
+        const uint8_t* src = out + op - distance;
+        uint8_t* dp = out + op;
+        uint8_t* const end = dp + len;
+        op += len;
+        // next symbol: refill and look up before the copy
+        const bool more = op < limit && ip <= in_fast_end;
+        if (more) {
+          KB_FAST_REFILL();
+          e = lit[bb & lmask];
+        }
+        if (distance >= 16) {
+          do { memcpy(dp, src, 16); dp += 16; src += 16; } while (dp < end);     // may overshoot into the slack
+        } else if (distance >= 8) {
+          do { memcpy(dp, src, 8); dp += 8; src += 8; } while (dp < end);
+        } else if (distance == 1) {
+          const uint64_t v = 0x0101010101010101ull * *src;
+          do { memcpy(dp, &v, 8); dp += 8; } while (dp < end);
+        } else {
+          while (dp < end) *dp++ = *src++;
+        }
+        if (!more) break;
       }
     }
+#undef KB_FAST_REFILL
     // ---- careful loop: the last bytes of the input (and the remainder after an error-free fast loop)
     // every iteration may write one match of up to 258 bytes (+ word-copy overshoot inside kSlack)
     while (!err && !eob && op < limit) {
