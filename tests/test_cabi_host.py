@@ -56,3 +56,24 @@ def test_no_device_fails_loudly():
     with pytest.raises(K.KallistoB200Error) as ei:
         K.KmerIndex(util.dataset("config1")["index"])
     assert ei.value.code == K.KB_ERR_NO_DEVICE
+
+
+def test_c99_example_compiles_links_and_fails_loudly_without_a_device(tmp_path):
+    """examples/minimal_quant.c is plain C99 against include/kallisto_b200.h and links against the shared library
+    alone (no Python, no torch, no explicit -lz/-lcudart): the boundary is a real C ABI.  Without a CUDA device the
+    first call that needs one returns an error -- there is no CPU path to fall back to."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "minimal_quant")
+    libdir = os.path.join(util.ROOT, "kallisto_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(util.ROOT, "include"),
+                        os.path.join(util.ROOT, "examples", "minimal_quant.c"), "-L" + libdir, "-lkallisto_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, os.path.join(util.GOLDEN, "config1", "transcripts.kidx")], capture_output=True, text=True)
+    if r.returncode == 0:                      # a GPU is present: the two (identical) fragments are processed
+        assert "2 fragments" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CUDA device available" in r.stderr
