@@ -1,0 +1,112 @@
+"""CPU: the host side of the command line (parser threads, parallel reader for plain files, gzip decoder + prefetch
+thread, lock-step hand-over of the per-file batches, writers) run end to end against tests/stub/stub_abi.cpp, a
+stand-in for the library that only digests the fragments it receives, in order.  Whatever the thread count, window
+size, batch cut or input compression, the device must be handed the same reads in the same order; one configuration
+also runs under ThreadSanitizer.  (The real kernels behind the same CLI are covered by tests/test_gpu_cli.py.)"""
+import gzip
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from tests import util
+
+CSRC = os.path.join(util.ROOT, "kallisto_b200", "csrc")
+INC = os.path.join(util.ROOT, "include")
+pytestmark = pytest.mark.skipif(not shutil.which("g++"), reason="no g++")
+
+
+def build(dst, extra=()):
+    os.makedirs(dst, exist_ok=True)
+    lib = os.path.join(dst, "libkallisto_b200.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I" + INC, *extra, "-o", lib,
+                           os.path.join(util.ROOT, "tests", "stub", "stub_abi.cpp")])
+    exe = os.path.join(dst, "cli")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-I" + INC, "-I" + CSRC, *extra, "-o", exe,
+                           os.path.join(CSRC, "cli_main.cpp"), "-L" + dst, "-lkallisto_b200", "-Wl,-rpath," + dst, "-lz", "-lpthread"])
+    return exe
+
+
+@pytest.fixture(scope="module")
+def setup(tmp_path_factory):
+    d = tmp_path_factory.mktemp("stubcli")
+    exe = build(str(d / "plain"))
+    ds = os.path.join(util.GOLDEN, "synth_small")
+    plain = []
+    for m in (1, 2):
+        p = d / ("r%d.fq" % m)
+        p.write_bytes(gzip.open(os.path.join(ds, "reads_%d.fastq.gz" % m)).read())
+        plain.append(str(p))
+    gz = [os.path.join(ds, "reads_%d.fastq.gz" % m) for m in (1, 2)]
+    return dict(dir=d, exe=exe, plain=plain, gz=gz, idx=os.path.join(ds, "transcripts.kidx"))
+
+
+def quant(exe, idx, out, args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([exe, "quant", "-i", idx, "-o", str(out), "--plaintext"] + args, capture_output=True, text=True, env=e, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    return open(os.path.join(str(out), "abundance.tsv")).read(), r.stderr
+
+
+def test_same_reads_in_the_same_order_whatever_the_ingest_configuration(setup):
+    s = setup
+    base, _ = quant(s["exe"], s["idx"], s["dir"] / "o0", ["-t", "1"] + s["plain"])
+    assert "digest_lo" in base
+    configs = [
+        (["-t", "8"] + s["plain"], {"KB_FASTX_WINDOW": "30000", "KB_CLI_BATCH_READS": "700,1100"}),
+        (["-t", "4"] + s["plain"], {"KB_FASTX_WINDOW": "5000", "KB_CLI_BATCH_READS": "333,1000"}),
+        (["-t", "2"] + s["plain"], {"KB_CLI_BATCH_READS": "1,7"}),
+        (["-t", "1"] + s["gz"], {}),
+        (["-t", "8"] + s["gz"], {"KB_CLI_BATCH_READS": "512,4096"}),
+        (["-t", "1"] + s["gz"], {"KB_FASTGZ": "0"}),
+        (["-t", "3", s["plain"][0], s["gz"][1]], {"KB_FASTX_WINDOW": "9999"}),       # one plain, one compressed
+    ]
+    for i, (args, env) in enumerate(configs):
+        got, _ = quant(s["exe"], s["idx"], s["dir"] / ("o%d" % (i + 1)), args, env)
+        assert got == base, (args, env)
+    # single-end: only the first file, a different digest, but again independent of the configuration
+    se = ["--single", "-l", "200", "-s", "20"]
+    b1, _ = quant(s["exe"], s["idx"], s["dir"] / "s0", se + ["-t", "1", s["plain"][0]])
+    b2, _ = quant(s["exe"], s["idx"], s["dir"] / "s1", se + ["-t", "8", s["plain"][0]], {"KB_FASTX_WINDOW": "20000"})
+    b3, _ = quant(s["exe"], s["idx"], s["dir"] / "s2", se + ["-t", "8", s["gz"][0]])
+    assert b1 == b2 == b3 and b1 != base
+
+
+def test_files_with_different_read_counts_are_rejected(setup):
+    s = setup
+    short = s["dir"] / "short.fq"
+    short.write_bytes(b"".join(open(s["plain"][1], "rb").readlines()[:4 * 100]))
+    r = subprocess.run([s["exe"], "quant", "-i", s["idx"], "-o", str(s["dir"] / "bad"), "--plaintext", "-t", "4", s["plain"][0], str(short)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 1 and "different numbers of reads" in r.stderr
+
+
+def test_bus_records_in_read_order(setup):
+    s = setup
+    d = os.path.join(util.GOLDEN, "bus10x")
+    files = [os.path.join(d, "sc_reads_1.fastq.gz"), os.path.join(d, "sc_reads_2.fastq.gz")]
+    idx = os.path.join(util.GOLDEN, "config1", "transcripts.kidx")
+    outs = []
+    for i, env in enumerate([{}, {"KB_CLI_BATCH_READS": "300,470"}, {"KB_FASTGZ": "0", "KB_CLI_BATCH_READS": "1000,64"}]):
+        e = dict(os.environ)
+        e.update(env)
+        out = s["dir"] / ("b%d" % i)
+        r = subprocess.run([s["exe"], "bus", "-i", idx, "-o", str(out), "-x", "10xv2", "-t", "4"] + files, capture_output=True, text=True, env=e, timeout=600)
+        assert r.returncode == 0, r.stderr[-500:]
+        outs.append(open(out / "output.bus", "rb").read())
+    assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 1000
+
+
+def test_host_pipeline_under_thread_sanitizer(setup, tmp_path):
+    s = setup
+    probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", str(tmp_path / "probe")], input="int main(){}", text=True,
+                           capture_output=True)
+    if probe.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available")
+    exe = build(str(tmp_path / "tsan"), extra=("-fsanitize=thread",))
+    for args, env in [(["-t", "8"] + s["plain"], {"KB_FASTX_WINDOW": "30000", "KB_CLI_BATCH_READS": "700,1100"}),
+                      (["-t", "8"] + s["gz"], {"KB_CLI_BATCH_READS": "512,4096"})]:
+        _, err = quant(exe, s["idx"], tmp_path / "o", args, env)
+        assert "ThreadSanitizer" not in err, err[-2000:]
