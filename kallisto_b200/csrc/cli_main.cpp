@@ -379,6 +379,16 @@ void start_streams(std::vector<Stream>& streams, std::vector<std::thread>& reade
   }
 }
 
+void free_streams(std::vector<Stream>& streams) {
+  for (auto& s : streams)
+    for (auto& b : s.ring) {
+      kb_host_free(b.bases);
+      kb_host_free(b.off);
+      b.bases = nullptr;
+      b.off = nullptr;
+    }
+}
+
 // Lock-step consumer of the parser streams.  The streams cut their batches independently (by read count
 // or by bytes, whichever fills first), so a round hands out the reads that are available in EVERY stream
 // and leaves the rest of a longer batch for the next round.
@@ -564,6 +574,7 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
                       bs.data() + (size_t)b * T);
   }
   cerr << endl;
+  free_streams(streams);
   kb_quant_free(q);
   kb_index_free(ix);
   return st.n_pseudoaligned == 0 ? 1 : 0;
@@ -855,6 +866,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   write_run_info(opt.output + "/run_info.json", info.n_targets, 0, st.n_processed, st.n_pseudoaligned, st.n_unique, 13, info.k,
                  start_time, call);
   cerr << endl;
+  free_streams(streams);
   kb_quant_free(q);
   kb_index_free(ix);
   return st.n_pseudoaligned == 0 ? 1 : 0;
