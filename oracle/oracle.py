@@ -238,6 +238,22 @@ def ref_index(fasta, out, k=31, threads=1):
     return out
 
 
+def index_unitig_kinds(path):
+    """(n_long, n_short, n_abundant) from the GRAPH section of an index file (ext/bifrost/src/IO.tcc:1635-1738)."""
+    with open(path, "rb") as f:
+        b = f.read()
+    o = 16
+    _magic, _k, _g, n_long = struct.unpack_from("<QiiQ", b, o)
+    o += 24
+    for _ in range(n_long):
+        (ln,) = struct.unpack_from("<Q", b, o)
+        o += 8 + (ln + 3) // 4
+    (n_short,) = struct.unpack_from("<Q", b, o)
+    o += 8 + 8 * n_short
+    (n_abund,) = struct.unpack_from("<Q", b, o)
+    return n_long, n_short, n_abund
+
+
 def read_bus(path):
     """-> (header dict, structured array of records).  BUSData.h:30-38 / BUSTools.cpp:5-14"""
     with open(path, "rb") as f:

@@ -74,3 +74,42 @@ def test_bus_short_barcode_reads_are_skipped(setup):
     np.testing.assert_array_equal(rec["flags"], rec_full["flags"][keep])
     np.testing.assert_array_equal(rec["barcode"], rec_full["barcode"][keep])
     bp.close(); full.close()
+
+
+# ---- 10x v3 layout with mapped records (tests/golden/bus10xv3: 16-nt barcode + 12-nt UMI, 91-nt cDNA on the
+#      synth_small index; default --fr-stranded keeps the sense reads, --rf-stranded the antisense ones) ----
+D3 = os.path.join(util.GOLDEN, "bus10xv3")
+
+
+@pytest.fixture(scope="module")
+def setup_v3():
+    ix = K.KmerIndex(os.path.join(util.GOLDEN, "synth_small", "transcripts.kidx"), device=0)
+    s1 = O.read_fastq(os.path.join(D3, "sc_reads_1.fastq.gz"))
+    s2 = O.read_fastq(os.path.join(D3, "sc_reads_2.fastq.gz"))
+    yield ix, s1, s2
+    ix.close()
+
+
+@pytest.mark.parametrize("tag,kw", [("10xv3", {}), ("10xv3_num", {"num": True}), ("10xv3_unstranded", {"strand": "unstranded"}),
+                                     ("10xv3_rf", {"strand": "rf"})])
+def test_bus_10xv3_records_identical_to_reference(setup_v3, tag, kw):
+    ix, s1, s2 = setup_v3
+    _, ref = O.read_bus(os.path.join(D3, "ref_" + tag, "output.bus"))
+    info = json.load(open(os.path.join(D3, "ref_" + tag, "run_info.json")))
+    assert info["n_pseudoaligned"] > 1000          # the fixture has mapped records in every mode
+    bp = K.BUSProcessor(ix, "10xv3", **kw)
+    parts = []
+    for a, b in ((0, 5000), (5000, len(s1))):      # two batches: EC ids continue across batches
+        parts.append(bp.process_sets([O.to_batch(s1[a:b]), O.to_batch(s2[a:b])]))
+    rec = np.concatenate(parts)
+    assert len(rec) == len(ref)
+    assert rec.tobytes() == ref.tobytes()
+    st = bp.finalize()
+    assert st["n_processed"] == info["n_processed"]
+    assert st["n_pseudoaligned"] == info["n_pseudoaligned"]
+    assert st["n_unique"] == info["n_unique"]
+    eo, et, ec, eh = bp.ec_table()
+    assert util.ec_sets(eo, et) == O.read_matrix_ec(os.path.join(D3, "ref_" + tag, "matrix.ec"))
+    bc, um = bp.lengths()
+    assert bc[16] == um[12] and bc[16] >= info["n_processed"] - 40
+    bp.close()

@@ -10,7 +10,7 @@ from oracle import oracle as O
 from tests import util
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
 @pytest.mark.parametrize("mode", list(util.MODES))
 def test_per_fragment_ecs_match_reference(name, mode):
     ds = util.dataset(name)
@@ -29,7 +29,7 @@ def test_per_fragment_ecs_match_reference(name, mode):
         np.testing.assert_array_equal(run.flens(), g["flens"])
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
 def test_quant_text_identical_to_reference(name):
     """abundance.tsv of `kallisto quant --plaintext -t 1`, byte for byte (6 significant digits)."""
     ds = util.dataset(name)
@@ -50,7 +50,7 @@ def test_quant_text_identical_to_reference(name):
         assert rounds == 52
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
 def test_bootstrap_text_identical_to_reference(name):
     ds = util.dataset(name)
     ix = O.OracleIndex(ds["index"])
@@ -138,3 +138,10 @@ def test_functests_md5_goldens(case):
     alpha, _ = O.em(eo, et, ec, eff, ix.n_targets)
     txt = O.abundance_tsv(ix.target_names, ix.target_lens, eff, alpha, O.tpm(alpha, eff))
     assert hashlib.md5(txt.encode()).hexdigest() == case["md5"]
+
+
+def test_abundant_fixture_has_abundant_unitigs():
+    """The `abundant` data set exists to exercise the abundant-unitig branch of CompactedDBG::find
+    (ext/bifrost/src/CompactedDBG.tcc:1072-1119): the index must really contain some."""
+    n_long, n_short, n_abund = O.index_unitig_kinds(util.dataset("abundant")["index"])
+    assert n_abund > 100 and n_short > 100
