@@ -143,55 +143,90 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cli_run(idx, concat, lens, n_pairs, device):
-    """File to file: `kallisto_b200 quant` (the drop-in CLI, csrc/cli_main.cpp) on plain FASTQ in /dev/shm --
-    the same measurement the reference arm gets (start-up + index load of a one-pair run subtracted)."""
+CACHE_ROOT = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else DATA, "kb_bench_cache")
+
+
+def job_seeds(rank, W, K):
+    """Seeds of the K timed batches of `rank` (the W warm-up batches use the seeds before them)."""
+    return [1000 + rank * 100003 + s for s in range(W, W + K)]
+
+
+def fastq_job_files(genes, P, K, W, sim_factory):
+    """FASTQ files of rank 0's timed job (K batches of P pairs, plain text, in shared memory), shared by the
+    reference arm and our arm through a cache directory: both arms run back to back on the same box, and both
+    derive the reads from the same seeds anyway.  -> (dir, r1, r2, sample1, sample2, tiny1, tiny2)"""
+    import fcntl
+    import torch
+    key = "g%d_p%d_k%d_w%d_L%d" % (genes, P, K, W, READ_LEN)
+    d = os.path.join(CACHE_ROOT, key)
+    os.makedirs(d, exist_ok=True)
+    f1, f2 = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
+    s1, s2 = os.path.join(d, "sample_1.fq"), os.path.join(d, "sample_2.fq")
+    t1, t2 = os.path.join(d, "tiny_1.fq"), os.path.join(d, "tiny_2.fq")
+    done = os.path.join(d, "complete")
+    with open(os.path.join(d, ".lock"), "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            if not os.path.exists(done):
+                t0 = time.time()
+                sim = sim_factory()
+                for f in (f1, f2):
+                    open(f, "wb").close()
+                for j, seed in enumerate(job_seeds(0, W, K)):
+                    reads = sim.pairs(P, seed=seed)
+                    for f, m in ((f1, 0), (f2, 1)):
+                        img = benchdata.fastq_image(reads[:, m], m + 1, j * P)
+                        with open(f, "ab") as fh:
+                            img.cpu().numpy().tofile(fh)
+                    if j == 0:
+                        n_s = min(P, 2000000)
+                        for f, m in ((s1, 0), (s2, 1)):
+                            benchdata.fastq_image(reads[:n_s, m], m + 1, 0).cpu().numpy().tofile(f)
+                        for f, m in ((t1, 0), (t2, 1)):
+                            benchdata.fastq_image(reads[:1, m], m + 1, 0).cpu().numpy().tofile(f)
+                    del reads
+                if torch.cuda.is_available():
+                    torch.cuda.empty_cache()
+                open(done, "w").write("%d pairs\n" % (K * P))
+                log("FASTQ of the timed job (%d pairs, %.1f GB) written to %s in %.0f s" % (
+                    K * P, (os.path.getsize(f1) + os.path.getsize(f2)) / 1e9, d, time.time() - t0))
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
+    return d, f1, f2, s1, s2, t1, t2
+
+
+def cli_run(idx, files, n_pairs, devices, outdir, repeats=2):
+    """File to file through the drop-in command line: `kallisto_b200 quant` (csrc/cli_main.cpp) on plain FASTQ in
+    shared memory -> abundance.tsv + run_info.json.  The measurement SURVEY.md 8(d) defines: wall clock of the
+    process from start to outputs written, index load included (and listed)."""
     exe = os.path.join(ROOT, "kallisto_b200", "kallisto_b200")
     if not os.path.exists(exe):
         return None
     cores = os.cpu_count() or 1
     threads = min(cores, 64)
-    sim = benchdata.TorchSimulator(concat, lens, device, read_len=READ_LEN)
-    shm = "/dev/shm" if os.path.isdir("/dev/shm") else DATA
-    with tempfile.TemporaryDirectory(dir=shm) as td:
-        f1, f2 = os.path.join(td, "s_1.fq"), os.path.join(td, "s_2.fq")
-        chunk = 1000000
-        with open(f1, "wb") as a, open(f2, "wb") as b:
-            pass
-        for c0 in range(0, n_pairs, chunk):
-            reads = sim.pairs(min(chunk, n_pairs - c0), seed=5000 + c0).cpu().numpy()
-            benchdata.write_fastq_fast(f1, reads[:, 0], 1, append=True)
-            benchdata.write_fastq_fast(f2, reads[:, 1], 2, append=True)
-        t1, t2 = os.path.join(td, "t_1.fq"), os.path.join(td, "t_2.fq")
-        benchdata.write_fastq_fast(t1, reads[:1, 0], 1)
-        benchdata.write_fastq_fast(t2, reads[:1, 1], 2)
-
-        def run(files):
-            env = dict(os.environ, KB_CLI_TIMING="1")
-            t0 = time.perf_counter()
-            r = subprocess.run([exe, "quant", "-i", idx, "-o", os.path.join(td, "out"), "--plaintext", "-t", str(threads)] + files,
-                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env)
-            dt = time.perf_counter() - t0
-            if r.returncode != 0:
-                raise RuntimeError("kallisto_b200 quant failed: " + r.stderr[-300:])
-            ph = {}
-            for m in re.finditer(r"\[timing\] ([^:\n]+): ([0-9.eE+-]+) s \(at", r.stderr):
-                ph[m.group(1)] = float(m.group(2))
-            return dt, ph
-        run([t1, t2])                                  # page cache, driver start-up
-        best = None
-        for _ in range(2):
-            dt, ph = run([f1, f2])
-            work = sum(v for k2, v in ph.items() if k2 not in ("index load", "run set-up"))
-            if best is None or work < best[0]:
-                best = (work, dt, ph)
-    work, dt, ph = best
-    return {"value": n_pairs / max(1e-9, work), "unit": "pairs/s", "pairs": n_pairs, "threads": threads,
-            "seconds_reads_to_outputs": round(work, 4), "seconds_process_wall": round(dt, 3),
-            "pairs_per_s_process_wall": n_pairs / max(1e-9, dt),
-            "phases_s": {k2: round(v, 4) for k2, v in ph.items()},
-            "what": "kallisto_b200 quant --plaintext -t %d on plain FASTQ in /dev/shm -> abundance.tsv + run_info.json; value = pairs / "
-                    "(process wall clock minus its own index load and run set-up phases, which are listed; parsing starts while the index loads)" % threads}
+    runs = []
+    for _ in range(repeats):
+        env = dict(os.environ, KB_CLI_TIMING="1")
+        cmd = [exe, "quant", "-i", idx, "-o", outdir, "--plaintext", "-t", str(threads)]
+        if len(devices) > 1:
+            cmd += ["--devices", ",".join(str(x) for x in devices)]
+        else:
+            cmd += ["--device", str(devices[0])]
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd + files, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise RuntimeError("kallisto_b200 quant failed: " + r.stderr[-400:])
+        ph = {}
+        for m in re.finditer(r"\[timing\] ([^:\n]+): ([0-9.eE+-]+) s \(at", r.stderr):
+            ph[m.group(1)] = float(m.group(2))
+        runs.append((dt, ph))
+    dt, ph = runs[-1]       # the second run: page cache, driver and file system warm -- the first is listed
+    work = sum(v for k2, v in ph.items() if k2 not in ("index load", "run set-up"))
+    return {"seconds_process_wall": round(dt, 3), "seconds_process_wall_runs": [round(x[0], 3) for x in runs],
+            "seconds_reads_to_outputs": round(work, 4), "phases_s": {k2: round(v, 4) for k2, v in ph.items()},
+            "pairs": n_pairs, "threads": threads, "devices": list(devices),
+            "pairs_per_s_reads_to_outputs": n_pairs / max(1e-9, work)}
 
 
 def random_sector_peak(table_bytes):

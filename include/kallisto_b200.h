@@ -140,6 +140,31 @@ int kb_quant_export_device(kb_quant* q, uint32_t* d_off, uint32_t* d_tids, uint3
 int kb_quant_import_device(kb_quant* q, uint32_t n_sets, const uint32_t* d_off, const uint32_t* d_tids,
                            const uint32_t* d_counts, const uint64_t* d_first, uint64_t first_offset, uint64_t n_processed);
 
+/* The same exchange as ONE collective call in C++ over NCCL (csrc/comm.cu) -- what `kallisto_b200 quant --devices`
+ * and bench.py use.  Every rank calls kb_quant_merge_nccl after its last batch: a 4-word meta record per rank is
+ * all-gathered, ranks != 0 ncclSend their tables (and their ordered fragment-length samples) to rank 0, which
+ * folds all of them into its dictionary by content with one kernel launch and completes the fragment-length
+ * histogram in rank order (first 10000 unique pairs of the whole input, ProcessReads.cpp:985-1004).  Afterwards
+ * rank 0 runs kb_em_run.  first_stride: rank r's first-occurrence keys are offset by r * first_stride (ranks own
+ * consecutive slices of the input); 0 if the runs were fed global fragment indices (kb_quant_set_frag_base).
+ * NCCL is bound at run time (libnccl.so.2); the id is the 128-byte ncclUniqueId, created on rank 0 and
+ * distributed by the caller (torch.distributed / MPI / a file). */
+typedef struct kb_comm kb_comm;
+int kb_comm_unique_id(void* id_out /* 128 bytes */);
+int kb_comm_create(int n_ranks, int rank, const void* id /* 128 bytes */, int device, kb_comm** out);
+/* Wrap an existing ncclComm_t (not destroyed by kb_comm_free). */
+int kb_comm_create_from_nccl(void* nccl_comm, int n_ranks, int rank, int device, kb_comm** out);
+/* One process driving several GPUs (one host thread per GPU): ncclCommInitAll. out[] receives n_devices handles. */
+int kb_comm_create_all(const int* devices, int n_devices, kb_comm** out);
+/* Rank 0: size the receive area ahead of time (sets / entries expected per peer). */
+int kb_comm_reserve(kb_comm* c, uint64_t n_sets_per_rank, uint64_t n_entries_per_rank);
+void kb_comm_free(kb_comm* c);
+int kb_quant_merge_nccl(kb_quant* q, kb_comm* c, uint64_t first_stride, uint64_t* n_processed_total);
+/* Global index of the first fragment of the NEXT batch (several runs fed from one read stream). */
+int kb_quant_set_frag_base(kb_quant* q, uint64_t base);
+/* Size the EC-numbering / EM workspace ahead of time (kb_quant_create reserves for 2x the index's own EC sets). */
+int kb_quant_reserve(kb_quant* q, uint64_t n_ecs, uint64_t n_ec_entries);
+
 /* Replaces compute_mean_frag_lens_trunc / init_mean_fl_trunc + get_frag_len_means + calc_eff_lens +
  * calc_weights + EMAlgorithm::run(10000, 50) (src/MinCollector.cpp:629-651, src/weights.cpp,
  * src/EMAlgorithm.h:95-221).  fld_mean == 0 uses the estimated distribution, otherwise the

@@ -87,7 +87,9 @@ EXPORTED_SYMBOLS = [
     "kb_index_target_lens", "kb_index_inspect", "kb_quant_create", "kb_quant_free", "kb_pseudoalign_batch",
     "kb_pseudoalign_batch_pe", "kb_host_alloc", "kb_host_free", "kb_pseudoalign_batch_device", "kb_quant_sync", "kb_quant_set_stream", "kb_quant_enable_timing",
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
-    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device", "kb_bus_create", "kb_bus_batch", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
+    "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device",
+    "kb_comm_unique_id", "kb_comm_create", "kb_comm_create_from_nccl", "kb_comm_create_all", "kb_comm_reserve", "kb_comm_free",
+    "kb_quant_merge_nccl", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_bus_create", "kb_bus_batch", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -135,6 +137,15 @@ def lib():
     L.kb_quant_export_prepare.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.kb_quant_export_device.argtypes = [vp, vp, vp, vp, vp]
     L.kb_quant_import_device.argtypes = [vp, u32, vp, vp, vp, vp, u64, u64]
+    L.kb_comm_unique_id.argtypes = [vp]
+    L.kb_comm_create.argtypes = [C.c_int, C.c_int, vp, C.c_int, C.POINTER(vp)]
+    L.kb_comm_create_from_nccl.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.kb_comm_create_all.argtypes = [vp, C.c_int, vp]
+    L.kb_comm_reserve.argtypes = [vp, u64, u64]
+    L.kb_comm_free.argtypes = [vp]
+    L.kb_quant_merge_nccl.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.kb_quant_set_frag_base.argtypes = [vp, u64]
+    L.kb_quant_reserve.argtypes = [vp, u64, u64]
     L.kb_bus_create.argtypes = [vp, C.POINTER(kb_bus_opts), C.POINTER(vp)]
     L.kb_bus_batch.argtypes = [vp, vp, vp, u32, vp, C.POINTER(u32)]
     L.kb_bus_lengths.argtypes = [vp, vp, vp]
@@ -314,6 +325,20 @@ class MinCollector:
                                          n_processed))
         self._stats = None
 
+    def merge_nccl(self, comm, first_stride=1 << 40):
+        """Collective: fold every rank's equivalence classes into rank 0's run (csrc/comm.cu); returns the
+        number of fragments processed by all ranks."""
+        tot = C.c_uint64(0)
+        _ck(lib().kb_quant_merge_nccl(self._h, comm._h, first_stride, C.byref(tot)))
+        self._stats = None
+        return tot.value
+
+    def set_frag_base(self, base):
+        _ck(lib().kb_quant_set_frag_base(self._h, base))
+
+    def reserve(self, n_ecs, n_entries):
+        _ck(lib().kb_quant_reserve(self._h, n_ecs, n_entries))
+
     # -- EMAlgorithm::run / Bootstrap::run_em --------------------------------------------------
     def run_em(self, fld_mean=0.0, fld_sd=0.0, table=None):
         T = self.index.num_trans
@@ -338,6 +363,37 @@ class MinCollector:
         rounds = np.zeros(max(1, n_bootstrap), np.int32)
         _ck(lib().kb_bootstrap_run(self._h, fld_mean, fld_sd, seed, n_bootstrap, _p(est), _p(samples), _p(rounds)))
         return dict(est_counts=est, samples=samples, rounds=rounds[:n_bootstrap])
+
+
+class Comm:
+    """NCCL communicator of the multi-GPU merge (kb_comm_*).  `unique_id()` on rank 0, broadcast the 128 bytes
+    to the other ranks (torch.distributed, a file, ...), then every rank constructs Comm(n_ranks, rank, id, device)."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        _ck(lib().kb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, n_ranks, rank, uid, device):
+        self._h = C.c_void_p()
+        b = (C.c_ubyte * 128).from_buffer_copy(uid)
+        _ck(lib().kb_comm_create(n_ranks, rank, b, device, C.byref(self._h)))
+        self.n_ranks, self.rank = n_ranks, rank
+
+    def reserve(self, n_sets, n_entries):
+        _ck(lib().kb_comm_reserve(self._h, n_sets, n_entries))
+
+    def close(self):
+        if self._h:
+            lib().kb_comm_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BUSProcessor(MinCollector):

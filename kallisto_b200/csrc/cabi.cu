@@ -307,6 +307,64 @@ int kb_quant_import_device(kb_quant* q, uint32_t n_sets, const uint32_t* d_off, 
   });
 }
 
+struct kb_comm {
+  std::unique_ptr<kb::Comm> c;
+};
+
+int kb_comm_unique_id(void* id_out) {
+  if (!id_out) return fail(KB_ERR_INVALID, "kb_comm_unique_id: null argument");
+  return guarded([&] { kb::Comm::unique_id(id_out); });
+}
+int kb_comm_create(int n_ranks, int rank, const void* id, int device, kb_comm** out) {
+  if (!id || !out) return fail(KB_ERR_INVALID, "kb_comm_create: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    kb_comm* h = new kb_comm();
+    h->c.reset(new kb::Comm(n_ranks, rank, id, device));
+    *out = h;
+  });
+}
+int kb_comm_create_from_nccl(void* nccl_comm, int n_ranks, int rank, int device, kb_comm** out) {
+  if (!nccl_comm || !out) return fail(KB_ERR_INVALID, "kb_comm_create_from_nccl: null argument");
+  *out = nullptr;
+  return guarded([&] {
+    kb_comm* h = new kb_comm();
+    h->c.reset(new kb::Comm(nccl_comm, n_ranks, rank, device, false));
+    *out = h;
+  });
+}
+int kb_comm_create_all(const int* devices, int n_devices, kb_comm** out) {
+  if (!devices || !out || n_devices < 1) return fail(KB_ERR_INVALID, "kb_comm_create_all: bad argument");
+  return guarded([&] {
+    std::vector<kb::Comm*> cs = kb::Comm::init_all(std::vector<int>(devices, devices + n_devices));
+    for (int i = 0; i < n_devices; ++i) {
+      out[i] = new kb_comm();
+      out[i]->c.reset(cs[i]);
+    }
+  });
+}
+int kb_comm_reserve(kb_comm* c, uint64_t n_sets, uint64_t n_entries) {
+  if (!c) return fail(KB_ERR_INVALID, "kb_comm_reserve: null argument");
+  return guarded([&] { c->c->reserve(n_sets, n_entries); });
+}
+void kb_comm_free(kb_comm* c) { delete c; }
+int kb_quant_merge_nccl(kb_quant* q, kb_comm* c, uint64_t first_stride, uint64_t* n_processed_total) {
+  if (!q || !c) return fail(KB_ERR_INVALID, "kb_quant_merge_nccl: null argument");
+  return guarded([&] {
+    const uint64_t t = q->q->merge_to_root(*c->c, first_stride);
+    if (n_processed_total) *n_processed_total = t;
+  });
+}
+int kb_quant_set_frag_base(kb_quant* q, uint64_t base) {
+  if (!q) return fail(KB_ERR_INVALID, "kb_quant_set_frag_base: null argument");
+  q->q->set_frag_base(base);
+  return KB_OK;
+}
+int kb_quant_reserve(kb_quant* q, uint64_t n_ecs, uint64_t n_entries) {
+  if (!q) return fail(KB_ERR_INVALID, "kb_quant_reserve: null argument");
+  return guarded([&] { q->q->reserve_em(n_ecs, n_entries); });
+}
+
 int kb_bus_create(kb_index* ix, const kb_bus_opts* o, kb_quant** out) {
   if (!ix || !o || !out) return fail(KB_ERR_INVALID, "kb_bus_create: null argument");
   *out = nullptr;

@@ -42,6 +42,7 @@ struct Options {
   bool plaintext = false, single_end = false, single_overhang = false, verbose = false;
   int strand = 0;   // 0 none, 1 FR, 2 RF
   int device = 0;
+  std::vector<int> devices;   // --devices=0,1,...: reads are dealt to several GPUs, merged over NCCL (csrc/comm.cu)
   std::vector<std::string> files;
 };
 
@@ -87,6 +88,8 @@ void usage_quant() {
             << "                               end data, but are required when using --single)" << endl
             << "-t, --threads=INT             Number of host threads parsing input (default: 1)" << endl
             << "    --device=INT              CUDA device ordinal (default: 0)" << endl
+            << "    --devices=LIST            Comma-separated CUDA devices: batches of reads are dealt to all of them," << endl
+            << "                              index replicated, equivalence classes merged over NCCL before the EM" << endl
             << "    --verbose                 Print out progress information every 1M proccessed reads" << endl;
 }
 
@@ -108,6 +111,7 @@ void parse_quant(int argc, char** argv, Options& opt) {
       {"output-dir", required_argument, 0, 'o'},
       {"bootstrap-samples", required_argument, 0, 'b'},
       {"device", required_argument, 0, 'D'},
+      {"devices", required_argument, 0, 'G'},
       {0, 0, 0, 0}};
   int c, option_index = 0;
   while ((c = getopt_long(argc, argv, opt_string, long_options, &option_index)) != -1) {
@@ -120,10 +124,21 @@ void parse_quant(int argc, char** argv, Options& opt) {
       case 'b': std::stringstream(optarg) >> opt.bootstrap; break;
       case 'd': std::stringstream(optarg) >> opt.seed; break;
       case 'D': std::stringstream(optarg) >> opt.device; break;
+      case 'G': {
+        std::stringstream ss(optarg);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) {
+          int v = -1;
+          std::stringstream(tok) >> v;
+          opt.devices.push_back(v);
+        }
+        break;
+      }
       default: break;
     }
   }
   for (int i = optind; i < argc; i++) opt.files.push_back(argv[i]);
+  if (!opt.devices.empty()) opt.device = opt.devices[0];
   opt.verbose = verbose_flag;
   opt.plaintext = plaintext_flag;
   opt.single_end = single_flag;
@@ -326,13 +341,14 @@ void reader_thread(std::vector<std::string> files, Stream* s, size_t max_reads, 
         kb::ReadBatch& b = s->ring[slot];
         b.clear();
         const bool any = f.fill(b, max_reads);
-        if (!any) break;
+        if (!any) b.eof = true;     // end of this file: an empty marker batch, so that the consumer keeps file sets in step
         {
           std::lock_guard<std::mutex> lk(s->m);
           s->state[slot] = 1;
         }
         s->cv.notify_all();
         slot = (slot + 1) % s->ring.size();
+        if (!any) break;
       }
     }
   } catch (const std::exception& e) {
@@ -396,51 +412,71 @@ class LockStep {
  public:
   explicit LockStep(std::vector<Stream>& s) : st_(s), cur_(s.size(), 0), used_(s.size(), 0) {}
 
-  // false at the end of the input
+  // false at the end of the input.  Every input file ends with a marker batch.  When one stream reaches the end of
+  // its file, what the other streams still hold of THEIR current file is dropped and all streams move on to the
+  // next file set together -- FastqSequenceReader::fetchSequences (src/ProcessReads.cpp:3178-3262) stops a file set
+  // at its shortest file (all_l) and reopens the next set in step.
   bool next(size_t& n, const char** bases, const uint32_t** off) {
-    size_t with_data = 0;
-    n = (size_t)-1;
-    for (size_t i = 0; i < st_.size(); ++i) {
-      Stream& s = st_[i];
-      std::unique_lock<std::mutex> lk(s.m);
-      s.cv.wait(lk, [&] { return s.state[cur_[i]] == 1 || s.done; });
-      if (!s.error.empty()) {
-        cerr << endl << s.error << endl;
+    for (;;) {
+      size_t with_data = 0;
+      bool any_eof = false;
+      n = (size_t)-1;
+      for (size_t i = 0; i < st_.size(); ++i) {
+        if (!wait_slot(i)) continue;
+        ++with_data;
+        const kb::ReadBatch& b = st_[i].ring[cur_[i]];
+        if (b.eof) { any_eof = true; continue; }
+        n = std::min(n, b.n - used_[i]);
+        bases[i] = b.bases;
+        off[i] = b.off + used_[i];          // offsets are absolute positions in `bases`
+      }
+      if (with_data == 0) return false;
+      if (with_data != st_.size()) {
+        cerr << endl << "Error: input files hold different numbers of reads" << endl;
         exit(1);
       }
-      if (s.state[cur_[i]] != 1) continue;
-      ++with_data;
-      const kb::ReadBatch& b = s.ring[cur_[i]];
-      n = std::min(n, b.n - used_[i]);
-      bases[i] = b.bases;
-      off[i] = b.off + used_[i];          // offsets are absolute positions in `bases`
+      if (!any_eof) {
+        n_ = n;
+        return true;
+      }
+      for (size_t i = 0; i < st_.size(); ++i) {
+        while (wait_slot(i) && !st_[i].ring[cur_[i]].eof) advance(i);     // rest of a longer file
+        if (wait_slot(i)) advance(i);                                      // the marker itself
+      }
     }
-    if (with_data == 0) return false;
-    if (with_data != st_.size()) {
-      cerr << endl << "Error: input files hold different numbers of reads" << endl;
-      exit(1);
-    }
-    n_ = n;
-    return true;
   }
   // the reads of the last round have been consumed
   void release() {
     for (size_t i = 0; i < st_.size(); ++i) {
-      Stream& s = st_[i];
       used_[i] += n_;
-      if (used_[i] == s.ring[cur_[i]].n) {
-        {
-          std::lock_guard<std::mutex> lk(s.m);
-          s.state[cur_[i]] = 0;
-        }
-        s.cv.notify_all();
-        cur_[i] = (cur_[i] + 1) % s.ring.size();
-        used_[i] = 0;
-      }
+      if (used_[i] == st_[i].ring[cur_[i]].n) advance(i);
     }
   }
 
  private:
+  // waits for stream i's current slot; false when the stream has ended
+  bool wait_slot(size_t i) {
+    Stream& s = st_[i];
+    std::unique_lock<std::mutex> lk(s.m);
+    s.cv.wait(lk, [&] { return s.state[cur_[i]] == 1 || s.done; });
+    if (!s.error.empty()) {
+      cerr << endl << s.error << endl;
+      exit(1);
+    }
+    return s.state[cur_[i]] == 1;
+  }
+  // hands stream i's current slot back to its reader
+  void advance(size_t i) {
+    Stream& s = st_[i];
+    {
+      std::lock_guard<std::mutex> lk(s.m);
+      s.state[cur_[i]] = 0;
+    }
+    s.cv.notify_all();
+    cur_[i] = (cur_[i] + 1) % s.ring.size();
+    used_[i] = 0;
+  }
+
   std::vector<Stream>& st_;
   std::vector<size_t> cur_, used_;
   size_t n_ = 0;
@@ -465,7 +501,25 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   kb_index* ix = nullptr;
   // positions are needed only by the fragment-position filter (KmerIndex.h:78: load_positional_info)
   const int need_positions = (!opt.single_overhang && opt.fld > 0.0) ? 1 : 0;
-  KB_TRY(kb_index_load(opt.index.c_str(), opt.device, need_positions, std::min(16, std::max(1, opt.threads)), &ix));
+  // --devices: the index is replicated (one load per device, in parallel); device 0 of the list is the root
+  const int n_dev = std::max<int>(1, (int)opt.devices.size());
+  std::vector<kb_index*> ixs(n_dev, nullptr);
+  std::vector<kb_comm*> comms(n_dev, nullptr);
+  {
+    std::vector<std::string> errs(n_dev);
+    std::vector<std::thread> loaders;
+    const int lt = std::max(1, std::min(16, std::max(1, opt.threads)) / n_dev);
+    for (int d = 1; d < n_dev; ++d)
+      loaders.emplace_back([&, d] {
+        if (kb_index_load(opt.index.c_str(), opt.devices[d], need_positions, lt, &ixs[d]) != KB_OK) errs[d] = kb_last_error();
+      });
+    KB_TRY(kb_index_load(opt.index.c_str(), opt.device, need_positions, n_dev > 1 ? lt : std::min(16, std::max(1, opt.threads)), &ix));
+    ixs[0] = ix;
+    for (auto& t : loaders) t.join();
+    for (int d = 1; d < n_dev; ++d)
+      if (!errs[d].empty()) { cerr << endl << "Error: " << errs[d] << endl; return 1; }
+    if (n_dev > 1) KB_TRY(kb_comm_create_all(opt.devices.data(), n_dev, comms.data()));
+  }
   pt.mark("index load");
   kb_index_info info;
   kb_index_get_info(ix, &info);
@@ -494,6 +548,13 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   kb_quant* q = nullptr;
   KB_TRY(kb_quant_create(ix, &qo, &q));
   if (pt.on) kb_quant_enable_timing(q, 1);
+  std::vector<kb_quant*> qs(n_dev, nullptr);
+  qs[0] = q;
+  for (int d = 1; d < n_dev; ++d) {
+    kb_quant_opts qd = qo;
+    qd.collect_fld = 0;        // the fragment-length samples are the first 10000 of the stream: device 0 sees them (below)
+    KB_TRY(kb_quant_create(ixs[d], &qd, &qs[d]));
+  }
 
   pt.mark("run set-up");
   uint64_t n_done = 0;
@@ -502,10 +563,28 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     const char* bp[2] = {nullptr, nullptr};
     const uint32_t* op[2] = {nullptr, nullptr};
     size_t n = 0;
+    size_t round = 0;
+    bool fld_done = !(paired && opt.fld == 0.0) || n_dev == 1;
     while (ls.next(n, bp, op)) {
       const auto c0 = std::chrono::steady_clock::now();
-      if (paired) KB_TRY(kb_pseudoalign_batch_pe(q, bp[0], op[0], bp[1], op[1], (uint32_t)n, 0, nullptr));
-      else KB_TRY(kb_pseudoalign_batch(q, bp[0], op[0], (uint32_t)n, 0, nullptr));
+      // batches are dealt round-robin once the root has its 10000 fragment-length samples (ProcessReads.cpp:985-1004:
+      // they are the first qualifying pairs of the input); every batch carries its global fragment index, so EC ids
+      // come out in the order of the input whatever device saw a fragment first
+      kb_quant* qq = q;
+      if (n_dev > 1) {
+        if (fld_done) qq = qs[round % n_dev];
+        kb_quant_set_frag_base(qq, n_done);
+      }
+      if (paired) KB_TRY(kb_pseudoalign_batch_pe(qq, bp[0], op[0], bp[1], op[1], (uint32_t)n, 0, nullptr));
+      else KB_TRY(kb_pseudoalign_batch(qq, bp[0], op[0], (uint32_t)n, 0, nullptr));
+      ++round;
+      if (!fld_done) {
+        uint32_t fl[1000];
+        kb_quant_get_flens(q, fl);
+        uint64_t c = 0;
+        for (int i = 0; i < 1000; ++i) c += fl[i];
+        fld_done = c >= 10000;
+      }
       if (pt.verbose) cerr << endl << "[timing] round of " << n << " reads: call " << std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count()
                       << " s, at " << std::chrono::duration<double>(std::chrono::steady_clock::now() - pt.t0).count() << " s";
       n_done += n;
@@ -515,6 +594,19 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   }
   for (auto& t : readers) t.join();
   pt.mark("read + pseudoalign loop");
+  if (n_dev > 1) {
+    // the one exchange: every device's equivalence classes folded into the root's by content (collective)
+    std::vector<std::string> errs(n_dev);
+    std::vector<std::thread> ts;
+    for (int d = 0; d < n_dev; ++d)
+      ts.emplace_back([&, d] {
+        if (kb_quant_merge_nccl(qs[d], comms[d], 0, nullptr) != KB_OK) errs[d] = kb_last_error();
+      });
+    for (auto& t : ts) t.join();
+    for (int d = 0; d < n_dev; ++d)
+      if (!errs[d].empty()) { cerr << endl << "Error: " << errs[d] << endl; return 1; }
+    pt.mark("merge over NCCL");
+  }
   cerr << " done" << endl;
 
   const uint32_t T = info.n_targets;
@@ -575,8 +667,11 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   }
   cerr << endl;
   free_streams(streams);
-  kb_quant_free(q);
-  kb_index_free(ix);
+  for (int d = 0; d < n_dev; ++d) {
+    kb_quant_free(qs[d]);
+    if (comms[d]) kb_comm_free(comms[d]);
+    kb_index_free(ixs[d]);
+  }
   return st.n_pseudoaligned == 0 ? 1 : 0;
 }
 

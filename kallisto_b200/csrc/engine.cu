@@ -50,16 +50,6 @@ template <class T> void DBuf<T>::zero(cudaStream_t st) {
   if (n) KB_CK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
 }
 
-struct EmWs {   // grow-only device workspace of run_em_device
-  DBuf<uint32_t> used, scal, idx_in, order, handle, count, len, multi_len, is_multi, ec_off, m_off, multi_index;
-  DBuf<unsigned long long> key_in, key_out;
-  DBuf<uint8_t> tmp;
-  DBuf<uint32_t> ec_tid, multi_ec, m_rowoff, m_tid, m_row, m_iota, sortk, sortv, t_deg, t_off, t_midx;
-  DBuf<double> m_w, t_w, eff, alpha, norm;
-  DBuf<int32_t> t_single;
-  DBuf<int> emi;
-  DBuf<unsigned int> chcount;
-};
 
 // ------------------------------------------------------------------------------------------
 // Index
@@ -299,11 +289,39 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
   // resolve-kernel scratch: 2 x max_set_len words per warp, at most ~1 GiB in total
   const uint64_t stride = std::max<uint64_t>(64, 2ull * ix_.max_set_len);
   uint64_t warps = (1ull << 28) / stride;
-  warps = std::min<uint64_t>(148 * 32, std::max<uint64_t>(64, warps));   // the kernel is latency-bound: fill the SMs
+  warps = std::min<uint64_t>((uint64_t)device_sm_count() * 32, std::max<uint64_t>(64, warps));   // the kernel is latency-bound: fill the SMs
   n_resolve_warps_ = (uint32_t)(warps / 4 * 4);
   if (bws_->d_scratch.n < (size_t)n_resolve_warps_ * stride) bws_->d_scratch.alloc((size_t)n_resolve_warps_ * stride);
   scratch_stride_ = (uint32_t)stride;
+  // EM workspace: sized once per index for the EC tables runs on it normally end with (twice the index's own sets),
+  // so that the timed EM tail of a run does not allocate; it still grows on demand
+  if (!opt_.bus) reserve_em(2 * (size_t)nE + (1u << 16), 4 * (size_t)ix_.n_index_tids + (1u << 20));
   KB_CK(cudaStreamSynchronize(st));
+}
+
+void Quant::reserve_em(size_t n_ecs, size_t nnz) {
+  KB_CK(cudaSetDevice(ix_.device));
+  EmWs& w = *emws_;
+  const uint32_t T = ix_.flat.num_targets();
+  const size_t n1 = n_ecs + 1;
+  auto g32 = [](DBuf<uint32_t>& b, size_t need) { if (b.n < need) b.alloc(need); };
+  auto gd = [](DBuf<double>& b, size_t need) { if (b.n < need) b.alloc(need); };
+  if (w.used.n < ix_.dict_cap) w.used.alloc(ix_.dict_cap);
+  if (w.scal.n < 8) w.scal.alloc(8);
+  if (w.key_in.n < n1) { w.key_in.alloc(n1); w.key_out.alloc(n1); }
+  g32(w.idx_in, n1); g32(w.order, n1); g32(w.handle, n1); g32(w.count, n1); g32(w.len, n1);
+  g32(w.multi_len, n1); g32(w.is_multi, n1); g32(w.ec_off, n1); g32(w.m_off, n1); g32(w.multi_index, n1);
+  const size_t tmp_need = emprep_sort_bytes((uint32_t)n1, (uint32_t)std::max<size_t>(nnz, (size_t)T + 1));
+  if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
+  g32(w.ec_tid, std::max<size_t>(1, nnz)); g32(w.multi_ec, n1); g32(w.m_rowoff, n1 + 1);
+  const size_t nz = std::max<size_t>(1, nnz);
+  g32(w.m_tid, nz); g32(w.m_row, nz); g32(w.m_iota, nz); g32(w.sortk, nz); g32(w.sortv, nz); g32(w.t_midx, nz);
+  gd(w.m_w, nz); gd(w.t_w, nz);
+  g32(w.t_deg, (size_t)T + 1); g32(w.t_off, (size_t)T + 1);
+  if (w.t_single.n < T) w.t_single.alloc(T);
+  gd(w.eff, T); gd(w.alpha, T); gd(w.norm, n1);
+  if (w.emi.n < 8) w.emi.alloc(8);
+  if (w.chcount.n < 2) w.chcount.alloc(2);
 }
 
 Quant::~Quant() {
@@ -375,7 +393,8 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.n_frag = n_frag;
   ba.paired = opt_.paired;
   ba.strand_mode = opt_.strand_mode;
-  ba.frag_base = n_frag_total_;
+  ba.frag_base = have_frag_base_ ? frag_base_ : n_frag_total_;
+  have_frag_base_ = false;
   ba.handle_out = bws_->d_handles.p;
   const bool want_fld = opt_.paired && opt_.collect_fld && tlencount_ < 10000;   // ProcessReads.cpp:981-1017
   ba.tl_out = want_fld ? bws_->d_tl.p : nullptr;
@@ -427,7 +446,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
     uint32_t local = 0;
     for (uint32_t i = 0; i < n_frag && goal > 0; ++i) {
       const uint16_t tl = h_tl_[i];
-      if (tl > 0) { ++flens_[tl]; --goal; ++local; }
+      if (tl > 0) { ++flens_[tl]; tl_list_.push_back(tl); --goal; ++local; }
     }
     tlencount_ += local;
   }
@@ -602,7 +621,12 @@ void Quant::bus_lengths(uint32_t* bc_hist, uint32_t* umi_hist) {
   memcpy(umi_hist, h + 33, 33 * 4);
 }
 
-void Quant::set_flens(const uint32_t* f) { flens_.assign(f, f + 1000); }
+void Quant::set_flens(const uint32_t* f) {
+  flens_.assign(f, f + 1000);
+  tl_list_.clear();
+  tlencount_ = 0;
+  for (int i = 0; i < 1000; ++i) tlencount_ += flens_[i];
+}
 
 namespace {
 __global__ void gather_used_kernel(DevDict dd, const uint32_t* used, uint32_t n, uint32_t* cnt, unsigned long long* first,
@@ -965,8 +989,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   if (w.chcount.n < 2) w.chcount.alloc(2);
   w.emi.zero(st);
   w.chcount.zero(st);
-  std::vector<double> a0(T, 1.0 / T);   // uniform start (EMAlgorithm.h:38)
-  w.alpha.upload(a0.data(), T, st);
+  launch_fill_f64(w.alpha.p, T, 1.0 / T, st);   // uniform start (EMAlgorithm.h:38)
   EmProblem p{};
   p.n_ec = n; p.n_targets = T; p.n_multi = n_multi;
   p.multi_ec = w.multi_ec.p; p.m_off = w.m_rowoff.p; p.m_tid = w.m_tid.p; p.m_w = w.m_w.p;

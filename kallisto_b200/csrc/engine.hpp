@@ -42,7 +42,6 @@ struct DBuf {
 // Grow-only device work buffers.  They belong to the Index and are lent to one run at a time, so that
 // consecutive runs on the same index (the normal case) do not pay cudaMalloc again; a second run
 // created while the first is still alive gets private ones.
-struct EmWs;
 struct BatchWs {
   DBuf<uint8_t> stage_b[2][2];      // double-buffered input staging: H2D of batch i+1 overlaps the kernels of batch i
   DBuf<uint32_t> stage_o[2][2];
@@ -50,6 +49,17 @@ struct BatchWs {
   DBuf<uint32_t> d_spill, d_qbig_count, d_qbig;   // fragments with more than KB_MAX_E distinct EC sets
   DBuf<int32_t> d_handles;
   DBuf<uint16_t> d_tl;
+};
+
+struct EmWs {   // grow-only device workspace of run_em_device
+  DBuf<uint32_t> used, scal, idx_in, order, handle, count, len, multi_len, is_multi, ec_off, m_off, multi_index;
+  DBuf<unsigned long long> key_in, key_out;
+  DBuf<uint8_t> tmp;
+  DBuf<uint32_t> ec_tid, multi_ec, m_rowoff, m_tid, m_row, m_iota, sortk, sortv, t_deg, t_off, t_midx;
+  DBuf<double> m_w, t_w, eff, alpha, norm;
+  DBuf<int32_t> t_single;
+  DBuf<int> emi;
+  DBuf<unsigned int> chcount;
 };
 
 class Index {
@@ -81,6 +91,22 @@ class Index {
   bool ws_in_use = false;
   DBuf<uint4> fp_info;            // only when loaded with positions
   DBuf<uint32_t> blk_usize, target_len;
+};
+
+// One NCCL communicator per process/GPU plus the receive area of the merge (csrc/comm.cu).
+struct CommImpl;
+class Comm {
+ public:
+  static void unique_id(void* out128);                                  // ncclGetUniqueId (rank 0, then broadcast by the caller)
+  Comm(int n_ranks, int rank, const void* id128, int device);            // ncclCommInitRank
+  Comm(void* nccl_comm, int n_ranks, int rank, int device, bool take_ownership);   // an existing ncclComm_t
+  static std::vector<Comm*> init_all(const std::vector<int>& devices);   // one process, one communicator per device
+  ~Comm();
+  Comm(const Comm&) = delete;
+  Comm& operator=(const Comm&) = delete;
+  void reserve(size_t n_sets_per_rank, size_t n_entries_per_rank);       // root: size the receive area ahead of time
+  int n_ranks = 1, rank = 0, device = 0;
+  CommImpl* impl_ = nullptr;
 };
 
 struct QuantOptions {
@@ -167,6 +193,15 @@ class Quant {
   void import_sets_device(uint32_t n_sets, const uint32_t* d_off, const uint32_t* d_tids, const uint32_t* d_counts,
                           const unsigned long long* d_first, unsigned long long first_offset);
   void add_processed(uint64_t n) { n_frag_total_ += n; }
+  // The whole exchange in one collective call (csrc/comm.cu): tables gathered to rank 0 with NCCL send/recv and
+  // folded in by content with one kernel launch, fragment-length samples completed in rank order.  Returns the
+  // number of fragments processed by all ranks.
+  uint64_t merge_to_root(Comm& comm, uint64_t first_stride);
+  // Global index of the first fragment of the NEXT batch (multi-GPU drivers that deal batches of one read
+  // stream to several runs: first-occurrence order then is the order of the stream).  Default: running count.
+  void set_frag_base(uint64_t base) { frag_base_ = base; have_frag_base_ = true; }
+  // Size the EM / EC-numbering workspace ahead of time (no cudaMalloc on the first kb_em_run).
+  void reserve_em(size_t n_ecs, size_t n_entries);
 
   // Run on a caller-provided stream (e.g. the framework's current stream) instead of the run's own.
   void set_stream(cudaStream_t st);
@@ -216,6 +251,9 @@ class Quant {
   uint64_t n_frag_total_ = 0;
   std::vector<uint32_t> flens_;
   uint32_t tlencount_ = 0;
+  std::vector<uint16_t> tl_list_;        // the samples behind flens_, in read order (shipped to rank 0 by merge_to_root)
+  uint64_t frag_base_ = 0;
+  bool have_frag_base_ = false;
   std::vector<uint16_t> h_tl_;
   EcTable ecs_;
   bool ecs_valid_ = false;

@@ -45,7 +45,8 @@ struct ReadBatch {
   size_t cap_bases = 0, cap_reads = 0;
   size_t n = 0;               // reads in the batch
   uint32_t max_len = 0;
-  void clear() { n = 0; max_len = 0; if (off) off[0] = 0; }
+  bool eof = false;           // marker batch: the stream's current input file ended here (csrc/cli_main.cpp LockStep)
+  void clear() { n = 0; max_len = 0; eof = false; if (off) off[0] = 0; }
   size_t n_bases() const { return off ? off[n] : 0; }
 };
 
@@ -192,6 +193,7 @@ class FastxFile {
   // without the line terminator (a trailing '\r' is dropped); *got_nl tells whether '\n' was seen
   size_t rest_of_line(char* dst, size_t room, bool* got_nl) {
     size_t copied = 0;
+    char last_c = 0;
     *got_nl = false;
     for (;;) {
       if (pos_ >= end_) {
@@ -203,6 +205,7 @@ class FastxFile {
       const size_t avail = end_ - pos_;
       const char* nl = (const char*)memchr(s, '\n', avail);
       const size_t take = nl ? (size_t)(nl - s) : avail;
+      if (take) last_c = s[take - 1];
       if (dst) {
         if (copied + take > room) throw std::runtime_error("Error: sequence too long in " + path_);
         memcpy(dst + copied, s, take);
@@ -215,7 +218,8 @@ class FastxFile {
         break;
       }
     }
-    if (copied > 0 && dst && dst[copied - 1] == '\r') --copied;
+    // ks_getuntil2 (src/kseq.h:137) drops a trailing '\r' from copied and from discarded lines alike
+    if (copied > 0 && last_c == '\r') --copied;
     return copied;
   }
 
@@ -310,9 +314,8 @@ inline size_t parse_range(const char* d, size_t size, size_t pos, size_t stop, P
         size_t e = nl ? (size_t)(nl - d) : size;
         const bool got = nl != nullptr;
         const size_t next = nl ? e + 1 : size;
-        // FastxFile counts the characters of the line without a trailing '\r' only when it copies them;
-        // for discarded lines it counts every character before the '\n'
-        q += e - pos;
+        // a trailing '\r' does not count (ks_getuntil2, src/kseq.h:137)
+        q += (e > pos && d[e - 1] == '\r') ? e - pos - 1 : e - pos;
         pos = next;
         if (!got || q >= len) break;
       }

@@ -74,6 +74,7 @@ struct ResolveArgs {
 
 void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st);
 void launch_fill_i32(int32_t* p, uint64_t n, int32_t v, cudaStream_t st);
+void launch_fill_f64(double* p, uint64_t n, double v, cudaStream_t st);
 void launch_fill_memo2(Memo2Entry* p, uint64_t n, cudaStream_t st);
 void launch_build_table(const TableBuildArgs& a, cudaStream_t st);
 void launch_dict_init(const DictInitArgs& a, cudaStream_t st);
@@ -86,6 +87,17 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
 void launch_fld_finalize(const DevDict& dd, const BatchArgs& ba, cudaStream_t st);
 void launch_import_sets(const DevDict& dd, uint32_t n_sets, const uint32_t* off, const uint32_t* tids, const uint32_t* counts,
                         const unsigned long long* first, unsigned long long first_offset, cudaStream_t st);
+// Same for the tables of several ranks at once (Quant::merge_to_root): one launch, warp per incoming set.
+struct ImportSeg {
+  uint32_t n_sets;
+  const uint32_t* off;
+  const uint32_t* tids;
+  const uint32_t* counts;
+  const unsigned long long* first;
+};
+static constexpr int KB_IMPORT_SEGS = 16;
+void launch_import_segments(const DevDict& dd, const ImportSeg* segs, int n_segs, cudaStream_t st);
+int device_sm_count();
 // Compact the handles with count > 0: used[0..*n_used)
 void launch_collect_used(const DevDict& dd, uint32_t* used, uint32_t* n_used, cudaStream_t st);
 

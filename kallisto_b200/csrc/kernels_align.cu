@@ -948,12 +948,7 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
   cudaMemsetAsync(ba.qbig_count, 0, sizeof(uint32_t), st);
   // persistent grid: as many blocks as fit on the device at once
   const size_t smem = (size_t)tpb * 4 * ((size_t)KB_MAX_E + 3 + 4 * ba.nb);   // per lane: handle tuple, first-mate words, 2 x 2nb base words
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = device_sm_count();
   cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel, tpb, smem);
@@ -994,10 +989,62 @@ __global__ void __launch_bounds__(128) import_sets_kernel(DevDict dd, uint32_t n
   }
 }
 
+struct ImportSegs {
+  int n;
+  uint32_t prefix[KB_IMPORT_SEGS + 1];
+  ImportSeg seg[KB_IMPORT_SEGS];
+};
+__global__ void __launch_bounds__(128) import_segments_kernel(DevDict dd, ImportSegs a) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t total = a.prefix[a.n];
+  for (uint32_t g = w; g < total; g += nw) {
+    int k = 0;
+    while (g >= a.prefix[k + 1]) ++k;
+    const ImportSeg& sg = a.seg[k];
+    const uint32_t s = g - a.prefix[k];
+    const uint32_t o0 = sg.off[s], n = sg.off[s + 1] - o0;
+    if (n == 0) continue;
+    const int32_t h = dict_insert_warp(dd, sg.tids + o0, n, lane);
+    if (lane == 0 && h >= 0) {
+      atomicAdd(&dd.count[h], sg.counts[s]);
+      atomicMin(&dd.first[h], sg.first[s]);
+    }
+    __syncwarp();
+  }
+}
+
+int device_sm_count() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = v > 0 ? v : 1;
+  }
+  return sms[dev];
+}
+
+void launch_import_segments(const DevDict& dd, const ImportSeg* segs, int n_segs, cudaStream_t st) {
+  if (n_segs <= 0) return;
+  ImportSegs a;
+  a.n = n_segs;
+  a.prefix[0] = 0;
+  for (int i = 0; i < n_segs; ++i) { a.seg[i] = segs[i]; a.prefix[i + 1] = a.prefix[i] + segs[i].n_sets; }
+  if (a.prefix[n_segs] == 0) return;
+  const unsigned warps_needed = a.prefix[n_segs];
+  unsigned blocks = (unsigned)device_sm_count() * 16;
+  if (blocks > (warps_needed + 3) / 4) blocks = (warps_needed + 3) / 4;
+  import_segments_kernel<<<blocks, 128, 0, st>>>(dd, a);
+}
+
 void launch_import_sets(const DevDict& dd, uint32_t n_sets, const uint32_t* off, const uint32_t* tids, const uint32_t* counts,
                         const unsigned long long* first, unsigned long long first_offset, cudaStream_t st) {
   if (n_sets == 0) return;
-  import_sets_kernel<<<148 * 8, 128, 0, st>>>(dd, n_sets, off, tids, counts, first, first_offset);
+  import_sets_kernel<<<device_sm_count() * 8, 128, 0, st>>>(dd, n_sets, off, tids, counts, first, first_offset);
 }
 
 void launch_fld_finalize(const DevDict& dd, const BatchArgs& ba, cudaStream_t st) {
@@ -1007,7 +1054,7 @@ void launch_fld_finalize(const DevDict& dd, const BatchArgs& ba, cudaStream_t st
 
 void launch_collect_used(const DevDict& dd, uint32_t* used, uint32_t* n_used, cudaStream_t st) {
   cudaMemsetAsync(n_used, 0, sizeof(uint32_t), st);
-  collect_used_kernel<<<148 * 8, 256, 0, st>>>(dd, used, n_used);
+  collect_used_kernel<<<device_sm_count() * 8, 256, 0, st>>>(dd, used, n_used);
 }
 
 }  // namespace kb

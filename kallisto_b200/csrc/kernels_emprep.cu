@@ -155,7 +155,7 @@ void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, uint32_t* sor
     csc_fill_kernel<<<(nnz + 255) / 256, 256, 0, st>>>(p, sort_vals_out, nnz);
   }
   cudaMemsetAsync(stats2, 0, 16, st);
-  stats_kernel<<<148, 256, 0, st>>>(p.count, p.len, p.n_ec, stats2);
+  stats_kernel<<<device_sm_count(), 256, 0, st>>>(p.count, p.len, p.n_ec, stats2);
 }
 
 }  // namespace kb

@@ -89,6 +89,12 @@ int kb_counts_to_tpm(const double* est, const double* eff, uint32_t n, double* t
   for (uint32_t i = 0; i < n; ++i) tpm[i] = tot > 0 ? tpm[i] / tot * 1e6 : 0.0;
   return KB_OK;
 }
+// multi-device entry points: the stub has one "device"; --devices is covered by the GPU tests
+struct kb_comm { int unused; };
+int kb_comm_create_all(const int*, int n, kb_comm** out) { for (int i = 0; i < n; ++i) out[i] = new kb_comm(); return KB_OK; }
+void kb_comm_free(kb_comm* c) { delete c; }
+int kb_quant_merge_nccl(kb_quant*, kb_comm*, uint64_t, uint64_t*) { return KB_OK; }
+int kb_quant_set_frag_base(kb_quant*, uint64_t) { return KB_OK; }
 int kb_bus_create(kb_index*, const kb_bus_opts* o, kb_quant** out) { *out = new kb_quant(); (*out)->nfiles = o->nfiles; return KB_OK; }
 int kb_bus_batch(kb_quant* q, const char* const* bases, const uint32_t* const* offs, uint32_t n_sets, kb_bus_record* rec, uint32_t* n_rec) {
   // one record per read set: barcode = running digest, so that output.bus depends on content AND order

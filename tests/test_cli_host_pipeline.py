@@ -74,13 +74,23 @@ def test_same_reads_in_the_same_order_whatever_the_ingest_configuration(setup):
     assert b1 == b2 == b3 and b1 != base
 
 
-def test_files_with_different_read_counts_are_rejected(setup):
+def test_file_sets_stay_in_step_when_a_pair_is_ragged(setup):
+    """FastqSequenceReader::fetchSequences (src/ProcessReads.cpp:3178-3262) stops a file set at its SHORTEST file
+    and opens the next set in step.  A first pair whose second file holds only 100 reads must therefore give the
+    reads of (first 100 pairs) + (the whole second pair) -- not mates shifted by the difference."""
     s = setup
-    short = s["dir"] / "short.fq"
-    short.write_bytes(b"".join(open(s["plain"][1], "rb").readlines()[:4 * 100]))
-    r = subprocess.run([s["exe"], "quant", "-i", s["idx"], "-o", str(s["dir"] / "bad"), "--plaintext", "-t", "4", s["plain"][0], str(short)],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 1 and "different numbers of reads" in r.stderr
+    lines = [open(f, "rb").readlines() for f in s["plain"]]
+    short2 = s["dir"] / "short_2.fq"
+    short2.write_bytes(b"".join(lines[1][:4 * 100]))
+    short1 = s["dir"] / "short_1.fq"
+    short1.write_bytes(b"".join(lines[0][:4 * 100]))
+    want, _ = quant(s["exe"], s["idx"], s["dir"] / "rag0", ["-t", "1", str(short1), str(short2)] + s["plain"])
+    for i, (t, env) in enumerate([("1", {}), ("4", {"KB_FASTX_WINDOW": "30000"}), ("8", {"KB_CLI_BATCH_READS": "64,200"})]):
+        got, _ = quant(s["exe"], s["idx"], s["dir"] / ("rag%d" % (i + 1)), ["-t", t, s["plain"][0], str(short2)] + s["plain"], env)
+        assert got == want, (t, env)
+    # ... and the other way round (first file the short one)
+    got, _ = quant(s["exe"], s["idx"], s["dir"] / "rag9", ["-t", "4", str(short1), s["plain"][1]] + s["plain"])
+    assert got == want
 
 
 def test_bus_records_in_read_order(setup):

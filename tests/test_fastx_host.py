@@ -159,3 +159,30 @@ def test_garbage_input_never_crashes(tmp_path):
     assert set(out) == set(cases)
     for name, res in out.items():
         assert res["1"] == res["4"], (name, res)          # the parallel reader is the sequential parse, also on garbage
+
+
+def test_crlf_multiline_quality_counts_like_kseq(tmp_path, monkeypatch):
+    """ks_getuntil2 (src/kseq.h:137) drops the trailing CR of every line, quality lines included; counting it would
+    end a multi-line quality block early and turn a leftover quality line that starts with '@' into a phantom record.
+    Records: 20 bases on 10 CRLF lines, quality on 10 CRLF lines of which the 8th..10th start with '@'."""
+    import re
+    import subprocess
+    recs = []
+    want = []
+    for i in range(50):
+        seq = ("ACGTTGCAAC" * 2)[i % 7:][:20].ljust(20, "A")
+        want.append(seq.encode())
+        q = ["II"] * 7 + ["@I", "@+", "@>"]
+        recs.append("@r%d\r\n" % i + "".join(seq[j:j + 2] + "\r\n" for j in range(0, 20, 2)) + "+\r\n" + "".join(x + "\r\n" for x in q))
+    p = tmp_path / "crlf.fq"
+    p.write_bytes("".join(recs).encode())
+    n, nb, h1 = K.fastx_summary(str(p))
+    assert (n, nb) == (50, 1000)
+    monkeypatch.setenv("KB_FASTX_WINDOW", "300")
+    assert K.fastx_summary(str(p), threads=4) == (n, nb, h1)
+    if O.have_ref():   # the reference's own reader agrees on the record count
+        idx = os.path.join(util.GOLDEN, "config1", "transcripts.kidx")
+        r = subprocess.run([O.REF_BIN, "quant", "-i", idx, "-o", str(tmp_path / "o"), "--single", "-l", "200", "-s", "20", str(p)],
+                           capture_output=True, text=True)
+        m = re.search(r"processed ([0-9,]+) reads", r.stderr)
+        assert m and int(m.group(1).replace(",", "")) == 50
