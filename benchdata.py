@@ -257,3 +257,60 @@ def fastq_image(reads, tag, first_index):
     buf[:, o + 3:o + 3 + L] = ord("I")
     buf[:, o + 3 + L] = ord("\n")
     return buf
+
+
+class TorchSimulator10x:
+    """BASELINE config 3 reads: R1 = 16-nt barcode from a seeded whitelist of 6000 cells + 12-nt
+    random UMI; R2 = 91-nt cDNA from the last 400 nt of a transcript, sense strand (kept by the technology's
+    default --fr-stranded), transcript drawn from the same abundance model as the quant reads; 0.5 % substitutions,
+    0.1 % of reads carry one N, 5 % random sequence."""
+
+    def __init__(self, concat, lens, device, cdna_len=91, n_cells=6000, err=0.005, n_frac=0.001, random_frac=0.05):
+        import torch
+        self.torch = torch
+        self.dev = device
+        self.L = cdna_len
+        self.err, self.n_frac, self.random_frac = err, n_frac, random_frac
+        self.concat = torch.from_numpy(np.ascontiguousarray(concat)).to(device)
+        lens = np.asarray(lens, np.int64)
+        starts = np.zeros(len(lens), np.int64)
+        np.cumsum(lens[:-1], out=starts[1:])
+        self.lens = torch.from_numpy(lens).to(device)
+        self.starts = torch.from_numpy(starts).to(device)
+        self.cdf = torch.from_numpy(np.cumsum(_abundance_weights(lens, 200.0))).to(device)
+        self.acgt = torch.from_numpy(ACGT.copy()).to(device)
+        wl = np.random.default_rng(6000).integers(0, 4, (n_cells, 16))
+        self.whitelist = torch.from_numpy(ACGT[wl]).to(device)
+
+    def sets(self, n, seed):
+        """-> (r1 (n, 28) uint8, r2 (n, L) uint8) on the device."""
+        torch = self.torch
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(int(seed))
+        L = self.L
+        u = torch.rand(n, generator=g, device=self.dev, dtype=torch.float64)
+        t = torch.searchsorted(self.cdf, u).clamp_(max=len(self.lens) - 1)
+        tl = self.lens[t]
+        lo = (tl - 400).clamp_(min=0)
+        span = (tl - L - lo + 1).clamp_(min=1)
+        start = lo + (torch.rand(n, generator=g, device=self.dev, dtype=torch.float64) * span.double()).long()
+        base = self.starts[t] + start
+        ar = torch.arange(L, device=self.dev)
+        r2 = torch.empty((n, L), dtype=torch.uint8, device=self.dev)
+        CH = 1 << 21
+        nmax = self.concat.numel() - 1
+        for c0 in range(0, n, CH):
+            c1 = min(n, c0 + CH)
+            x = self.concat[(base[c0:c1, None] + ar[None, :]).clamp_(max=nmax)]
+            rnd = torch.rand(c1 - c0, generator=g, device=self.dev) < self.random_frac
+            x = torch.where(rnd[:, None], self.acgt[torch.randint(0, 4, (c1 - c0, L), generator=g, device=self.dev)], x)
+            m = torch.rand((c1 - c0, L), generator=g, device=self.dev) < self.err
+            x = torch.where(m, self.acgt[torch.randint(0, 4, (c1 - c0, L), generator=g, device=self.dev)], x)
+            nn = torch.rand(c1 - c0, generator=g, device=self.dev) < self.n_frac
+            pos = torch.randint(0, L, (c1 - c0,), generator=g, device=self.dev)
+            nmask = torch.zeros((c1 - c0, L), dtype=torch.bool, device=self.dev)
+            nmask.scatter_(1, pos[:, None], nn[:, None])
+            r2[c0:c1] = torch.where(nmask, torch.full_like(x, ord("N")), x)
+        bc = self.whitelist[torch.randint(0, self.whitelist.shape[0], (n,), generator=g, device=self.dev)]
+        umi = self.acgt[torch.randint(0, 4, (n, 12), generator=g, device=self.dev)]
+        return torch.cat([bc, umi], dim=1).contiguous(), r2

@@ -206,6 +206,11 @@ int kb_bus_create(kb_index* ix, const kb_bus_opts* opts, kb_quant** out);
  * EC ids (order of first occurrence = the ids of the reference with -t 1). */
 int kb_bus_batch(kb_quant* q, const char* const* bases, const uint32_t* const* offsets, uint32_t n_sets,
                  kb_bus_record* records_out, uint32_t* n_records_out);
+/* Same with the files of the batch already resident in DEVICE memory (offsets too); the records stay on the device:
+ * *d_records_out points to n_records records, valid until the next batch.  max_seq_len = longest read of the
+ * sequence file in the batch. */
+int kb_bus_batch_device(kb_quant* q, const void* const* d_bases, const uint32_t* const* d_offsets, uint32_t n_sets,
+                        uint32_t max_seq_len, uint32_t* n_records_out, const kb_bus_record** d_records_out);
 /* Observed barcode / UMI length histograms (33 bins), for the header of output.bus
  * (src/main.cpp:2470-2508). */
 int kb_bus_lengths(kb_quant* q, uint32_t* bc_hist, uint32_t* umi_hist);

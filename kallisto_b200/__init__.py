@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
     "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device",
     "kb_comm_unique_id", "kb_comm_create", "kb_comm_create_from_nccl", "kb_comm_create_all", "kb_comm_reserve", "kb_comm_free",
-    "kb_quant_merge_nccl", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_bus_create", "kb_bus_batch", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
+    "kb_quant_merge_nccl", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_bus_create", "kb_bus_batch", "kb_bus_batch_device", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -148,6 +148,7 @@ def lib():
     L.kb_quant_reserve.argtypes = [vp, u64, u64]
     L.kb_bus_create.argtypes = [vp, C.POINTER(kb_bus_opts), C.POINTER(vp)]
     L.kb_bus_batch.argtypes = [vp, vp, vp, u32, vp, C.POINTER(u32)]
+    L.kb_bus_batch_device.argtypes = [vp, vp, vp, u32, u32, C.POINTER(u32), C.POINTER(vp)]
     L.kb_bus_lengths.argtypes = [vp, vp, vp]
     L.kb_fastx_summary.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.kb_gz_summary.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(C.c_uint32)]
@@ -433,6 +434,16 @@ class BUSProcessor(MinCollector):
         _ck(lib().kb_bus_batch(self._h, bp, op, n, _p(rec), C.byref(nrec)))
         self._stats = None
         return rec[: nrec.value]
+
+    def process_sets_device(self, base_ptrs, offset_ptrs, n_sets, max_seq_len):
+        """Device pointers in (one per file of the technology), records stay on the device: -> (n_records, device pointer)."""
+        bp = (C.c_void_p * self.nfiles)(*base_ptrs)
+        op = (C.c_void_p * self.nfiles)(*offset_ptrs)
+        nrec = C.c_uint32(0)
+        drec = C.c_void_p()
+        _ck(lib().kb_bus_batch_device(self._h, bp, op, n_sets, max_seq_len, C.byref(nrec), C.byref(drec)))
+        self._stats = None
+        return nrec.value, drec.value
 
     def lengths(self):
         b, u = np.zeros(33, np.uint32), np.zeros(33, np.uint32)

@@ -407,6 +407,16 @@ int kb_bus_batch(kb_quant* q, const char* const* bases, const uint32_t* const* o
   return guarded([&] { q->q->bus_batch_host(bases, offsets, n_sets, (kb::BusRecord*)records_out, n_records_out); });
 }
 
+int kb_bus_batch_device(kb_quant* q, const void* const* d_bases, const uint32_t* const* d_offsets, uint32_t n_sets,
+                        uint32_t max_seq_len, uint32_t* n_records_out, const kb_bus_record** d_records_out) {
+  if (!q || !d_bases || !d_offsets) return fail(KB_ERR_INVALID, "kb_bus_batch_device: null argument");
+  return guarded([&] {
+    const uint32_t n = q->q->bus_batch_device((const uint8_t* const*)d_bases, d_offsets, n_sets, max_seq_len);
+    if (n_records_out) *n_records_out = n;
+    if (d_records_out) *d_records_out = (const kb_bus_record*)q->q->bus_records_device();
+  });
+}
+
 int kb_bus_lengths(kb_quant* q, uint32_t* bc_hist, uint32_t* umi_hist) {
   if (!q || !bc_hist || !umi_hist) return fail(KB_ERR_INVALID, "kb_bus_lengths: null argument");
   return guarded([&] { q->q->bus_lengths(bc_hist, umi_hist); });

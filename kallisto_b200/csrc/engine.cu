@@ -553,7 +553,8 @@ void Quant::bus_batch_host(const char* const* bases, const uint32_t* const* offs
   if (n_sets == 0) return;
   const BusSpec& sp = opt_.bus_spec;
   cudaStream_t st = stream_;
-  BusArgs a{};
+  const uint8_t* db[4] = {nullptr, nullptr, nullptr, nullptr};
+  const uint32_t* dofs[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int k = 0; k < sp.nfiles; ++k) {
     if (!bases[k] || !offs[k]) throw Error("kallisto_b200: bus batch needs bases and offsets for every file of the technology");
     const uint64_t nbz = offs[k][n_sets];
@@ -561,9 +562,38 @@ void Quant::bus_batch_host(const char* const* bases, const uint32_t* const* offs
     if (bus_o_[k].n < (size_t)n_sets + 1) bus_o_[k].alloc(std::max<size_t>((size_t)n_sets + 1, (size_t)opt_.max_batch_reads + 1));
     KB_CK(cudaMemcpyAsync(bus_b_[k].p, bases[k], nbz, cudaMemcpyHostToDevice, st));
     KB_CK(cudaMemcpyAsync(bus_o_[k].p, offs[k], ((size_t)n_sets + 1) * 4, cudaMemcpyHostToDevice, st));
-    a.bases[k] = bus_b_[k].p;
-    a.off[k] = bus_o_[k].p;
+    db[k] = bus_b_[k].p;
+    dofs[k] = bus_o_[k].p;
   }
+  // longest cDNA read of the batch (sizes the packed-read layout)
+  uint32_t maxlen = 0;
+  const uint32_t* so = offs[sp.seq_file];
+  for (uint32_t i = 0; i < n_sets; ++i) maxlen = std::max(maxlen, so[i + 1] - so[i]);
+  const uint32_t n_rec = bus_core(db, dofs, n_sets, maxlen);
+  if (n_rec && records_out) {
+    bus_rec_.download(records_out, n_rec, 0, st);
+    KB_CK(cudaStreamSynchronize(st));
+  }
+  if (n_records_out) *n_records_out = n_rec;
+}
+
+// Same with the files of the batch already resident in device memory; the records stay on the device
+// (bus_records_device(), valid until the next batch).
+uint32_t Quant::bus_batch_device(const uint8_t* const* d_bases, const uint32_t* const* d_offs, uint32_t n_sets,
+                                 uint32_t max_seq_len) {
+  KB_CK(cudaSetDevice(ix_.device));
+  if (!opt_.bus) throw Error("kallisto_b200: not a bus run");
+  if (n_sets == 0) return 0;
+  for (int k = 0; k < opt_.bus_spec.nfiles; ++k)
+    if (!d_bases[k] || !d_offs[k]) throw Error("kallisto_b200: bus batch needs bases and offsets for every file of the technology");
+  return bus_core(d_bases, d_offs, n_sets, max_seq_len);
+}
+
+uint32_t Quant::bus_core(const uint8_t* const* db, const uint32_t* const* dofs, uint32_t n_sets, uint32_t maxlen) {
+  const BusSpec& sp = opt_.bus_spec;
+  cudaStream_t st = stream_;
+  BusArgs a{};
+  for (int k = 0; k < sp.nfiles; ++k) { a.bases[k] = db[k]; a.off[k] = dofs[k]; }
   const size_t n1 = (size_t)n_sets + 1;
   auto grow = [&](auto& b, size_t need) { if (b.n < need) b.alloc(std::max<size_t>(need, (size_t)opt_.max_batch_reads + 1)); };
   grow(bus_bc_, n1); grow(bus_umi_, n1); grow(bus_flags_, n1); grow(bus_skip_, n1);
@@ -582,33 +612,27 @@ void Quant::bus_batch_host(const char* const* bases, const uint32_t* const* offs
   launch_bus_fields(a, st);
   KB_CK(cudaGetLastError());
   // the cDNA read: single-read pseudoalignment with the strand filter of the technology
-  uint32_t maxlen = 0;
-  const uint32_t* so = offs[sp.seq_file];
-  for (uint32_t i = 0; i < n_sets; ++i) maxlen = std::max(maxlen, so[i + 1] - so[i]);
   maxlen = maxlen > (uint32_t)sp.seq_start ? maxlen - sp.seq_start : 1;
   const uint64_t base = n_frag_total_;
   cur_skip_ = bus_skip_.p;
   cur_start_ = (uint32_t)sp.seq_start;
-  run_batch(bus_b_[sp.seq_file].p, bus_o_[sp.seq_file].p, n_sets, 0, maxlen);
+  run_batch(db[sp.seq_file], dofs[sp.seq_file], n_sets, 0, maxlen);
   cur_skip_ = nullptr;
   cur_start_ = 0;
   launch_bus_records(dd_, bws_->d_handles.p, n_sets, base, bus_next_id_, bus_idof_.p, bus_isnew_.p, bus_newrank_.p,
                      bus_ismapped_.p, bus_rank_.p, (const uint64_t*)bus_bc_.p, (const uint64_t*)bus_umi_.p, bus_flags_.p,
                      bus_rec_.p, bus_tmp_.p, bus_tmp_.n, st);
   KB_CK(cudaGetLastError());
+  n_kernel_launches += 4;      // bus_fields, bus_newflag, bus_newid, bus_records (CUB scans not counted)
   uint32_t n_new = 0, n_rec = 0;
   unsigned long long n_valid = 0;
   bus_newrank_.download(&n_new, 1, n_sets, st);
   bus_rank_.download(&n_rec, 1, n_sets, st);
   bus_nvalid_.download(&n_valid, 1, 0, st);
   KB_CK(cudaStreamSynchronize(st));
-  if (n_rec && records_out) {
-    bus_rec_.download(records_out, n_rec, 0, st);
-    KB_CK(cudaStreamSynchronize(st));
-  }
   bus_next_id_ += n_new;
   bus_valid_total_ += n_valid;
-  if (n_records_out) *n_records_out = n_rec;
+  return n_rec;
 }
 
 void Quant::bus_lengths(uint32_t* bc_hist, uint32_t* umi_hist) {

@@ -161,6 +161,8 @@ class Quant {
   // offsets each).  Writes the BUS records of the pseudoaligned sets, in read order, EC ids final.
   void bus_batch_host(const char* const* bases, const uint32_t* const* offs, uint32_t n_sets, BusRecord* records_out,
                       uint32_t* n_records_out);
+  uint32_t bus_batch_device(const uint8_t* const* d_bases, const uint32_t* const* d_offs, uint32_t n_sets, uint32_t max_seq_len);
+  const BusRecord* bus_records_device() const { return bus_rec_.p; }
   void bus_lengths(uint32_t* bc_hist, uint32_t* umi_hist);
   // Same, inputs already resident in device memory; handles stay on the device
   // (device_handles(), valid until the next batch).
@@ -223,6 +225,7 @@ class Quant {
   void run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
                  uint32_t max_read_len, const uint8_t* d_bases2 = nullptr, const uint32_t* d_off2 = nullptr);
   void check_device_errors();
+  uint32_t bus_core(const uint8_t* const* db, const uint32_t* const* dofs, uint32_t n_sets, uint32_t maxlen);
 
   Index& ix_;
   QuantOptions opt_;

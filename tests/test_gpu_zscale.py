@@ -6,7 +6,8 @@ table, 711 k index EC sets, 45 k short unitigs), >= 2 M synthetic 2x100 bp pairs
     ProcessReads.cpp:1643-1701) on 8 consecutive slices of the input in parallel processes; every fragment's
     transcript SET must be identical, and so must the EC count multiset, n_processed / n_pseudoaligned / n_unique,
     the fragment-length histogram (first slice = first 10 000 unique pairs of the run) and the order in which ECs
-    are first seen (ids of the first slice);
+    are first seen (ids of the first slice; the first slice is 30 % of the input so that it contains the 10 000
+    fragment-length samples of the run);
   * quantification: `kallisto quant --plaintext -t 1 -b 2 --seed 42` on the whole input; abundance.tsv and
     bs_abundance_{0,1}.tsv must be TEXT-identical, both through the library and through the kallisto_b200 CLI.
 
@@ -60,7 +61,11 @@ def scale():
         f1, f2 = os.path.join(td, "all_1.fq"), os.path.join(td, "all_2.fq")
         benchdata.write_fastq_fast(f1, reads[:, 0], 1)
         benchdata.write_fastq_fast(f2, reads[:, 1], 2)
-        bounds = [N_PAIRS * i // N_SLICES for i in range(N_SLICES + 1)]
+        # the first slice is large enough to hold the first 10 000 fragment-length samples of the run (only ~2.5 % of the
+        # pairs qualify: unique transcript and both mates on one unitig, ProcessReads.cpp:1174-1181), so that its
+        # flens.txt is the histogram of the whole run; the others share the rest
+        n0 = N_PAIRS * 3 // 10
+        bounds = [0] + [n0 + (N_PAIRS - n0) * i // (N_SLICES - 1) for i in range(N_SLICES)]
         procs = []
         env = dict(os.environ)
         qdir = os.path.join(td, "ref_quant")
@@ -158,7 +163,10 @@ def test_per_fragment_sets_counts_and_order(scale):
             # EC ids = order of first occurrence: the first slice's ECs are the first ECs of the whole run, in order
             assert mine_sets[:len(sets)] == sets
             fl = np.array([int(x) for x in open(os.path.join(d, "flens.txt")).read().split()], np.uint32)
-            np.testing.assert_array_equal(scale["flens"], fl)
+            if N_PAIRS >= 2000000:
+                assert int(fl.sum()) == 10000      # premise: the quota is filled inside the first slice
+            if int(fl.sum()) == 10000:
+                np.testing.assert_array_equal(scale["flens"], fl)
     st = scale["st"]
     assert (st["n_processed"], st["n_pseudoaligned"], st["n_unique"]) == (n_proc, n_pa, n_uniq)
     assert {int(c): int(n) for c, n in zip(mine_c, ec)} == ref_counts     # EC multiset, bit-exact
