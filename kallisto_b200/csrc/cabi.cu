@@ -188,6 +188,8 @@ int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out) {
     out->em_ms = q->q->last_em_seconds * 1e3;
     out->em_prep_ms = q->q->last_prep_seconds * 1e3;
     out->kernel_launches = q->q->n_kernel_launches;
+    out->bs_resample_ms = q->q->last_bs_resample_ms;
+    out->bs_em_ms = q->q->last_bs_em_ms;
   });
 }
 
@@ -278,11 +280,14 @@ int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed,
                      double* est_counts_out, uint32_t* samples_out, int32_t* rounds_out) {
   if (!q || !est_counts_out || n_bootstrap < 0) return fail(KB_ERR_INVALID, "kb_bootstrap_run: bad argument");
   return guarded([&] {
-    const kb::EcTable& ecs = q->q->finalize_ecs();
     const auto fl = q->q->mean_fl_trunc(fld_mean, fld_sd);
     std::vector<double> alpha;
     std::vector<uint32_t> samples;
-    std::vector<int> rounds = q->q->run_bootstrap(ecs, fl, seed, n_bootstrap, alpha, samples_out ? &samples : nullptr);
+    // on the matrices kb_em_run left on the device (built now if it has not run yet)
+    double ms[2] = {0, 0};
+    std::vector<int> rounds = q->q->run_bootstrap_device(fl, seed, n_bootstrap, alpha, samples_out ? &samples : nullptr, ms);
+    q->q->last_bs_resample_ms = ms[0];
+    q->q->last_bs_em_ms = ms[1];
     memcpy(est_counts_out, alpha.data(), alpha.size() * sizeof(double));
     if (samples_out) memcpy(samples_out, samples.data(), samples.size() * sizeof(uint32_t));
     if (rounds_out)

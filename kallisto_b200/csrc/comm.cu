@@ -243,6 +243,7 @@ uint64_t Quant::merge_to_root(Comm& cm, uint64_t first_stride) {
   KB_NCK(api.GroupEnd());
   ecs_valid_ = false;
   dev_stats_valid_ = false;
+  dev_problem_valid_ = false;
   for (size_t i = 0; i < segs.size(); i += KB_IMPORT_SEGS) {
     launch_import_segments(dd_, segs.data() + i, (int)std::min<size_t>(KB_IMPORT_SEGS, segs.size() - i), st);
     KB_CK(cudaGetLastError());

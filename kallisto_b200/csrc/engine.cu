@@ -311,11 +311,14 @@ void Quant::reserve_em(size_t n_ecs, size_t nnz) {
   if (w.key_in.n < n1) { w.key_in.alloc(n1); w.key_out.alloc(n1); }
   g32(w.idx_in, n1); g32(w.order, n1); g32(w.handle, n1); g32(w.count, n1); g32(w.len, n1);
   g32(w.multi_len, n1); g32(w.is_multi, n1); g32(w.ec_off, n1); g32(w.m_off, n1); g32(w.multi_index, n1);
+  g32(w.minkey, n1); g32(w.ckey, n1); g32(w.cval, n1); g32(w.ckey_out, n1); g32(w.rlen, n1 + 1);
   const size_t tmp_need = emprep_sort_bytes((uint32_t)n1, (uint32_t)std::max<size_t>(nnz, (size_t)T + 1));
   if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
   g32(w.ec_tid, std::max<size_t>(1, nnz)); g32(w.multi_ec, n1); g32(w.m_rowoff, n1 + 1);
   const size_t nz = std::max<size_t>(1, nnz);
-  g32(w.m_tid, nz); g32(w.m_row, nz); g32(w.m_iota, nz); g32(w.sortk, nz); g32(w.sortv, nz); g32(w.t_midx, nz);
+  g32(w.m_tid, nz); g32(w.m_row, nz); g32(w.m_iota, nz); g32(w.sortv, nz); g32(w.t_midx, nz);
+  if (w.k64_in.n < nz) { w.k64_in.alloc(nz); w.k64_out.alloc(nz); }
+  if (w.bar.n < 1) w.bar.alloc(1);
   gd(w.m_w, nz); gd(w.t_w, nz);
   g32(w.t_deg, (size_t)T + 1); g32(w.t_off, (size_t)T + 1);
   if (w.t_single.n < T) w.t_single.alloc(T);
@@ -384,6 +387,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   if (n_frag == 0) return;
   ecs_valid_ = false;
   dev_stats_valid_ = false;
+  dev_problem_valid_ = false;
   BatchArgs ba{};
   ba.bases = d_bases;
   ba.off = d_off;
@@ -830,8 +834,8 @@ struct EmDevice {
   DBuf<uint32_t> multi_ec, m_off, m_tid, t_off, t_midx, counts;
   DBuf<double> m_w, t_w, alpha, norm;
   DBuf<int32_t> t_single;
-  DBuf<int> rounds, state, fstate;
-  DBuf<unsigned int> chcount;
+  DBuf<int> rounds, fstate;
+  DBuf<unsigned int> chcount, bar;
 };
 
 void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, EmProblem& p, cudaStream_t st) {
@@ -848,7 +852,7 @@ void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, 
   d.alpha.alloc((size_t)nb * T);
   d.norm.alloc(std::max<size_t>(1, (size_t)nb * nm));
   d.rounds.alloc(nb); d.rounds.zero(st);
-  d.state.alloc((size_t)nb * 2); d.state.zero(st);
+  d.bar.alloc(1);
   d.fstate.alloc(nb); d.fstate.zero(st);
   d.chcount.alloc((size_t)nb * 2); d.chcount.zero(st);
   p = EmProblem();
@@ -856,7 +860,7 @@ void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, 
   p.multi_ec = d.multi_ec.p; p.m_off = d.m_off.p; p.m_tid = d.m_tid.p; p.m_w = d.m_w.p;
   p.t_off = d.t_off.p; p.t_midx = d.t_midx.p; p.t_w = d.t_w.p; p.t_single = d.t_single.p;
   p.nb = nb; p.counts = d.counts.p; p.alpha = d.alpha.p; p.norm = d.norm.p;
-  p.rounds = d.rounds.p; p.state = d.state.p; p.chcount = d.chcount.p; p.fstate = d.fstate.p;
+  p.rounds = d.rounds.p; p.bar = d.bar.p; p.chcount = d.chcount.p; p.fstate = d.fstate.p;
 }
 
 void em_fetch(const EmProblem& p, EmDevice& d, int nb, uint32_t T, std::vector<double>& alpha, std::vector<int>& rounds,
@@ -966,6 +970,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   if (w.key_in.n < n1) { w.key_in.alloc(n1 + n1 / 4); w.key_out.alloc(n1 + n1 / 4); }
   grow32(w.idx_in, n1); grow32(w.order, n1); grow32(w.handle, n1); grow32(w.count, n1); grow32(w.len, n1);
   grow32(w.multi_len, n1); grow32(w.is_multi, n1); grow32(w.ec_off, n1); grow32(w.m_off, n1); grow32(w.multi_index, n1);
+  grow32(w.minkey, n1); grow32(w.ckey, n1); grow32(w.cval, n1); grow32(w.ckey_out, n1); grow32(w.rlen, n1 + 1);
   const uint32_t nnz_guess = std::max<uint32_t>(n * 4, 1u << 20);
   size_t tmp_need = emprep_sort_bytes(n + 1, std::max<uint32_t>(nnz_guess, T + 1));
   if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
@@ -978,7 +983,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   EmPrep ep{};
   ep.n_ec = n; ep.n_targets = T;
   ep.handle = w.handle.p; ep.count = w.count.p; ep.len = w.len.p; ep.ec_off = w.ec_off.p; ep.m_off = w.m_off.p;
-  ep.multi_index = w.multi_index.p;
+  ep.multi_index = w.multi_index.p; ep.minkey = w.minkey.p;
   emprep_meta(dd_, w.used.p, w.order.p, n, ep, w.multi_len.p, w.is_multi.p, w.tmp.p, w.tmp.n, st);
   uint32_t tot[3] = {0, 0, 0};
   w.ec_off.download(&tot[0], 1, n, st);
@@ -992,7 +997,9 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
   grow32(w.ec_tid, std::max<uint32_t>(1, nnz_all)); grow32(w.multi_ec, (size_t)n_multi + 1); grow32(w.m_rowoff, (size_t)n_multi + 2);
   const size_t nz = std::max<uint32_t>(1, nnz);
-  grow32(w.m_tid, nz); grow32(w.m_row, nz); grow32(w.m_iota, nz); grow32(w.sortk, nz); grow32(w.sortv, nz); grow32(w.t_midx, nz);
+  grow32(w.m_tid, nz); grow32(w.m_row, nz); grow32(w.m_iota, nz); grow32(w.sortv, nz); grow32(w.t_midx, nz);
+  if (w.k64_in.n < nz) { w.k64_in.alloc(nz + nz / 4); w.k64_out.alloc(nz + nz / 4); }
+  if (w.bar.n < 1) w.bar.alloc(1);
   growd(w.m_w, nz); growd(w.t_w, nz);
   grow32(w.t_deg, (size_t)T + 1); grow32(w.t_off, (size_t)T + 1);
   if (w.t_single.n < T) w.t_single.alloc(T);
@@ -1005,8 +1012,9 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   ep.n_multi = n_multi;
   ep.ec_tid = w.ec_tid.p; ep.multi_ec = w.multi_ec.p; ep.m_rowoff = w.m_rowoff.p; ep.m_tid = w.m_tid.p; ep.m_w = w.m_w.p;
   ep.m_row = w.m_row.p; ep.m_iota = w.m_iota.p; ep.t_deg = w.t_deg.p; ep.t_off = w.t_off.p; ep.t_midx = w.t_midx.p;
-  ep.t_w = w.t_w.p; ep.t_single = w.t_single.p; ep.eff = w.eff.p;
-  emprep_fill(dd_, ep, nnz, w.sortk.p, w.sortv.p, w.tmp.p, w.tmp.n, (unsigned long long*)w.key_in.p, st);
+  ep.t_w = w.t_w.p; ep.t_single = w.t_single.p; ep.eff = w.eff.p; ep.k64_in = w.k64_in.p;
+  emprep_rows(ep, w.is_multi.p, w.ckey.p, w.cval.p, w.ckey_out.p, w.rlen.p, w.tmp.p, w.tmp.n, st);
+  emprep_fill(dd_, ep, nnz, w.k64_out.p, w.sortv.p, w.tmp.p, w.tmp.n, (unsigned long long*)w.key_in.p, st);
   KB_CK(cudaGetLastError());
   // ---- EM
   if (w.emi.n < 8) w.emi.alloc(8);
@@ -1019,11 +1027,11 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   p.multi_ec = w.multi_ec.p; p.m_off = w.m_rowoff.p; p.m_tid = w.m_tid.p; p.m_w = w.m_w.p;
   p.t_off = w.t_off.p; p.t_midx = w.t_midx.p; p.t_w = w.t_w.p; p.t_single = w.t_single.p;
   p.nb = 1; p.counts = w.count.p; p.alpha = w.alpha.p; p.norm = w.norm.p;
-  p.rounds = w.emi.p; p.state = w.emi.p + 1; p.fstate = w.emi.p + 3; p.chcount = w.chcount.p;
+  p.rounds = w.emi.p; p.bar = w.bar.p; p.fstate = w.emi.p + 3; p.chcount = w.chcount.p;
   p.max_iter = max_iter; p.min_rounds = min_rounds;
   mark("fill launches + uploads");
-  // collect_used, gather_used, ec_meta, ec_fill, csc_fill, stats, fill_i32 + em_kernel
-  n_kernel_launches += 7 + 1;
+  // collect_used, gather_used, ec_meta, multi_compact, row_len, ec_fill, csc_fill, stats, fill_i32, fill_f64 + em_kernel
+  n_kernel_launches += 10 + 1;
   KB_CK(cudaEventRecord(e1, st));
   launch_em(p, em_tpb(), st);
   KB_CK(cudaGetLastError());
@@ -1047,8 +1055,126 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   last_em_seconds = res.seconds;
   last_prep_seconds = ms_prep * 1e-3;
   dev_stats_valid_ = true;
+  dev_problem_valid_ = true;
+  dev_n_multi_ = n_multi;
   dev_n_ecs_ = n; dev_nnz_ = nnz_all; dev_pseudoaligned_ = s2[0]; dev_unique_ = s2[1];
   return res;
+}
+
+std::vector<int> Quant::run_bootstrap_device(const std::vector<double>& fl_trunc, uint64_t seed, int B, std::vector<double>& alpha_out,
+                                             std::vector<uint32_t>* samples_out, double* ms_out) {
+  KB_CK(cudaSetDevice(ix_.device));
+  std::vector<int> rounds;
+  if (B <= 0) { alpha_out.clear(); return rounds; }
+  if (!dev_problem_valid_) run_em_device(fl_trunc);      // builds the matrices (and runs the main EM once)
+  const uint32_t T = ix_.flat.num_targets();
+  alpha_out.assign((size_t)B * T, 0.0);
+  rounds.assign(B, 0);
+  if (!dev_problem_valid_) return rounds;                // nothing pseudoaligned
+  cudaStream_t st = stream_;
+  EmWs& w = *emws_;
+  const uint32_t nE = (uint32_t)dev_n_ecs_, n_multi = dev_n_multi_;
+  // seeds (src/main.cpp:2746-2752)
+  std::mt19937_64 rnd;
+  rnd.seed(seed);
+  std::vector<uint32_t> x0(B);
+  for (int b = 0; b < B; ++b) {
+    const uint64_t s = rnd();
+    uint32_t x = (uint32_t)(s % 2147483647ull);      // minstd_rand0 seeding (libstdc++ linear_congruential_engine::seed)
+    if (x == 0) x = 1;
+    x0[b] = x;
+  }
+  // std::discrete_distribution<int>(counts): normalised probabilities and their partial sums, in the host's own
+  // sequential double arithmetic (a parallel scan would round differently)
+  std::vector<uint32_t> cnt(nE);
+  w.count.download(cnt.data(), nE, 0, st);
+  KB_CK(cudaStreamSynchronize(st));
+  uint64_t N = 0;
+  for (uint32_t e = 0; e < nE; ++e) N += cnt[e];
+  const int n_draws = (int)N;   // Multinomial::n_ is an int
+  if (w.bs_counts.n < (size_t)B * nE) w.bs_counts.alloc((size_t)B * nE);
+  cudaEvent_t e0, e1, e2;
+  KB_CK(cudaEventCreate(&e0)); KB_CK(cudaEventCreate(&e1)); KB_CK(cudaEventCreate(&e2));
+  KB_CK(cudaEventRecord(e0, st));
+  if (nE >= 2) {
+    std::vector<double> prob(cnt.begin(), cnt.end());
+    const double sum = std::accumulate(prob.begin(), prob.end(), 0.0);
+    for (auto& v : prob) v /= sum;
+    std::vector<double> cp(nE);
+    std::partial_sum(prob.begin(), prob.end(), cp.begin());
+    cp[nE - 1] = 1.0;
+    if (w.bs_cp.n < nE) w.bs_cp.alloc(nE);
+    if (w.bs_x0.n < (size_t)B) w.bs_x0.alloc(B);
+    w.bs_cp.upload(cp.data(), nE, st);
+    w.bs_x0.upload(x0.data(), B, st);
+    ResampleArgs ra{};
+    ra.cp = w.bs_cp.p; ra.n_ec = nE; ra.n_draws = n_draws > 0 ? (uint64_t)n_draws : 0; ra.nb = B; ra.x0 = w.bs_x0.p;
+    ra.samp = w.bs_counts.p;
+    launch_resample(ra, st);
+    KB_CK(cudaGetLastError());
+    KB_CK(cudaStreamSynchronize(st));     // cp / x0 are local vectors
+    ++n_kernel_launches;
+  } else {
+    // a single class: discrete_distribution returns 0 without consuming the engine
+    std::vector<uint32_t> s1((size_t)B * nE, 0);
+    for (int b = 0; b < B && nE == 1; ++b) s1[b] = n_draws > 0 ? (uint32_t)n_draws : 0;
+    w.bs_counts.upload(s1.data(), s1.size(), st);
+    KB_CK(cudaStreamSynchronize(st));
+  }
+  KB_CK(cudaEventRecord(e1, st));
+  if (samples_out) {
+    samples_out->resize((size_t)B * nE);
+    w.bs_counts.download(samples_out->data(), samples_out->size(), 0, st);
+    KB_CK(cudaStreamSynchronize(st));
+  }
+  // the B problems, `chunk` at a time: alpha + norm + counts of a chunk are meant to stay in L2 next to the shared matrices
+  int chunk = B;
+  {
+    const size_t per = ((size_t)T + n_multi) * 8 + (size_t)nE * 4;
+    const size_t budget = 64u << 20;
+    chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, budget / std::max<size_t>(1, per)));
+    if (const char* s = getenv("KB_BS_CHUNK")) { const int v = atoi(s); if (v > 0) chunk = std::min(B, v); }   // tuning knob
+  }
+  if (w.bs_alpha.n < (size_t)chunk * T) w.bs_alpha.alloc((size_t)chunk * T);
+  if (w.bs_norm.n < (size_t)chunk * std::max<uint32_t>(1, n_multi)) w.bs_norm.alloc((size_t)chunk * std::max<uint32_t>(1, n_multi));
+  if (w.bs_emi.n < (size_t)2 * chunk) w.bs_emi.alloc((size_t)2 * chunk);
+  if (w.bs_ch.n < (size_t)2 * chunk) w.bs_ch.alloc((size_t)2 * chunk);
+  std::vector<int> emi((size_t)2 * chunk);
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    launch_fill_f64(w.bs_alpha.p, (uint64_t)nb * T, 1.0 / T, st);
+    w.bs_emi.zero(st);
+    w.bs_ch.zero(st);
+    EmProblem p{};
+    p.n_ec = nE; p.n_targets = T; p.n_multi = n_multi;
+    p.multi_ec = w.multi_ec.p; p.m_off = w.m_rowoff.p; p.m_tid = w.m_tid.p; p.m_w = w.m_w.p;
+    p.t_off = w.t_off.p; p.t_midx = w.t_midx.p; p.t_w = w.t_w.p; p.t_single = w.t_single.p;
+    p.nb = nb; p.counts = w.bs_counts.p + (size_t)b0 * nE; p.alpha = w.bs_alpha.p; p.norm = w.bs_norm.p;
+    p.rounds = w.bs_emi.p; p.fstate = w.bs_emi.p + chunk; p.bar = w.bar.p; p.chcount = w.bs_ch.p;
+    p.max_iter = 10000; p.min_rounds = 50;
+    launch_em(p, em_tpb(), st);
+    KB_CK(cudaGetLastError());
+    n_kernel_launches += 2;
+    w.bs_alpha.download(alpha_out.data() + (size_t)b0 * T, (size_t)nb * T, 0, st);
+    w.bs_emi.download(emi.data(), (size_t)2 * chunk, 0, st);
+    KB_CK(cudaStreamSynchronize(st));
+    for (int b = 0; b < nb; ++b) {
+      rounds[b0 + b] = emi[b];
+      if (emi[chunk + b] == 3)   // stop detected on the last allowed iteration: zero small alphas (EMAlgorithm.h:213-216)
+        for (uint32_t t = 0; t < T; ++t)
+          if (alpha_out[(size_t)(b0 + b) * T + t] < 1e-7 / 10.0) alpha_out[(size_t)(b0 + b) * T + t] = 0.0;
+    }
+  }
+  KB_CK(cudaEventRecord(e2, st));
+  KB_CK(cudaEventSynchronize(e2));
+  if (ms_out) {
+    float a = 0, b = 0;
+    KB_CK(cudaEventElapsedTime(&a, e0, e1));
+    KB_CK(cudaEventElapsedTime(&b, e1, e2));
+    ms_out[0] = a; ms_out[1] = b;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  return rounds;
 }
 
 void Quant::export_prepare(uint32_t* n_sets, uint32_t* n_entries) {
@@ -1070,6 +1196,7 @@ void Quant::export_prepare(uint32_t* n_sets, uint32_t* n_entries) {
     if (w.key_in.n < n1) { w.key_in.alloc(n1 + n1 / 4); w.key_out.alloc(n1 + n1 / 4); }
     grow32(w.idx_in, n1); grow32(w.order, n1); grow32(w.handle, n1); grow32(w.count, n1); grow32(w.len, n1);
     grow32(w.multi_len, n1); grow32(w.is_multi, n1); grow32(w.ec_off, n1); grow32(w.m_off, n1); grow32(w.multi_index, n1);
+    grow32(w.minkey, n1);
     const size_t tmp_need = emprep_sort_bytes(n + 1, 1u << 20);
     if (w.tmp.n < tmp_need) w.tmp.alloc(tmp_need);
     KB_CK(cudaMemsetAsync(w.len.p + n, 0, 4, st));
@@ -1079,7 +1206,7 @@ void Quant::export_prepare(uint32_t* n_sets, uint32_t* n_entries) {
     EmPrep ep{};
     ep.n_ec = n; ep.n_targets = ix_.flat.num_targets();
     ep.handle = w.handle.p; ep.count = w.count.p; ep.len = w.len.p; ep.ec_off = w.ec_off.p; ep.m_off = w.m_off.p;
-    ep.multi_index = w.multi_index.p;
+    ep.multi_index = w.multi_index.p; ep.minkey = w.minkey.p;
     emprep_meta(dd_, w.used.p, w.order.p, n, ep, w.multi_len.p, w.is_multi.p, w.tmp.p, w.tmp.n, st);
     w.ec_off.download(&exp_nnz_, 1, n, st);
     KB_CK(cudaStreamSynchronize(st));
@@ -1112,6 +1239,7 @@ void Quant::import_sets_device(uint32_t n_sets, const uint32_t* d_off, const uin
   KB_CK(cudaSetDevice(ix_.device));
   ecs_valid_ = false;
   dev_stats_valid_ = false;
+  dev_problem_valid_ = false;
   launch_import_sets(dd_, n_sets, d_off, d_tids, d_counts, d_first, first_offset, stream_);
   KB_CK(cudaGetLastError());
   KB_CK(cudaStreamSynchronize(stream_));

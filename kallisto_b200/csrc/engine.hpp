@@ -55,7 +55,15 @@ struct EmWs {   // grow-only device workspace of run_em_device
   DBuf<uint32_t> used, scal, idx_in, order, handle, count, len, multi_len, is_multi, ec_off, m_off, multi_index;
   DBuf<unsigned long long> key_in, key_out;
   DBuf<uint8_t> tmp;
-  DBuf<uint32_t> ec_tid, multi_ec, m_rowoff, m_tid, m_row, m_iota, sortk, sortv, t_deg, t_off, t_midx;
+  DBuf<uint32_t> ec_tid, multi_ec, m_rowoff, m_tid, m_row, m_iota, sortv, t_deg, t_off, t_midx;
+  DBuf<uint32_t> minkey, ckey, cval, ckey_out, rlen;     // row order of the EM matrices (emprep_rows)
+  DBuf<unsigned long long> k64_in, k64_out;              // CSC sort keys
+  DBuf<unsigned> bar;                                    // grid-barrier counter of em_kernel
+  // bootstrap over the same matrices (run_bootstrap_device)
+  DBuf<uint32_t> bs_counts, bs_x0;
+  DBuf<double> bs_alpha, bs_norm, bs_cp;
+  DBuf<int> bs_emi;
+  DBuf<unsigned int> bs_ch;
   DBuf<double> m_w, t_w, eff, alpha, norm;
   DBuf<int32_t> t_single;
   DBuf<int> emi;
@@ -205,6 +213,12 @@ class Quant {
   // Size the EM / EC-numbering workspace ahead of time (no cudaMalloc on the first kb_em_run).
   void reserve_em(size_t n_ecs, size_t n_entries);
 
+  // Same result on the EM matrices run_em_device left on the device (no EC table on the host, no second set-up);
+  // the B problems are solved `chunk` at a time so that their alpha / norm vectors stay in L2.  ms_out (optional):
+  // {resample ms, EM ms} measured with CUDA events.
+  std::vector<int> run_bootstrap_device(const std::vector<double>& fl_trunc, uint64_t seed, int B, std::vector<double>& alpha_out,
+                                        std::vector<uint32_t>* samples_out = nullptr, double* ms_out = nullptr);
+  bool dev_problem_valid() const { return dev_problem_valid_; }
   // Run on a caller-provided stream (e.g. the framework's current stream) instead of the run's own.
   void set_stream(cudaStream_t st);
   // Per-kernel device time, measured with CUDA events on the launching stream.
@@ -215,10 +229,11 @@ class Quant {
   Index& index() { return ix_; }
   const QuantOptions& options() const { return opt_; }
   cudaStream_t stream() const { return stream_; }
-  double last_em_seconds = 0, last_prep_seconds = 0;
+  double last_em_seconds = 0, last_prep_seconds = 0, last_bs_resample_ms = 0, last_bs_em_ms = 0;
   uint64_t n_kernel_launches = 0;   // launches of this library's own kernels by this run (CUB's are not counted)
   // filled by run_em_device
-  bool dev_stats_valid_ = false;
+  bool dev_stats_valid_ = false, dev_problem_valid_ = false;
+  uint32_t dev_n_multi_ = 0;
   uint64_t dev_n_ecs_ = 0, dev_nnz_ = 0, dev_pseudoaligned_ = 0, dev_unique_ = 0;
 
  private:

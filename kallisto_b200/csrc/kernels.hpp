@@ -122,7 +122,7 @@ struct EmProblem {
   double* alpha;                // nb x n_targets (in/out)
   double* norm;                 // nb x n_multi scratch: counts/denom or 0
   int* rounds;                  // nb: iterations run (the reference's "ran for i rounds")
-  int* state;                   // 2 x nb (double-buffered by iteration parity): 0 running, 1 final round, >= 2 done
+  unsigned* bar;                // arrival counter of the kernel's grid barrier (zeroed by launch_em)
   int* fstate;                  // nb: final state (2 finished, 3 finished + host must zero small alphas)
   unsigned int* chcount;        // nb x 2 (double-buffered) change counters
   int max_iter, min_rounds;
@@ -139,7 +139,8 @@ struct EmPrep {
   uint32_t* len;           // n_ec + 1
   uint32_t* ec_off;        // n_ec + 1: offsets of the EC table
   uint32_t* m_off;         // n_ec + 1: offsets into the multi-EC entry arrays (0-length for singletons)
-  uint32_t* multi_index;   // n_ec + 1: row index among the multi-transcript ECs
+  uint32_t* multi_index;   // n_ec + 1: after the scan the rank among the multi-transcript ECs, after emprep_rows the ROW of the EC
+  uint32_t* minkey;        // n_ec: smallest transcript id of the EC
   uint32_t* ec_tid;        // EC table entries
   // multi-transcript ECs, CSR
   uint32_t* multi_ec;      // n_multi
@@ -147,7 +148,8 @@ struct EmPrep {
   uint32_t* m_tid;
   double* m_w;
   uint32_t* m_row;         // entry -> row
-  uint32_t* m_iota;        // entry -> entry (values for the stable sort)
+  uint32_t* m_iota;        // entry -> entry (values of the CSC sort)
+  unsigned long long* k64_in;   // entry -> tid << 32 | EC id (keys of the CSC sort)
   // CSC
   uint32_t* t_deg;         // n_targets + 1 (zeroed by the caller)
   uint32_t* t_off;         // n_targets + 1
@@ -162,8 +164,10 @@ void emprep_sort_by_first(const DevDict& dd, const uint32_t* used, uint32_t n_us
                           cudaStream_t st);
 void emprep_meta(const DevDict& dd, const uint32_t* used, const uint32_t* order, uint32_t n, const EmPrep& p,
                  uint32_t* multi_len, uint32_t* is_multi, void* tmp, size_t tmp_bytes, cudaStream_t st);
+void emprep_rows(const EmPrep& p, const uint32_t* is_multi, uint32_t* ckey, uint32_t* cval, uint32_t* ckey_out, uint32_t* rlen,
+                 void* tmp, size_t tmp_bytes, cudaStream_t st);
 void emprep_fill_table(const DevDict& dd, const EmPrep& p, cudaStream_t st);
-void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, uint32_t* sort_keys_out, uint32_t* sort_vals_out,
+void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, unsigned long long* sort_keys_out, uint32_t* sort_vals_out,
                  void* tmp, size_t tmp_bytes, unsigned long long* stats2, cudaStream_t st);
 
 // ---- BUS (kernels_bus.cu) ----

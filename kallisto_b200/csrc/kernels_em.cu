@@ -1,7 +1,7 @@
 // K4/K5: fp64 EM over the sparse EC x transcript layout, and bootstrap resampling.
 //
 // EMAlgorithm::run (src/EMAlgorithm.h:95-221) restated as two segmented passes per iteration
-// inside ONE persistent cooperative kernel (no atomics, no dense contraction, no tensor cores):
+// inside ONE persistent kernel with a hand-rolled grid barrier (no dense contraction, no tensor cores):
 //   pass A  per multi-transcript EC (CSR by EC):     denom = sum_j alpha[t_j] * w_j ; norm = count/denom
 //   pass B  per transcript (CSC, entries by EC id):  next[t] = count(singleton {t}) + sum (w*alpha[t]) * norm
 //           + the convergence test and alpha <- next
@@ -10,14 +10,11 @@
 // (the reference is built without FMA contraction: no -march on src/), so alpha is
 // bit-identical to the CPU result, iteration count included.  A batch dimension runs the B
 // bootstrap EMs of Bootstrap::run_em (src/Bootstrap.cpp:4-13) concurrently over the same structure.
-#include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
 
 #include "kb_device.cuh"
 #include "kernels.hpp"
-
-namespace cg = cooperative_groups;
 
 namespace kb {
 
@@ -28,40 +25,71 @@ constexpr double kAlphaChange = 1e-2;         // :103
 constexpr double kTolerance = 4.9406564584124654e-324;   // std::numeric_limits<double>::denorm_min()
 }
 
+// Grid-wide barrier of the persistent kernel: a monotonically increasing arrival counter in global memory
+// (zeroed by the launcher), one atomic per block and one spinning thread per block.  The kernel is launched
+// cooperatively only for the co-residency guarantee; cooperative_groups' grid.sync() cost ~5 us of a 26 us round
+// with 592 blocks, this one well under 2.  The fences around the spin order the other threads' plain loads and
+// stores (and drop stale L1 lines) exactly as grid.sync() does.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// `add_to` (optional): the block's contribution *s_add is added to it by the arriving thread (one global atomic per
+// block instead of one per warp) and *s_add is cleared.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& gen, unsigned* add_to = nullptr, unsigned* s_add = nullptr) {
+  __syncthreads();
+  ++gen;
+  if (threadIdx.x == 0) {
+    if (add_to) {
+      const unsigned v = *s_add;
+      if (v) atomicAdd(add_to, v);
+      *s_add = 0;
+    }
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = gen * gridDim.x;
+    while (ld_acquire_u32(bar) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 template <int TPB>
 __global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4))) em_kernel(EmProblem p) {
-  cg::grid_group grid = cg::this_grid();
-  extern __shared__ int s_state[];    // per problem: 0 running, 1 final round, >= 2 finished
+  extern __shared__ int s_state[];    // per problem: 0 running, 1 final round, >= 2 finished (every block keeps its own, identical copy)
   const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
   const unsigned lane = threadIdx.x & 31;
   const uint64_t nA = (uint64_t)p.nb * p.n_multi;
   const uint64_t nB = (uint64_t)p.nb * p.n_targets;
   const double zero_below = kAlphaLimit / 10.0;
+  unsigned gen = 0;
+  __shared__ unsigned s_changed;
+  if (threadIdx.x == 0) s_changed = 0;
+  for (int b = threadIdx.x; b < p.nb; b += blockDim.x) s_state[b] = 0;
 
   for (int it = 0;; ++it) {
-    // ---------------- state machine per problem (:202-221), evaluated redundantly by every block
-    // from the change counters of the iteration that just finished (two grid syncs per iteration)
-    for (int b = threadIdx.x; b < p.nb; b += blockDim.x) {
-      int st = 0;
-      if (it > 0) {
-        const int i = it - 1;                                       // the iteration that just ran
-        st = p.state[(i & 1) * p.nb + b];
+    // ---------------- state machine per problem (:202-221), evaluated redundantly by every block from the change
+    // counters of the iteration that just finished
+    if (it > 0) {
+      const int i = it - 1;                                         // the iteration that just ran
+      for (int b = threadIdx.x; b < p.nb; b += blockDim.x) {
+        int st = s_state[b];
         if (st < 2) {
-          const unsigned ch = p.chcount[2 * b + (i & 1)];
-          if (st == 1) { st = 2; p.rounds[b] = i; }                 // if (finalRound) break;
+          const unsigned ch = __ldcg(&p.chcount[2 * b + (i & 1)]);
+          if (st == 1) { st = 2; if (blockIdx.x == 0) p.rounds[b] = i; }     // if (finalRound) break;
           else if (ch == 0 && i > p.min_rounds) st = 1;             // stopEM -> finalRound
           if (st < 2 && i + 1 == p.max_iter) {
             // loop runs out: i == n_iter.  If the stop was detected on the very last iteration the
             // reference still zeroes the small alphas (:213-216); the host does that for state 3.
-            p.rounds[b] = p.max_iter;
+            if (blockIdx.x == 0) p.rounds[b] = p.max_iter;
             st = (st == 1) ? 3 : 2;
           }
-          if (st >= 2) p.fstate[b] = st;
+          if (st >= 2 && blockIdx.x == 0) p.fstate[b] = st;
+          s_state[b] = st;
         }
       }
-      p.state[(it & 1) * p.nb + b] = st;    // every block writes the same value
-      s_state[b] = st;
     }
     __syncthreads();
     bool mine_done = true;
@@ -87,11 +115,12 @@ __global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4)))
       }
       p.norm[(size_t)b * p.n_multi + r] = nrm;
     }
-    grid.sync();
-    // the other parity of the change counters was consumed by every block before the sync above
+    // the other parity of the change counters was consumed by every block before it arrives here
+    grid_barrier(p.bar, gen);
     if (blockIdx.x == 0)
       for (int b = threadIdx.x; b < p.nb; b += blockDim.x) p.chcount[2 * b + ((it + 1) & 1)] = 0;
     // ---------------- pass B: numerators, convergence test, alpha <- next ----------------
+    unsigned n_changed = 0;       // nb == 1: counted per thread, reduced per block
     for (uint64_t i0 = gtid - lane; i0 < nB; i0 += gstride) {
       const uint64_t i = i0 + lane;
       bool changed = false;
@@ -114,17 +143,28 @@ __global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4)))
           al[t] = acc;
         }
       }
-      // one atomic per warp when the warp sits inside one problem (the common case)
-      const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, b, 0), b31 = __shfl_sync(0xFFFFFFFFu, b, 31);
-      const bool full = (i0 + 31 < nB) && b0 == b31;
-      if (full) {
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, changed);
-        if (lane == 0 && m) atomicAdd(&p.chcount[2 * b0 + (it & 1)], (unsigned)__popc(m));
-      } else if (changed) {
-        atomicAdd(&p.chcount[2 * b + (it & 1)], 1u);
+      if (p.nb == 1) {
+        n_changed += changed ? 1u : 0u;
+      } else {
+        // one atomic per warp when the warp sits inside one problem (the common case)
+        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, b, 0), b31 = __shfl_sync(0xFFFFFFFFu, b, 31);
+        const bool full = (i0 + 31 < nB) && b0 == b31;
+        if (full) {
+          const unsigned m = __ballot_sync(0xFFFFFFFFu, changed);
+          if (lane == 0 && m) atomicAdd(&p.chcount[2 * b0 + (it & 1)], (unsigned)__popc(m));
+        } else if (changed) {
+          atomicAdd(&p.chcount[2 * b + (it & 1)], 1u);
+        }
       }
     }
-    grid.sync();
+    if (p.nb == 1) {
+      // one global atomic per block, issued by the thread that arrives at the grid barrier
+      for (int o = 16; o > 0; o >>= 1) n_changed += __shfl_xor_sync(0xFFFFFFFFu, n_changed, o);
+      if (lane == 0 && n_changed) atomicAdd(&s_changed, n_changed);
+      grid_barrier(p.bar, gen, &p.chcount[it & 1], &s_changed);
+    } else {
+      grid_barrier(p.bar, gen);
+    }
   }
 }
 
@@ -147,6 +187,7 @@ void launch_em(const EmProblem& p, int tpb_req, cudaStream_t st) {
   if (const char* s = getenv("KB_EM_BLOCKS")) { const int v = atoi(s); if (v > 0) blocks = std::min(maxb, v); }   // tuning knob
   if (blocks < 1) blocks = 1;
   EmProblem pp = p;
+  cudaMemsetAsync(pp.bar, 0, sizeof(unsigned), st);
   void* args[] = {&pp};
   void* fn = tpb == 1024 ? (void*)em_kernel<1024> : (tpb == 512 ? (void*)em_kernel<512> : (void*)em_kernel<256>);
   cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);

@@ -25,16 +25,39 @@ __global__ void gather_used_kernel(DevDict dd, const uint32_t* used, uint32_t n,
 
 // After the sort: EC id e <- used[order[e]]
 __global__ void ec_meta_kernel(DevDict dd, const uint32_t* used, const uint32_t* order, uint32_t n, uint32_t* handle,
-                               uint32_t* count, uint32_t* len, uint32_t* multi_len, uint32_t* is_multi) {
+                               uint32_t* count, uint32_t* len, uint32_t* multi_len, uint32_t* is_multi, uint32_t* minkey) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const uint32_t h = used[order[e]];
-  const uint32_t l = (uint32_t)((dd.dslots[h] >> 32) & 0xFFFFFFu);
+  const unsigned long long word = dd.dslots[h];
+  const uint32_t l = (uint32_t)((word >> 32) & 0xFFFFFFu);
   handle[e] = h;
   count[e] = dd.count[h];
   len[e] = l;
   multi_len[e] = l > 1 ? l : 0;
   is_multi[e] = l > 1 ? 1u : 0u;
+  minkey[e] = l > 0 ? dd.pool[(uint32_t)word] : 0u;     // smallest transcript id of the set (lists are sorted)
+}
+
+// Rows of the EM matrices = the multi-transcript ECs, laid out in order of their SMALLEST TRANSCRIPT ID instead of EC
+// id: ECs of one gene (adjacent transcript ids) become adjacent rows, so the alpha gathers of neighbouring rows and
+// the norm gathers of neighbouring transcripts fall into the same 32-byte sectors.  The arithmetic does not change:
+// a row is still accumulated in its own order and a transcript's entries stay in increasing EC id.
+__global__ void multi_compact_kernel(const uint32_t* is_multi, const uint32_t* multi_index, const uint32_t* minkey, uint32_t n,
+                                     uint32_t* ckey, uint32_t* cval) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || !is_multi[e]) return;
+  const uint32_t r0 = multi_index[e];
+  ckey[r0] = minkey[e];
+  cval[r0] = e;
+}
+__global__ void row_len_kernel(const uint32_t* multi_ec, const uint32_t* len, uint32_t n_multi, uint32_t* rlen, uint32_t* rowpos) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_multi) return;
+  if (r == n_multi) { rlen[r] = 0; return; }     // the scan runs over n_multi + 1 items
+  const uint32_t e = multi_ec[r];
+  rlen[r] = len[e];
+  rowpos[e] = r;
 }
 
 // One warp per EC: copy its transcript ids, compute the weights, count transcript degrees.
@@ -53,13 +76,8 @@ __global__ void ec_fill_kernel(DevDict dd, EmPrep p) {
     if (lane == 0) p.t_single[src[0]] = (int32_t)e;
     return;
   }
-  const uint32_t r = p.multi_index[e];
-  const uint32_t mo = p.m_off[e];          // exclusive scan of multi_len: start of this row
-  if (lane == 0) {
-    p.multi_ec[r] = e;
-    p.m_rowoff[r] = mo;
-    if (r + 1 == p.n_multi) p.m_rowoff[p.n_multi] = mo + l;
-  }
+  const uint32_t r = p.multi_index[e];     // row of this EC (rows are ordered by smallest transcript id)
+  const uint32_t mo = p.m_rowoff[r];
   const double c = (double)p.count[e];
   for (uint32_t j = lane; j < l; j += 32) {
     const uint32_t t = src[j];
@@ -67,6 +85,7 @@ __global__ void ec_fill_kernel(DevDict dd, EmPrep p) {
     p.m_w[mo + j] = __ddiv_rn(c, p.eff[t]);        // calc_weights: counts[ec] / eff_lens[tr]
     p.m_row[mo + j] = r;
     p.m_iota[mo + j] = mo + j;
+    p.k64_in[mo + j] = ((unsigned long long)t << 32) | e;    // CSC order: transcript, then EC id
     atomicAdd(&p.t_deg[t], 1u);
   }
 }
@@ -109,12 +128,14 @@ __global__ void stats_kernel(const uint32_t* count, const uint32_t* len, uint32_
 }  // namespace
 
 size_t emprep_sort_bytes(uint32_t n_used, uint32_t nnz_max) {
-  size_t a = 0, b = 0, c = 0;
+  size_t a = 0, b = 0, c = 0, d = 0;
+  const int big = (int)std::max(n_used, nnz_max);
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_used);
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, big);
   cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)nnz_max);
-  cub::DeviceScan::ExclusiveSum(nullptr, c, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)std::max(n_used, nnz_max) + 1);
+                                  (uint32_t*)nullptr, big);
+  cub::DeviceScan::ExclusiveSum(nullptr, c, (const uint32_t*)nullptr, (uint32_t*)nullptr, big + 1);
+  (void)d;
   return std::max(a, std::max(b, c)) + 256;
 }
 
@@ -129,11 +150,24 @@ void emprep_sort_by_first(const DevDict& dd, const uint32_t* used, uint32_t n_us
 void emprep_meta(const DevDict& dd, const uint32_t* used, const uint32_t* order, uint32_t n, const EmPrep& p,
                  uint32_t* multi_len, uint32_t* is_multi, void* tmp, size_t tmp_bytes, cudaStream_t st) {
   if (n == 0) return;
-  ec_meta_kernel<<<(n + 255) / 256, 256, 0, st>>>(dd, used, order, n, p.handle, p.count, p.len, multi_len, is_multi);
+  ec_meta_kernel<<<(n + 255) / 256, 256, 0, st>>>(dd, used, order, n, p.handle, p.count, p.len, multi_len, is_multi, p.minkey);
   // n + 1 items so that the totals land in [n]
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, p.len, p.ec_off, (int)n + 1, st);
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, multi_len, p.m_off, (int)n + 1, st);
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, is_multi, p.multi_index, (int)n + 1, st);
+}
+
+// Row order of the EM matrices: multi-transcript ECs sorted by their smallest transcript id (stable: ties in EC id
+// order).  Fills multi_ec (row -> EC id), m_rowoff (n_multi + 1) and overwrites multi_index (EC id -> row).
+void emprep_rows(const EmPrep& p, const uint32_t* is_multi, uint32_t* ckey, uint32_t* cval, uint32_t* ckey_out, uint32_t* rlen,
+                 void* tmp, size_t tmp_bytes, cudaStream_t st) {
+  if (p.n_multi == 0) return;
+  multi_compact_kernel<<<(p.n_ec + 255) / 256, 256, 0, st>>>(is_multi, p.multi_index, p.minkey, p.n_ec, ckey, cval);
+  int bits = 1;
+  while ((1u << bits) < p.n_targets && bits < 32) ++bits;
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ckey, ckey_out, cval, p.multi_ec, (int)p.n_multi, 0, bits, st);
+  row_len_kernel<<<(p.n_multi + 1 + 255) / 256, 256, 0, st>>>(p.multi_ec, p.len, p.n_multi, rlen, p.multi_index);
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rlen, p.m_rowoff, (int)p.n_multi + 1, st);
 }
 
 void emprep_fill_table(const DevDict& dd, const EmPrep& p, cudaStream_t st) {
@@ -142,7 +176,7 @@ void emprep_fill_table(const DevDict& dd, const EmPrep& p, cudaStream_t st) {
   ec_table_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dd, p);
 }
 
-void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, uint32_t* sort_keys_out, uint32_t* sort_vals_out,
+void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, unsigned long long* sort_keys_out, uint32_t* sort_vals_out,
                  void* tmp, size_t tmp_bytes, unsigned long long* stats2, cudaStream_t st) {
   if (p.n_ec == 0) return;
   const uint64_t threads = (uint64_t)p.n_ec * 32;
@@ -151,7 +185,9 @@ void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, uint32_t* sor
   if (nnz) {
     int bits = 1;
     while ((1u << bits) < p.n_targets && bits < 32) ++bits;
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p.m_tid, sort_keys_out, p.m_iota, sort_vals_out, (int)nnz, 0, bits, st);
+    // (transcript, EC id) order: a transcript's entries are accumulated in increasing EC id (EMAlgorithm.h:125-169
+    // walks the ECs in id order), whatever the row order of the matrices
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p.k64_in, sort_keys_out, p.m_iota, sort_vals_out, (int)nnz, 0, 32 + bits, st);
     csc_fill_kernel<<<(nnz + 255) / 256, 256, 0, st>>>(p, sort_vals_out, nnz);
   }
   cudaMemsetAsync(stats2, 0, 16, st);
