@@ -43,7 +43,7 @@ def setup(tmp_path_factory):
 
 
 def quant(exe, idx, out, args, env=None):
-    e = dict(os.environ)
+    e = dict(os.environ, KB_CLI_CLEANUP="1")      # orderly release at the end (what the sanitizer runs look at)
     e.update(env or {})
     r = subprocess.run([exe, "quant", "-i", idx, "-o", str(out), "--plaintext"] + args, capture_output=True, text=True, env=e, timeout=600)
     assert r.returncode == 0, r.stderr[-500:]

@@ -108,8 +108,8 @@ for san in thread address,undefined; do
   d=$W/cli_${san%%,*}; mkdir -p $d
   g++ -O1 -g -fsanitize=$san -std=c++17 -fPIC -shared -Iinclude -o $d/libkallisto_b200.so tests/stub/stub_abi.cpp
   g++ -O1 -g -fsanitize=$san -std=c++17 -Iinclude -Ikallisto_b200/csrc -o $d/cli kallisto_b200/csrc/cli_main.cpp -L$d -lkallisto_b200 -Wl,-rpath,$d -lz -lpthread
-  KB_FASTX_WINDOW=30000 KB_CLI_BATCH_READS=700,1100 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o1 --plaintext -t 8 $W/data/r1.fq $W/data/r2.fq > /dev/null 2> $d/e1 || true
-  KB_CLI_BATCH_READS=512,4096 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o2 --plaintext -t 8 tests/golden/synth_small/reads_1.fastq.gz tests/golden/synth_small/reads_2.fastq.gz > /dev/null 2> $d/e2 || true
+  KB_CLI_CLEANUP=1 KB_FASTX_WINDOW=30000 KB_CLI_BATCH_READS=700,1100 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o1 --plaintext -t 8 $W/data/r1.fq $W/data/r2.fq > /dev/null 2> $d/e1 || true
+  KB_CLI_CLEANUP=1 KB_CLI_BATCH_READS=512,4096 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o2 --plaintext -t 8 tests/golden/synth_small/reads_1.fastq.gz tests/golden/synth_small/reads_2.fastq.gz > /dev/null 2> $d/e2 || true
   KB_CLI_BATCH_READS=300,470 $d/cli bus -i tests/golden/config1/transcripts.kidx -o $d/o3 -x 10xv2 -t 4 tests/golden/bus10x/sc_reads_1.fastq.gz tests/golden/bus10x/sc_reads_2.fastq.gz > /dev/null 2> $d/e3 || true
   if grep -q -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3; then echo "command line under -fsanitize=$san: report"; grep -h -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3 | head; fail=1; fi
   cmp -s $d/o1/abundance.tsv $d/o2/abundance.tsv || { echo "plain and gzip input gave different digests"; fail=1; }
