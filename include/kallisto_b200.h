@@ -183,6 +183,20 @@ int kb_em_run_table(kb_quant* q, uint32_t n_ecs, const uint64_t* ec_offsets, con
 int kb_bootstrap_run(kb_quant* q, double fld_mean, double fld_sd, uint64_t seed, int32_t n_bootstrap,
                      double* est_counts_out, uint32_t* samples_out, int32_t* rounds_out);
 
+/* ---- `kallisto quant-tcc` (src/main.cpp:2802-3220): one EM per sample (row of a transcript-compatibility-count matrix)
+ * over ONE shared equivalence-class table (the lines of matrix.ec, EC id = line number), batched on the device; a
+ * sample's weights are its own counts / eff_len (calc_weights, src/weights.cpp:220-246).  The TCC matrix comes as
+ * CSR (row_offsets / ec_ids / counts); eff_lens has n_targets entries, or n_samples x n_targets with
+ * per_sample_eff != 0 (one fragment-length distribution per sample).  est_counts_out: n_samples x n_targets. */
+int kb_tcc_run(kb_index* ix, uint32_t n_ecs, const uint64_t* ec_offsets, const uint32_t* tids, uint32_t n_samples,
+               const uint64_t* row_offsets, const uint32_t* ec_ids, const uint32_t* counts, const double* eff_lens,
+               int32_t per_sample_eff, double* est_counts_out, int32_t* rounds_out);
+/* mean_fl_trunc -> eff_lens exactly as the reference forms them (get_frag_len_means + calc_eff_lens, src/weights.cpp:7-28,
+ * 58-79): fld_mean > 0: truncated Gaussian (-l/-s); else the histogram flens[1000]; both 0/NULL: eff_len = 1 for every
+ * target (quant-tcc without fragment-length information).  Host arithmetic. */
+int kb_eff_lens(const kb_index* ix, const uint32_t* flens, double fld_mean, double fld_sd, double* eff_lens_out,
+                double* mean_fl_out, double* sd_fl_out);
+
 /* ---- `kallisto bus`: replaces BUSProcessor::processBuffer (src/ProcessReads.cpp:1380-1832) + the
  * record writing / EC id assignment of MasterProcessor::update (:603-624) ------------------------ */
 typedef struct kb_bus_substr { int32_t fileno, start, stop; } kb_bus_substr;   /* BUSOptionSubstr, src/common.h:29-36 */

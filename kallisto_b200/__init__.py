@@ -90,7 +90,7 @@ EXPORTED_SYMBOLS = [
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
     "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device",
     "kb_comm_unique_id", "kb_comm_create", "kb_comm_create_from_nccl", "kb_comm_create_all", "kb_comm_reserve", "kb_comm_free",
-    "kb_quant_merge_nccl", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_bus_create", "kb_bus_batch", "kb_bus_batch_device", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
+    "kb_quant_merge_nccl", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_tcc_run", "kb_eff_lens", "kb_bus_create", "kb_bus_batch", "kb_bus_batch_device", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -147,6 +147,8 @@ def lib():
     L.kb_quant_merge_nccl.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.kb_quant_set_frag_base.argtypes = [vp, u64]
     L.kb_quant_reserve.argtypes = [vp, u64, u64]
+    L.kb_tcc_run.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, i32, vp, vp]
+    L.kb_eff_lens.argtypes = [vp, vp, dbl, dbl, vp, C.POINTER(dbl), C.POINTER(dbl)]
     L.kb_bus_create.argtypes = [vp, C.POINTER(kb_bus_opts), C.POINTER(vp)]
     L.kb_bus_batch.argtypes = [vp, vp, vp, u32, vp, C.POINTER(u32)]
     L.kb_bus_batch_device.argtypes = [vp, vp, vp, u32, u32, C.POINTER(u32), C.POINTER(vp)]
@@ -450,6 +452,42 @@ class BUSProcessor(MinCollector):
         b, u = np.zeros(33, np.uint32), np.zeros(33, np.uint32)
         _ck(lib().kb_bus_lengths(self._h, _p(b), _p(u)))
         return b, u
+
+
+def eff_lens(index, flens=None, fld_mean=0.0, fld_sd=0.0):
+    """Effective lengths as the reference forms them (kb_eff_lens) -> (eff_lens, mean_fl, sd_fl)."""
+    out = np.zeros(index.num_trans, np.float64)
+    m, s = C.c_double(0), C.c_double(0)
+    fl = None if flens is None else np.ascontiguousarray(flens, np.uint32)
+    _ck(lib().kb_eff_lens(index._h, _p(fl), fld_mean, fld_sd, _p(out), C.byref(m), C.byref(s)))
+    return out, m.value, s.value
+
+
+def tcc_run(index, ec_sets, rows, eff):
+    """`kallisto quant-tcc` on the device: ec_sets = list of sorted transcript-id tuples (EC id = position), rows = per sample
+    a list of (ec id, count); eff = effective lengths (n_targets, or n_samples x n_targets) -> (est_counts (S, T), rounds (S))."""
+    T = index.num_trans
+    eo = np.zeros(len(ec_sets) + 1, np.uint64)
+    tids = []
+    for i, s_ in enumerate(ec_sets):
+        tids.extend(s_)
+        eo[i + 1] = len(tids)
+    tids = np.asarray(tids, np.uint32) if tids else np.zeros(1, np.uint32)
+    ro = np.zeros(len(rows) + 1, np.uint64)
+    ids, vals = [], []
+    for i, r in enumerate(rows):
+        for e, c in r:
+            ids.append(e); vals.append(c)
+        ro[i + 1] = len(ids)
+    ids = np.asarray(ids, np.uint32) if ids else np.zeros(1, np.uint32)
+    vals = np.asarray(vals, np.uint32) if vals else np.zeros(1, np.uint32)
+    eff = np.ascontiguousarray(eff, np.float64)
+    per_sample = int(eff.ndim == 2)
+    est = np.zeros((len(rows), T), np.float64)
+    rounds = np.zeros(max(1, len(rows)), np.int32)
+    _ck(lib().kb_tcc_run(index._h, len(ec_sets), _p(eo), _p(tids), len(rows), _p(ro), _p(ids), _p(vals), _p(eff), per_sample,
+                         _p(est), _p(rounds)))
+    return est, rounds[: len(rows)]
 
 
 def fastx_summary(path, threads=1):

@@ -1,6 +1,8 @@
 // extern "C" boundary: include/kallisto_b200.h implemented on top of kb::Index / kb::Quant.
+#include <cmath>
 #include <cstring>
 #include <exception>
+#include <limits>
 #include <string>
 
 #include "../../include/kallisto_b200.h"
@@ -368,6 +370,77 @@ int kb_quant_set_frag_base(kb_quant* q, uint64_t base) {
 int kb_quant_reserve(kb_quant* q, uint64_t n_ecs, uint64_t n_entries) {
   if (!q) return fail(KB_ERR_INVALID, "kb_quant_reserve: null argument");
   return guarded([&] { q->q->reserve_em(n_ecs, n_entries); });
+}
+
+int kb_tcc_run(kb_index* ix, uint32_t n_ecs, const uint64_t* ec_offsets, const uint32_t* tids, uint32_t n_samples,
+               const uint64_t* row_offsets, const uint32_t* ec_ids, const uint32_t* counts, const double* eff_lens,
+               int32_t per_sample_eff, double* est_counts_out, int32_t* rounds_out) {
+  if (!ix || !ec_offsets || !row_offsets || !eff_lens || !est_counts_out || (n_ecs && !tids))
+    return fail(KB_ERR_INVALID, "kb_tcc_run: null argument");
+  return guarded([&] {
+    kb::TccInput in;
+    in.n_ecs = n_ecs; in.ec_off = ec_offsets; in.tids = tids; in.n_samples = n_samples; in.row_off = row_offsets;
+    in.ec_ids = ec_ids; in.counts = counts; in.eff_lens = eff_lens; in.per_sample_eff = per_sample_eff != 0;
+    std::vector<double> alpha;
+    const std::vector<int> rounds = kb::tcc_run(*ix->ix, in, alpha);
+    memcpy(est_counts_out, alpha.data(), alpha.size() * sizeof(double));
+    if (rounds_out)
+      for (uint32_t i = 0; i < n_samples; ++i) rounds_out[i] = rounds[i];
+  });
+}
+
+int kb_eff_lens(const kb_index* ix, const uint32_t* flens, double fld_mean, double fld_sd, double* eff_out, double* mean_out,
+                double* sd_out) {
+  if (!ix || !eff_out) return fail(KB_ERR_INVALID, "kb_eff_lens: null argument");
+  const auto& tl = ix->ix->flat.target_len;
+  const size_t T = tl.size();
+  if (!flens && fld_mean == 0.0) {
+    // no fragment-length information: fl_means = target lengths, so every effective length is len - len + 1 (main.cpp:3025-3027)
+    for (size_t t = 0; t < T; ++t) {
+      const double len = static_cast<double>(tl[t]);
+      double e = len - len + 1;
+      if (e < 1.0) e = len;
+      eff_out[t] = e;
+    }
+    return KB_OK;
+  }
+  static const uint32_t zeros[1000] = {0};
+  const uint32_t* fl = flens ? flens : zeros;
+  const std::vector<double> trunc = kb::mean_fl_trunc_of(fl, fld_mean, fld_sd);
+  const double marginal = trunc[999];
+  for (size_t t = 0; t < T; ++t) {
+    const double mean = tl[t] >= 1000 ? marginal : trunc[tl[t]];
+    const double len = static_cast<double>(tl[t]);
+    double e = len - mean + 1;
+    if (e < 1.0) e = len;
+    eff_out[t] = e;
+  }
+  // MinCollector::get_mean_frag_len(true) / get_sd_frag_len (src/MinCollector.cpp:583-627)
+  double mean_fl;
+  if (fld_mean != 0.0) {
+    mean_fl = trunc[999];
+  } else {
+    auto total_counts = 0;
+    double total_mass = 0.0;
+    for (size_t i = 0; i < 1000; ++i) {
+      total_counts += fl[i];
+      total_mass += static_cast<double>(fl[i] * i);
+    }
+    mean_fl = total_counts == 0 ? std::numeric_limits<double>::max() : total_mass / static_cast<double>(total_counts);
+  }
+  if (mean_out) *mean_out = mean_fl;
+  if (sd_out) {
+    const uint32_t* sf = fld_mean != 0.0 ? zeros : fl;     // with -l the collector's histogram stays empty
+    size_t total_counts = 0;
+    double total_mass = 0.0;
+    const double m = mean_fl;
+    for (size_t i = 0; i < 1000; ++i) {
+      total_counts += sf[i];
+      total_mass += sf[i] * (i - m) * (i - m);
+    }
+    *sd_out = std::sqrt(total_mass / total_counts);
+  }
+  return KB_OK;
 }
 
 int kb_bus_create(kb_index* ix, const kb_bus_opts* o, kb_quant** out) {

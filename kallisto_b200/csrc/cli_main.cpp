@@ -981,6 +981,325 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   return st.n_pseudoaligned == 0 ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// kallisto quant-tcc (src/main.cpp:394-513 ParseOptionsTCCQuant, 1807-1967 CheckOptionsTCCQuant, 2802-3220 body):
+// abundances from pre-computed transcript-compatibility counts.  Every row of the TCC matrix is one EM over the
+// equivalence classes of the EC file; all rows are solved on the device by the batched EM kernel (kb_tcc_run).
+// Supported: -i, -e (required here), -o, -l/-s, -f, -t, --matrix-to-files, --plaintext.  Gene-level output
+// (-g/-G), priors, --long, -T and bootstraps are refused loudly.
+// ------------------------------------------------------------------------------------------------
+void usage_tcc() {
+  std::cout << "kallisto_b200 " << KALLISTO_VERSION << " (B200 build)" << endl
+            << "Quantifies abundance from pre-computed transcript-compatibility counts" << endl << endl
+            << "Usage: kallisto_b200 quant-tcc [arguments] transcript-compatibility-counts-file" << endl << endl
+            << "Required arguments:" << endl
+            << "-o, --output-dir=STRING       Directory to write output to" << endl
+            << "-i, --index=STRING            Filename for the kallisto index to be used" << endl
+            << "-e, --ec-file=FILE            File containing equivalence classes (matrix.ec of kallisto bus)" << endl << endl
+            << "Optional arguments:" << endl
+            << "-f, --fragment-file=FILE      File containing fragment length distribution" << endl
+            << "                              (default: effective length normalization is not performed)" << endl
+            << "-l, --fragment-length=DOUBLE  Estimated average fragment length" << endl
+            << "-s, --sd=DOUBLE               Estimated standard deviation of fragment length" << endl
+            << "-t, --threads=INT             Number of host threads (default: 1)" << endl
+            << "    --matrix-to-files         Reorganize matrix output into abundance tsv files" << endl
+            << "    --device=INT              CUDA device ordinal (default: 0)" << endl;
+}
+
+void write_sparse_matrix(const std::string& path, const std::vector<std::vector<std::pair<int, double>>>& data, size_t cols) {
+  // writeSparseBatchMatrix, src/PlaintextWriter.h:72-105
+  uint64_t n = 0;
+  for (auto& v : data)
+    for (auto& x : v)
+      if (x.second != 0.0) ++n;
+  std::string out = "%%MatrixMarket matrix coordinate real general\n";
+  out += std::to_string(data.size()) + "\t" + std::to_string(cols) + "\t" + std::to_string(n) + "\n";
+  for (size_t j = 0; j < data.size(); ++j)
+    for (auto& x : data[j])
+      if (x.second != 0.0) {
+        out += std::to_string(j + 1) + "\t" + std::to_string(x.first + 1) + "\t";
+        append_double(out, x.second);
+        out += "\n";
+      }
+  std::ofstream of(path, std::ios::out | std::ios::binary);
+  of.write(out.data(), (std::streamsize)out.size());
+}
+
+int cmd_quant_tcc(int argc, char** argv) {
+  std::string index, ecfile, output, fldfile, tccfile, genemap, gtf, priors, txnames;
+  double fld = 0.0, sd = 0.0;
+  int threads = 1, device = 0, bootstrap = 0;
+  int matrix_to_files = 0, matrix_to_dirs = 0, plaintext = 0, long_flag = 0;
+  const char* opt_string = "o:i:T:e:f:P:l:s:t:g:G:b:d:p:D:";
+  static struct option long_options[] = {{"plaintext", no_argument, &plaintext, 1},
+                                         {"matrix-to-files", no_argument, &matrix_to_files, 1},
+                                         {"matrix-to-directories", no_argument, &matrix_to_dirs, 1},
+                                         {"index", required_argument, 0, 'i'},
+                                         {"txnames", required_argument, 0, 'T'},
+                                         {"threads", required_argument, 0, 't'},
+                                         {"fragment-file", required_argument, 0, 'f'},
+                                         {"long", no_argument, &long_flag, 1},
+                                         {"platform", required_argument, 0, 'P'},
+                                         {"fragment-length", required_argument, 0, 'l'},
+                                         {"sd", required_argument, 0, 's'},
+                                         {"output-dir", required_argument, 0, 'o'},
+                                         {"ec-file", required_argument, 0, 'e'},
+                                         {"genemap", required_argument, 0, 'g'},
+                                         {"gtf", required_argument, 0, 'G'},
+                                         {"bootstrap-samples", required_argument, 0, 'b'},
+                                         {"seed", required_argument, 0, 'd'},
+                                         {"priors", required_argument, 0, 'p'},
+                                         {"device", required_argument, 0, 'D'},
+                                         {0, 0, 0, 0}};
+  int c, oi = 0;
+  while ((c = getopt_long(argc, argv, opt_string, long_options, &oi)) != -1) {
+    switch (c) {
+      case 't': std::stringstream(optarg) >> threads; break;
+      case 'f': fldfile = optarg; break;
+      case 'l': std::stringstream(optarg) >> fld; break;
+      case 's': std::stringstream(optarg) >> sd; break;
+      case 'o': output = optarg; break;
+      case 'i': index = optarg; break;
+      case 'e': ecfile = optarg; break;
+      case 'g': genemap = optarg; break;
+      case 'G': gtf = optarg; break;
+      case 'b': std::stringstream(optarg) >> bootstrap; break;
+      case 'T': txnames = optarg; break;
+      case 'p': priors = optarg; break;
+      case 'D': std::stringstream(optarg) >> device; break;
+      default: break;
+    }
+  }
+  if (optind < argc) tccfile = argv[optind];
+  // ---- CheckOptionsTCCQuant
+  bool ret = true;
+  struct stat stt;
+  cerr << endl;
+  if (index.empty()) {
+    cerr << ERROR_STR << " a kallisto index file needs to be supplied (a transcripts file alone, -T, is not supported by this build)" << endl;
+    ret = false;
+  } else if (stat(index.c_str(), &stt) != 0) {
+    cerr << ERROR_STR << " kallisto index file not found " << index << endl;
+    ret = false;
+  }
+  if (tccfile.empty()) { cerr << ERROR_STR << " transcript-compatibility counts file missing" << endl; ret = false; }
+  else if (stat(tccfile.c_str(), &stt) != 0) { cerr << ERROR_STR << " transcript-compatibility counts file not found " << tccfile << endl; ret = false; }
+  if (ecfile.empty()) { cerr << ERROR_STR << " equivalence class file must be supplied (-e)" << endl; ret = false; }
+  else if (stat(ecfile.c_str(), &stt) != 0) { cerr << ERROR_STR << " equivalence class file not found " << ecfile << endl; ret = false; }
+  if (!fldfile.empty() && stat(fldfile.c_str(), &stt) != 0) { cerr << ERROR_STR << " fragment length distribution file not found " << fldfile << endl; ret = false; }
+  if (!genemap.empty() || !gtf.empty()) { cerr << ERROR_STR << " gene-level output (--genemap / --gtf) is not supported by this build" << endl; ret = false; }
+  if (!priors.empty() || long_flag || !txnames.empty()) { cerr << ERROR_STR << " --priors, --long and --txnames are not supported by this build" << endl; ret = false; }
+  if (bootstrap != 0) { cerr << ERROR_STR << " bootstrapping of quant-tcc is not supported by this build" << endl; ret = false; }
+  if (matrix_to_dirs) { cerr << ERROR_STR << " --matrix-to-directories is not supported by this build (use --matrix-to-files)" << endl; ret = false; }
+  if ((fld != 0.0 || sd != 0.0) && !fldfile.empty()) { cerr << ERROR_STR << " cannot supply mean or sd while also supplying a fragment length distribution file" << endl; ret = false; }
+  if ((fld != 0.0 && sd == 0.0) || (sd != 0.0 && fld == 0.0)) { cerr << ERROR_STR << " cannot supply mean/sd without supplying both -l and -s" << endl; ret = false; }
+  if (ret && fld > 0.0 && sd > 0.0) cerr << "[tcc] fragment length distribution is truncated gaussian with mean = " << fld << ", sd = " << sd << endl;
+  if (fld < 0.0) { cerr << ERROR_STR << " invalid value for mean fragment length " << fld << endl; ret = false; }
+  if (sd < 0.0) { cerr << ERROR_STR << " invalid value for fragment length standard deviation " << sd << endl; ret = false; }
+  if (output.empty()) { cerr << ERROR_STR << " need to specify output directory " << output << endl; ret = false; }
+  else if (stat(output.c_str(), &stt) == 0) {
+    if (!S_ISDIR(stt.st_mode)) { cerr << ERROR_STR << " file " << output << " exists and is not a directory" << endl; ret = false; }
+  } else if (mkdir(output.c_str(), 0777) == -1) { cerr << ERROR_STR << " could not create directory " << output << endl; ret = false; }
+  if (threads <= 0) { cerr << ERROR_STR << " invalid number of threads " << threads << endl; ret = false; }
+  if (!ret) { cerr << endl; usage_tcc(); return 1; }
+
+  kb_index* ix = nullptr;
+  KB_TRY(kb_index_load(index.c_str(), device, 0, std::min(16, std::max(1, threads)), &ix));
+  kb_index_info info;
+  kb_index_get_info(ix, &info);
+  const uint32_t T = info.n_targets;
+  // ---- EC file (KmerIndex::loadECsFromFile, src/KmerIndex.cpp:1561-1600)
+  std::vector<uint64_t> ec_off{0};
+  std::vector<uint32_t> ec_tids;
+  {
+    std::ifstream in(ecfile);
+    if (!in.is_open()) { cerr << "Error: could not open file " << ecfile << endl; return 1; }
+    std::string line;
+    int32_t i = 0;
+    std::vector<uint32_t> tmp;
+    while (getline(in, line)) {
+      std::stringstream ss(line);
+      int ec;
+      std::string transcripts;
+      ss >> ec >> transcripts;
+      if (i != ec) {
+        cerr << "Error: equivalence class file has a misplaced equivalence class. Found " << ec << ", expected " << i << endl;
+        return 1;
+      }
+      tmp.clear();
+      std::stringstream ss2(transcripts);
+      while (ss2.good()) {
+        std::string v;
+        getline(ss2, v, ',');
+        const int x = std::atoi(v.c_str());
+        if (x < 0 || x >= (int)T) {
+          cerr << "Error: equivalence class file has invalid value: " << v << " in " << transcripts << endl;
+          return 1;
+        }
+        tmp.push_back((uint32_t)x);
+      }
+      std::sort(tmp.begin(), tmp.end());                       // a Roaring set: sorted, no duplicates
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      ec_tids.insert(ec_tids.end(), tmp.begin(), tmp.end());
+      ec_off.push_back(ec_tids.size());
+      ++i;
+    }
+    cerr << "[index] number of equivalence classes loaded from file: " << pretty_num(ec_off.size() - 1) << endl;
+  }
+  const uint32_t n_ecs = (uint32_t)(ec_off.size() - 1);
+  // ---- TCC file (src/main.cpp:2817-2903)
+  std::vector<uint64_t> row_off;
+  std::vector<uint32_t> ids, vals;
+  bool is_matrix = false;
+  size_t nrow = 0, ncol = 0, nlines = 0;
+  {
+    std::ifstream in(tccfile);
+    if (!in.is_open()) { cerr << "Error: could not open file " << tccfile << endl; return 1; }
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> rows;
+    std::string line;
+    bool first = true;
+    size_t i = 0;
+    int prev_row = 0, prev_col = 0;
+    while (getline(in, line)) {
+      if (first) {
+        first = false;
+        if (line.rfind("%%MatrixMarket", 0) == 0) {
+          cerr << "[tcc] Parsing transcript-compatibility counts (TCC) file as a matrix file" << endl;
+          is_matrix = true;
+          while (getline(in, line) && line.rfind("%", 0) == 0) {}
+          std::stringstream ss(line);
+          ss >> nrow >> ncol >> nlines;
+          cerr << "[tcc] Matrix dimensions: " << pretty_num(nrow) << " x " << pretty_num(ncol) << endl;
+          rows.assign(nrow, {});
+          continue;
+        }
+        cerr << "[tcc] Transcript-compatibility counts (TCC) file is not in matrix format; it will not be parsed as a matrix file" << endl;
+        rows.assign(1, {});
+      }
+      std::stringstream ss(line);
+      int row, col, val;
+      if (is_matrix) {
+        if (i >= nlines) {
+          cerr << "[tcc] Warning: TCC matrix file contains additional lines which will not be read; only " << pretty_num(nlines)
+               << " entries, as specified on the first line, will be read." << endl;
+          break;
+        }
+        ss >> row >> col >> val;
+        if ((size_t)row > nrow || (size_t)col > ncol) {
+          cerr << "Error: TCC matrix file is malformed; row numbers or column numbers exceed the dimensions of the matrix." << endl;
+          return 1;
+        }
+      } else {
+        ss >> col >> val;
+        col += 1;
+        row = 1;
+        nrow = 1;
+        if (ncol < (size_t)col) ncol = col;
+      }
+      if (row <= 0 || col <= 0) { cerr << "Error: Invalid indices in TCC file." << endl; return 1; }
+      if (row < prev_row || (row == prev_row && col <= prev_col)) { cerr << "Error: TCC file is not sorted." << endl; return 1; }
+      prev_row = row;
+      prev_col = col;
+      if ((uint32_t)(col - 1) >= n_ecs) { cerr << "Error: TCC file refers to equivalence class " << col - 1 << ", the EC file holds " << n_ecs << endl; return 1; }
+      rows[row - 1].push_back({(uint32_t)(col - 1), (uint32_t)val});
+      ++i;
+    }
+    if (is_matrix && i < nlines) {
+      cerr << "Error: Found only " << pretty_num(i) << " entries in TCC matrix file, expected " << pretty_num(nlines) << endl;
+      return 1;
+    }
+    row_off.push_back(0);
+    for (auto& r : rows) {
+      for (auto& x : r) { ids.push_back(x.first); vals.push_back(x.second); }
+      row_off.push_back(ids.size());
+    }
+    nrow = rows.size();
+  }
+  // ---- effective lengths (src/main.cpp:2998-3028)
+  const bool calc_eff = !fldfile.empty() || fld != 0.0;
+  std::vector<std::vector<uint32_t>> flds;
+  if (!fldfile.empty()) {
+    std::ifstream in(fldfile);
+    if (!in.is_open()) { cerr << "Error: could not open file " << fldfile << endl; return 1; }
+    std::string line;
+    while (getline(in, line)) {
+      if (line.empty() || line.rfind("#", 0) == 0) continue;
+      std::vector<uint32_t> v;
+      std::stringstream ss(line);
+      while (ss.good()) {
+        std::string tv;
+        getline(ss, tv, ' ');
+        const int x = std::atoi(tv.c_str());
+        if (x < 0) { cerr << "Error: Fragment length distribution file contains invalid value: " << x << endl; return 1; }
+        v.push_back((uint32_t)x);
+      }
+      if (v.size() != 1000) { cerr << "Error: Fragment length distribution file contains a line with " << v.size() << " values; expected: 1000" << endl; return 1; }
+      flds.push_back(v);
+    }
+    if (flds.size() != 1 && flds.size() != nrow) {
+      cerr << "Error: Fragment length distribution file contains " << flds.size() << " valid lines; expected: " << nrow << endl;
+      return 1;
+    }
+  }
+  const bool per_sample = flds.size() > 1;
+  std::vector<double> eff((per_sample ? nrow : 1) * (size_t)T);
+  std::vector<std::pair<double, double>> fld_mat(nrow, {0.0, 0.0});
+  for (size_t r = 0; r < (per_sample ? nrow : 1); ++r) {
+    double m = 0, s = 0;
+    const uint32_t* fl = flds.empty() ? nullptr : flds[per_sample ? r : 0].data();
+    KB_TRY(kb_eff_lens(ix, fl, fld, sd, eff.data() + r * T, &m, &s));
+    if (per_sample) fld_mat[r] = {m, s};
+    else for (auto& x : fld_mat) x = {m, s};
+  }
+  cerr << "[quant] Running EM algorithm..." << endl;
+  std::vector<double> est(nrow * (size_t)T);
+  std::vector<int32_t> rounds(nrow + 1);
+  KB_TRY(kb_tcc_run(ix, n_ecs, ec_off.data(), ec_tids.empty() ? nullptr : ec_tids.data(), (uint32_t)nrow, row_off.data(),
+                    ids.empty() ? nullptr : ids.data(), vals.empty() ? nullptr : vals.data(), eff.data(), per_sample ? 1 : 0,
+                    est.data(), rounds.data()));
+  cerr << " done" << endl << endl;
+  // ---- outputs (src/main.cpp:2928-2946, 3040-3215)
+  std::vector<std::string> names(T);
+  std::vector<uint32_t> lens(T);
+  for (uint32_t i = 0; i < T; ++i) names[i] = kb_index_target_name(ix, i);
+  kb_index_target_lens(ix, lens.data());
+  {
+    std::string out;
+    for (uint32_t i = 0; i < T; ++i) { out += names[i]; out += "\n"; }
+    std::ofstream of(output + "/transcripts.txt", std::ios::binary);
+    of.write(out.data(), (std::streamsize)out.size());
+  }
+  if (is_matrix) {
+    std::vector<std::vector<std::pair<int, double>>> ab(nrow), tpm_m(nrow), el(nrow);
+    std::vector<double> tpm(T);
+    for (size_t r = 0; r < nrow; ++r) {
+      const double* a = est.data() + r * T;
+      const double* e = eff.data() + (per_sample ? r : 0) * (size_t)T;
+      kb_counts_to_tpm(a, e, T, tpm.data());
+      for (uint32_t i = 0; i < T; ++i)
+        if (a[i] > 0.0) {
+          ab[r].push_back({(int)i, a[i]});
+          tpm_m[r].push_back({(int)i, tpm[i]});
+          if (calc_eff) el[r].push_back({(int)i, e[i]});
+        }
+      if (matrix_to_files) write_abundance(output + "/abundance_" + std::to_string(r + 1) + ".tsv", names, lens, e, a);
+    }
+    write_sparse_matrix(output + "/matrix.abundance.mtx", ab, T);
+    write_sparse_matrix(output + "/matrix.abundance.tpm.mtx", tpm_m, T);
+    if (calc_eff) write_sparse_matrix(output + "/matrix.efflens.mtx", el, T);
+  } else {
+    write_abundance(output + "/abundance.tsv", names, lens, eff.data(), est.data());
+  }
+  if (calc_eff) {
+    std::ofstream of(output + "/matrix.fld.tsv");                 // writeFLD, src/PlaintextWriter.cpp:287-298
+    for (size_t j = 0; j < fld_mat.size(); ++j) of << j << "\t" << fld_mat[j].first << "\t" << fld_mat[j].second << "\n";
+    std::ofstream tl(output + "/transcript_lengths.txt");
+    for (uint32_t i = 0; i < T; ++i) tl << names[i] << " " << lens[i] << "\n";
+  }
+  kb_index_free(ix);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -1021,6 +1340,13 @@ int main(int argc, char** argv) {
       return 0;
     }
     return cmd_bus(argc - 1, argv + 1, call, tbuf);
+  }
+  if (cmd == "quant-tcc") {
+    if (argc == 2) {
+      usage_tcc();
+      return 0;
+    }
+    return cmd_quant_tcc(argc - 1, argv + 1);
   }
   cerr << "Error: invalid command " << cmd << endl;
   return 1;

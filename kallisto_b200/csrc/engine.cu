@@ -171,6 +171,22 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   if (const char* s = getenv("KB_TABLE_FACTOR")) { const double v = atof(s); if (v >= 1.25 && v <= 64.0) factor = v; }
   ix->table_cap = pow2_ge(std::max<uint64_t>(1024, (uint64_t)((double)f.n_kmers * factor)));
   ix->slots.alloc(ix->table_cap);
+  // presence filter: 2^KB_FILTER_LOG2 bits (default: about 3.5 bits per k-mer, at most 2^29 bits = 64 MB so that it
+  // fits the persisting part of the 126 MB L2; 0 = off).  Single hash: a miss passes it with probability
+  // 1 - exp(-n / bits).
+  uint32_t filter_bits = 0;
+  {
+    int lg = 0;
+    while ((1ull << lg) < f.n_kmers * 3 && lg < 29) ++lg;
+    if (lg < 16) lg = 16;
+    if (const char* s = getenv("KB_FILTER_LOG2")) lg = atoi(s);
+    if (lg >= 10 && lg <= 32) filter_bits = lg == 32 ? 0 : (1u << lg);
+    if (lg == 32) filter_bits = 0;
+  }
+  if (filter_bits) {
+    ix->filter.alloc(filter_bits / 32);
+    ix->filter.zero(st);
+  }
   DBuf<int> err;
   err.alloc(1);
   err.zero(st);
@@ -191,6 +207,7 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
     a.blk_off = d_blkoff.p; a.blk_lb = d_lb.p; a.blk_ub = d_ub.p; a.blk_ec = ix->blk_ec.p;
     a.n_long = f.n_long; a.n_unitigs = nU; a.k = f.k; a.n_kmers = f.n_kmers;
     a.slots = ix->slots.p; a.mask = ix->table_cap - 1; a.error = err.p;
+    a.filter = filter_bits ? ix->filter.p : nullptr; a.filter_mask = filter_bits ? filter_bits - 1 : 0;
     launch_build_table(a, st);
     KB_CK(cudaGetLastError());
     KB_CK(cudaStreamSynchronize(st));
@@ -203,6 +220,18 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   DevIndex& d = ix->dev;
   d.slots = ix->slots.p;
   d.mask = ix->table_cap - 1;
+  d.filter = filter_bits ? ix->filter.p : nullptr;
+  d.filter_mask = filter_bits ? filter_bits - 1 : 0;
+  if (filter_bits) {
+    // keep the filter in L2: persisting carve-out as large as the device allows (the access window itself is set on the
+    // stream of every run, Quant::apply_l2_window)
+    int max_persist = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+    size_t want = std::min<size_t>((size_t)filter_bits / 8, (size_t)std::max(0, max_persist));
+    if (const char* s = getenv("KB_L2_PERSIST_MB")) want = std::min<size_t>((size_t)atoll(s) << 20, (size_t)std::max(0, max_persist));
+    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) ix->l2_persist_bytes = want;
+    else cudaGetLastError();
+  }
   d.k = f.k;
   d.n_ec = f.n_ec();
   d.n_targets = f.num_targets();
@@ -243,6 +272,7 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
     KB_CK(cudaEventCreateWithFlags(&ev_done_[i], cudaEventDisableTiming));
   }
   cudaStream_t st = stream_;
+  apply_l2_window();
   const uint64_t nE = ix_.flat.n_ec();
   // pools and tables of this run
   const uint64_t pool_cap =
@@ -357,6 +387,23 @@ void Quant::set_stream(cudaStream_t st) {
   if (stream_ && own_stream_) cudaStreamDestroy(stream_);
   stream_ = st;
   own_stream_ = false;
+  apply_l2_window();
+}
+
+// Kernels launched on the run's stream treat the presence filter as persisting in L2; everything else streams.
+void Quant::apply_l2_window() {
+  if (!ix_.filter.p || ix_.l2_persist_bytes == 0) return;
+  int max_win = 0;
+  cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ix_.device);
+  const size_t bytes = std::min<size_t>(ix_.filter.n * 4, (size_t)std::max(0, max_win));
+  if (bytes == 0) return;
+  cudaStreamAttrValue v{};
+  v.accessPolicyWindow.base_ptr = (void*)ix_.filter.p;
+  v.accessPolicyWindow.num_bytes = bytes;
+  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ix_.l2_persist_bytes / (double)bytes);
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(stream_, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
 }
 
 Quant::Timings Quant::timings() {
@@ -758,16 +805,16 @@ Stats Quant::stats() {
 // MinCollector::compute_mean_frag_lens_trunc (src/MinCollector.cpp:629-651) when fld_mean == 0,
 // MinCollector::init_mean_fl_trunc + trunc_gaussian_fld (src/MinCollector.cpp:583-627,
 // src/weights.cpp:248-296) otherwise.
-std::vector<double> Quant::mean_fl_trunc(double fld_mean, double fld_sd) const {
+std::vector<double> mean_fl_trunc_of(const uint32_t* flens, double fld_mean, double fld_sd) {
   const int MAXF = 1000;
   std::vector<double> out(MAXF, 0.0);
   if (fld_mean == 0.0) {
     std::vector<int> counts(MAXF, 0);
     std::vector<double> mass(MAXF, 0.0);
-    counts[0] = (int)flens_[0];
+    counts[0] = (int)flens[0];
     for (size_t i = 1; i < (size_t)MAXF; ++i) {
-      mass[i] = static_cast<double>(flens_[i] * i) + mass[i - 1];
-      counts[i] = (int)flens_[i] + counts[i - 1];
+      mass[i] = static_cast<double>(flens[i] * i) + mass[i - 1];
+      counts[i] = (int)flens[i] + counts[i - 1];
       if (counts[i] > 0) out[i] = mass[i] / static_cast<double>(counts[i]);
     }
   } else {
@@ -785,6 +832,10 @@ std::vector<double> Quant::mean_fl_trunc(double fld_mean, double fld_sd) const {
     out = mean_fl;
   }
   return out;
+}
+
+std::vector<double> Quant::mean_fl_trunc(double fld_mean, double fld_sd) const {
+  return mean_fl_trunc_of(flens_.data(), fld_mean, fld_sd);
 }
 
 namespace {
@@ -1325,6 +1376,107 @@ std::vector<int> Quant::run_bootstrap(const EcTable& ecs, const std::vector<doub
   return rounds;
 }
 
+std::vector<int> tcc_run(Index& ix, const TccInput& in, std::vector<double>& alpha_out) {
+  KB_CK(cudaSetDevice(ix.device));
+  const uint32_t T = ix.flat.num_targets(), nE = in.n_ecs, S = in.n_samples;
+  alpha_out.assign((size_t)S * T, 0.0);
+  std::vector<int> rounds(S, 0);
+  if (S == 0) return rounds;
+  // structure of the problem on the host, from the EC table (EC ids = line numbers of matrix.ec)
+  std::vector<uint32_t> multi_ec, m_off{0}, m_tid, m_ec, t_off(T + 1, 0), t_midx, t_ec, t_tid;
+  std::vector<int32_t> t_single(T, -1);
+  for (uint32_t e = 0; e < nE; ++e) {
+    const uint64_t b = in.ec_off[e], n = in.ec_off[e + 1] - b;
+    for (uint64_t j = 0; j < n; ++j)
+      if (in.tids[b + j] >= T) throw Error("kallisto_b200: equivalence class file has a transcript id out of range");
+    if (n == 1) { t_single[in.tids[b]] = (int32_t)e; continue; }
+    if (n == 0) continue;
+    multi_ec.push_back(e);
+    for (uint64_t j = 0; j < n; ++j) {
+      m_tid.push_back(in.tids[b + j]);
+      m_ec.push_back(e);
+      ++t_off[in.tids[b + j] + 1];
+    }
+    m_off.push_back((uint32_t)m_tid.size());
+  }
+  const uint64_t nnz = m_tid.size();
+  const uint32_t n_multi = (uint32_t)multi_ec.size();
+  for (uint32_t t = 0; t < T; ++t) t_off[t + 1] += t_off[t];
+  t_midx.resize(nnz); t_ec.resize(nnz); t_tid.resize(nnz);
+  {
+    std::vector<uint32_t> fill(t_off.begin(), t_off.end() - 1);
+    for (uint32_t r = 0; r < n_multi; ++r)
+      for (uint32_t j = m_off[r]; j < m_off[r + 1]; ++j) {
+        const uint32_t t = m_tid[j], at = fill[t]++;
+        t_midx[at] = r; t_ec[at] = multi_ec[r]; t_tid[at] = t;
+      }
+  }
+  for (uint64_t i = 0; i < in.row_off[S]; ++i)
+    if (in.ec_ids[i] >= nE) throw Error("kallisto_b200: TCC file refers to an equivalence class that is not in the EC file");
+  cudaStream_t st = nullptr;
+  KB_CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DBuf<uint32_t> d_multi_ec, d_m_off, d_m_tid, d_m_ec, d_t_off, d_t_midx, d_t_ec, d_t_tid, d_ecid, d_val, d_counts;
+  DBuf<int32_t> d_single;
+  DBuf<unsigned long long> d_rowoff;
+  DBuf<double> d_eff, d_mw, d_tw, d_alpha, d_norm;
+  DBuf<int> d_emi;
+  DBuf<unsigned> d_ch, d_bar;
+  auto up32 = [&](DBuf<uint32_t>& d, const std::vector<uint32_t>& h) { d.alloc(std::max<size_t>(1, h.size())); d.upload(h.data(), h.size(), st); };
+  up32(d_multi_ec, multi_ec); up32(d_m_off, m_off); up32(d_m_tid, m_tid); up32(d_m_ec, m_ec);
+  up32(d_t_off, t_off); up32(d_t_midx, t_midx); up32(d_t_ec, t_ec); up32(d_t_tid, t_tid);
+  d_single.upload(t_single.data(), T, st);
+  d_ecid.alloc(std::max<uint64_t>(1, in.row_off[S])); d_ecid.upload(in.ec_ids, in.row_off[S], st);
+  d_val.alloc(std::max<uint64_t>(1, in.row_off[S])); d_val.upload(in.counts, in.row_off[S], st);
+  // samples per chunk: weights dominate (16 bytes per entry and sample); ~2 GB of work space
+  const size_t per = (size_t)nnz * 16 + (size_t)nE * 4 + ((size_t)T + n_multi) * 8;
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>(S, ((size_t)2 << 30) / std::max<size_t>(1, per)));
+  if (const char* s = getenv("KB_TCC_CHUNK")) { const int v = atoi(s); if (v > 0) chunk = std::min<int>((int)S, v); }   // tests
+  d_counts.alloc((size_t)chunk * std::max<uint32_t>(1, nE));
+  d_mw.alloc(std::max<size_t>(1, (size_t)chunk * nnz)); d_tw.alloc(std::max<size_t>(1, (size_t)chunk * nnz));
+  d_alpha.alloc((size_t)chunk * T); d_norm.alloc(std::max<size_t>(1, (size_t)chunk * n_multi));
+  d_eff.alloc(in.per_sample_eff ? (size_t)chunk * T : (size_t)T);
+  if (!in.per_sample_eff) d_eff.upload(in.eff_lens, T, st);
+  d_emi.alloc((size_t)2 * chunk); d_ch.alloc((size_t)2 * chunk); d_bar.alloc(1);
+  d_rowoff.alloc((size_t)chunk + 1);
+  std::vector<unsigned long long> ro((size_t)chunk + 1);
+  std::vector<int> emi((size_t)2 * chunk);
+  for (uint32_t s0 = 0; s0 < S; s0 += (uint32_t)chunk) {
+    const int nb = (int)std::min<uint32_t>((uint32_t)chunk, S - s0);
+    for (int b = 0; b <= nb; ++b) ro[b] = in.row_off[s0 + b];
+    d_rowoff.upload(ro.data(), (size_t)nb + 1, st);
+    if (in.per_sample_eff) d_eff.upload(in.eff_lens + (size_t)s0 * T, (size_t)nb * T, st);
+    TccFill f{};
+    f.n_ec = nE; f.n_targets = T; f.nb = (uint32_t)nb; f.row_off = d_rowoff.p; f.ec_ids = d_ecid.p; f.vals = d_val.p;
+    f.counts = d_counts.p; f.nnz = nnz; f.m_ec = d_m_ec.p; f.m_tid = d_m_tid.p; f.t_ec = d_t_ec.p; f.t_tid = d_t_tid.p;
+    f.eff = d_eff.p; f.eff_stride = in.per_sample_eff ? T : 0; f.m_w = d_mw.p; f.t_w = d_tw.p;
+    launch_tcc_fill(f, st);
+    KB_CK(cudaGetLastError());
+    launch_fill_f64(d_alpha.p, (uint64_t)nb * T, 1.0 / T, st);
+    d_emi.zero(st);
+    d_ch.zero(st);
+    EmProblem p{};
+    p.n_ec = nE; p.n_targets = T; p.n_multi = n_multi;
+    p.multi_ec = d_multi_ec.p; p.m_off = d_m_off.p; p.m_tid = d_m_tid.p; p.m_w = d_mw.p;
+    p.t_off = d_t_off.p; p.t_midx = d_t_midx.p; p.t_w = d_tw.p; p.t_single = d_single.p;
+    p.nb = nb; p.counts = d_counts.p; p.alpha = d_alpha.p; p.norm = d_norm.p;
+    p.rounds = d_emi.p; p.fstate = d_emi.p + chunk; p.bar = d_bar.p; p.chcount = d_ch.p;
+    p.max_iter = 10000; p.min_rounds = 50; p.w_stride = nnz;
+    launch_em(p, em_tpb(), st);
+    KB_CK(cudaGetLastError());
+    d_alpha.download(alpha_out.data() + (size_t)s0 * T, (size_t)nb * T, 0, st);
+    d_emi.download(emi.data(), (size_t)2 * chunk, 0, st);
+    KB_CK(cudaStreamSynchronize(st));
+    for (int b = 0; b < nb; ++b) {
+      rounds[s0 + b] = emi[b];
+      if (emi[chunk + b] == 3)
+        for (uint32_t t = 0; t < T; ++t)
+          if (alpha_out[(size_t)(s0 + b) * T + t] < 1e-7 / 10.0) alpha_out[(size_t)(s0 + b) * T + t] = 0.0;
+    }
+  }
+  cudaStreamDestroy(st);
+  return rounds;
+}
+
 template struct DBuf<uint8_t>;
 template struct DBuf<uint16_t>;
 template struct DBuf<uint32_t>;
@@ -1336,5 +1488,6 @@ template struct DBuf<KmerSlot>;
 template struct DBuf<Memo2Entry>;
 template struct DBuf<BusRecord>;
 template struct DBuf<uint4>;
+
 
 }  // namespace kb

@@ -86,6 +86,8 @@ class Index {
   double load_seconds = 0, build_seconds = 0;
 
   DBuf<KmerSlot> slots;
+  DBuf<uint32_t> filter;          // presence filter of the k-mer table (L2-resident, see DevIndex)
+  size_t l2_persist_bytes = 0;    // persisting-L2 carve-out set aside for it
   DBuf<uint32_t> ec_off;
   DBuf<uint32_t> index_pool;      // the index's EC sets (copied to the front of every run's pool)
   DBuf<unsigned long long> dslots_init;
@@ -240,6 +242,7 @@ class Quant {
   void run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
                  uint32_t max_read_len, const uint8_t* d_bases2 = nullptr, const uint32_t* d_off2 = nullptr);
   void check_device_errors();
+  void apply_l2_window();
   uint32_t bus_core(const uint8_t* const* db, const uint32_t* const* dofs, uint32_t n_sets, uint32_t maxlen);
 
   Index& ix_;
@@ -289,5 +292,22 @@ class Quant {
   const uint8_t* cur_skip_ = nullptr;
   uint32_t cur_start_ = 0;
 };
+
+std::vector<double> mean_fl_trunc_of(const uint32_t* flens /* 1000 */, double fld_mean, double fld_sd);
+
+// `kallisto quant-tcc` (src/main.cpp:2802-3220): one EM per sample (row of a transcript-compatibility-count matrix) over
+// one shared equivalence-class table (the lines of matrix.ec), on the device in chunks of samples.
+struct TccInput {
+  uint32_t n_ecs = 0;
+  const uint64_t* ec_off = nullptr;     // n_ecs + 1
+  const uint32_t* tids = nullptr;       // sorted transcript ids of every EC
+  uint32_t n_samples = 0;
+  const uint64_t* row_off = nullptr;    // n_samples + 1 offsets into ec_ids / counts
+  const uint32_t* ec_ids = nullptr;
+  const uint32_t* counts = nullptr;
+  const double* eff_lens = nullptr;     // n_targets, or n_samples x n_targets when per_sample_eff
+  bool per_sample_eff = false;
+};
+std::vector<int> tcc_run(Index& ix, const TccInput& in, std::vector<double>& alpha_out /* n_samples x n_targets */);
 
 }  // namespace kb

@@ -38,6 +38,11 @@ static_assert(sizeof(KmerSlot) == 32, "slot must be one 32-byte sector");
 struct DevIndex {
   const KmerSlot* slots;
   uint64_t mask;             // capacity - 1 (capacity is a power of two)
+  // presence filter of the k-mer table, kept in L2 (persisting window): bit ((mix64(kmer) >> 32) & filter_mask) is set
+  // for every k-mer of the table.  69 % of KmerIndex::match's lookups are misses; a clear bit answers them without
+  // touching HBM.  nullptr = no filter.
+  const uint32_t* filter;
+  uint32_t filter_mask;      // bits - 1 (a power of two)
   int k;
   uint32_t n_ec;             // index EC sets
   uint32_t n_targets;

@@ -20,6 +20,8 @@ struct TableBuildArgs {
   uint64_t n_kmers;
   KmerSlot* slots;
   uint64_t mask;
+  uint32_t* filter;         // optional presence filter (zeroed by the caller)
+  uint32_t filter_mask;
   int* error;
 };
 
@@ -126,8 +128,25 @@ struct EmProblem {
   int* fstate;                  // nb: final state (2 finished, 3 finished + host must zero small alphas)
   unsigned int* chcount;        // nb x 2 (double-buffered) change counters
   int max_iter, min_rounds;
+  // 0: the weights m_w / t_w are shared by all problems (quant, bootstrap); nnz: problem b has its own at [b * w_stride]
+  // (quant-tcc: the weights are the SAMPLE's counts / eff_len, src/weights.cpp:220-246)
+  uint64_t w_stride;
 };
 int em_max_blocks(int threads_per_block);
+// quant-tcc helpers: dense per-sample count vectors from the sparse TCC rows, and per-sample weights in CSR and CSC order
+struct TccFill {
+  uint32_t n_ec, n_targets, nb;        // samples in this chunk
+  const unsigned long long* row_off;    // chunk's rows: nb + 1 offsets into ec_ids / vals
+  const uint32_t* ec_ids;
+  const uint32_t* vals;
+  uint32_t* counts;                     // nb x n_ec (zeroed by the launcher)
+  // entry -> (EC id, transcript) of the CSR (m_*) and CSC (t_*) layouts
+  uint64_t nnz;
+  const uint32_t* m_ec; const uint32_t* m_tid; const uint32_t* t_ec; const uint32_t* t_tid;
+  const double* eff; uint64_t eff_stride;   // nb x n_targets when eff_stride == n_targets, shared when 0
+  double* m_w; double* t_w;             // nb x nnz
+};
+void launch_tcc_fill(const TccFill& a, cudaStream_t st);
 void launch_em(const EmProblem& p, int threads_per_block, cudaStream_t st);
 
 // Device-side EM problem construction (kernels_emprep.cu)

@@ -518,19 +518,30 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
     }
     // ------------------------------------------------------------------ one lookup per active lane
     if (st <= S_BACKOFF) {
+      bool absent = false;
       if (need_prep) {
         const int pq = (st == S_JUMP) ? p2 : ((st == S_MIDDLE) ? p3 : p);
         const uint64_t fwd = rv.kmer(pq);
         const uint64_t rc = kb_revcomp(fwd, k);
         is_canon = fwd < rc;
         canon = is_canon ? fwd : rc;
-        slot = kb_mix64(canon) & ix.mask;
+        const uint64_t hsh = kb_mix64(canon);
+        slot = hsh & ix.mask;
         need_prep = false;
         ++n_probes;
+        // presence filter (L2 resident): a clear bit means the k-mer is not in the index -- no HBM sector is touched
+        if (ix.filter) {
+          const uint32_t fidx = (uint32_t)(hsh >> 32) & ix.filter_mask;
+          absent = ((__ldg(ix.filter + (fidx >> 5)) >> (fidx & 31)) & 1u) == 0;
+        }
       }
       uint32_t v[8];
-      ld256_probe(ix.slots + slot, v);
-      ++n_visits;
+      if (!absent) {
+        ld256_probe(ix.slots + slot, v);
+        ++n_visits;
+      } else {
+        v[0] = v[1] = 0xFFFFFFFFu;     // reads as an empty slot: a miss
+      }
       const uint64_t key = (uint64_t)v[0] | ((uint64_t)v[1] << 32);
       if (key != canon && key != KB_EMPTY_KEY) {
         slot = (slot + 1) & ix.mask;              // linear probing: one more iteration

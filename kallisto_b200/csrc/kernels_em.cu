@@ -104,12 +104,13 @@ __global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4)))
       double nrm = 0.0;
       if (c != 0) {
         const double* al = p.alpha + (size_t)b * p.n_targets;
+        const double* mw = p.m_w + (size_t)b * p.w_stride;
         double denom = 0.0;
         const uint32_t e0 = p.m_off[r], e1 = p.m_off[r + 1];
         for (uint32_t j = e0; j < e1; ++j) {
           double a = al[p.m_tid[j]];
           if (st == 1 && a < zero_below) a = 0.0;          // alpha zeroed before the final round (:213-216)
-          denom = __dadd_rn(denom, __dmul_rn(a, p.m_w[j]));
+          denom = __dadd_rn(denom, __dmul_rn(a, mw[j]));
         }
         if (!(denom < kTolerance)) nrm = __ddiv_rn((double)c, denom);
       }
@@ -136,9 +137,10 @@ __global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4)))
           const int32_t s = p.t_single[t];
           double acc = s >= 0 ? (double)p.counts[(size_t)b * p.n_ec + s] : 0.0;     // :119-123
           const double* nr = p.norm + (size_t)b * p.n_multi;
+          const double* tw = p.t_w + (size_t)b * p.w_stride;
           const uint32_t e0 = p.t_off[t], e1 = p.t_off[t + 1];
           for (uint32_t j = e0; j < e1; ++j)
-            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(p.t_w[j], a), nr[p.t_midx[j]]));   // :154-156
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(tw[j], a), nr[p.t_midx[j]]));   // :154-156
           changed = acc > kAlphaChangeLimit && (fabs(__dadd_rn(acc, -a)) / acc) > kAlphaChange;   // :178
           al[t] = acc;
         }
@@ -191,6 +193,36 @@ void launch_em(const EmProblem& p, int tpb_req, cudaStream_t st) {
   void* args[] = {&pp};
   void* fn = tpb == 1024 ? (void*)em_kernel<1024> : (tpb == 512 ? (void*)em_kernel<512> : (void*)em_kernel<256>);
   cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// quant-tcc (src/main.cpp:2802-3220): every sample (row of the TCC matrix) is its own EM over the SAME equivalence
+// classes; its weights are its own counts / eff_len (calc_weights), so they are formed per sample here and the
+// batched em_kernel reads them through w_stride.
+__global__ void tcc_scatter_kernel(TccFill a) {
+  const uint32_t b = blockIdx.y;
+  const unsigned long long r0 = a.row_off[b], r1 = a.row_off[b + 1];
+  for (unsigned long long i = r0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < r1;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    a.counts[(size_t)b * a.n_ec + a.ec_ids[i]] = a.vals[i];
+}
+__global__ void tcc_weights_kernel(TccFill a) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t* cnt = a.counts + (size_t)b * a.n_ec;
+  const double* eff = a.eff + (size_t)b * a.eff_stride;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.nnz; j += (uint64_t)gridDim.x * blockDim.x) {
+    a.m_w[(size_t)b * a.nnz + j] = __ddiv_rn((double)cnt[a.m_ec[j]], eff[a.m_tid[j]]);
+    a.t_w[(size_t)b * a.nnz + j] = __ddiv_rn((double)cnt[a.t_ec[j]], eff[a.t_tid[j]]);
+  }
+}
+void launch_tcc_fill(const TccFill& a, cudaStream_t st) {
+  if (a.nb == 0) return;
+  cudaMemsetAsync(a.counts, 0, (size_t)a.nb * a.n_ec * sizeof(uint32_t), st);
+  tcc_scatter_kernel<<<dim3(64, a.nb), 256, 0, st>>>(a);
+  if (a.nnz) {
+    const unsigned gx = (unsigned)std::min<uint64_t>(1024, (a.nnz + 255) / 256);
+    tcc_weights_kernel<<<dim3(gx, a.nb), 256, 0, st>>>(a);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -42,7 +42,12 @@ __global__ void __launch_bounds__(256) build_table_kernel(TableBuildArgs a) {
     if (a.blk_lb[mid] <= dist) blo = mid; else bhi = mid;
   }
   KmerSlot* slots = a.slots;
-  uint64_t h = kb_mix64(canon) & a.mask;
+  const uint64_t hsh = kb_mix64(canon);
+  if (a.filter) {
+    const uint32_t fi = (uint32_t)(hsh >> 32) & a.filter_mask;
+    atomicOr(&a.filter[fi >> 5], 1u << (fi & 31));
+  }
+  uint64_t h = hsh & a.mask;
   for (;;) {
     const unsigned long long old =
         atomicCAS((unsigned long long*)&slots[h].key, (unsigned long long)KB_EMPTY_KEY, (unsigned long long)canon);

@@ -95,6 +95,9 @@ int kb_comm_create_all(const int*, int n, kb_comm** out) { for (int i = 0; i < n
 void kb_comm_free(kb_comm* c) { delete c; }
 int kb_quant_merge_nccl(kb_quant*, kb_comm*, uint64_t, uint64_t*) { return KB_OK; }
 int kb_quant_set_frag_base(kb_quant*, uint64_t) { return KB_OK; }
+int kb_tcc_run(kb_index*, uint32_t, const uint64_t*, const uint32_t*, uint32_t, const uint64_t*, const uint32_t*, const uint32_t*, const double*, int32_t,
+               double*, int32_t*) { return KB_OK; }
+int kb_eff_lens(const kb_index*, const uint32_t*, double, double, double*, double*, double*) { return KB_OK; }
 int kb_bus_create(kb_index*, const kb_bus_opts* o, kb_quant** out) { *out = new kb_quant(); (*out)->nfiles = o->nfiles; return KB_OK; }
 int kb_bus_batch(kb_quant* q, const char* const* bases, const uint32_t* const* offs, uint32_t n_sets, kb_bus_record* rec, uint32_t* n_rec) {
   // one record per read set: barcode = running digest, so that output.bus depends on content AND order
