@@ -91,8 +91,6 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   const double t1 = now_s();
   ix->load_seconds = t1 - t0;
   FlatIndex& f = ix->flat;
-  if (f.dlist_n != 0)
-    throw Error("kallisto_b200: indices with a D-list (distinguishing flanking k-mers) are not supported yet");
   if (f.onlist.size() != f.target_len.size())
     throw Error("kallisto_b200: indices whose on-list does not cover every target are not supported yet");
   if (f.ec_tid.size() >= 0xFFFFFFFFull) throw Error("kallisto_b200: index EC sets exceed 2^32 entries");
@@ -243,6 +241,20 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   d.fp_info = f.has_positions ? ix->fp_info.p : nullptr;
   d.blk_usize = f.has_positions ? ix->blk_usize.p : nullptr;
   d.target_len = f.has_positions ? ix->target_len.p : nullptr;
+  if (f.dlist_n) {
+    // D-list k-mers: open-addressing set, built on the host (the list is a small fraction of the k-mer table)
+    const uint64_t cap = pow2_ge(2 * f.dlist_n + 16);
+    std::vector<unsigned long long> tab(cap, ~0ULL);
+    for (uint64_t km : f.dlist) {
+      uint64_t h = kb_mix64(km) & (cap - 1);
+      while (tab[h] != ~0ULL && tab[h] != km) h = (h + 1) & (cap - 1);
+      tab[h] = km;
+    }
+    ix->dfk.upload(tab.data(), cap, st);
+    KB_CK(cudaStreamSynchronize(st));
+    d.dfk = ix->dfk.p;
+    d.dfk_mask = cap - 1;
+  }
   ix->build_seconds = now_s() - t1;
   return ix;
 }
@@ -477,6 +489,17 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.empty_ec = ix_.empty_ec;
   ba.refill_min = opt_.refill_min;
   ba.skip = cur_skip_;
+  ba.skip_w = nullptr;
+  if (ix_.dev.dfk) {
+    // D-list: fragments holding a distinguishing flanking k-mer are marked by dlist_scan_kernel (after packing)
+    if (cur_skip_) {
+      ba.skip_w = const_cast<uint8_t*>(cur_skip_);          // bus: the scan adds to the bad-barcode marks
+    } else {
+      if (bws_->d_skip.n < n_frag) bws_->d_skip.alloc(std::max<size_t>(n_frag, opt_.max_batch_reads));
+      KB_CK(cudaMemsetAsync(bws_->d_skip.p, 0, n_frag, stream_));
+      ba.skip = ba.skip_w = bws_->d_skip.p;
+    }
+  }
   ba.fp_fl = opt_.fp_fl;
   ba.start = cur_start_;
   ResolveArgs ra{};
@@ -497,7 +520,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   }
   launch_pseudoalign(ix_.dev, dd_, ba, ra, tpb, stream_, ev);
   KB_CK(cudaGetLastError());
-  n_kernel_launches += 3;          // pack_kernel, match_kernel, resolve_kernel
+  n_kernel_launches += 3 + (ba.skip_w ? 1 : 0);   // pack_kernel, [dlist_scan_kernel,] match_kernel, resolve_kernel
   if (want_fld) {
     launch_fld_finalize(dd_, ba, stream_);
     ++n_kernel_launches;

@@ -49,6 +49,7 @@ struct BatchWs {
   DBuf<uint32_t> d_spill, d_qbig_count, d_qbig;   // fragments with more than KB_MAX_E distinct EC sets
   DBuf<int32_t> d_handles;
   DBuf<uint16_t> d_tl;
+  DBuf<uint8_t> d_skip;             // per fragment: holds a D-list k-mer (only when the index has a D-list)
 };
 
 struct EmWs {   // grow-only device workspace of run_em_device
@@ -86,6 +87,7 @@ class Index {
   double load_seconds = 0, build_seconds = 0;
 
   DBuf<KmerSlot> slots;
+  DBuf<unsigned long long> dfk;   // D-list k-mer set
   DBuf<uint32_t> filter;          // presence filter of the k-mer table (L2-resident, see DevIndex)
   size_t l2_persist_bytes = 0;    // persisting-L2 carve-out set aside for it
   DBuf<uint32_t> ec_off;

@@ -226,8 +226,8 @@ void load_index_v13(const std::string& path, FlatIndex& fi, bool load_positions,
   dbg_bytes &= (~0ULL >> 1);
   if (dbg_bytes == 0) throw std::runtime_error("kallisto index: empty de Bruijn graph");
   {
-    Cursor g{c.p, c.p + dbg_bytes};
-    c.bytes(dbg_bytes);
+    const uint8_t* gb = c.bytes(dbg_bytes);       // validates the length before the sub-cursor is formed
+    Cursor g{gb, gb + dbg_bytes};
     const uint64_t fmt = g.get<uint64_t>();
     if ((fmt >> 32) != 0x7e215f3fULL) throw std::runtime_error("kallisto index: bad Bifrost graph header");
     fi.k = g.get<int32_t>();
@@ -284,7 +284,15 @@ void load_index_v13(const std::string& path, FlatIndex& fi, bool load_positions,
   // 2.2 D-list (KmerIndex.cpp:1385-1403)
   fi.dlist_n = c.get<uint64_t>();
   c.get<uint64_t>();  // overhang
-  c.bytes(fi.dlist_n * 8);
+  {
+    const uint8_t* dl = c.bytes(fi.dlist_n * 8);
+    fi.dlist.resize(fi.dlist_n);
+    for (uint64_t i = 0; i < fi.dlist_n; ++i) {
+      uint64_t w;
+      memcpy(&w, dl + i * 8, 8);
+      fi.dlist[i] = w >> (64 - 2 * fi.k);     // Kmer: left-aligned 2-bit words, already canonical (rep(), KmerIndex.cpp:946)
+    }
+  }
 
   const int k = fi.k;
   const uint32_t nU = fi.n_unitigs();
@@ -510,6 +518,16 @@ void load_index_v13(const std::string& path, FlatIndex& fi, bool load_positions,
   num_trans -= (int32_t)fi.dlist_n;
   fi.target_len.resize(num_trans);
   for (int32_t i = 0; i < num_trans; ++i) fi.target_len[i] = (uint32_t)c.get<int32_t>();
+  {
+    // every transcript id of every equivalence class must name a target (an index with a D-list also uses id
+    // num_trans: the off-list pseudo-target of the dummy k-mer's unitig), and the lists must be strictly ascending
+    const uint32_t limit = (uint32_t)num_trans + (fi.dlist_n ? 1u : 0u);
+    for (uint32_t e = 0; e < fi.n_ec(); ++e)
+      for (uint64_t i = fi.ec_off[e]; i < fi.ec_off[e + 1]; ++i) {
+        if (fi.ec_tid[i] >= limit) throw std::runtime_error("kallisto index: equivalence class with a transcript id out of range");
+        if (i > fi.ec_off[e] && fi.ec_tid[i] <= fi.ec_tid[i - 1]) throw std::runtime_error("kallisto index: unsorted equivalence class");
+      }
+  }
   fi.target_name.resize(num_trans);
   for (int32_t i = 0; i < num_trans; ++i) {
     const uint64_t n = c.get<uint64_t>();

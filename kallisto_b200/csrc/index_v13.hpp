@@ -63,6 +63,7 @@ struct FlatIndex {
   std::vector<std::string> target_name;
   std::vector<uint32_t>    onlist;      // sorted transcript ids on the on-list
   uint64_t dlist_n = 0;
+  std::vector<uint64_t> dlist;   // D-list: canonical k-mers (right-aligned 2k bits); [0] is the dummy, the only one that is in the graph
   uint32_t num_targets() const { return (uint32_t)target_len.size(); }
 };
 

@@ -43,6 +43,10 @@ struct DevIndex {
   // touching HBM.  nullptr = no filter.
   const uint32_t* filter;
   uint32_t filter_mask;      // bits - 1 (a power of two)
+  // D-list (distinguishing flanking k-mers, src/KmerIndex.cpp:1385-1403): open-addressing set of canonical k-mers
+  // (KB_EMPTY_KEY = free); nullptr = the index has none
+  const unsigned long long* dfk;
+  uint64_t dfk_mask;
   int k;
   uint32_t n_ec;             // index EC sets
   uint32_t n_targets;

@@ -59,7 +59,8 @@ struct BatchArgs {
   uint32_t pstride;         // 32-bit words per packed read (multiple of 8 = 32 bytes)
   uint32_t empty_ec;        // handle of the empty index EC set, or 0xFFFFFFFF
   int refill_min;           // finished lanes of a warp that trigger a finalise + refill round
-  const uint8_t* skip;      // optional per fragment: 1 = treat as having no sequence (bus: bad barcode/UMI)
+  const uint8_t* skip;      // optional per fragment: 1 = treat as having no sequence (bus: bad barcode/UMI; D-list hit)
+  uint8_t* skip_w;          // the same array, writable: set when the index has a D-list (dlist_scan_kernel marks fragments)
   int fp_fl;                // >= 0: apply the fragment-position filter of ProcessReads.cpp:1095-1136 with this mean fragment length
   uint32_t start;           // first base of every read that is matched (bus: BUSOptionSubstr.start of the sequence)
 };

@@ -238,6 +238,51 @@ __global__ void __launch_bounds__(256) pack_kernel(BatchArgs ba, uint32_t n_read
 }
 
 // ---------------------------------------------------------------------------------------------
+// dlist_scan_kernel: the D-list rule of KmerIndex::match (src/KmerIndex.cpp:1818-1826, 1928-1939).  The reference
+// appends a hit on the dummy unitig -- whose equivalence class is the single off-list target -- to a read's hit list
+// when any of the read's k-mers is a distinguishing flanking k-mer; the intersection with the on-list targets
+// (ProcessReads.cpp:1072) is then empty.  Net effect with default flags: a fragment holding a D-list k-mer in either
+// mate is not pseudoaligned.  One thread per (read, window of 32 k-mer start positions) over the packed 2-bit reads;
+// a hit marks the fragment in the skip array match_kernel honours.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dlist_scan_kernel(DevIndex ix, BatchArgs ba, uint32_t n_reads) {
+  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nb = ba.nb;
+  if (gid >= (uint64_t)n_reads * nb) return;
+  const uint32_t r = (uint32_t)(gid / nb), w = (uint32_t)(gid % nb);
+  const uint32_t frag = ba.paired ? (r >> 1) : r;
+  uint64_t off;
+  int len;
+  const uint8_t* unused;
+  read_span(ba, r, unused, off, len);
+  const int k = ix.k;
+  const int p0 = (int)w * 32;
+  if (len < k || p0 > len - k) return;
+  const uint32_t* pk = ba.packed + (size_t)r * ba.pstride;
+  const unsigned long long* bw = reinterpret_cast<const unsigned long long*>(pk);
+  const unsigned long long w0 = bw[w], w1 = (w + 1 < nb) ? bw[w + 1] : 0ull;
+  const unsigned long long inv = (unsigned long long)pk[2 * nb + w] | ((w + 1 < nb) ? ((unsigned long long)pk[2 * nb + w + 1] << 32) : 0xFFFFFFFF00000000ull);
+  const unsigned long long wmask = (1ull << k) - 1;
+  for (int j = 0; j < 32; ++j) {
+    const int p = p0 + j;
+    if (p > len - k) break;
+    if ((inv >> j) & wmask) continue;                       // a base other than A/C/G/T in the window
+    unsigned long long x = w0 << (2 * j);
+    if (j) x |= w1 >> (64 - 2 * j);
+    const uint64_t fwd = x >> (64 - 2 * k);
+    const uint64_t rc = kb_revcomp(fwd, k);
+    const uint64_t canon = fwd < rc ? fwd : rc;
+    uint64_t h = kb_mix64(canon) & ix.dfk_mask;
+    for (;;) {
+      const unsigned long long key = __ldg(ix.dfk + h);
+      if (key == canon) { ba.skip_w[frag] = 1; return; }
+      if (key == KB_EMPTY_KEY) break;
+      h = (h + 1) & ix.dfk_mask;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // match_kernel: persistent warps, 32 independent fragment state machines per warp.
 //
 // KmerIndex::match (src/KmerIndex.cpp:1698-1940, default flags, empty D-list) is a chain of
@@ -971,6 +1016,7 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
     const uint32_t n_reads = ba.paired ? 2 * ba.n_frag : ba.n_frag;
     const uint64_t total = (uint64_t)n_reads * ba.nb;
     pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ba, n_reads, const_cast<uint32_t*>(ba.packed));
+    if (ix.dfk && ba.skip_w) dlist_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ix, ba, n_reads);
   }
   if (ev) cudaEventRecord(ev[0], st);
   match_kernel<<<blocks, tpb, smem, st>>>(ix, dd, ba);

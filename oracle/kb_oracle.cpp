@@ -24,6 +24,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 namespace {
@@ -56,6 +57,10 @@ struct OIndex {
   std::vector<uint32_t> target_len;
   std::vector<std::string> target_name;
   TidSet onlist;
+  // D-list (distinguishing flanking k-mers, src/KmerIndex.cpp:1385-1403): canonical k-mers; the first one is the dummy,
+  // the only one that is part of the graph (its unitig carries the single off-list target id)
+  std::unordered_set<uint64_t> d_list;
+  uint64_t dummy_dfk = 0;
 };
 
 struct Reader {
@@ -189,8 +194,11 @@ OIndex* load_index(const char* path) {
   r.take(r.get<uint64_t>());   // BBHash MPHF: Bifrost-internal, not needed by a flat dictionary
   const uint64_t dlist_n = r.get<uint64_t>();
   r.get<uint64_t>();
-  r.take(dlist_n * 8);
-  if (dlist_n) throw std::runtime_error("oracle: D-list indices are out of scope");
+  for (uint64_t i = 0; i < dlist_n; ++i) {
+    const uint64_t w = r.get<uint64_t>() >> (64 - 2 * ix->k);     // Kmer: left-aligned 2-bit words (Kmer.cpp:92-107)
+    ix->d_list.insert(w);
+    if (i == 0) ix->dummy_dfk = w;
+  }
   const int k = ix->k;
   for (uint32_t u = 0; u < ix->unitigs.size(); ++u) {
     const std::string& s = ix->unitigs[u].seq;
@@ -232,6 +240,7 @@ OIndex* load_index(const char* path) {
     }
   }
   int32_t nt = r.get<int32_t>();
+  nt -= (int32_t)dlist_n;     // the stored count includes one pseudo-target per D-list k-mer (src/KmerIndex.cpp:1470-1472)
   for (int32_t i = 0; i < nt; ++i) ix->target_len.push_back((uint32_t)r.get<int32_t>());
   for (int32_t i = 0; i < nt; ++i) {
     const uint64_t n = r.get<uint64_t>();
@@ -339,9 +348,16 @@ typedef std::vector<std::pair<Um, int>> HitVec;
 // [7] = largest number of distinct non-empty EC sets hit by one fragment
 static uint64_t g_kind[8];
 
-// KmerIndex::match, src/KmerIndex.cpp:1698-1940 (default flags; no D-list)
+// KmerIndex::match, src/KmerIndex.cpp:1698-1940 (default flags; D-list: 1818-1826 and 1928-1939)
 void match(const OIndex& ix, const char* s, int l, HitVec& v, bool partial, uint64_t* n_find) {
   const int k = ix.k;
+  auto rep = [&](uint64_t km) { const uint64_t t = twin(km, k); return km < t ? km : t; };
+  auto dlist_tail = [&]() {   // lines 1928-1939
+    if (ix.d_list.empty() || !(v.size() > 0 || !partial)) return;
+    const Um um_dummy = find(ix, ix.dummy_dfk);
+    for (KIt kd = KIt::begin(s, k); !kd.invalid; kd.inc())
+      if (ix.d_list.count(rep(kd.km))) { v.push_back({um_dummy, kd.p}); break; }
+  };
   KIt kit = KIt::begin(s, k);
   bool backOff = false;
   int nextPosOuter = 0;   // the outer `nextPos` (line 1748) is never updated: the inner one shadows it
@@ -397,12 +413,15 @@ void match(const OIndex& ix, const char* s, int l, HitVec& v, bool partial, uint
             found2pos = pos + dist;
           }
           if (found2) {
+            const bool is_in_dlist = um2.isEmpty && !ix.d_list.empty() && ix.d_list.count(rep(kit2.km));   // :1818
             if (found2pos >= l - k) {
               v.push_back({um, l - k});
+              if (partial && is_in_dlist) { v.push_back({find(ix, ix.dummy_dfk), kit2.p}); return; }
               break;
             } else {
               v.push_back({um, found2pos});
               kit = kit2;
+              if (partial && is_in_dlist) { v.push_back({find(ix, ix.dummy_dfk), kit2.p}); return; }
             }
           } else {
             bool foundMiddle = false;
@@ -460,6 +479,7 @@ void match(const OIndex& ix, const char* s, int l, HitVec& v, bool partial, uint
       }
     }
   }
+  dlist_tail();
 }
 
 TidSet intersect(const TidSet& a, const TidSet& b) {

@@ -19,14 +19,14 @@ REL_TOL = 1e-4   # north_star tolerance for floating point outputs
 @pytest.fixture(scope="module")
 def indices():
     out = {}
-    for name in ("config1", "synth_small", "manyecs", "abundant"):
+    for name in ("config1", "synth_small", "manyecs", "abundant", "dlist"):
         out[name] = K.KmerIndex(util.dataset(name)["index"], device=0)
     yield out
     for ix in out.values():
         ix.close()
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant", "dlist"])
 @pytest.mark.parametrize("mode", list(util.MODES))
 def test_per_fragment_ecs(indices, name, mode):
     ds = util.dataset(name)
@@ -49,7 +49,7 @@ def test_per_fragment_ecs(indices, name, mode):
     mc.close()
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant", "dlist"])
 def test_batching_does_not_change_results(indices, name):
     ds = util.dataset(name)
     g = util.golden_ecs(ds, "paired")
@@ -66,7 +66,7 @@ def test_batching_does_not_change_results(indices, name):
     mc.close()
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant", "dlist"])
 def test_quant_matches_reference(indices, name):
     ds = util.dataset(name)
     ix = indices[name]
@@ -99,7 +99,7 @@ def test_quant_matches_reference(indices, name):
     mc.close()
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant", "dlist"])
 def test_bootstrap_matches_reference(indices, name):
     ds = util.dataset(name)
     ix = indices[name]

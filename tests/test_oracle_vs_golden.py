@@ -10,7 +10,7 @@ from oracle import oracle as O
 from tests import util
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant", "dlist"])
 @pytest.mark.parametrize("mode", list(util.MODES))
 def test_per_fragment_ecs_match_reference(name, mode):
     ds = util.dataset(name)
@@ -29,7 +29,7 @@ def test_per_fragment_ecs_match_reference(name, mode):
         np.testing.assert_array_equal(run.flens(), g["flens"])
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant", "dlist"])
 def test_quant_text_identical_to_reference(name):
     """abundance.tsv of `kallisto quant --plaintext -t 1`, byte for byte (6 significant digits)."""
     ds = util.dataset(name)
@@ -50,7 +50,7 @@ def test_quant_text_identical_to_reference(name):
         assert rounds == 52
 
 
-@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant"])
+@pytest.mark.parametrize("name", ["config1", "synth_small", "manyecs", "abundant", "dlist"])
 def test_bootstrap_text_identical_to_reference(name):
     ds = util.dataset(name)
     ix = O.OracleIndex(ds["index"])
