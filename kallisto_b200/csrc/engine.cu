@@ -58,14 +58,11 @@ template <class T> void DBuf<T>::zero(cudaStream_t st) {
 Index::~Index() { delete shared_emws; }
 
 std::unique_ptr<Index> Index::load(const std::string& path, int device, bool load_positions, int threads) {
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    throw Error("kallisto_b200: no CUDA device available (this build has no CPU path)");
-  if (device < 0 || device >= ndev) throw Error("kallisto_b200: invalid CUDA device ordinal");
   std::unique_ptr<Index> ix(new Index());
   ix->device = device;
   const double t0 = now_s();
-  // the file is parsed on its own thread while this one brings the CUDA context up (0.3-0.5 s in a fresh process)
+  // the file is parsed on its own thread while this one initialises the driver and brings the CUDA context up
+  // (0.3 s + 0.3-0.5 s in a fresh process)
   std::exception_ptr parse_err;
   std::thread parser([&] {
     try {
@@ -74,6 +71,13 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
       parse_err = std::current_exception();
     }
   });
+  int ndev = 0;
+  const bool have_dev = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
+  if (!have_dev || device < 0 || device >= ndev) {
+    parser.join();
+    if (!have_dev) throw Error("kallisto_b200: no CUDA device available (this build has no CPU path)");
+    throw Error("kallisto_b200: invalid CUDA device ordinal");
+  }
   cudaError_t init_err = cudaSetDevice(device);
   if (init_err == cudaSuccess) init_err = cudaFree(0);
   if (init_err == cudaSuccess) {
@@ -1005,6 +1009,8 @@ EmResult Quant::run_em(const EcTable& ecs, const std::vector<double>& fl_trunc, 
 EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter, int min_rounds) {
   KB_CK(cudaSetDevice(ix_.device));
   check_device_errors();
+  // the EM works out of L2: give it the part that the k-mer presence filter held as persisting lines during pseudoalignment
+  if (ix_.l2_persist_bytes) cudaCtxResetPersistingL2Cache();
   const FlatIndex& f = ix_.flat;
   const uint32_t T = f.num_targets();
   cudaStream_t st = stream_;
@@ -1157,6 +1163,7 @@ std::vector<int> Quant::run_bootstrap_device(const std::vector<double>& fl_trunc
   alpha_out.assign((size_t)B * T, 0.0);
   rounds.assign(B, 0);
   if (!dev_problem_valid_) return rounds;                // nothing pseudoaligned
+  if (ix_.l2_persist_bytes) cudaCtxResetPersistingL2Cache();
   cudaStream_t st = stream_;
   EmWs& w = *emws_;
   const uint32_t nE = (uint32_t)dev_n_ecs_, n_multi = dev_n_multi_;
