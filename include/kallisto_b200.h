@@ -161,6 +161,11 @@ int kb_comm_create_all(const int* devices, int n_devices, kb_comm** out);
 int kb_comm_reserve(kb_comm* c, uint64_t n_sets_per_rank, uint64_t n_entries_per_rank);
 void kb_comm_free(kb_comm* c);
 int kb_quant_merge_nccl(kb_quant* q, kb_comm* c, uint64_t first_stride, uint64_t* n_processed_total);
+/* The same merge when all runs belong to THIS process (one host thread per GPU or one thread driving all): the other
+ * runs' tables are copied to the root's device with cudaMemcpyPeerAsync (NVLink) and folded in by content; no
+ * communicator.  The runs must have been fed global fragment indices (kb_quant_set_frag_base) and only the root
+ * collects the fragment-length distribution. */
+int kb_quant_merge_local(kb_quant* root, kb_quant* const* others, int32_t n_others, uint64_t* n_processed_total);
 /* Global index of the first fragment of the NEXT batch (several runs fed from one read stream). */
 int kb_quant_set_frag_base(kb_quant* q, uint64_t base);
 /* Size the EC-numbering / EM workspace ahead of time (kb_quant_create reserves for 2x the index's own EC sets). */

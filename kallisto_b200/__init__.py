@@ -90,7 +90,7 @@ EXPORTED_SYMBOLS = [
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
     "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device",
     "kb_comm_unique_id", "kb_comm_create", "kb_comm_create_from_nccl", "kb_comm_create_all", "kb_comm_reserve", "kb_comm_free",
-    "kb_quant_merge_nccl", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_tcc_run", "kb_eff_lens", "kb_bus_create", "kb_bus_batch", "kb_bus_batch_device", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
+    "kb_quant_merge_nccl", "kb_quant_merge_local", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_tcc_run", "kb_eff_lens", "kb_bus_create", "kb_bus_batch", "kb_bus_batch_device", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -145,6 +145,7 @@ def lib():
     L.kb_comm_reserve.argtypes = [vp, u64, u64]
     L.kb_comm_free.argtypes = [vp]
     L.kb_quant_merge_nccl.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.kb_quant_merge_local.argtypes = [vp, vp, i32, C.POINTER(u64)]
     L.kb_quant_set_frag_base.argtypes = [vp, u64]
     L.kb_quant_reserve.argtypes = [vp, u64, u64]
     L.kb_tcc_run.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, i32, vp, vp]
@@ -334,6 +335,14 @@ class MinCollector:
         number of fragments processed by all ranks."""
         tot = C.c_uint64(0)
         _ck(lib().kb_quant_merge_nccl(self._h, comm._h, first_stride, C.byref(tot)))
+        self._stats = None
+        return tot.value
+
+    def merge_local(self, others):
+        """Fold the equivalence classes of other runs of THIS process (any devices) into this one by content."""
+        arr = (C.c_void_p * len(others))(*[o._h for o in others])
+        tot = C.c_uint64(0)
+        _ck(lib().kb_quant_merge_local(self._h, arr, len(others), C.byref(tot)))
         self._stats = None
         return tot.value
 

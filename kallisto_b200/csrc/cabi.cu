@@ -362,6 +362,18 @@ int kb_quant_merge_nccl(kb_quant* q, kb_comm* c, uint64_t first_stride, uint64_t
     if (n_processed_total) *n_processed_total = t;
   });
 }
+int kb_quant_merge_local(kb_quant* root, kb_quant* const* others, int32_t n_others, uint64_t* n_processed_total) {
+  if (!root || (n_others > 0 && !others) || n_others < 0) return fail(KB_ERR_INVALID, "kb_quant_merge_local: bad argument");
+  return guarded([&] {
+    std::vector<kb::Quant*> o;
+    for (int i = 0; i < n_others; ++i) {
+      if (!others[i]) throw std::invalid_argument("kb_quant_merge_local: null run");
+      o.push_back(others[i]->q.get());
+    }
+    const uint64_t t = root->q->merge_local(o, 0);
+    if (n_processed_total) *n_processed_total = t;
+  });
+}
 int kb_quant_set_frag_base(kb_quant* q, uint64_t base) {
   if (!q) return fail(KB_ERR_INVALID, "kb_quant_set_frag_base: null argument");
   q->q->set_frag_base(base);

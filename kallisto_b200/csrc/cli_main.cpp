@@ -501,9 +501,25 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     return 1;
   }
   PhaseTimer pt;
+  // The driver initialises every VISIBLE GPU when the first CUDA call is made (about 0.1 s apiece on an 8-GPU node):
+  // unless the caller set CUDA_VISIBLE_DEVICES already, only the devices this run uses are made visible.
+  if (!getenv("CUDA_VISIBLE_DEVICES")) {
+    std::string vis;
+    if (opt.devices.empty()) {
+      vis = std::to_string(opt.device);
+      opt.device = 0;
+    } else {
+      for (size_t i = 0; i < opt.devices.size(); ++i) {
+        vis += (i ? "," : "") + std::to_string(opt.devices[i]);
+        opt.devices[i] = (int)i;
+      }
+      opt.device = 0;
+    }
+    setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+  }
   const bool paired = !opt.single_end;
-  const size_t max_reads = 1u << 20;                 // reads per batch and mate
-  const size_t max_bases = (size_t)max_reads * 160 + kb::FastxFile::kMaxRead;
+  const size_t max_reads = 1u << 19;                 // reads per batch and mate (pinned ring: 4 x 2 x ~70 MB)
+  const size_t max_bases = (size_t)max_reads * 136 + kb::FastxFile::kMaxRead;
   const int n_streams = paired ? 2 : 1;
   std::vector<Stream> streams(n_streams);
   std::vector<std::thread> readers;
@@ -514,7 +530,6 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   // --devices: the index is replicated (one load per device, in parallel); device 0 of the list is the root
   const int n_dev = std::max<int>(1, (int)opt.devices.size());
   std::vector<kb_index*> ixs(n_dev, nullptr);
-  std::vector<kb_comm*> comms(n_dev, nullptr);
   {
     std::vector<std::string> errs(n_dev);
     std::vector<std::thread> loaders;
@@ -528,7 +543,6 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     for (auto& t : loaders) t.join();
     for (int d = 1; d < n_dev; ++d)
       if (!errs[d].empty()) { cerr << endl << "Error: " << errs[d] << endl; return 1; }
-    if (n_dev > 1) KB_TRY(kb_comm_create_all(opt.devices.data(), n_dev, comms.data()));
   }
   pt.mark("index load");
   kb_index_info info;
@@ -606,18 +620,17 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   }
   for (auto& t : readers) t.join();
   pt.mark("read + pseudoalign loop");
+  // the pinned rings are not needed any more: un-pinning ~0.5 GB takes a few tenths of a second, so it runs on its own
+  // thread next to the merge, the EM and the writers instead of at process exit
+  struct Joiner {
+    std::thread t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } ring_free{std::thread([&] { free_streams(streams); })};
   if (n_dev > 1) {
-    // the one exchange: every device's equivalence classes folded into the root's by content (collective)
-    std::vector<std::string> errs(n_dev);
-    std::vector<std::thread> ts;
-    for (int d = 0; d < n_dev; ++d)
-      ts.emplace_back([&, d] {
-        if (kb_quant_merge_nccl(qs[d], comms[d], 0, nullptr) != KB_OK) errs[d] = kb_last_error();
-      });
-    for (auto& t : ts) t.join();
-    for (int d = 0; d < n_dev; ++d)
-      if (!errs[d].empty()) { cerr << endl << "Error: " << errs[d] << endl; return 1; }
-    pt.mark("merge over NCCL");
+    // the one exchange: every device's equivalence classes copied to the root over NVLink and folded in by content
+    // (all runs live in this process, so no NCCL communicator is needed; multi-process drivers use kb_quant_merge_nccl)
+    KB_TRY(kb_quant_merge_local(qs[0], qs.data() + 1, n_dev - 1, nullptr));
+    pt.mark("merge (peer copies)");
   }
   cerr << " done" << endl;
 
@@ -678,11 +691,10 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
                       bs.data() + (size_t)b * T);
   }
   cerr << endl;
+  ring_free.t.join();
   if (!getenv("KB_CLI_CLEANUP")) finish(st.n_pseudoaligned == 0 ? 1 : 0);
-  free_streams(streams);
   for (int d = 0; d < n_dev; ++d) {
     kb_quant_free(qs[d]);
-    if (comms[d]) kb_comm_free(comms[d]);
     kb_index_free(ixs[d]);
   }
   return st.n_pseudoaligned == 0 ? 1 : 0;

@@ -377,6 +377,7 @@ void Quant::reserve_em(size_t n_ecs, size_t nnz) {
   g32(w.m_tid, nz); g32(w.m_row, nz); g32(w.m_iota, nz); g32(w.sortv, nz); g32(w.t_midx, nz);
   if (w.k64_in.n < nz) { w.k64_in.alloc(nz); w.k64_out.alloc(nz); }
   if (w.bar.n < 1) w.bar.alloc(1);
+  g32(w.cnt_row, n1); gd(w.single_cnt, T);
   gd(w.m_w, nz); gd(w.t_w, nz);
   g32(w.t_deg, (size_t)T + 1); g32(w.t_off, (size_t)T + 1);
   if (w.t_single.n < T) w.t_single.alloc(T);
@@ -926,6 +927,8 @@ struct EmDevice {
   DBuf<int32_t> t_single;
   DBuf<int> rounds, fstate;
   DBuf<unsigned int> chcount, bar;
+  DBuf<uint32_t> cnt_row;
+  DBuf<double> single_cnt;
 };
 
 void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, EmProblem& p, cudaStream_t st) {
@@ -943,6 +946,8 @@ void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, 
   d.norm.alloc(std::max<size_t>(1, (size_t)nb * nm));
   d.rounds.alloc(nb); d.rounds.zero(st);
   d.bar.alloc(1);
+  d.cnt_row.alloc(std::max<size_t>(1, (size_t)nb * nm));
+  d.single_cnt.alloc((size_t)nb * T);
   d.fstate.alloc(nb); d.fstate.zero(st);
   d.chcount.alloc((size_t)nb * 2); d.chcount.zero(st);
   p = EmProblem();
@@ -951,6 +956,7 @@ void em_upload(const EmHost& h, uint32_t n_ec, uint32_t T, int nb, EmDevice& d, 
   p.t_off = d.t_off.p; p.t_midx = d.t_midx.p; p.t_w = d.t_w.p; p.t_single = d.t_single.p;
   p.nb = nb; p.counts = d.counts.p; p.alpha = d.alpha.p; p.norm = d.norm.p;
   p.rounds = d.rounds.p; p.bar = d.bar.p; p.chcount = d.chcount.p; p.fstate = d.fstate.p;
+  p.cnt_row = d.cnt_row.p; p.single_cnt = d.single_cnt.p;
 }
 
 void em_fetch(const EmProblem& p, EmDevice& d, int nb, uint32_t T, std::vector<double>& alpha, std::vector<int>& rounds,
@@ -1096,6 +1102,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   grow32(w.t_deg, (size_t)T + 1); grow32(w.t_off, (size_t)T + 1);
   if (w.t_single.n < T) w.t_single.alloc(T);
   growd(w.eff, T); growd(w.alpha, T); growd(w.norm, (size_t)n_multi + 1);
+  grow32(w.cnt_row, (size_t)n_multi + 1); growd(w.single_cnt, T);
   mark("phase-2 buffers");
   KB_CK(cudaMemsetAsync(w.t_deg.p, 0, ((size_t)T + 1) * 4, st));
   launch_fill_i32(w.t_single.p, T, -1, st);
@@ -1120,6 +1127,7 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   p.t_off = w.t_off.p; p.t_midx = w.t_midx.p; p.t_w = w.t_w.p; p.t_single = w.t_single.p;
   p.nb = 1; p.counts = w.count.p; p.alpha = w.alpha.p; p.norm = w.norm.p;
   p.rounds = w.emi.p; p.bar = w.bar.p; p.fstate = w.emi.p + 3; p.chcount = w.chcount.p;
+  p.cnt_row = w.cnt_row.p; p.single_cnt = w.single_cnt.p;
   p.max_iter = max_iter; p.min_rounds = min_rounds;
   mark("fill launches + uploads");
   // collect_used, gather_used, ec_meta, multi_compact, row_len, ec_fill, csc_fill, stats, fill_i32, fill_f64 + em_kernel
@@ -1230,6 +1238,8 @@ std::vector<int> Quant::run_bootstrap_device(const std::vector<double>& fl_trunc
   }
   if (w.bs_alpha.n < (size_t)chunk * T) w.bs_alpha.alloc((size_t)chunk * T);
   if (w.bs_norm.n < (size_t)chunk * std::max<uint32_t>(1, n_multi)) w.bs_norm.alloc((size_t)chunk * std::max<uint32_t>(1, n_multi));
+  if (w.cnt_row.n < (size_t)chunk * std::max<uint32_t>(1, n_multi)) w.cnt_row.alloc((size_t)chunk * std::max<uint32_t>(1, n_multi));
+  if (w.single_cnt.n < (size_t)chunk * T) w.single_cnt.alloc((size_t)chunk * T);
   if (w.bs_emi.n < (size_t)2 * chunk) w.bs_emi.alloc((size_t)2 * chunk);
   if (w.bs_ch.n < (size_t)2 * chunk) w.bs_ch.alloc((size_t)2 * chunk);
   std::vector<int> emi((size_t)2 * chunk);
@@ -1244,6 +1254,7 @@ std::vector<int> Quant::run_bootstrap_device(const std::vector<double>& fl_trunc
     p.t_off = w.t_off.p; p.t_midx = w.t_midx.p; p.t_w = w.t_w.p; p.t_single = w.t_single.p;
     p.nb = nb; p.counts = w.bs_counts.p + (size_t)b0 * nE; p.alpha = w.bs_alpha.p; p.norm = w.bs_norm.p;
     p.rounds = w.bs_emi.p; p.fstate = w.bs_emi.p + chunk; p.bar = w.bar.p; p.chcount = w.bs_ch.p;
+    p.cnt_row = w.cnt_row.p; p.single_cnt = w.single_cnt.p;
     p.max_iter = 10000; p.min_rounds = 50;
     launch_em(p, em_tpb(), st);
     KB_CK(cudaGetLastError());
@@ -1325,6 +1336,56 @@ void Quant::export_copy(uint32_t* d_off, uint32_t* d_tids, uint32_t* d_counts, u
     KB_CK(cudaMemsetAsync(d_off, 0, 4, st));
   }
   KB_CK(cudaStreamSynchronize(st));
+}
+
+uint64_t Quant::merge_local(const std::vector<Quant*>& others, uint64_t first_stride) {
+  uint64_t total = n_frag_total_;
+  size_t sum_n = 0, sum_nnz = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> sizes;
+  for (Quant* o : others) {
+    uint32_t n = 0, nnz = 0;
+    o->export_prepare(&n, &nnz);                 // numbers o's ECs on ITS device (synchronises o's stream)
+    sizes.push_back({n, nnz});
+    sum_n += n;
+    sum_nnz += nnz;
+    total += o->n_frag_total_;
+  }
+  KB_CK(cudaSetDevice(ix_.device));
+  check_device_errors();
+  if (lm_off_.n < sum_n + others.size() + 1) lm_off_.alloc(sum_n + others.size() + 1);
+  if (lm_counts_.n < sum_n + 1) lm_counts_.alloc(sum_n + 1);
+  if (lm_first_.n < sum_n + 1) lm_first_.alloc(sum_n + 1);
+  if (lm_tids_.n < sum_nnz + 1) lm_tids_.alloc(sum_nnz + 1);
+  std::vector<ImportSeg> segs;
+  size_t o_off = 0, o_n = 0, o_nnz = 0;
+  for (size_t i = 0; i < others.size(); ++i) {
+    Quant* o = others[i];
+    const uint32_t n = sizes[i].first, nnz = sizes[i].second;
+    if (n) {
+      EmWs& w = *o->emws_;
+      const int src = o->ix_.device, dst = ix_.device;
+      KB_CK(cudaMemcpyPeerAsync(lm_off_.p + o_off, dst, w.ec_off.p, src, ((size_t)n + 1) * 4, stream_));
+      KB_CK(cudaMemcpyPeerAsync(lm_tids_.p + o_nnz, dst, w.ec_tid.p, src, (size_t)nnz * 4, stream_));
+      KB_CK(cudaMemcpyPeerAsync(lm_counts_.p + o_n, dst, w.count.p, src, (size_t)n * 4, stream_));
+      KB_CK(cudaMemcpyPeerAsync(lm_first_.p + o_n, dst, w.key_out.p, src, (size_t)n * 8, stream_));
+      ImportSeg sg;
+      sg.n_sets = n; sg.off = lm_off_.p + o_off; sg.tids = lm_tids_.p + o_nnz; sg.counts = lm_counts_.p + o_n; sg.first = lm_first_.p + o_n;
+      segs.push_back(sg);
+      if (first_stride) throw Error("kallisto_b200: merge_local expects runs fed with global fragment indices");
+    }
+    o_off += (size_t)n + 1; o_n += n; o_nnz += nnz;
+  }
+  ecs_valid_ = false;
+  dev_stats_valid_ = false;
+  dev_problem_valid_ = false;
+  for (size_t i = 0; i < segs.size(); i += KB_IMPORT_SEGS) {
+    launch_import_segments(dd_, segs.data() + i, (int)std::min<size_t>(KB_IMPORT_SEGS, segs.size() - i), stream_);
+    KB_CK(cudaGetLastError());
+    ++n_kernel_launches;
+  }
+  KB_CK(cudaStreamSynchronize(stream_));
+  n_frag_total_ = total;
+  return total;
 }
 
 void Quant::import_sets_device(uint32_t n_sets, const uint32_t* d_off, const uint32_t* d_tids, const uint32_t* d_counts,
@@ -1448,7 +1509,8 @@ std::vector<int> tcc_run(Index& ix, const TccInput& in, std::vector<double>& alp
   DBuf<uint32_t> d_multi_ec, d_m_off, d_m_tid, d_m_ec, d_t_off, d_t_midx, d_t_ec, d_t_tid, d_ecid, d_val, d_counts;
   DBuf<int32_t> d_single;
   DBuf<unsigned long long> d_rowoff;
-  DBuf<double> d_eff, d_mw, d_tw, d_alpha, d_norm;
+  DBuf<double> d_eff, d_mw, d_tw, d_alpha, d_norm, d_single_cnt;
+  DBuf<uint32_t> d_cnt_row;
   DBuf<int> d_emi;
   DBuf<unsigned> d_ch, d_bar;
   auto up32 = [&](DBuf<uint32_t>& d, const std::vector<uint32_t>& h) { d.alloc(std::max<size_t>(1, h.size())); d.upload(h.data(), h.size(), st); };
@@ -1464,6 +1526,7 @@ std::vector<int> tcc_run(Index& ix, const TccInput& in, std::vector<double>& alp
   d_counts.alloc((size_t)chunk * std::max<uint32_t>(1, nE));
   d_mw.alloc(std::max<size_t>(1, (size_t)chunk * nnz)); d_tw.alloc(std::max<size_t>(1, (size_t)chunk * nnz));
   d_alpha.alloc((size_t)chunk * T); d_norm.alloc(std::max<size_t>(1, (size_t)chunk * n_multi));
+  d_cnt_row.alloc(std::max<size_t>(1, (size_t)chunk * n_multi)); d_single_cnt.alloc((size_t)chunk * T);
   d_eff.alloc(in.per_sample_eff ? (size_t)chunk * T : (size_t)T);
   if (!in.per_sample_eff) d_eff.upload(in.eff_lens, T, st);
   d_emi.alloc((size_t)2 * chunk); d_ch.alloc((size_t)2 * chunk); d_bar.alloc(1);
@@ -1490,6 +1553,7 @@ std::vector<int> tcc_run(Index& ix, const TccInput& in, std::vector<double>& alp
     p.t_off = d_t_off.p; p.t_midx = d_t_midx.p; p.t_w = d_tw.p; p.t_single = d_single.p;
     p.nb = nb; p.counts = d_counts.p; p.alpha = d_alpha.p; p.norm = d_norm.p;
     p.rounds = d_emi.p; p.fstate = d_emi.p + chunk; p.bar = d_bar.p; p.chcount = d_ch.p;
+    p.cnt_row = d_cnt_row.p; p.single_cnt = d_single_cnt.p;
     p.max_iter = 10000; p.min_rounds = 50; p.w_stride = nnz;
     launch_em(p, em_tpb(), st);
     KB_CK(cudaGetLastError());

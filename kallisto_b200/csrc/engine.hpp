@@ -60,6 +60,8 @@ struct EmWs {   // grow-only device workspace of run_em_device
   DBuf<uint32_t> minkey, ckey, cval, ckey_out, rlen;     // row order of the EM matrices (emprep_rows)
   DBuf<unsigned long long> k64_in, k64_out;              // CSC sort keys
   DBuf<unsigned> bar;                                    // grid-barrier counter of em_kernel
+  DBuf<uint32_t> cnt_row;                                // row-ordered counts (launch_em fills them)
+  DBuf<double> single_cnt;
   // bootstrap over the same matrices (run_bootstrap_device)
   DBuf<uint32_t> bs_counts, bs_x0;
   DBuf<double> bs_alpha, bs_norm, bs_cp;
@@ -211,6 +213,9 @@ class Quant {
   // folded in by content with one kernel launch, fragment-length samples completed in rank order.  Returns the
   // number of fragments processed by all ranks.
   uint64_t merge_to_root(Comm& comm, uint64_t first_stride);
+  // Same merge when all runs live in THIS process (one host thread drives several GPUs, `kallisto_b200 quant --devices`):
+  // the other runs' tables are copied with cudaMemcpyPeerAsync (NVLink) -- no communicator to set up.  Called on the root.
+  uint64_t merge_local(const std::vector<Quant*>& others, uint64_t first_stride);
   // Global index of the first fragment of the NEXT batch (multi-GPU drivers that deal batches of one read
   // stream to several runs: first-occurrence order then is the order of the stream).  Default: running count.
   void set_frag_base(uint64_t base) { frag_base_ = base; have_frag_base_ = true; }
@@ -289,6 +294,8 @@ class Quant {
   DBuf<BusRecord> bus_rec_;
   DBuf<uint8_t> bus_tmp_;
   uint32_t exp_n_ = 0, exp_nnz_ = 0;
+  DBuf<uint32_t> lm_off_, lm_tids_, lm_counts_;       // merge_local: receive area on the root
+  DBuf<unsigned long long> lm_first_;
   uint32_t bus_next_id_ = 0;
   uint64_t bus_valid_total_ = 0;
   const uint8_t* cur_skip_ = nullptr;

@@ -126,6 +126,9 @@ struct EmProblem {
   double* norm;                 // nb x n_multi scratch: counts/denom or 0
   int* rounds;                  // nb: iterations run (the reference's "ran for i rounds")
   unsigned* bar;                // arrival counter of the kernel's grid barrier (zeroed by launch_em)
+  // filled by launch_em before the EM kernel starts (one dependent load less per row and per round):
+  uint32_t* cnt_row;            // nb x n_multi: counts of the multi-transcript ECs in row order
+  double* single_cnt;           // nb x n_targets: count of the singleton EC {t}, or 0
   int* fstate;                  // nb: final state (2 finished, 3 finished + host must zero small alphas)
   unsigned int* chcount;        // nb x 2 (double-buffered) change counters
   int max_iter, min_rounds;

@@ -100,13 +100,14 @@ __global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4)))
       const uint32_t b = (uint32_t)(i / p.n_multi), r = (uint32_t)(i % p.n_multi);
       const int st = s_state[b];
       if (st >= 2) continue;
-      const uint32_t c = p.counts[(size_t)b * p.n_ec + p.multi_ec[r]];
+      // count and row bounds are independent loads; the row is only walked when it has reads
+      const uint32_t c = p.cnt_row[i];
+      const uint32_t e0 = p.m_off[r], e1 = p.m_off[r + 1];
       double nrm = 0.0;
       if (c != 0) {
         const double* al = p.alpha + (size_t)b * p.n_targets;
         const double* mw = p.m_w + (size_t)b * p.w_stride;
         double denom = 0.0;
-        const uint32_t e0 = p.m_off[r], e1 = p.m_off[r + 1];
         for (uint32_t j = e0; j < e1; ++j) {
           double a = al[p.m_tid[j]];
           if (st == 1 && a < zero_below) a = 0.0;          // alpha zeroed before the final round (:213-216)
@@ -134,8 +135,7 @@ __global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4)))
           double* al = p.alpha + (size_t)b * p.n_targets;
           double a = al[t];
           if (st == 1 && a < zero_below) a = 0.0;
-          const int32_t s = p.t_single[t];
-          double acc = s >= 0 ? (double)p.counts[(size_t)b * p.n_ec + s] : 0.0;     // :119-123
+          double acc = p.single_cnt[i];                                             // :119-123
           const double* nr = p.norm + (size_t)b * p.n_multi;
           const double* tw = p.t_w + (size_t)b * p.w_stride;
           const uint32_t e0 = p.t_off[t], e1 = p.t_off[t + 1];
@@ -170,6 +170,24 @@ __global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4)))
   }
 }
 
+// Row-ordered copies of the counts the passes need: cnt_row[b][r] = counts[b][multi_ec[r]],
+// single_cnt[b][t] = counts[b][t_single[t]] (as a double) or 0.
+__global__ void em_gather_counts_kernel(EmProblem p) {
+  const uint64_t nA = (uint64_t)p.nb * p.n_multi, nB = (uint64_t)p.nb * p.n_targets;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nA + nB; i += stride) {
+    if (i < nA) {
+      const uint32_t b = (uint32_t)(i / p.n_multi), r = (uint32_t)(i % p.n_multi);
+      p.cnt_row[i] = p.counts[(size_t)b * p.n_ec + p.multi_ec[r]];
+    } else {
+      const uint64_t k = i - nA;
+      const uint32_t b = (uint32_t)(k / p.n_targets), t = (uint32_t)(k % p.n_targets);
+      const int32_t s = p.t_single[t];
+      p.single_cnt[k] = s >= 0 ? (double)p.counts[(size_t)b * p.n_ec + s] : 0.0;
+    }
+  }
+}
+
 int em_max_blocks(int tpb) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
@@ -190,6 +208,11 @@ void launch_em(const EmProblem& p, int tpb_req, cudaStream_t st) {
   if (blocks < 1) blocks = 1;
   EmProblem pp = p;
   cudaMemsetAsync(pp.bar, 0, sizeof(unsigned), st);
+  {
+    const uint64_t n = (uint64_t)p.nb * ((uint64_t)p.n_multi + p.n_targets);
+    const unsigned g = (unsigned)std::min<uint64_t>((uint64_t)device_sm_count() * 8, (n + 255) / 256);
+    if (g) em_gather_counts_kernel<<<g, 256, 0, st>>>(pp);
+  }
   void* args[] = {&pp};
   void* fn = tpb == 1024 ? (void*)em_kernel<1024> : (tpb == 512 ? (void*)em_kernel<512> : (void*)em_kernel<256>);
   cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);

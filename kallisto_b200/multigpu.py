@@ -1,4 +1,9 @@
-"""Multi-GPU plumbing for read-sharded `quant` (one process per GPU, torch.distributed).
+"""Multi-GPU exchange of equivalence-class tables over torch.distributed -- TEST TRANSPORT.
+
+The product path is the C++/NCCL merge of csrc/comm.cu (kb_quant_merge_nccl: what `kallisto_b200 quant --devices`
+and bench.py call).  This module keeps the same export -> transport -> import-by-content scheme on top of
+torch.distributed so that the exchange logic can be exercised on a CPU box over gloo (tests/test_multigpu_host.py)
+and the export / import kernels on one GPU (tests/test_gpu_multi.py).
 
 Reads shard naturally: every rank pseudoaligns its own contiguous slice of the input against a
 replicated index and ends up with its own set dictionary.  There is exactly one exchange step, at

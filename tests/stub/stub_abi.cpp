@@ -95,6 +95,7 @@ int kb_comm_create_all(const int*, int n, kb_comm** out) { for (int i = 0; i < n
 void kb_comm_free(kb_comm* c) { delete c; }
 int kb_quant_merge_nccl(kb_quant*, kb_comm*, uint64_t, uint64_t*) { return KB_OK; }
 int kb_quant_set_frag_base(kb_quant*, uint64_t) { return KB_OK; }
+int kb_quant_merge_local(kb_quant*, kb_quant* const*, int32_t, uint64_t*) { return KB_OK; }
 int kb_tcc_run(kb_index*, uint32_t, const uint64_t*, const uint32_t*, uint32_t, const uint64_t*, const uint32_t*, const uint32_t*, const double*, int32_t,
                double*, int32_t*) { return KB_OK; }
 int kb_eff_lens(const kb_index*, const uint32_t*, double, double, double*, double*, double*) { return KB_OK; }
