@@ -393,8 +393,8 @@ void start_streams(std::vector<Stream>& streams, std::vector<std::thread>& reade
                    size_t max_bases, size_t max_reads, int threads) {
   const int n_streams = (int)streams.size();
   for (int s = 0; s < n_streams; ++s) {
-    streams[s].ring.resize(4);
-    streams[s].state.assign(4, 0);
+    streams[s].ring.resize(3);      // pinned memory is slow to pin and to release: keep the rings small
+    streams[s].state.assign(3, 0);
     for (auto& b : streams[s].ring) {
       b.cap_bases = max_bases;
       b.cap_reads = max_reads;
@@ -518,7 +518,7 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
   }
   const bool paired = !opt.single_end;
-  const size_t max_reads = 1u << 19;                 // reads per batch and mate (pinned ring: 4 x 2 x ~70 MB)
+  const size_t max_reads = 1u << 19;                 // reads per batch and mate (pinned rings: 3 x 2 x ~70 MB)
   const size_t max_bases = (size_t)max_reads * 136 + kb::FastxFile::kMaxRead;
   const int n_streams = paired ? 2 : 1;
   std::vector<Stream> streams(n_streams);
@@ -620,12 +620,6 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   }
   for (auto& t : readers) t.join();
   pt.mark("read + pseudoalign loop");
-  // the pinned rings are not needed any more: un-pinning ~0.5 GB takes a few tenths of a second, so it runs on its own
-  // thread next to the merge, the EM and the writers instead of at process exit
-  struct Joiner {
-    std::thread t;
-    ~Joiner() { if (t.joinable()) t.join(); }
-  } ring_free{std::thread([&] { free_streams(streams); })};
   if (n_dev > 1) {
     // the one exchange: every device's equivalence classes copied to the root over NVLink and folded in by content
     // (all runs live in this process, so no NCCL communicator is needed; multi-process drivers use kb_quant_merge_nccl)
@@ -691,8 +685,8 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
                       bs.data() + (size_t)b * T);
   }
   cerr << endl;
-  ring_free.t.join();
   if (!getenv("KB_CLI_CLEANUP")) finish(st.n_pseudoaligned == 0 ? 1 : 0);
+  free_streams(streams);
   for (int d = 0; d < n_dev; ++d) {
     kb_quant_free(qs[d]);
     kb_index_free(ixs[d]);

@@ -55,8 +55,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& gen, unsig
   __syncthreads();
 }
 
-template <int TPB>
-__global__ void __launch_bounds__(TPB, (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4))) em_kernel(EmProblem p) {
+// OCC = 2: compiled for 2048 resident threads per SM (32 registers, 16 bytes of spill): both passes are bound by the
+// latency of dependent L2 loads, so twice the threads in flight beat the few spilled values (tools/em_sweep.py).
+template <int TPB, int OCC>
+__global__ void __launch_bounds__(TPB, OCC * (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4))) em_kernel(EmProblem p) {
   extern __shared__ int s_state[];    // per problem: 0 running, 1 final round, >= 2 finished (every block keeps its own, identical copy)
   const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
@@ -188,13 +190,23 @@ __global__ void em_gather_counts_kernel(EmProblem p) {
   }
 }
 
+namespace {
+int em_occ() {
+  if (const char* s = getenv("KB_EM_OCC")) return atoi(s) >= 2 ? 2 : 1;   // tuning knob
+  return 2;
+}
+void* em_fn(int tpb, int occ) {
+  if (occ >= 2) return tpb == 1024 ? (void*)em_kernel<1024, 2> : (tpb == 512 ? (void*)em_kernel<512, 2> : (void*)em_kernel<256, 2>);
+  return tpb == 1024 ? (void*)em_kernel<1024, 1> : (tpb == 512 ? (void*)em_kernel<512, 1> : (void*)em_kernel<256, 1>);
+}
+}  // namespace
+
 int em_max_blocks(int tpb) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (tpb >= 1024) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel<1024>, 1024, 4096);
-  else if (tpb >= 512) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel<512>, 512, 4096);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_kernel<256>, 256, 4096);
+  const int t = tpb >= 1024 ? 1024 : (tpb >= 512 ? 512 : 256);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_fn(t, em_occ()), t, 4096);
   return sms * per_sm;
 }
 
@@ -214,8 +226,7 @@ void launch_em(const EmProblem& p, int tpb_req, cudaStream_t st) {
     if (g) em_gather_counts_kernel<<<g, 256, 0, st>>>(pp);
   }
   void* args[] = {&pp};
-  void* fn = tpb == 1024 ? (void*)em_kernel<1024> : (tpb == 512 ? (void*)em_kernel<512> : (void*)em_kernel<256>);
-  cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);
+  cudaLaunchCooperativeKernel(em_fn(tpb, em_occ()), dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);
 }
 
 // ---------------------------------------------------------------------------------------------

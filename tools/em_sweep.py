@@ -29,10 +29,9 @@ def main():
         del b
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     ref = None
-    for tpb in (256, 512, 1024):
-        for bps in (1, 2, 4, 8):
-            if tpb * bps > 2048:
-                continue
+    for occ, tpb, bps in [(1, 256, 4), (1, 1024, 1), (2, 256, 4), (2, 256, 8), (2, 512, 2), (2, 512, 4), (2, 1024, 1), (2, 1024, 2)]:
+        if True:
+            os.environ["KB_EM_OCC"] = str(occ)
             os.environ["KB_EM_TPB"] = str(tpb)
             os.environ["KB_EM_BLOCKS"] = str(sms * bps)
             best = None
@@ -44,7 +43,7 @@ def main():
             if ref is None:
                 ref = r["est_counts"].copy()
             same = bool((r["est_counts"] == ref).all())
-            print(json.dumps({"tpb": tpb, "blocks_per_sm": bps, "em_ms": best[0], "rounds": best[1], "us_per_round": best[0] * 1e3 / best[1],
+            print(json.dumps({"occ": occ, "tpb": tpb, "blocks_per_sm": bps, "em_ms": best[0], "rounds": best[1], "us_per_round": best[0] * 1e3 / best[1],
                               "prep_ms": best[2], "bit_identical_to_first": same}), flush=True)
     mc.close()
     ix.close()
