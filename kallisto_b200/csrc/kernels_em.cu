@@ -55,8 +55,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& gen, unsig
   __syncthreads();
 }
 
-// OCC = 2: compiled for 2048 resident threads per SM (32 registers, 16 bytes of spill): both passes are bound by the
-// latency of dependent L2 loads, so twice the threads in flight beat the few spilled values (tools/em_sweep.py).
+// OCC = 2 (KB_EM_OCC=2, experiment): compiled for 2048 resident threads per SM (32 registers, 16 bytes of spill).
+// Measured slower than the 62-register build at every launch shape (27-36 vs 21 us per round, tools/em_sweep.py):
+// not the default.
 template <int TPB, int OCC>
 __global__ void __launch_bounds__(TPB, OCC * (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 : 4))) em_kernel(EmProblem p) {
   extern __shared__ int s_state[];    // per problem: 0 running, 1 final round, >= 2 finished (every block keeps its own, identical copy)
@@ -193,7 +194,7 @@ __global__ void em_gather_counts_kernel(EmProblem p) {
 namespace {
 int em_occ() {
   if (const char* s = getenv("KB_EM_OCC")) return atoi(s) >= 2 ? 2 : 1;   // tuning knob
-  return 2;
+  return 1;
 }
 void* em_fn(int tpb, int occ) {
   if (occ >= 2) return tpb == 1024 ? (void*)em_kernel<1024, 2> : (tpb == 512 ? (void*)em_kernel<512, 2> : (void*)em_kernel<256, 2>);
