@@ -372,7 +372,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     idx, concat, lens = workload(args.genes)
     files = None
-    if rank == 0:
+    need_files = (not os.environ.get("KB_BENCH_NO_CLI")) or (not args.no_cpu_baseline and world == 1)
+    if rank == 0 and need_files:
         files = fastq_job_files(args.genes, P, K, W, sim_factory)     # before the big allocations: uses the GPU for simulation
     t0 = time.time()
     index = K200.KmerIndex(idx, device=local_rank, threads=min(16, os.cpu_count() or 4))

@@ -341,8 +341,11 @@ class ParallelFastx {
       data_ = (const char*)m;
       madvise((void*)data_, size_, MADV_SEQUENTIAL);
     }
-    if (threads_ > 16) threads_ = 16;         // more parser threads than this only fight over memory bandwidth
-    copy_threads_ = std::max(1, std::min(4, threads_ / 2));
+    int cap = 16, copy_cap = 4;               // defaults from the round-1 measurements; KB_FASTX_CAP / KB_FASTX_COPY: experiments
+    if (const char* s = getenv("KB_FASTX_CAP")) { const int v = atoi(s); if (v > 0) cap = v; }
+    if (const char* s = getenv("KB_FASTX_COPY")) { const int v = atoi(s); if (v > 0) copy_cap = v; }
+    if (threads_ > cap) threads_ = cap;
+    copy_threads_ = std::max(1, std::min(copy_cap, threads_ / 2));
     window_ = (size_t)4 << 20;                // bytes per parser thread and window
     if (const char* s = getenv("KB_FASTX_WINDOW")) { const long long v = atoll(s); if (v > 0) window_ = (size_t)v; }   // tests
     window_ *= (size_t)threads_;
