@@ -24,7 +24,11 @@
 #define KB_MATCH_MIN_BLOCKS 4
 #endif
 #ifndef KB_LOOKAHEAD
-#define KB_LOOKAHEAD 4      // k-mers of the linear scan whose presence-filter bits are fetched together (match_kernel)
+// Experiment (off): inside a run of misses fetch the presence-filter bits of the next KB_LOOKAHEAD k-mers together.
+// Measured slower than one k-mer per iteration (2 / 4 / 8: 1.52 / 1.57 / 1.93 ms against 1.44 ms per 2 M pairs,
+// profiles/match_lookahead_r02.log): the kernel is bound by instruction issue at 12 of 32 lanes active, and the
+// extra hashes cost more than the saved iterations.
+#define KB_LOOKAHEAD 0
 #endif
 
 namespace kb {
@@ -343,7 +347,9 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
   uint32_t hu = 0, he = 0, h2u = 0, h2e = 0;
   int n_e = 0;
   bool overflow = false, need_prep = false;
+#if KB_LOOKAHEAD > 1
   bool in_run = false;      // the last MAIN lookup of this lane missed: the scan is inside a run of misses
+#endif
   // first hit of the mate being matched (findFirstMappingKmer / mapPair) and hit flags of both mates
   bool v_cur = false, s_cur = false, v_first = false, s_first = false, f_strand = false;
   uint32_t f_blk = 0, f_dist = 0;
@@ -570,6 +576,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
       bool absent = false;
       if (need_prep) {
         bool known_present = false;
+#if KB_LOOKAHEAD > 1
         if (st == S_MAIN && in_run && ix.filter && !rv.has_invalid) {
           // Look-ahead of the linear scan (MAIN: a miss just moves on to the next k-mer, KmerIndex.cpp:1750-1753).  69 % of
           // all lookups are such misses and they come in runs (31 k-mers around every sequencing error, whole unmappable
@@ -600,6 +607,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
           n_probes += (uint32_t)adv;
           absent = !known_present;
         }
+#endif
         const int pq = (st == S_JUMP) ? p2 : ((st == S_MIDDLE) ? p3 : p);
         const uint64_t fwd = rv.kmer(pq);
         const uint64_t rc = kb_revcomp(fwd, k);
@@ -634,7 +642,9 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
         bool push = false, end_mate = false, to_backoff = false;
         int nv_from = -1;      // >= 0: continue with p = next_valid(nv_from) in MAIN (or BACKOFF)
         if (st == S_MAIN) {
+#if KB_LOOKAHEAD > 1
           in_run = !f;
+#endif
           if (!f) {
             nv_from = p + 1;
           } else {

@@ -94,3 +94,20 @@ def test_long_reads_use_bigger_tiles():
     o_run = O.OracleRun(O.OracleIndex(ds["index"]), True, 0, True)
     np.testing.assert_array_equal(util.handles_to_ids(h, eh), o_run.pseudoalign(bases, off))
     mc.close(); ix.close()
+
+
+@pytest.mark.parametrize("name", ["synth_small", "manyecs"])
+def test_lookup_count_equals_the_reference_match(name):
+    """Paired reads without fragment-length sampling (no mapPair scans): the kernel must execute -- or, inside a run of
+    misses, answer from the presence filter -- exactly the k-mer lookups of KmerIndex::match, not one more or less."""
+    ds = util.dataset(name)
+    bases, off = util.batch(ds, True)
+    ix = K.KmerIndex(ds["index"], device=0)
+    mc = K.MinCollector(ix, paired=True, collect_fld=False)
+    mc.process_buffer(bases, off, want_handles=False)
+    st = mc.finalize()
+    o_run = O.OracleRun(O.OracleIndex(ds["index"]), True, 0, False)
+    o_run.pseudoalign(bases, off)
+    assert st["n_probes"] == o_run.n_find()
+    assert st["n_slot_visits"] < st["n_probes"]        # the presence filter answers part of them without touching the table
+    mc.close(); ix.close()
