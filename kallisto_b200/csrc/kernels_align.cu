@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
   unsigned inv_flags = 0;    // bit m: mate m holds a base other than A/C/G/T
   uint64_t canon = 0, slot = 0;
   bool is_canon = false;
-  uint32_t n_probes = 0, n_visits = 0, n_memo = 0;
+  uint32_t n_probes = 0, n_visits = 0, n_memo = 0;   // per-lane totals: touched once per fragment (they live in local memory)
+  uint32_t pv = 0;          // hot-loop counter of the current fragment: lookups in the low half, slot visits in the high half
   ReadView rv;
   rv.stride = nt;
   rv.k = k;
@@ -382,6 +383,9 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
     if (idle == 0xFFFFFFFFu && fin == 0 && !work_left) break;
     if (idle == 0xFFFFFFFFu || (work_left && __popc(idle) >= ba.refill_min)) {
       if (st == S_FIN) {
+        n_probes += pv & 0xFFFFu;     // a fragment executes at most a few hundred lookups
+        n_visits += pv >> 16;
+        pv = 0;
         // ---- MinCollector::intersectKmers, net effect (MinCollector.cpp:160-218) ----
         bool v0 = v_cur, s0 = s_cur, v1 = false, s1 = false;
         if (mate == 1) { v0 = v_first; s0 = s_first; v1 = v_cur; s1 = s_cur; }
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
             if (i < m && ((fw[i] >> (fi[i] & 31)) & 1u)) { adv = i; known_present = true; }
           // (the loop runs downwards, so adv ends up as the FIRST position whose bit is set)
           p += adv;
-          n_probes += (uint32_t)adv;
+          pv += (uint32_t)adv;
           absent = !known_present;
         }
 #endif
@@ -616,7 +620,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
         const uint64_t hsh = kb_mix64(canon);
         slot = hsh & ix.mask;
         need_prep = false;
-        ++n_probes;
+        ++pv;
         // presence filter (L2 resident): a clear bit means the k-mer is not in the index -- no HBM sector is touched
         if (ix.filter && !known_present && !absent) {
           const uint32_t fidx = (uint32_t)(hsh >> 32) & ix.filter_mask;
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
       uint32_t v[8];
       if (!absent) {
         ld256_probe(ix.slots + slot, v);
-        ++n_visits;
+        pv += 0x10000u;
       } else {
         v[0] = v[1] = 0xFFFFFFFFu;     // reads as an empty slot: a miss
       }
@@ -739,6 +743,8 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
     }
   }
   // statistics: probes and slot visits
+  n_probes += pv & 0xFFFFu;
+  n_visits += pv >> 16;
   for (int o = 16; o > 0; o >>= 1) {
     n_probes += __shfl_xor_sync(0xFFFFFFFFu, n_probes, o);
     n_visits += __shfl_xor_sync(0xFFFFFFFFu, n_visits, o);
