@@ -378,7 +378,6 @@ void Quant::reserve_em(size_t n_ecs, size_t nnz) {
   if (w.k64_in.n < nz) { w.k64_in.alloc(nz); w.k64_out.alloc(nz); }
   if (w.bar.n < 1) w.bar.alloc(1);
   g32(w.cnt_row, n1); gd(w.single_cnt, T);
-  g32(w.t_order, (size_t)T + 1); g32(w.t_pos, (size_t)T + 1); g32(w.t_key, (size_t)T + 1); g32(w.t_key2, (size_t)T + 1); g32(w.t_val, (size_t)T + 1);
   gd(w.m_w, nz); gd(w.t_w, nz);
   g32(w.t_deg, (size_t)T + 1); g32(w.t_off, (size_t)T + 1);
   if (w.t_single.n < T) w.t_single.alloc(T);
@@ -1104,8 +1103,6 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   if (w.t_single.n < T) w.t_single.alloc(T);
   growd(w.eff, T); growd(w.alpha, T); growd(w.norm, (size_t)n_multi + 1);
   grow32(w.cnt_row, (size_t)n_multi + 1); growd(w.single_cnt, T);
-  grow32(w.t_order, (size_t)T + 1); grow32(w.t_pos, (size_t)T + 1); grow32(w.t_key, (size_t)T + 1); grow32(w.t_key2, (size_t)T + 1);
-  grow32(w.t_val, (size_t)T + 1);
   mark("phase-2 buffers");
   KB_CK(cudaMemsetAsync(w.t_deg.p, 0, ((size_t)T + 1) * 4, st));
   launch_fill_i32(w.t_single.p, T, -1, st);
@@ -1115,7 +1112,6 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   ep.ec_tid = w.ec_tid.p; ep.multi_ec = w.multi_ec.p; ep.m_rowoff = w.m_rowoff.p; ep.m_tid = w.m_tid.p; ep.m_w = w.m_w.p;
   ep.m_row = w.m_row.p; ep.m_iota = w.m_iota.p; ep.t_deg = w.t_deg.p; ep.t_off = w.t_off.p; ep.t_midx = w.t_midx.p;
   ep.t_w = w.t_w.p; ep.t_single = w.t_single.p; ep.eff = w.eff.p; ep.k64_in = w.k64_in.p;
-  ep.t_order = w.t_order.p; ep.t_pos = w.t_pos.p; ep.t_key = w.t_key.p; ep.t_key2 = w.t_key2.p; ep.t_val = w.t_val.p;
   emprep_rows(ep, w.is_multi.p, w.ckey.p, w.cval.p, w.ckey_out.p, w.rlen.p, w.tmp.p, w.tmp.n, st);
   emprep_fill(dd_, ep, nnz, w.k64_out.p, w.sortv.p, w.tmp.p, w.tmp.n, (unsigned long long*)w.key_in.p, st);
   KB_CK(cudaGetLastError());
@@ -1131,12 +1127,11 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   p.t_off = w.t_off.p; p.t_midx = w.t_midx.p; p.t_w = w.t_w.p; p.t_single = w.t_single.p;
   p.nb = 1; p.counts = w.count.p; p.alpha = w.alpha.p; p.norm = w.norm.p;
   p.rounds = w.emi.p; p.bar = w.bar.p; p.fstate = w.emi.p + 3; p.chcount = w.chcount.p;
-  p.cnt_row = w.cnt_row.p; p.single_cnt = w.single_cnt.p; p.t_order = w.t_order.p;
+  p.cnt_row = w.cnt_row.p; p.single_cnt = w.single_cnt.p;
   p.max_iter = max_iter; p.min_rounds = min_rounds;
   mark("fill launches + uploads");
-  // collect_used, gather_used, ec_meta, multi_compact, row_len x2, window_len_key x2, ec_fill, t_pos, csc_key, csc_fill, stats,
-  // fill_i32, fill_f64, em_gather_counts + em_kernel
-  n_kernel_launches += 16 + 1;
+  // collect_used, gather_used, ec_meta, multi_compact, row_len, ec_fill, csc_fill, stats, fill_i32, fill_f64 + em_kernel
+  n_kernel_launches += 10 + 1;
   KB_CK(cudaEventRecord(e1, st));
   launch_em(p, em_tpb(), st);
   KB_CK(cudaGetLastError());
@@ -1259,7 +1254,7 @@ std::vector<int> Quant::run_bootstrap_device(const std::vector<double>& fl_trunc
     p.t_off = w.t_off.p; p.t_midx = w.t_midx.p; p.t_w = w.t_w.p; p.t_single = w.t_single.p;
     p.nb = nb; p.counts = w.bs_counts.p + (size_t)b0 * nE; p.alpha = w.bs_alpha.p; p.norm = w.bs_norm.p;
     p.rounds = w.bs_emi.p; p.fstate = w.bs_emi.p + chunk; p.bar = w.bar.p; p.chcount = w.bs_ch.p;
-    p.cnt_row = w.cnt_row.p; p.single_cnt = w.single_cnt.p; p.t_order = w.t_order.p;
+    p.cnt_row = w.cnt_row.p; p.single_cnt = w.single_cnt.p;
     p.max_iter = 10000; p.min_rounds = 50;
     launch_em(p, em_tpb(), st);
     KB_CK(cudaGetLastError());

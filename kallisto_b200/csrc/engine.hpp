@@ -60,7 +60,6 @@ struct EmWs {   // grow-only device workspace of run_em_device
   DBuf<uint32_t> minkey, ckey, cval, ckey_out, rlen;     // row order of the EM matrices (emprep_rows)
   DBuf<unsigned long long> k64_in, k64_out;              // CSC sort keys
   DBuf<unsigned> bar;                                    // grid-barrier counter of em_kernel
-  DBuf<uint32_t> t_order, t_pos, t_key, t_key2, t_val;   // pass B's processing order (windows sorted by degree)
   DBuf<uint32_t> cnt_row;                                // row-ordered counts (launch_em fills them)
   DBuf<double> single_cnt;
   // bootstrap over the same matrices (run_bootstrap_device)

@@ -119,9 +119,6 @@ struct EmProblem {
   const uint32_t* t_midx;       // nnz: index into the multi arrays (row of the EC)
   const double* t_w;            // nnz
   const int32_t* t_single;      // n_targets: EC id of the singleton EC {t}, or -1
-  // optional: pass B walks the transcripts in this order (t_off is then indexed by POSITION in it): windows of 1024
-  // consecutive ids sorted by degree, so that the 32 rows of a warp have similar lengths.  nullptr: natural order.
-  const uint32_t* t_order;
   // per problem (nb of them)
   int nb;
   const uint32_t* counts;       // nb x n_ec
@@ -175,12 +172,7 @@ struct EmPrep {
   double* m_w;
   uint32_t* m_row;         // entry -> row
   uint32_t* m_iota;        // entry -> entry (values of the CSC sort)
-  unsigned long long* k64_in;   // entry -> position of the transcript in t_order << 32 | EC id (keys of the CSC sort)
-  uint32_t* t_order;       // n_targets: processing order of pass B
-  uint32_t* t_pos;         // n_targets: inverse of t_order
-  uint32_t* t_key;         // n_targets + 1 scratch (sort keys in, then degrees in processing order)
-  uint32_t* t_key2;        // n_targets + 1 scratch (sort keys out)
-  uint32_t* t_val;         // n_targets scratch (sort values in)
+  unsigned long long* k64_in;   // entry -> tid << 32 | EC id (keys of the CSC sort)
   // CSC
   uint32_t* t_deg;         // n_targets + 1 (zeroed by the caller)
   uint32_t* t_off;         // n_targets + 1

@@ -132,17 +132,16 @@ __global__ void __launch_bounds__(TPB, OCC * (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 
       uint32_t b = 0;
       if (i < nB) {
         b = (uint32_t)(i / p.n_targets);
-        const uint32_t tt = (uint32_t)(i % p.n_targets);             // position in the processing order
-        const uint32_t t = p.t_order ? p.t_order[tt] : tt;           // the transcript (independent of the offsets below)
-        const uint32_t e0 = p.t_off[tt], e1 = p.t_off[tt + 1];
+        const uint32_t t = (uint32_t)(i % p.n_targets);
         const int st = s_state[b];
         if (st < 2) {
           double* al = p.alpha + (size_t)b * p.n_targets;
           double a = al[t];
           if (st == 1 && a < zero_below) a = 0.0;
-          double acc = p.single_cnt[(size_t)b * p.n_targets + t];                   // :119-123
+          double acc = p.single_cnt[i];                                             // :119-123
           const double* nr = p.norm + (size_t)b * p.n_multi;
           const double* tw = p.t_w + (size_t)b * p.w_stride;
+          const uint32_t e0 = p.t_off[t], e1 = p.t_off[t + 1];
           for (uint32_t j = e0; j < e1; ++j)
             acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(tw[j], a), nr[p.t_midx[j]]));   // :154-156
           changed = acc > kAlphaChangeLimit && (fabs(__dadd_rn(acc, -a)) / acc) > kAlphaChange;   // :178

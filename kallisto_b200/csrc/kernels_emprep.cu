@@ -85,34 +85,9 @@ __global__ void ec_fill_kernel(DevDict dd, EmPrep p) {
     p.m_w[mo + j] = __ddiv_rn(c, p.eff[t]);        // calc_weights: counts[ec] / eff_lens[tr]
     p.m_row[mo + j] = r;
     p.m_iota[mo + j] = mo + j;
+    p.k64_in[mo + j] = ((unsigned long long)t << 32) | e;    // CSC order: transcript, then EC id
     atomicAdd(&p.t_deg[t], 1u);
   }
-}
-
-// Length-sorted windows (SELL-C-sigma style): the 32 rows a warp walks together should have similar lengths, otherwise
-// every warp pays for its longest row; sorting by length inside windows of 1024 consecutive rows keeps the locality of
-// the global order.  Keys: window << 8 | min(length, 255).
-__global__ void window_len_key_kernel(const uint32_t* len, uint32_t n, uint32_t* key, uint32_t* val_iota) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t l = len[i];
-  key[i] = ((i >> 10) << 8) | (l > 255u ? 255u : l);
-  if (val_iota) val_iota[i] = i;
-}
-__global__ void t_pos_kernel(const uint32_t* t_order, const uint32_t* t_deg, uint32_t T, uint32_t* t_pos, uint32_t* deg_p) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > T) return;
-  if (i == T) { deg_p[i] = 0; return; }
-  const uint32_t t = t_order[i];
-  t_pos[t] = i;
-  deg_p[i] = t_deg[t];
-}
-__global__ void csc_key_kernel(EmPrep p, uint32_t nnz) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nnz) return;
-  // CSC order: position of the transcript in pass B's processing order, then EC id (a transcript's entries are
-  // accumulated in increasing EC id, EMAlgorithm.h:125-169)
-  p.k64_in[j] = ((unsigned long long)p.t_pos[p.m_tid[j]] << 32) | p.multi_ec[p.m_row[j]];
 }
 
 // EC table only (export to other ranks): one warp per EC copies its transcript ids
@@ -191,11 +166,6 @@ void emprep_rows(const EmPrep& p, const uint32_t* is_multi, uint32_t* ckey, uint
   int bits = 1;
   while ((1u << bits) < p.n_targets && bits < 32) ++bits;
   cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ckey, ckey_out, cval, p.multi_ec, (int)p.n_multi, 0, bits, st);
-  // inside windows of 1024 rows of that order: by length, so that a warp's 32 rows are alike
-  row_len_kernel<<<(p.n_multi + 1 + 255) / 256, 256, 0, st>>>(p.multi_ec, p.len, p.n_multi, rlen, p.multi_index);
-  window_len_key_kernel<<<(p.n_multi + 255) / 256, 256, 0, st>>>(rlen, p.n_multi, ckey, nullptr);
-  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ckey, ckey_out, p.multi_ec, cval, (int)p.n_multi, 0, 32, st);
-  cudaMemcpyAsync(p.multi_ec, cval, (size_t)p.n_multi * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
   row_len_kernel<<<(p.n_multi + 1 + 255) / 256, 256, 0, st>>>(p.multi_ec, p.len, p.n_multi, rlen, p.multi_index);
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, rlen, p.m_rowoff, (int)p.n_multi + 1, st);
 }
@@ -211,20 +181,13 @@ void emprep_fill(const DevDict& dd, const EmPrep& p, uint32_t nnz, unsigned long
   if (p.n_ec == 0) return;
   const uint64_t threads = (uint64_t)p.n_ec * 32;
   ec_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dd, p);
-  // processing order of pass B: windows of 1024 consecutive transcripts sorted by degree; t_off in that order
-  const uint32_t T = p.n_targets;
-  window_len_key_kernel<<<(T + 255) / 256, 256, 0, st>>>(p.t_deg, T, p.t_key, p.t_val);
-  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p.t_key, p.t_key2, p.t_val, p.t_order, (int)T, 0, 32, st);
-  t_pos_kernel<<<(T + 1 + 255) / 256, 256, 0, st>>>(p.t_order, p.t_deg, T, p.t_pos, p.t_key);
-  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, p.t_key, p.t_off, (int)T + 1, st);
-  if (nnz) csc_key_kernel<<<(nnz + 255) / 256, 256, 0, st>>>(p, nnz);
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, p.t_deg, p.t_off, (int)p.n_targets + 1, st);
   if (nnz) {
     int bits = 1;
     while ((1u << bits) < p.n_targets && bits < 32) ++bits;
     // (transcript, EC id) order: a transcript's entries are accumulated in increasing EC id (EMAlgorithm.h:125-169
     // walks the ECs in id order), whatever the row order of the matrices
     cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p.k64_in, sort_keys_out, p.m_iota, sort_vals_out, (int)nnz, 0, 32 + bits, st);
-    (void)bits;
     csc_fill_kernel<<<(nnz + 255) / 256, 256, 0, st>>>(p, sort_vals_out, nnz);
   }
   cudaMemsetAsync(stats2, 0, 16, st);
