@@ -1130,8 +1130,9 @@ EmResult Quant::run_em_device(const std::vector<double>& fl_trunc, int max_iter,
   p.cnt_row = w.cnt_row.p; p.single_cnt = w.single_cnt.p;
   p.max_iter = max_iter; p.min_rounds = min_rounds;
   mark("fill launches + uploads");
-  // collect_used, gather_used, ec_meta, multi_compact, row_len, ec_fill, csc_fill, stats, fill_i32, fill_f64 + em_kernel
-  n_kernel_launches += 10 + 1;
+  // collect_used, gather_used, ec_meta, multi_compact, row_len, ec_fill, csc_fill, stats, fill_i32, fill_f64,
+  // em_gather_counts + em_kernel
+  n_kernel_launches += 11 + 1;
   KB_CK(cudaEventRecord(e1, st));
   launch_em(p, em_tpb(), st);
   KB_CK(cudaGetLastError());
