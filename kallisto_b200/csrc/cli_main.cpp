@@ -100,7 +100,9 @@ void usage_quant() {
             << "    --device=INT              CUDA device ordinal (default: 0)" << endl
             << "    --devices=LIST            Comma-separated CUDA devices: batches of reads are dealt to all of them," << endl
             << "                              index replicated, equivalence classes merged over NCCL before the EM" << endl
-            << "    --verbose                 Print out progress information every 1M proccessed reads" << endl;
+            << "    --verbose                 Print out progress information every 1M proccessed reads" << endl << endl
+            << "Limits of this build (a run stops with an error, never with a wrong answer): reads longer than ~12.6 kb," << endl
+            << "more than 128 distinct equivalence classes hit by one fragment, more than 16.7 M targets." << endl;
 }
 
 void parse_quant(int argc, char** argv, Options& opt) {

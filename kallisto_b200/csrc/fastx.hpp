@@ -225,6 +225,7 @@ class FastxFile {
 
   bool next(ReadBatch& b) {
     int c;
+    if (stopped_) return false;
     if (last_ == 0) {
       while ((c = getc()) != -1 && c != '>' && c != '@') {}
       if (c == -1) return false;
@@ -250,6 +251,12 @@ class FastxFile {
         q += rest_of_line(nullptr, 0, &got);
         if (!got || q >= len) break;                    // EOF inside the quality string, or complete
       }
+      if (q != len) {
+        // kseq_read returns -2 (quality string of a different length); FastqSequenceReader::fetchSequences treats any
+        // negative length as the end of this file (src/ProcessReads.cpp:3178-3182): the record is dropped, the file ends
+        stopped_ = true;
+        return false;
+      }
     }
     b.off[b.n + 1] = b.off[b.n] + (uint32_t)len;
     if (len > b.max_len) b.max_len = (uint32_t)len;
@@ -264,6 +271,7 @@ class FastxFile {
   const char* cur_ = nullptr;
   size_t pos_ = 0, end_ = 0;
   bool eof_ = false;
+  bool stopped_ = false;      // a record with a quality string of the wrong length ended the file (kseq's -2)
   int last_ = 0;
 };
 
@@ -318,6 +326,12 @@ inline size_t parse_range(const char* d, size_t size, size_t pos, size_t stop, P
         q += (e > pos && d[e - 1] == '\r') ? e - pos - 1 : e - pos;
         pos = next;
         if (!got || q >= len) break;
+      }
+      if (q != len) {
+        // kseq's -2: the record is dropped and the file ends here (see FastxFile::next); reporting the end of the data as
+        // this segment's end makes the caller discard every later segment of the window and stop
+        out.bases.resize(first);
+        return size;
       }
     }
     if (out.bases.size() > 0xFFFFFFFFull) throw std::runtime_error("Error: parse window too large");

@@ -186,3 +186,26 @@ def test_crlf_multiline_quality_counts_like_kseq(tmp_path, monkeypatch):
                            capture_output=True, text=True)
         m = re.search(r"processed ([0-9,]+) reads", r.stderr)
         assert m and int(m.group(1).replace(",", "")) == 50
+
+
+def test_wrong_length_quality_ends_the_file_like_kseq(tmp_path, monkeypatch):
+    """kseq_read returns -2 for a record whose quality string has another length than its sequence, and
+    FastqSequenceReader::fetchSequences ends the file there (src/ProcessReads.cpp:3178-3182): the record and everything
+    after it are not processed."""
+    import re
+    import subprocess
+    good = "".join("@r%d\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\n%s\n" % (i, "I" * 36) for i in range(300))
+    bad = "@bad\nACGTACGTAC\n+\nIIII\n"
+    p = tmp_path / "trunc.fq"
+    p.write_bytes((good + bad + good).encode())
+    n, nb, h1 = K.fastx_summary(str(p))
+    assert n == 300 and nb == 300 * 36
+    for w in ("200", "3000", "100000"):
+        monkeypatch.setenv("KB_FASTX_WINDOW", w)
+        assert K.fastx_summary(str(p), threads=4) == (n, nb, h1)
+    if O.have_ref():
+        idx = os.path.join(util.GOLDEN, "config1", "transcripts.kidx")
+        r = subprocess.run([O.REF_BIN, "quant", "-i", idx, "-o", str(tmp_path / "o"), "--single", "-l", "200", "-s", "20", str(p)],
+                           capture_output=True, text=True)
+        m = re.search(r"processed ([0-9,]+) reads", r.stderr)
+        assert m and int(m.group(1).replace(",", "")) == 300
