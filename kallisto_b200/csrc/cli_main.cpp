@@ -511,11 +511,17 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
       vis = std::to_string(opt.device);
       opt.device = 0;
     } else {
+      std::vector<int> uniq;                     // a device may be listed twice (two runs on one GPU)
       for (size_t i = 0; i < opt.devices.size(); ++i) {
-        vis += (i ? "," : "") + std::to_string(opt.devices[i]);
-        opt.devices[i] = (int)i;
+        size_t j = 0;
+        while (j < uniq.size() && uniq[j] != opt.devices[i]) ++j;
+        if (j == uniq.size()) {
+          uniq.push_back(opt.devices[i]);
+          vis += (vis.empty() ? "" : ",") + std::to_string(opt.devices[i]);
+        }
+        opt.devices[i] = (int)j;
       }
-      opt.device = 0;
+      opt.device = opt.devices[0];
     }
     setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
   }

@@ -159,3 +159,37 @@ def test_bus_unequal_batch_cuts(tmp_path, monkeypatch):
     ref = os.path.join(d, "ref_10xv2")
     for fn in ("output.bus", "matrix.ec", "transcripts.txt"):
         assert open(out / fn, "rb").read() == open(os.path.join(ref, fn), "rb").read(), fn
+
+
+@pytest.mark.parametrize("extra", [[], ["--fr-stranded"], ["--single", "-l", "200", "-s", "20"]], ids=["paired", "fr", "single"])
+def test_quant_devices_equals_one_device(extra, tmp_path, monkeypatch):
+    """`--devices a,b,c`: batches dealt to several runs (here three runs on the one GPU of the test box), merged by content
+    through peer copies, numbered by global fragment index -- every output byte as with one run, bootstraps included, and
+    equal to the reference's files."""
+    ds = util.dataset("synth_small")
+    monkeypatch.setenv("KB_CLI_BATCH_READS", "1700")          # many small batches, so that every run gets some
+    files = [os.path.join(ds["dir"], "reads_1.fastq.gz")] + ([] if "--single" in extra else [os.path.join(ds["dir"], "reads_2.fastq.gz")])
+    outs = []
+    for tag, dv in (("one", ["--device", "0"]), ("three", ["--devices", "0,0,0"])):
+        out = tmp_path / tag
+        r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "-b", "2", "-t", "4"] + dv + extra + files)
+        assert r.returncode == 0, r.stderr
+        outs.append([open(out / f).read() for f in ("abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv")])
+        if tag == "three":
+            same_run_info(out / "run_info.json", tmp_path / "one" / "run_info.json")
+    assert outs[0] == outs[1]
+    ref = {"paired": "ref_quant_paired", "fr": "ref_quant_paired_fr", "single": "ref_quant_single"}["single" if "--single" in extra else ("fr" if extra else "paired")]
+    assert outs[0][0] == open(os.path.join(ds["dir"], ref, "abundance.tsv")).read()
+
+
+def test_quant_on_a_dlist_index(tmp_path):
+    """An index built with `kallisto index -d`: fragments that hold a distinguishing flanking k-mer are discarded."""
+    ds = util.dataset("dlist")
+    out = tmp_path / "o"
+    r = run(["quant", "-i", ds["index"], "-o", str(out), "--plaintext", "-b", "3", "--seed", "42",
+             os.path.join(ds["dir"], "reads_1.fastq.gz"), os.path.join(ds["dir"], "reads_2.fastq.gz")])
+    assert r.returncode == 0, r.stderr
+    ref = os.path.join(ds["dir"], "ref_quant_paired")
+    for fn in ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv", "bs_abundance_2.tsv"]:
+        assert open(out / fn).read() == open(os.path.join(ref, fn)).read(), fn
+    same_run_info(out / "run_info.json", os.path.join(ref, "run_info.json"))
