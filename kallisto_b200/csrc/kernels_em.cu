@@ -173,6 +173,70 @@ __global__ void __launch_bounds__(TPB, OCC * (TPB >= 1024 ? 1 : (TPB >= 512 ? 2 
   }
 }
 
+// One problem (the main EM of `quant`): the same two passes and the same stop logic without the batch dimension --
+// no 64-bit div/mod per row, no per-problem state in shared memory, 32-bit indices -- so that more threads fit an SM
+// (the round time follows the number of resident threads, tools/em_sweep.py).  Bit-identical to em_kernel with nb == 1.
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) em_single_kernel(EmProblem p) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gstride = gridDim.x * blockDim.x;
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t nA = p.n_multi, nB = p.n_targets;
+  const double zero_below = kAlphaLimit / 10.0;
+  unsigned gen = 0;
+  __shared__ unsigned s_changed;
+  if (threadIdx.x == 0) s_changed = 0;
+  int st = 0;      // 0 running, 1 final round, >= 2 finished: every thread evolves it from the same counters
+  for (int it = 0;; ++it) {
+    if (it > 0) {   // (:202-221) from the change counter of the iteration that just ran
+      const int i = it - 1;
+      const unsigned ch = __ldcg(&p.chcount[i & 1]);
+      if (st == 1) { st = 2; if (gtid == 0) p.rounds[0] = i; }
+      else if (ch == 0 && i > p.min_rounds) st = 1;
+      if (st < 2 && i + 1 == p.max_iter) {
+        if (gtid == 0) p.rounds[0] = p.max_iter;
+        st = (st == 1) ? 3 : 2;
+      }
+      if (st >= 2 && gtid == 0) p.fstate[0] = st;
+    }
+    if (st >= 2) break;
+    const bool fin = st == 1;
+    // ---------------- pass A: denominators ----------------
+    for (uint32_t r = gtid; r < nA; r += gstride) {
+      const uint32_t c = p.cnt_row[r];
+      const uint32_t e0 = p.m_off[r], e1 = p.m_off[r + 1];
+      double nrm = 0.0;
+      if (c != 0) {
+        double denom = 0.0;
+        for (uint32_t j = e0; j < e1; ++j) {
+          double a = p.alpha[p.m_tid[j]];
+          if (fin && a < zero_below) a = 0.0;
+          denom = __dadd_rn(denom, __dmul_rn(a, p.m_w[j]));
+        }
+        if (!(denom < kTolerance)) nrm = __ddiv_rn((double)c, denom);
+      }
+      p.norm[r] = nrm;
+    }
+    grid_barrier(p.bar, gen);
+    if (gtid == 0) p.chcount[(it + 1) & 1] = 0;
+    // ---------------- pass B: numerators, convergence test, alpha <- next ----------------
+    unsigned n_changed = 0;
+    for (uint32_t t = gtid; t < nB; t += gstride) {
+      double a = p.alpha[t];
+      if (fin && a < zero_below) a = 0.0;
+      double acc = p.single_cnt[t];
+      const uint32_t e0 = p.t_off[t], e1 = p.t_off[t + 1];
+      for (uint32_t j = e0; j < e1; ++j)
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(p.t_w[j], a), p.norm[p.t_midx[j]]));
+      n_changed += (acc > kAlphaChangeLimit && (fabs(__dadd_rn(acc, -a)) / acc) > kAlphaChange) ? 1u : 0u;
+      p.alpha[t] = acc;
+    }
+    for (int o = 16; o > 0; o >>= 1) n_changed += __shfl_xor_sync(0xFFFFFFFFu, n_changed, o);
+    if (lane == 0 && n_changed) atomicAdd(&s_changed, n_changed);
+    grid_barrier(p.bar, gen, &p.chcount[it & 1], &s_changed);
+  }
+}
+
 // Row-ordered copies of the counts the passes need: cnt_row[b][r] = counts[b][multi_ec[r]],
 // single_cnt[b][t] = counts[b][t_single[t]] (as a double) or 0.
 __global__ void em_gather_counts_kernel(EmProblem p) {
@@ -200,6 +264,19 @@ void* em_fn(int tpb, int occ) {
   if (occ >= 2) return tpb == 1024 ? (void*)em_kernel<1024, 2> : (tpb == 512 ? (void*)em_kernel<512, 2> : (void*)em_kernel<256, 2>);
   return tpb == 1024 ? (void*)em_kernel<1024, 1> : (tpb == 512 ? (void*)em_kernel<512, 1> : (void*)em_kernel<256, 1>);
 }
+// launch shapes of the single-problem kernel: threads per block x blocks per SM (KB_EM_SHAPE: 0..3; -1: use em_kernel)
+struct SingleShape { void* fn; int tpb; };
+SingleShape em_single_shape() {
+  int sh = 0;
+  if (const char* s = getenv("KB_EM_SHAPE")) sh = atoi(s);
+  switch (sh) {
+    case 1: return {(void*)em_single_kernel<512, 3>, 512};     // 1536 threads per SM, 42 registers
+    case 2: return {(void*)em_single_kernel<768, 2>, 768};     // 1536 threads per SM
+    case 3: return {(void*)em_single_kernel<1024, 2>, 1024};   // 2048 threads per SM, 32 registers
+    case -1: return {nullptr, 0};
+    default: return {(void*)em_single_kernel<1024, 1>, 1024};  // 1024 threads per SM
+  }
+}
 }  // namespace
 
 int em_max_blocks(int tpb) {
@@ -212,13 +289,6 @@ int em_max_blocks(int tpb) {
 }
 
 void launch_em(const EmProblem& p, int tpb_req, cudaStream_t st) {
-  const int tpb = tpb_req >= 1024 ? 1024 : (tpb_req >= 512 ? 512 : 256);
-  const int maxb = em_max_blocks(tpb);
-  const uint64_t work = (uint64_t)p.nb * (p.n_multi > p.n_targets ? p.n_multi : p.n_targets);
-  int blocks = (int)((work + tpb - 1) / tpb);
-  if (blocks > maxb) blocks = maxb;
-  if (const char* s = getenv("KB_EM_BLOCKS")) { const int v = atoi(s); if (v > 0) blocks = std::min(maxb, v); }   // tuning knob
-  if (blocks < 1) blocks = 1;
   EmProblem pp = p;
   cudaMemsetAsync(pp.bar, 0, sizeof(unsigned), st);
   {
@@ -227,6 +297,23 @@ void launch_em(const EmProblem& p, int tpb_req, cudaStream_t st) {
     if (g) em_gather_counts_kernel<<<g, 256, 0, st>>>(pp);
   }
   void* args[] = {&pp};
+  const SingleShape ss = em_single_shape();
+  if (p.nb == 1 && p.w_stride == 0 && ss.fn) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ss.fn, ss.tpb, 0);
+    int blocks = device_sm_count() * std::max(1, per_sm);
+    const uint32_t work = p.n_multi > p.n_targets ? p.n_multi : p.n_targets;
+    blocks = std::max(1, std::min<int>(blocks, (int)((work + ss.tpb - 1) / ss.tpb)));
+    cudaLaunchCooperativeKernel(ss.fn, dim3(blocks), dim3(ss.tpb), args, 0, st);
+    return;
+  }
+  const int tpb = tpb_req >= 1024 ? 1024 : (tpb_req >= 512 ? 512 : 256);
+  const int maxb = em_max_blocks(tpb);
+  const uint64_t work = (uint64_t)p.nb * (p.n_multi > p.n_targets ? p.n_multi : p.n_targets);
+  int blocks = (int)((work + tpb - 1) / tpb);
+  if (blocks > maxb) blocks = maxb;
+  if (const char* s = getenv("KB_EM_BLOCKS")) { const int v = atoi(s); if (v > 0) blocks = std::min(maxb, v); }   // tuning knob
+  if (blocks < 1) blocks = 1;
   cudaLaunchCooperativeKernel(em_fn(tpb, em_occ()), dim3(blocks), dim3(tpb), args, (size_t)pp.nb * sizeof(int), st);
 }
 

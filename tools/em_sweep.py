@@ -29,22 +29,24 @@ def main():
         del b
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     ref = None
-    for occ, tpb, bps in [(1, 256, 4), (1, 1024, 1), (2, 256, 4), (2, 256, 8), (2, 512, 2), (2, 512, 4), (2, 1024, 1), (2, 1024, 2)]:
-        if True:
-            os.environ["KB_EM_OCC"] = str(occ)
-            os.environ["KB_EM_TPB"] = str(tpb)
-            os.environ["KB_EM_BLOCKS"] = str(sms * bps)
-            best = None
-            for _ in range(2):
-                r = mc.run_em()
-                tm = mc.timings()
-                if best is None or tm["em_ms"] < best[0]:
-                    best = (tm["em_ms"], r["rounds"], tm["em_prep_ms"])
-            if ref is None:
-                ref = r["est_counts"].copy()
-            same = bool((r["est_counts"] == ref).all())
-            print(json.dumps({"occ": occ, "tpb": tpb, "blocks_per_sm": bps, "em_ms": best[0], "rounds": best[1], "us_per_round": best[0] * 1e3 / best[1],
-                              "prep_ms": best[2], "bit_identical_to_first": same}), flush=True)
+    # KB_EM_SHAPE: launch shape of the single-problem kernel (-1: the batched kernel with one problem, KB_EM_TPB x KB_EM_BLOCKS)
+    for shape, name in [(-1, "em_kernel<1024,1> (batched kernel, nb = 1)"), (0, "em_single 1024 x 1"), (1, "em_single 512 x 3"),
+                        (2, "em_single 768 x 2"), (3, "em_single 1024 x 2")]:
+        os.environ["KB_EM_SHAPE"] = str(shape)
+        os.environ["KB_EM_TPB"] = "1024"
+        os.environ.pop("KB_EM_BLOCKS", None)
+        os.environ["KB_EM_OCC"] = "1"
+        best = None
+        for _ in range(3):
+            r = mc.run_em()
+            tm = mc.timings()
+            if best is None or tm["em_ms"] < best[0]:
+                best = (tm["em_ms"], r["rounds"], tm["em_prep_ms"])
+        if ref is None:
+            ref = r["est_counts"].copy()
+        same = bool((r["est_counts"] == ref).all())
+        print(json.dumps({"shape": shape, "kernel": name, "em_ms": best[0], "rounds": best[1], "us_per_round": best[0] * 1e3 / best[1],
+                          "prep_ms": best[2], "bit_identical_to_first": same}), flush=True)
     mc.close()
     ix.close()
 
