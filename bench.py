@@ -490,7 +490,8 @@ def main():
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                 "bytes_per_pair": bytes_per_pair, "probes_per_pair": probes_per_pair,
                 "slot_visits_per_pair": visits_per_pair, "ms_per_launch": match_ms_per_launch,
-                "resolve_ms_per_launch": tm["resolve_ms"] / max(1, tm["resolve_launches"]), "em_ms": tm["em_ms"],
+                "resolve_ms_per_launch": tm["resolve_ms"] / max(1, tm["resolve_launches"]),
+                "pack_ms_per_launch": tm["pack_ms"] / max(1, tm["match_launches"]), "em_ms": tm["em_ms"],
                 "em_prep_ms": tm["em_prep_ms"], "em_rounds": em["rounds"] if em else None}
     if world == 1 and not os.environ.get("KB_BENCH_NO_RANDBENCH"):
         rs = random_sector_peak(index.info["table_slots"] * 32)

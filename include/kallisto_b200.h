@@ -107,6 +107,7 @@ typedef struct kb_kernel_timings {
   uint64_t kernel_launches;   /* launches of the library's own kernels by this run so far (pack, match, resolve,
                                  fld, EC numbering / CSR / CSC construction, EM); CUB sort/scan launches not counted */
   double bs_resample_ms, bs_em_ms;   /* last kb_bootstrap_run: multinomial resampling, batched EM (CUDA events) */
+  double pack_ms;             /* pack_kernel (+ dlist_scan_kernel with a D-list index), same launches as match_ms */
 } kb_kernel_timings;
 int kb_quant_enable_timing(kb_quant* q, int on);
 int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out);

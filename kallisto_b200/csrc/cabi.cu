@@ -192,6 +192,7 @@ int kb_quant_get_timings(kb_quant* q, kb_kernel_timings* out) {
     out->kernel_launches = q->q->n_kernel_launches;
     out->bs_resample_ms = q->q->last_bs_resample_ms;
     out->bs_em_ms = q->q->last_bs_em_ms;
+    out->pack_ms = t.pack_ms;
   });
 }
 

@@ -311,9 +311,13 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
   launch_fill_i32(mn_val_.p, mn_cap, KB_H_NOTREADY, st);
   const uint64_t tpool_cap = mn_cap * 8;
   tpool_.alloc(tpool_cap);
-  counters_.alloc(8);
+  // pool_top, tpool_top and the statistics live in separate 128-byte lines: atomics on one line are served one after
+  // the other by the L2, and resolve_kernel allocates from both pools once per fragment (with the counters side by
+  // side, and a statistics increment per fragment on the same line, those atomics were 30 % of the kernel's time)
+  counters_.alloc(48);
   {
-    unsigned long long init[8] = {ix_.n_index_tids, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long init[48] = {};
+    init[0] = ix_.n_index_tids;
     KB_CK(cudaMemcpyAsync(counters_.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     KB_CK(cudaStreamSynchronize(st));   // init is a stack array
   }
@@ -325,8 +329,8 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
   dd_.count = count_.p; dd_.first = first_.p;
   dd_.m2 = m2_.p; dd_.m2_mask = m2_cap - 1;
   dd_.mn_key = mn_key_.p; dd_.mn_val = mn_val_.p; dd_.mn_mask = mn_cap - 1;
-  dd_.tpool = tpool_.p; dd_.tpool_top = counters_.p + 1; dd_.tpool_cap = tpool_cap;
-  dd_.error = error_.p; dd_.stats = counters_.p + 2;
+  dd_.tpool = tpool_.p; dd_.tpool_top = counters_.p + 16; dd_.tpool_cap = tpool_cap;
+  dd_.error = error_.p; dd_.stats = counters_.p + 32;
 
   // batch staging
   const uint32_t max_frag = opt_.max_batch_reads;
@@ -344,11 +348,17 @@ Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(10
     const size_t lanes = (size_t)sms * (size_t)tpsm;
     if (bws_->d_spill.n < lanes * KB_SPILL) bws_->d_spill.alloc(lanes * KB_SPILL);
   }
-  // resolve-kernel scratch: 2 x max_set_len words per warp, at most ~1 GiB in total
+  // resolve-kernel scratch: 2 x max_set_len words per lane group, at most ~1 GiB in total
+  {
+    const char* e = getenv("KB_RESOLVE_G");
+    const int g = e ? atoi(e) : 32;
+    resolve_group_ = (g == 4 || g == 8 || g == 16 || g == 32) ? (uint32_t)g : 32u;
+  }
   const uint64_t stride = std::max<uint64_t>(64, 2ull * ix_.max_set_len);
   uint64_t warps = (1ull << 28) / stride;
-  warps = std::min<uint64_t>((uint64_t)device_sm_count() * 32, std::max<uint64_t>(64, warps));   // the kernel is latency-bound: fill the SMs
-  n_resolve_warps_ = (uint32_t)(warps / 4 * 4);
+  // the kernel is latency-bound: fill the SMs (32 warps each), every warp split into 32 / group lane groups
+  warps = std::min<uint64_t>((uint64_t)device_sm_count() * 32 * (32 / resolve_group_), std::max<uint64_t>(64, warps));
+  n_resolve_warps_ = (uint32_t)(warps / 16 * 16);
   if (bws_->d_scratch.n < (size_t)n_resolve_warps_ * stride) bws_->d_scratch.alloc((size_t)n_resolve_warps_ * stride);
   scratch_stride_ = (uint32_t)stride;
   // EM workspace: sized once per index for the EC tables runs on it normally end with (twice the index's own sets),
@@ -425,10 +435,12 @@ void Quant::apply_l2_window() {
 
 Quant::Timings Quant::timings() {
   KB_CK(cudaStreamSynchronize(stream_));
-  for (size_t i = 0; i + 2 < events_.size(); i += 3) {
-    float a = 0, b = 0;
-    KB_CK(cudaEventElapsedTime(&a, events_[i], events_[i + 1]));
-    KB_CK(cudaEventElapsedTime(&b, events_[i + 1], events_[i + 2]));
+  for (size_t i = 0; i + 3 < events_.size(); i += 4) {
+    float a = 0, b = 0, c = 0;
+    KB_CK(cudaEventElapsedTime(&c, events_[i], events_[i + 1]));
+    KB_CK(cudaEventElapsedTime(&a, events_[i + 1], events_[i + 2]));
+    KB_CK(cudaEventElapsedTime(&b, events_[i + 2], events_[i + 3]));
+    tacc_.pack_ms += c;
     tacc_.match_ms += a;
     tacc_.resolve_ms += b;
     ++tacc_.match_launches;
@@ -488,6 +500,8 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.pstride = (3 * ba.nb + 7) & ~7u;
   {
     const size_t need = (size_t)n_reads * ba.pstride;
+    if ((uint64_t)n_reads * ba.nb >= (1ull << 32))      // pack_kernel / dlist_scan_kernel index (read, word) with 32 bits
+      throw Error("kallisto_b200: batch too large for its longest read (reads x ceil(max length / 32) must be < 2^32)");
     if (bws_->d_packed.n < need) bws_->d_packed.alloc(std::max(need, (size_t)opt_.max_batch_reads * 2 * 16));
   }
   ba.packed = bws_->d_packed.p;
@@ -511,6 +525,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ra.scratch = bws_->d_scratch.p;
   ra.scratch_stride = scratch_stride_;
   ra.n_warps = n_resolve_warps_;
+  ra.group = resolve_group_;
 
   int tpb = opt_.threads_per_block;
   const size_t per_thread = (size_t)4 * (KB_MAX_E + 3 + 4 * ba.nb);   // match_kernel's shared memory per lane
@@ -519,8 +534,8 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   cudaEvent_t* ev = nullptr;
   if (timing_) {
     const size_t base = events_.size();
-    events_.resize(base + 3);
-    for (int i = 0; i < 3; ++i) KB_CK(cudaEventCreate(&events_[base + i]));
+    events_.resize(base + 4);
+    for (int i = 0; i < 4; ++i) KB_CK(cudaEventCreate(&events_[base + i]));
     ev = events_.data() + base;
   }
   launch_pseudoalign(ix_.dev, dd_, ba, ra, tpb, stream_, ev);

@@ -231,7 +231,7 @@ class Quant {
   // Run on a caller-provided stream (e.g. the framework's current stream) instead of the run's own.
   void set_stream(cudaStream_t st);
   // Per-kernel device time, measured with CUDA events on the launching stream.
-  struct Timings { double match_ms = 0, resolve_ms = 0; uint64_t match_launches = 0, resolve_launches = 0; };
+  struct Timings { double match_ms = 0, resolve_ms = 0, pack_ms = 0; uint64_t match_launches = 0, resolve_launches = 0; };
   void enable_timing(bool on) { timing_ = on; }
   Timings timings();
 
@@ -263,7 +263,7 @@ class Quant {
   // run state on the device
   DBuf<uint32_t> pool_;
   DBuf<Memo2Entry> m2_;
-  DBuf<unsigned long long> dslots_, first_, mn_key_, counters_;   // counters_: pool_top, tpool_top, stats[4]
+  DBuf<unsigned long long> dslots_, first_, mn_key_, counters_;   // counters_: pool_top, tpool_top, stats[4], one 128-byte line each
   DBuf<uint32_t> count_, tpool_;
   DBuf<int32_t> mn_val_;
   DBuf<int> error_;
@@ -273,7 +273,7 @@ class Quant {
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t ev_copied_[2] = {nullptr, nullptr}, ev_done_[2] = {nullptr, nullptr};
   int stage_idx_ = 0;
-  uint32_t n_resolve_warps_ = 0, scratch_stride_ = 0;
+  uint32_t n_resolve_warps_ = 0, scratch_stride_ = 0, resolve_group_ = 32;
   uint32_t* h_off_pinned_ = nullptr;
   // host-side run state
   uint64_t n_frag_total_ = 0;

@@ -70,9 +70,10 @@ static constexpr int KB_QBIG_STRIDE = 2 + KB_MAX_E + KB_SPILL + 6;
 static constexpr uint32_t KB_QBIG_CAP = 1u << 16;      // wide-queue entries per batch
 
 struct ResolveArgs {
-  uint32_t* scratch;        // per warp: scratch_stride entries
+  uint32_t* scratch;        // per lane group: scratch_stride entries
   uint32_t scratch_stride;
-  uint32_t n_warps;
+  uint32_t n_warps;         // number of lane groups (one fragment each at a time)
+  uint32_t group;           // lanes per group: 32, 16, 8 or 4
 };
 
 void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t st);

@@ -185,63 +185,72 @@ enum : int {
 
 // ---------------------------------------------------------------------------------------------
 // pack_kernel: ASCII reads -> 2-bit bases + invalid-base masks, one thread per (read, 32-base word).
-// Streaming and fully convergent: aligned 32-bit loads (whatever the byte offset of the read), 4
-// bases at a time with SWAR arithmetic
-//   code  = ((c >> 1) & 3) ^ (((c >> 1) & 3) >> 1)          == Kmer::set_kmer (Kmer.cpp:92-107) on A/C/G/T
-//   valid = (c & 0xDF) in {A,C,G,T}                          == isDNA(c & 0xDF)  (KmerIterator.cpp:12-14)
+// Streaming and convergent: nine aligned 32-bit loads per thread (whatever the byte offset of the read; never past
+// the word that holds the read's last base), then 4 bases at a time with SWAR arithmetic
+//   idx   = (c >> 1) & 3                      A 0, C 1, T 2, G 3
+//   code  = idx ^ (idx >> 1)                  == Kmer::set_kmer (Kmer.cpp:92-107) on A/C/G/T
+//   valid = (c & 0xDF) == "ACTG"[idx]         == isDNA(c & 0xDF)  (KmerIterator.cpp:12-14); the four expected letters
+//                                             of a group come from ONE byte permute of the constant "ACTG" with the
+//                                             indices as selector, so a group costs 13 instructions; the per-base mask
+//                                             is only assembled for words that hold a non-ACGT letter or the read's end
 // Packed read = nb 64-bit base words, then nb 32-bit invalid masks, padded (with "invalid") to a
-// multiple of 32 bytes.
+// multiple of 32 bytes.  Bases past the end of the read are packed as A and marked invalid.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_kernel(BatchArgs ba, uint32_t n_reads, uint32_t* out) {
-  const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;     // launch_pseudoalign: n_reads * nb < 2^32
   const uint32_t nb = ba.nb;
-  const uint64_t total = (uint64_t)n_reads * nb;
-  if (gid >= total) return;
-  const uint32_t r = (uint32_t)(gid / nb), w = (uint32_t)(gid % nb);
+  if (gid >= n_reads * nb) return;
+  const uint32_t r = gid / nb, w = gid - r * nb;
   uint64_t off;
   int len;
   const uint8_t* src_bases;
   read_span(ba, r, src_bases, off, len);
   const int base = (int)w * 32;
-  uint64_t bwv = 0;
-  uint32_t inv32 = ~0u;
+  uint32_t hi = 0, lo = 0, inv32 = ~0u;
   if (base < len) {
     const int n = min(32, len - base);
     const uint64_t a = off + (uint64_t)base;
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(src_bases + (a & ~3ull));
     const int sh = (int)(a & 3) * 8;
-    const int ng = (n + 3) >> 2;
-    uint32_t cur = __ldg(wp);
-    inv32 = 0;
+    const int last = ((int)(a & 3) + n - 1) >> 2;       // index of the aligned word holding base n-1
+    uint32_t wd[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) wd[q] = __ldg(wp + min(q, last));
+    uint32_t d[8], pr[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      if (q < ng) {
-        int m = n - 4 * q;
-        m = m > 4 ? 4 : m;
-        uint32_t nxt = 0;
-        if (((int)(a & 3) + m > 4) || (q + 1 < ng)) nxt = __ldg(wp + q + 1);
-        const uint32_t four = sh ? __funnelshift_r(cur, nxt, sh) : cur;
-        cur = nxt;
-        uint32_t x = (four >> 1) & 0x03030303u;
-        x ^= (x >> 1) & 0x01010101u;
-        const uint32_t code8 = (x * 0x40100401u) >> 24;                     // b0<<6 | b1<<4 | b2<<2 | b3
-        const uint32_t u = four & 0xDFDFDFDFu;
-        uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) |
-                      __vcmpeq4(u, 0x54545454u);
-        if (m < 4) ok &= 0xFFFFFFFFu >> (8 * (4 - m));
-        const uint32_t inv4 = (((~ok) & 0x01010101u) * 0x01020408u) >> 24;   // bit j = base j invalid
-        bwv |= (uint64_t)code8 << (56 - 8 * q);
-        inv32 |= inv4 << (4 * q);
-      } else {
-        inv32 |= 0xFu << (4 * q);
+      const uint32_t four = __funnelshift_r(wd[q], wd[q + 1], sh);
+      uint32_t x = (four >> 1) & 0x03030303u;
+      const uint32_t y = (x | (x >> 4)) & 0x00330033u;                  // index nibbles of bytes 0,1 and of bytes 2,3
+      d[q] = (four & 0xDFDFDFDFu) ^ __byte_perm(0x47544341u, 0u, y | (y >> 8));   // 0 where the letter is the expected one
+      x ^= (x >> 1) & 0x01010101u;
+      pr[q] = x * 0x40100401u;                                          // byte 3 = b0<<6 | b1<<4 | b2<<2 | b3
+    }
+    hi = __byte_perm(__byte_perm(pr[3], pr[2], 0x0073u), __byte_perm(pr[1], pr[0], 0x0073u), 0x5410u);
+    lo = __byte_perm(__byte_perm(pr[7], pr[6], 0x0073u), __byte_perm(pr[5], pr[4], 0x0073u), 0x5410u);
+    const bool full = (n == 32);
+    uint32_t any = full ? (d[0] | d[1] | d[2] | d[3] | d[4] | d[5] | d[6] | d[7]) : 1u;
+    inv32 = 0;
+    if (any) {
+      const int ng = (n + 3) >> 2;    // a warp whose only lanes here are read ends (4 bases of a 100-base read) leaves after one group
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q >= ng) break;
+        uint32_t t = (d[q] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+        t = (t | d[q]) & 0x80808080u;                                   // bit 7 of a byte = letter differs
+        inv32 |= (((t >> 7) * 0x01020408u) >> 24) << (4 * q);           // bit j = base j invalid
       }
+    }
+    if (!full) {                      // n in [1, 31]: bases n.. are not part of the read
+      inv32 |= ~0u << n;
+      if (n > 16) lo &= ~0u << (64 - 2 * n);
+      else { lo = 0; if (n < 16) hi &= ~0u << (32 - 2 * n); }
     }
   }
   uint32_t* dst = out + (size_t)r * ba.pstride;
-  reinterpret_cast<uint2*>(dst)[w] = make_uint2((uint32_t)bwv, (uint32_t)(bwv >> 32));
+  reinterpret_cast<uint2*>(dst)[w] = make_uint2(lo, hi);
   dst[2 * nb + w] = inv32;
-  if (w == 0)
-    for (uint32_t j = 3 * nb; j < ba.pstride; ++j) dst[j] = ~0u;   // padding reads as "invalid"
+  for (uint32_t j = 3 * nb + w; j < ba.pstride; j += nb) dst[j] = ~0u;   // padding reads as "invalid"
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -770,13 +779,23 @@ __device__ __forceinline__ bool bsearch_contains(const uint32_t* s, uint32_t n, 
   return lo < n && __ldcg(s + lo) == v;
 }
 
-// Warp-cooperative lookup-or-insert of a sorted transcript-id list in the content-addressed set
+// Lane groups: G consecutive lanes of a warp (G = 32, 16, 8 or 4) work on one item; the groups of a warp are
+// independent of each other (every collective below names only the group's lanes).
+template <int G>
+__device__ __forceinline__ unsigned group_mask(unsigned lane_in_warp) {
+  return G == 32 ? 0xFFFFFFFFu : (((1u << (G & 31)) - 1u) << (lane_in_warp & ~(unsigned)(G - 1)));
+}
+
+// Group-cooperative lookup-or-insert of a sorted transcript-id list in the content-addressed set
 // dictionary (ecmapinv semantics: equal sets share one handle).  `src` may be shared or global memory
-// readable by all lanes.  Returns the handle, or KB_H_UNMAPPED after flagging an error.
-__device__ __forceinline__ int32_t dict_insert_warp(const DevDict& dd, const uint32_t* src, uint32_t nres, unsigned lane) {
+// readable by all lanes of the group; `lane` is the lane's index inside its group, `gmask` the group's lanes.
+// Returns the handle, or KB_H_UNMAPPED after flagging an error.
+template <int G = 32>
+__device__ __forceinline__ int32_t dict_insert_warp(const DevDict& dd, const uint32_t* src, uint32_t nres, unsigned lane,
+                                                    unsigned gmask = 0xFFFFFFFFu) {
   uint64_t sum = 0;
-  for (uint32_t i = lane; i < nres; i += 32) sum += kb_mix64((uint64_t)src[i] + 0x9E3779B97F4A7C15ULL);
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  for (uint32_t i = lane; i < nres; i += G) sum += kb_mix64((uint64_t)src[i] + 0x9E3779B97F4A7C15ULL);
+  for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(gmask, sum, o);
   const uint64_t hsh = kb_mix64(sum ^ nres);
   const unsigned long long tag = hsh >> 56;
   uint64_t s = hsh & dd.dmask;
@@ -785,32 +804,32 @@ __device__ __forceinline__ int32_t dict_insert_warp(const DevDict& dd, const uin
   for (;;) {
     unsigned long long word = 0;
     if (lane == 0) word = ld_acquire_u64(&dd.dslots[s]);
-    word = __shfl_sync(0xFFFFFFFFu, word, 0);
+    word = __shfl_sync(gmask, word, 0, G);
     if (word == ~0ULL) {
       if (my_word == ~0ULL) {
         unsigned long long off = 0;
         if (lane == 0) off = atomicAdd(dd.pool_top, (unsigned long long)nres);
-        off = __shfl_sync(0xFFFFFFFFu, off, 0);
+        off = __shfl_sync(gmask, off, 0, G);
         if (off + nres > dd.pool_cap || off + nres > 0xFFFFFFFFULL) {
           if (lane == 0) atomicOr(dd.error, KB_DEVERR_POOL_FULL);
           return KB_H_UNMAPPED;
         }
-        for (uint32_t i = lane; i < nres; i += 32) dd.pool[off + i] = src[i];
+        for (uint32_t i = lane; i < nres; i += G) dd.pool[off + i] = src[i];
         __threadfence();
-        __syncwarp();
+        __syncwarp(gmask);
         my_word = off | ((unsigned long long)nres << 32) | (tag << 56);
       }
       unsigned long long old = 0;
       if (lane == 0) old = atomicCAS(&dd.dslots[s], ~0ULL, my_word);
-      old = __shfl_sync(0xFFFFFFFFu, old, 0);
+      old = __shfl_sync(gmask, old, 0, G);
       if (old == ~0ULL) return (int32_t)s;
       word = old;   // somebody else took the slot: compare against theirs
     }
     if ((word >> 56) == tag && ((word >> 32) & 0xFFFFFFu) == nres) {
       const uint32_t* S = dd.pool + (uint32_t)word;
       bool eq = true;
-      for (uint32_t i = lane; i < nres; i += 32) eq = eq && (__ldcg(S + i) == src[i]);
-      if (__all_sync(0xFFFFFFFFu, eq)) return (int32_t)s;
+      for (uint32_t i = lane; i < nres; i += G) eq = eq && (__ldcg(S + i) == src[i]);
+      if (__all_sync(gmask, eq)) return (int32_t)s;
     }
     s = (s + 1) & dd.dmask;
     if (++visited > dd.dmask) {
@@ -822,10 +841,16 @@ __device__ __forceinline__ int32_t dict_insert_warp(const DevDict& dd, const uin
 
 }  // namespace
 
-// One warp per queued fragment.
+// One group of G lanes per queued fragment (ra.n_warps counts groups).  The kernel is a chain of dependent memory
+// accesses per fragment (queue entry -> memo -> set descriptors -> set elements -> binary searches -> dictionary ->
+// memo), so what sets its speed is the number of fragments in flight: the sets are short (2.5 ids on average), 8
+// lanes hold them, and a warp then carries four fragments instead of one.
+template <int G>
 __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd, BatchArgs ba, ResolveArgs ra) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & (G - 1);                          // lane inside its group
+  const unsigned gmask = group_mask<G>(threadIdx.x & 31);
+  const unsigned gshift = (threadIdx.x & 31) & ~(unsigned)(G - 1);      // the group's first lane of the warp
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / G;    // group index
   if (warp >= ra.n_warps) return;
   uint32_t* scratch = ra.scratch + (size_t)warp * ra.scratch_stride;
   const uint32_t* pool = dd.pool;
@@ -835,6 +860,7 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
   const uint32_t nq = pass == 0 ? *ba.q_count : min(*ba.qbig_count, ba.qbig_cap);
   const uint32_t* entries = pass == 0 ? ba.q_entries : ba.qbig_entries;
   const size_t stride = pass == 0 ? (size_t)KB_Q_STRIDE : (size_t)KB_QBIG_STRIDE;
+  if (warp == 0 && lane == 0 && nq) atomicAdd(&dd.stats[1], (unsigned long long)nq);   // fragments finished here
   for (uint32_t q = warp; q < nq; q += ra.n_warps) {
     const uint32_t* e = entries + (size_t)q * stride;
     const uint32_t f = e[0];
@@ -849,7 +875,7 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
     // 1. has somebody else resolved the same tuple in the meantime?
     int32_t handle = KB_H_NOTREADY;
     if (lane == 0 && !no_memo) handle = use_m2 ? memo2_lookup(dd, w[0], w[1]) : memon_lookup(dd, w, n, 1);
-    handle = __shfl_sync(0xFFFFFFFFu, handle, 0);
+    handle = __shfl_sync(gmask, handle, 0, G);
 
     if (handle == KB_H_NOTREADY) {
       // 2. intersection of the n_e sets: lanes own elements of the smallest one
@@ -862,7 +888,7 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
       }
       const uint32_t* A = pool + (uint32_t)dd.dslots[w[sm]];
       uint32_t nres = 0;
-      for (uint32_t base = 0; base < sm_len; base += 32) {
+      for (uint32_t base = 0; base < sm_len; base += G) {
         const uint32_t i = base + lane;
         bool alive = i < sm_len;
         const uint32_t a = alive ? __ldcg(A + i) : 0;
@@ -873,11 +899,11 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
           const uint32_t blen = (uint32_t)((bw_ >> 32) & 0xFFFFFFu);
           if (alive) alive = bsearch_contains(B, blen, a, nullptr);
         }
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
+        const unsigned bal = (__ballot_sync(gmask, alive) >> gshift);
         if (alive) scratch[nres + __popc(bal & ((1u << lane) - 1))] = a;
         nres += __popc(bal);
       }
-      __syncwarp();
+      __syncwarp(gmask);
       // 2b. fragment-position filter (ProcessReads.cpp:1095-1136 with KmerIndex::findPosition,
       //     KmerIndex.cpp:2188-2292): keep the transcripts the fragment fits into
       if (has_fp && nres > 0) {
@@ -891,7 +917,7 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
         const uint32_t blen = (uint32_t)((bword >> 32) & 0xFFFFFFu);
         const uint4* info = ix.fp_info + ix.blk_strand_off[blk];
         uint32_t n_v = 0;
-        for (uint32_t base = 0; base < nres; base += 32) {
+        for (uint32_t base = 0; base < nres; base += G) {
           const uint32_t i = base + lane;
           bool keep = false;
           const uint32_t tr = i < nres ? scratch[i] : 0;
@@ -914,16 +940,16 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
               keep = (s && xi + (int)fl <= (int)ix.target_len[tr]) || (!s && xi - (int)fl >= 0);
             }
           }
-          const unsigned bv = __ballot_sync(0xFFFFFFFFu, keep);
+          const unsigned bv = (__ballot_sync(gmask, keep) >> gshift);
           if (keep) scratch[ra.scratch_stride / 2 + n_v + __popc(bv & ((1u << lane) - 1))] = tr;
           n_v += __popc(bv);
         }
-        __syncwarp();
+        __syncwarp(gmask);
         if (n_v < nres) {
-          for (uint32_t i = lane; i < n_v; i += 32) scratch[i] = scratch[ra.scratch_stride / 2 + i];
+          for (uint32_t i = lane; i < n_v; i += G) scratch[i] = scratch[ra.scratch_stride / 2 + i];
           nres = n_v;
         }
-        __syncwarp();
+        __syncwarp(gmask);
       }
       // 3. doStrandSpecificity (ProcessReads.cpp:61-124), first mate then second mate
       if (stranded) {
@@ -943,7 +969,7 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
           uint32_t n_u = 0, n_v = 0;
           // two passes over scratch, compacting in place: first u &= ec (keeping a flag per kept
           // element in the top of the scratch area is avoided by recomputing the predicate)
-          for (uint32_t base = 0; base < nres; base += 32) {
+          for (uint32_t base = 0; base < nres; base += G) {
             const uint32_t i = base + lane;
             bool in_u = i < nres;
             const uint32_t a = in_u ? scratch[i] : 0;
@@ -954,27 +980,27 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
               const uint8_t sense = sb[rank];
               in_v = ((um_strand == (sense != 0)) == want) || sense == 2;
             }
-            const unsigned bu = __ballot_sync(0xFFFFFFFFu, in_u);
-            const unsigned bv = __ballot_sync(0xFFFFFFFFu, in_v);
-            __syncwarp();
+            const unsigned bu = (__ballot_sync(gmask, in_u) >> gshift);
+            const unsigned bv = (__ballot_sync(gmask, in_v) >> gshift);
+            __syncwarp(gmask);
             // u goes to the front of scratch (in place: n_u <= base), v to the second half
             if (in_u) scratch[n_u + __popc(bu & ((1u << lane) - 1))] = a;
             if (in_v) scratch[ra.scratch_stride / 2 + n_v + __popc(bv & ((1u << lane) - 1))] = a;
             n_u += __popc(bu);
             n_v += __popc(bv);
-            __syncwarp();
+            __syncwarp(gmask);
           }
           if (n_v < n_u) {
-            for (uint32_t i = lane; i < n_v; i += 32) scratch[i] = scratch[ra.scratch_stride / 2 + i];
+            for (uint32_t i = lane; i < n_v; i += G) scratch[i] = scratch[ra.scratch_stride / 2 + i];
             nres = n_v;
           } else {
             nres = n_u;
           }
-          __syncwarp();
+          __syncwarp(gmask);
         }
       }
       // 4. set -> handle through the content-addressed dictionary
-      handle = nres == 0 ? KB_H_UNMAPPED : dict_insert_warp(dd, scratch, nres, lane);
+      handle = nres == 0 ? KB_H_UNMAPPED : dict_insert_warp<G>(dd, scratch, nres, lane, gmask);
       // 5. publish tuple -> handle (not for position-filtered fragments: the result depends on the read)
       if (lane == 0 && !no_memo) {
         if (use_m2) {
@@ -1024,9 +1050,8 @@ __global__ void __launch_bounds__(128, 8) resolve_kernel(DevIndex ix, DevDict dd
         atomicAdd(&dd.count[handle], 1u);
         atomicMin(&dd.first[handle], (unsigned long long)(ba.frag_base + f));
       }
-      atomicAdd(&dd.stats[1], 1ULL);
     }
-    __syncwarp();
+    __syncwarp(gmask);
   }
   }
 }
@@ -1064,17 +1089,23 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
   unsigned blocks = (unsigned)(sms * per_sm);
   const unsigned need = (ba.n_frag + tpb - 1) / tpb;   // never more lanes than fragments
   if (blocks > need) blocks = need;
+  if (ev) cudaEventRecord(ev[0], st);
   {
     const uint32_t n_reads = ba.paired ? 2 * ba.n_frag : ba.n_frag;
-    const uint64_t total = (uint64_t)n_reads * ba.nb;
+    const uint64_t total = (uint64_t)n_reads * ba.nb;     // < 2^32: engine.cu bounds a batch by 2^31 bases
     pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ba, n_reads, const_cast<uint32_t*>(ba.packed));
     if (ix.dfk && ba.skip_w) dlist_scan_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ix, ba, n_reads);
   }
-  if (ev) cudaEventRecord(ev[0], st);
-  match_kernel<<<blocks, tpb, smem, st>>>(ix, dd, ba);
   if (ev) cudaEventRecord(ev[1], st);
-  resolve_kernel<<<(ra.n_warps * 32 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra);
+  match_kernel<<<blocks, tpb, smem, st>>>(ix, dd, ba);
   if (ev) cudaEventRecord(ev[2], st);
+  switch (ra.group) {      // lanes per fragment (engine.cu: KB_RESOLVE_G, default 8)
+    case 4: resolve_kernel<4><<<(ra.n_warps * 4 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra); break;
+    case 8: resolve_kernel<8><<<(ra.n_warps * 8 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra); break;
+    case 16: resolve_kernel<16><<<(ra.n_warps * 16 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra); break;
+    default: resolve_kernel<32><<<(ra.n_warps * 32 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra); break;
+  }
+  if (ev) cudaEventRecord(ev[3], st);
 }
 
 // Multi-GPU merge: equivalence classes exported by another rank (CSR of transcript ids, counts, first

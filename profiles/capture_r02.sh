@@ -10,6 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-fi
 # 2. one full capture of the hot kernels in steady state.  bench.py --steps 3 --warmup 3 launches, of the kernels named
 #    below: 3 warm-up steps x (pack, match, resolve) + the warm-up EM = 10, the untimed job 3 x 3 + EM = 10, then the
 #    first timed job; its third step is launches 26-28 and its EM launch 29.
-ncu --set full --clock-control none --import-source on -k regex:"pack_kernel|match_kernel|resolve_kernel|em_kernel" -s 26 -c 4 \
+ncu --set full --clock-control none --import-source on -k regex:"pack_kernel|match_kernel|resolve_kernel|em_kernel|em_single_kernel" -s 26 -c 4 \
     -f -o $out/prof_$tag python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $out/ncu_$tag.log 2>&1
 tail -3 $out/ncu_$tag.log

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """match_kernel A/B on the benchmark workload: presence-filter size (KB_FILTER_LOG2; 32 = off), table load factor
-(KB_TABLE_FACTOR) and persisting-L2 carve-out (KB_L2_PERSIST_MB).  One JSON line per configuration: ms per launch of
+(KB_TABLE_FACTOR), persisting-L2 carve-out (KB_L2_PERSIST_MB) and lanes per fragment of resolve_kernel (KB_RESOLVE_G).  One JSON line per configuration: ms per launch of
 2 M pairs, slot visits per pair (HBM sectors), probes per pair, and a digest of the EC counts (must not change)."""
 import hashlib
 import json
@@ -28,7 +28,7 @@ def main():
     if len(sys.argv) > 1:
         configs = [json.loads(a) for a in sys.argv[1:]]
     for cfg in configs:
-        for k in ("KB_FILTER_LOG2", "KB_L2_PERSIST_MB", "KB_TABLE_FACTOR"):
+        for k in ("KB_FILTER_LOG2", "KB_L2_PERSIST_MB", "KB_TABLE_FACTOR", "KB_RESOLVE_G"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         ix = K.KmerIndex(idx, device=0, threads=16)
@@ -45,7 +45,7 @@ def main():
             mc.close()
             ms = tm["match_ms"] / tm["match_launches"]
             if best is None or ms < best["match_ms_per_launch"]:
-                best = {"match_ms_per_launch": ms, "resolve_ms_per_launch": tm["resolve_ms"] / tm["resolve_launches"],
+                best = {"pack_ms_per_launch": tm["pack_ms"] / tm["match_launches"], "match_ms_per_launch": ms, "resolve_ms_per_launch": tm["resolve_ms"] / tm["resolve_launches"],
                         "slot_visits_per_pair": st["n_slot_visits"] / (steps * P), "probes_per_pair": st["n_probes"] / (steps * P),
                         "ec_digest": dig, "table_slots": ix.info["table_slots"]}
         print(json.dumps({**cfg, **best}), flush=True)
