@@ -208,13 +208,18 @@ int kb_eff_lens(const kb_index* ix, const uint32_t* flens, double fld_mean, doub
 typedef struct kb_bus_substr { int32_t fileno, start, stop; } kb_bus_substr;   /* BUSOptionSubstr, src/common.h:29-36 */
 typedef struct kb_bus_opts {
   int32_t nfiles;                 /* files per read set (technology), <= 4 */
-  int32_t n_bc;  kb_bus_substr bc[4];    /* n_bc == 0: no barcode (fake barcode of 16 A) */
-  int32_t n_umi; kb_bus_substr umi[4];
+  int32_t n_bc;  kb_bus_substr bc[4];    /* n_bc == 0: no barcode (fake barcode of 16 A, or the sample of kb_bus_begin_sample) */
+  int32_t n_umi; kb_bus_substr umi[4];   /* n_umi == 1 and umi[0].fileno == -1: no UMI ("bulk_like", src/ProcessReads.cpp:1393):
+                                          * the records carry UMI = ~0 */
   kb_bus_substr seq;              /* the read that is pseudoaligned; stop must be 0 (to the end of the read) */
   int32_t strand_mode;            /* 0 unstranded, 1 --fr-stranded (default of the 10x technologies), 2 --rf-stranded */
   int32_t num;                    /* --num: flags = read number */
   uint32_t max_batch_sets;        /* 0 = default */
   uint64_t max_batch_bases;
+  int32_t paired;                 /* busopt.paired (src/main.cpp:1366-1395,1424-1426; `bus -x BULK --paired`): seq and seq2 are
+                                   * pseudoaligned as a pair (match x 2 + intersectKmers + mapPair, :1646-1650,1747-1756);
+                                   * the fragment-length histogram is read with kb_quant_get_flens */
+  kb_bus_substr seq2;             /* second sequence read when paired; stop must be 0 */
 } kb_bus_opts;
 typedef struct kb_bus_record {    /* BUSData, src/BUSData.h:30-38: 32 bytes, as written to output.bus */
   uint64_t barcode, umi;
@@ -232,6 +237,12 @@ int kb_bus_batch(kb_quant* q, const char* const* bases, const uint32_t* const* o
  * sequence file in the batch. */
 int kb_bus_batch_device(kb_quant* q, const void* const* d_bases, const uint32_t* const* d_offsets, uint32_t n_sets,
                         uint32_t max_seq_len, uint32_t* n_records_out, const kb_bus_record** d_records_out);
+/* Batch mode (`kallisto bus -x BULK`: one sample per file set, src/ProcessReads.cpp:371-404): the read sets of the
+ * following batches belong to the sample whose fake barcode is `barcode` (BUSProcessor writes
+ * binaryToString(batch_id_mapping[id], 16), :1603-1607); the fragment-length sampling restarts from an empty histogram
+ * (batchFlens[id] / tlencounts[id], :486-493) -- read the finished sample's with kb_quant_get_flens first.  Needs a
+ * technology without a barcode read (n_bc == 0). */
+int kb_bus_begin_sample(kb_quant* q, uint64_t barcode);
 /* Observed barcode / UMI length histograms (33 bins), for the header of output.bus
  * (src/main.cpp:2470-2508). */
 int kb_bus_lengths(kb_quant* q, uint32_t* bc_hist, uint32_t* umi_hist);

@@ -52,7 +52,8 @@ class kb_bus_substr(C.Structure):
 class kb_bus_opts(C.Structure):
     _fields_ = [("nfiles", C.c_int32), ("n_bc", C.c_int32), ("bc", kb_bus_substr * 4), ("n_umi", C.c_int32),
                 ("umi", kb_bus_substr * 4), ("seq", kb_bus_substr), ("strand_mode", C.c_int32), ("num", C.c_int32),
-                ("max_batch_sets", C.c_uint32), ("max_batch_bases", C.c_uint64)]
+                ("max_batch_sets", C.c_uint32), ("max_batch_bases", C.c_uint64), ("paired", C.c_int32),
+                ("seq2", kb_bus_substr)]
 
 
 BUS_RECORD_DTYPE = np.dtype([("barcode", "<u8"), ("umi", "<u8"), ("ec", "<i4"), ("count", "<u4"), ("flags", "<u4"),
@@ -73,6 +74,13 @@ TECHNOLOGIES = {
     "CELSEQ2": (2, [(0, 6, 12)], [(0, 0, 6)], (1, 0, 0), 1),
     "SPLIT-SEQ": (2, [(1, 10, 18), (1, 48, 56), (1, 78, 86)], [(1, 0, 10)], (0, 0, 0), 1),
     "SCRBSEQ": (2, [(0, 0, 6)], [(0, 6, 16)], (1, 0, 0), 0),
+    # technologies without a UMI read ("bulk_like") and / or with two sequence reads (busopt.paired); a sixth entry
+    # is the second sequence read
+    "BULK": (1, [], [(-1, -1, -1)], (0, 0, 0), 0),                                # `bus -x BULK`: one sample per file
+    "BULK-PAIRED": (2, [], [(-1, -1, -1)], (0, 0, 0), 0, (1, 0, 0)),              # `bus -x BULK --paired`
+    "SMARTSEQ2": (3, [(0, 0, 0), (1, 0, 0)], [(-1, -1, -1)], (2, 0, 0), 0),
+    "SMARTSEQ2-PAIRED": (4, [(0, 0, 0), (1, 0, 0)], [(-1, -1, -1)], (2, 0, 0), 0, (3, 0, 0)),
+    "STORM-SEQ": (2, [], [(1, 0, 8)], (0, 0, 0), 2, (1, 14, 0)),
 }
 
 
@@ -90,7 +98,7 @@ EXPORTED_SYMBOLS = [
     "kb_quant_get_timings", "kb_quant_finalize", "kb_quant_ec_table", "kb_quant_get_flens",
     "kb_quant_set_flens", "kb_em_run", "kb_em_run_table", "kb_bootstrap_run", "kb_quant_export_prepare", "kb_quant_export_device", "kb_quant_import_device",
     "kb_comm_unique_id", "kb_comm_create", "kb_comm_create_from_nccl", "kb_comm_create_all", "kb_comm_reserve", "kb_comm_free",
-    "kb_quant_merge_nccl", "kb_quant_merge_local", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_tcc_run", "kb_eff_lens", "kb_bus_create", "kb_bus_batch", "kb_bus_batch_device", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
+    "kb_quant_merge_nccl", "kb_quant_merge_local", "kb_quant_set_frag_base", "kb_quant_reserve", "kb_tcc_run", "kb_eff_lens", "kb_bus_create", "kb_bus_batch", "kb_bus_batch_device", "kb_bus_begin_sample", "kb_bus_lengths", "kb_fastx_summary", "kb_fastx_summary_mt", "kb_gz_summary", "kb_counts_to_tpm",
 ]
 
 _lib = None
@@ -154,6 +162,7 @@ def lib():
     L.kb_bus_batch.argtypes = [vp, vp, vp, u32, vp, C.POINTER(u32)]
     L.kb_bus_batch_device.argtypes = [vp, vp, vp, u32, u32, C.POINTER(u32), C.POINTER(vp)]
     L.kb_bus_lengths.argtypes = [vp, vp, vp]
+    L.kb_bus_begin_sample.argtypes = [vp, C.c_uint64]
     L.kb_fastx_summary.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.kb_gz_summary.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(C.c_uint32)]
     L.kb_fastx_summary_mt.argtypes = [C.c_char_p, C.c_int, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
@@ -415,8 +424,13 @@ class BUSProcessor(MinCollector):
     def __init__(self, index, technology, strand="default", num=False, max_batch_sets=0):
         self.index = index
         self.paired = False
-        nfiles, bc, umi, seq, dstrand = TECHNOLOGIES[technology.upper()] if isinstance(technology, str) else technology
+        tech = TECHNOLOGIES[technology.upper()] if isinstance(technology, str) else technology
+        nfiles, bc, umi, seq, dstrand = tech[:5]
         o = kb_bus_opts()
+        if len(tech) > 5:
+            o.paired = 1
+            o.seq2 = kb_bus_substr(*tech[5])
+            self.paired = True
         o.nfiles = nfiles
         o.n_bc = len(bc)
         for i, t in enumerate(bc):
@@ -456,6 +470,10 @@ class BUSProcessor(MinCollector):
         _ck(lib().kb_bus_batch_device(self._h, bp, op, n_sets, max_seq_len, C.byref(nrec), C.byref(drec)))
         self._stats = None
         return nrec.value, drec.value
+
+    def begin_sample(self, barcode):
+        """Batch mode (`bus -x BULK`): the following read sets belong to the sample with this fake barcode."""
+        _ck(lib().kb_bus_begin_sample(self._h, C.c_uint64(barcode)))
 
     def lengths(self):
         b, u = np.zeros(33, np.uint32), np.zeros(33, np.uint32)

@@ -464,10 +464,14 @@ int kb_bus_create(kb_index* ix, const kb_bus_opts* o, kb_quant** out) {
       throw std::invalid_argument("kb_bus_create: unsupported technology layout");
     if (o->seq.stop != 0 || o->seq.fileno < 0 || o->seq.fileno >= o->nfiles || o->seq.start < 0)
       throw std::invalid_argument("kb_bus_create: the sequence must run to the end of its read (stop == 0)");
+    if (o->paired && (o->seq2.stop != 0 || o->seq2.fileno < 0 || o->seq2.fileno >= o->nfiles || o->seq2.start < 0 ||
+                      o->seq2.fileno == o->seq.fileno))
+      throw std::invalid_argument("kb_bus_create: the second sequence of a paired technology must be another file, running to the end of its read");
+    const bool no_umi = o->n_umi == 1 && o->umi[0].fileno == -1;
     kb::QuantOptions q;
-    q.paired = 0;
+    q.paired = o->paired ? 1 : 0;
     q.strand_mode = o->strand_mode;
-    q.collect_fld = 0;
+    q.collect_fld = o->paired ? 1 : 0;     // findFragmentLength = tcount < 10000 && busopt.paired (src/ProcessReads.cpp:1400)
     q.bus = true;
     if (o->max_batch_sets) q.max_batch_reads = o->max_batch_sets;
     if (o->max_batch_bases) q.max_batch_bases = o->max_batch_bases;
@@ -480,10 +484,17 @@ int kb_bus_create(kb_index* ix, const kb_bus_opts* o, kb_quant** out) {
         throw std::invalid_argument("kb_bus_create: bad barcode/UMI location");
     };
     for (int i = 0; i < o->n_bc; ++i) { chk(o->bc[i]); s.bc_f[i] = o->bc[i].fileno; s.bc_a[i] = o->bc[i].start; s.bc_b[i] = o->bc[i].stop; }
-    for (int i = 0; i < o->n_umi; ++i) { chk(o->umi[i]); s.umi_f[i] = o->umi[i].fileno; s.umi_a[i] = o->umi[i].start; s.umi_b[i] = o->umi[i].stop; }
+    s.no_umi = no_umi ? 1 : 0;
+    if (no_umi) s.n_umi = 0;
+    else
+      for (int i = 0; i < o->n_umi; ++i) { chk(o->umi[i]); s.umi_f[i] = o->umi[i].fileno; s.umi_a[i] = o->umi[i].start; s.umi_b[i] = o->umi[i].stop; }
     s.seq_file = o->seq.fileno;
     s.seq_start = o->seq.start;
     s.num_flag = o->num;
+    s.paired = o->paired ? 1 : 0;
+    s.seq2_file = o->paired ? o->seq2.fileno : 0;
+    s.seq2_start = o->paired ? o->seq2.start : 0;
+    s.fake_bc = 0;
     kb_quant* h = new kb_quant();
     h->owner = ix;
     h->q.reset(new kb::Quant(*ix->ix, q));
@@ -506,6 +517,11 @@ int kb_bus_batch_device(kb_quant* q, const void* const* d_bases, const uint32_t*
     if (n_records_out) *n_records_out = n;
     if (d_records_out) *d_records_out = (const kb_bus_record*)q->q->bus_records_device();
   });
+}
+
+int kb_bus_begin_sample(kb_quant* q, uint64_t barcode) {
+  if (!q) return fail(KB_ERR_INVALID, "kb_bus_begin_sample: null argument");
+  return guarded([&] { q->q->bus_begin_sample(barcode); });
 }
 
 int kb_bus_lengths(kb_quant* q, uint32_t* bc_hist, uint32_t* umi_hist) {

@@ -455,8 +455,11 @@ class LockStep {
         while (wait_slot(i) && !st_[i].ring[cur_[i]].eof) advance(i);     // rest of a longer file
         if (wait_slot(i)) advance(i);                                      // the marker itself
       }
+      ++set_;
     }
   }
+  // index of the file set (one file per stream) the reads of the last round came from
+  size_t file_set() const { return set_; }
   // the reads of the last round have been consumed
   void release() {
     for (size_t i = 0; i < st_.size(); ++i) {
@@ -491,7 +494,7 @@ class LockStep {
 
   std::vector<Stream>& st_;
   std::vector<size_t> cur_, used_;
-  size_t n_ = 0;
+  size_t n_ = 0, set_ = 0;
 };
 
 int cmd_quant(int argc, char** argv, const std::string& call, const std::string& start_time) {
@@ -710,11 +713,18 @@ struct Tech {
   int nfiles;
   std::vector<kb_bus_substr> bc, umi;
   kb_bus_substr seq;
-  int strand;   // default strand of the technology: 0 none, 1 FR
+  int strand;   // default strand of the technology: 0 none, 1 FR, 2 RF
+  kb_bus_substr seq2 = {-1, 0, 0};   // paired technologies: the second sequence read
 };
 
-const std::vector<Tech>& tech_table() {   // src/main.cpp:1283-1437 (technologies with one cDNA read, no tag sequence)
+const std::vector<Tech>& tech_table() {   // src/main.cpp:1283-1407: every technology but SMARTSEQ3, which needs a tag sequence.
+                                          // SMARTSEQ2 grows a fourth file with --paired (cmd_bus).  "STORM-seq" cannot be
+                                          // selected in the reference either: -x is upper-cased (:619) before it is compared
+                                          // with the mixed-case name (:1358); its layout is -x -1,-1,-1:1,0,8:0,0,0,1,14,0
   static const std::vector<Tech> t = {
+      {"SMARTSEQ2", 3, {{0, 0, 0}, {1, 0, 0}}, {{-1, -1, -1}}, {2, 0, 0}, 0},
+      {"BDWTA", 2, {{0, 0, 9}, {0, 21, 30}, {0, 43, 52}}, {{0, 52, 60}}, {1, 0, 0}, 1},
+      {"VASA-SEQ", 1, {{0, 6, 14}}, {{0, 0, 6}}, {0, 14, 0}, 1},
       {"10XV1", 3, {{0, 0, 14}}, {{1, 0, 10}}, {2, 0, 0}, 1},
       {"10XV2", 2, {{0, 0, 16}}, {{0, 16, 26}}, {1, 0, 0}, 1},
       {"10XV3", 2, {{0, 0, 16}}, {{0, 16, 28}}, {1, 0, 0}, 1},
@@ -744,6 +754,43 @@ bool parse_triplets(const std::string& s, std::vector<kb_bus_substr>& out) {
   return true;
 }
 
+// index.saved of `kallisto bus` (KmerIndex::write(fn, false), src/KmerIndex.cpp:1226-1327): the index without graph,
+// D-list and nodes -- what `quant-tcc` needs next to matrix.ec: version, three empty sections, then the number of real
+// targets followed by the input file's own tail (target lengths, names, on-list), which the reference re-serialises
+// unchanged.  The tail is found by walking the sections of the v13 file.
+void write_index_saved(const std::string& in_path, const std::string& out_path, int k) {
+  std::ifstream in(in_path, std::ios::binary);
+  auto rd64 = [&]() { uint64_t v = 0; in.read((char*)&v, 8); return v; };
+  const uint64_t version = rd64();
+  uint64_t dbg_bytes = rd64();
+  dbg_bytes &= ~(1ull << 63);
+  in.seekg((std::streamoff)dbg_bytes, std::ios::cur);
+  const uint64_t mphf_bytes = rd64();
+  in.seekg((std::streamoff)mphf_bytes, std::ios::cur);
+  const uint64_t dlist_n = rd64();
+  rd64();      // D-list overhang
+  in.seekg((std::streamoff)(dlist_n * 8), std::ios::cur);
+  const uint64_t n_nodes = rd64();
+  for (uint64_t i = 0; i < n_nodes && in; ++i) {
+    in.seekg(k, std::ios::cur);
+    uint32_t nb = 0;
+    in.read((char*)&nb, 4);
+    in.seekg(nb, std::ios::cur);
+  }
+  int32_t num_trans = 0;
+  in.read((char*)&num_trans, 4);
+  if (!in || version != 13) {
+    cerr << "Error: could not read " << in_path << " to write index.saved" << endl;
+    exit(1);
+  }
+  num_trans -= (int32_t)dlist_n;
+  std::ofstream out(out_path, std::ios::binary);
+  const uint64_t head[5] = {13, 0, 0, 1, 0};      // version, graph bytes, D-list size, D-list overhang, nodes
+  out.write((const char*)head, sizeof(head));
+  out.write((const char*)&num_trans, 4);
+  out << in.rdbuf();
+}
+
 void usage_bus() {
   std::cout << "kallisto_b200 " << KALLISTO_VERSION << " (B200 build)" << endl
             << "Generates BUS files for single-cell sequencing" << endl << endl
@@ -753,11 +800,14 @@ void usage_bus() {
             << "                              pseudoalignment" << endl
             << "-o, --output-dir=STRING       Directory to write output to" << endl
             << "-x, --technology=STRING       Single-cell technology used (10xv1, 10xv2, 10xv3, visium, surecell," << endl
-            << "                              dropseq, indropsv1/2/3, celseq, celseq2, split-seq, scrbseq) or a" << endl
-            << "                              custom bc:umi:seq string of file,start,stop triplets" << endl << endl
+            << "                              dropseq, indropsv1/2/3, celseq, celseq2, split-seq, scrbseq, bdwta," << endl
+            << "                              vasa-seq, smartseq2), a custom bc:umi:seq string of file,start,stop" << endl
+            << "                              triplets, or bulk (every file or file pair is a sample of its own)" << endl << endl
             << "Optional arguments:" << endl
             << "-t, --threads=INT             Number of host threads (default: 1)" << endl
             << "-n, --num                     Output number of read in flag column" << endl
+            << "    --paired                  Treat reads as paired (bulk, smartseq2, custom technologies with two" << endl
+            << "                              sequence reads)" << endl
             << "    --fr-stranded / --rf-stranded / --unstranded   Strand specificity" << endl
             << "    --device=INT              CUDA device ordinal (default: 0)" << endl;
 }
@@ -765,9 +815,10 @@ void usage_bus() {
 int cmd_bus(int argc, char** argv, const std::string& call, const std::string& start_time) {
   Options opt;
   std::string technology;
-  int num_flag = 0, fr = 0, rf = 0, unstranded = 0, verbose_flag = 0;
+  int num_flag = 0, fr = 0, rf = 0, unstranded = 0, verbose_flag = 0, paired_flag = 0;
   const char* opt_string = "i:o:x:t:nD:";
   static struct option long_options[] = {{"verbose", no_argument, &verbose_flag, 1},
+                                         {"paired", no_argument, &paired_flag, 1},
                                          {"num", no_argument, 0, 'n'},
                                          {"fr-stranded", no_argument, &fr, 1},
                                          {"rf-stranded", no_argument, &rf, 1},
@@ -802,12 +853,27 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   for (auto& fn : opt.files)
     if (stat(fn.c_str(), &stt) != 0) { cerr << ERROR_STR << " file not found " << fn << endl; ret = false; }
   kb_bus_opts bo{};
+  bo.seq2 = kb_bus_substr{-1, 0, 0};
   int tech_strand = 0;
+  bool batch_mode = false;      // -x BULK: every file (pair) is a sample of its own (src/main.cpp:1050-1107)
   std::string tech_upper = technology;
   for (auto& ch : tech_upper) ch = (char)toupper(ch);
   if (technology.empty()) {
     if (ret) cerr << "Error: the technology must be specified via -x, use \"bulk\" for regular RNA-seq reads" << endl;   // src/main.cpp:1058
     ret = false;
+  } else if (tech_upper == "BULK") {
+    // batch mode without a technology (:1050-1107, 1190-1214): no barcode read, no UMI, the whole read(s) are the sequence
+    batch_mode = true;
+    if (ret && paired_flag && opt.files.size() % 2 != 0) {
+      cerr << "Error: paired-end mode requires an even number of input files" << endl;
+      ret = false;
+    }
+    bo.nfiles = paired_flag ? 2 : 1;
+    bo.n_bc = 0;
+    bo.n_umi = 1;
+    bo.umi[0] = kb_bus_substr{-1, -1, -1};
+    bo.seq = kb_bus_substr{0, 0, 0};
+    if (paired_flag) { bo.paired = 1; bo.seq2 = kb_bus_substr{1, 0, 0}; }
   } else {
     std::string up = technology;
     for (auto& ch : up) ch = (char)toupper(ch);
@@ -815,10 +881,19 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     for (auto& t : tech_table())
       if (up == t.name) found = &t;
     std::vector<kb_bus_substr> bc, umi, seq;
-    if (found) {
+    if (up == "SMARTSEQ3") {
+      cerr << "Error: this build does not handle UMI tag sequences (SMARTSEQ3, --tag)" << endl;
+      ret = false;
+    } else if (found) {
       bo.nfiles = found->nfiles;
       bc = found->bc; umi = found->umi; seq = {found->seq};
       tech_strand = found->strand;
+      if (found->seq2.fileno >= 0) seq.push_back(found->seq2);
+      if (up == "SMARTSEQ2" && paired_flag) {      // src/main.cpp:1386-1392
+        bo.nfiles++;
+        seq.push_back(kb_bus_substr{3, 0, 0});
+      }
+      if (bc.size() == 1 && bc[0].fileno == -1) bc.clear();
     } else if (technology.find(':') != std::string::npos) {
       std::vector<std::string> parts;
       std::stringstream ss(technology);
@@ -844,8 +919,16 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
       ret = false;
     }
     if (ret) {
-      if (seq.size() != 1 || seq[0].stop != 0 || bc.size() > 4 || umi.empty() || umi.size() > 4 || bo.nfiles > 4) {
-        cerr << "Error: this build handles technologies with one sequence read running to the end of its file" << endl;
+      // two sequence reads are a pair when the technology says so or with --paired (src/main.cpp:1424-1426); without
+      // --paired the reference glues them together with an N in between (:1568-1580), which this build does not do
+      const bool tech_paired = found && found->seq2.fileno >= 0;
+      const bool two = seq.size() == 2 && (tech_paired || paired_flag);
+      bool bad = (seq.size() != 1 && !two) || bc.size() > 4 || umi.empty() || umi.size() > 4 || bo.nfiles > 4;
+      for (auto& x : seq) bad = bad || x.stop != 0 || x.fileno < 0;
+      if (two && seq[0].fileno == seq[1].fileno) bad = true;
+      for (auto& x : umi) if (x.fileno < 0 && umi.size() != 1) bad = true;
+      if (bad) {
+        cerr << "Error: this build handles technologies with one sequence read, or two that form a pair, running to the end of their files" << endl;
         ret = false;
       } else {
         bo.n_bc = (int)bc.size();
@@ -853,7 +936,12 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
         bo.n_umi = (int)umi.size();
         for (size_t i = 0; i < umi.size(); ++i) bo.umi[i] = umi[i];
         bo.seq = seq[0];
+        if (two) { bo.paired = 1; bo.seq2 = seq[1]; }
       }
+    }
+    if (ret && paired_flag && !bo.paired) {      // src/main.cpp:1472-1475
+      cerr << "Error: Paired reads are not compatible with the specified technology" << endl;
+      ret = false;
     }
   }
   if (ret && opt.files.size() % bo.nfiles != 0) {
@@ -865,9 +953,10 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   if (fr) strand = 1;
   else if (rf) strand = 2;
   else if (unstranded) strand = 0;
-  else if (ret) {
+  else if (ret && !batch_mode) {      // -x BULK leaves CheckOptionsBus before the technology defaults (:1214): unstranded
     strand = tech_strand;
     if (strand == 1) cerr << "[bus] Note: Strand option was not specified; setting it to --fr-stranded for specified technology" << endl;
+    else if (strand == 2) cerr << "[bus] Note: Strand option was not specified; setting it to --rf-stranded for specified technology" << endl;
     else cerr << "[bus] Note: Strand option was not specified; setting it to --unstranded for specified technology" << endl;
   }
   if (opt.output.empty()) { cerr << "Error: need to specify output directory " << opt.output << endl; ret = false; }
@@ -907,6 +996,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     return r;
   };
   uint32_t bclen = (uint32_t)spec_len(bo.bc, bo.n_bc), umilen = (uint32_t)spec_len(bo.umi, bo.n_umi);
+  if (batch_mode) umilen = 1;      // writeBUSHeader(busf_out, BUSFORMAT_FAKE_BARCODE_LEN, 1), src/ProcessReads.h:241-242
   const uint32_t hdr_bclen = bo.n_bc == 0 ? 16u : bclen;
   const std::string busfile = opt.output + "/output.bus";
   std::ofstream busf(busfile, std::ios::out | std::ios::binary);
@@ -926,12 +1016,22 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   std::vector<std::thread> readers;
   start_streams(streams, readers, opt.files, max_bases, max_reads, opt.threads);
   std::vector<kb_bus_record> recs(max_reads);
+  const size_t n_samples = batch_mode ? opt.files.size() / (size_t)bo.nfiles : 1;
+  std::vector<std::vector<uint32_t>> sample_flens(n_samples, std::vector<uint32_t>(1000, 0));
+  size_t cur_sample = (size_t)-1;
   {
     LockStep ls(streams);
     const char* bp[4] = {nullptr, nullptr, nullptr, nullptr};
     const uint32_t* op[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t n = 0;
     while (ls.next(n, bp, op)) {
+      if (batch_mode && ls.file_set() != cur_sample) {
+        // the reads of the next file (pair) are the next sample: its id is the fake barcode of its records and it
+        // samples its own fragment lengths (src/ProcessReads.cpp:371-404,486-493,1603-1607)
+        if (cur_sample != (size_t)-1) KB_TRY(kb_quant_get_flens(q, sample_flens[cur_sample].data()));
+        cur_sample = ls.file_set();
+        KB_TRY(kb_bus_begin_sample(q, (uint64_t)cur_sample));
+      }
       uint32_t nrec = 0;
       KB_TRY(kb_bus_batch(q, bp, op, (uint32_t)n, recs.data(), &nrec));
       busf.write((const char*)recs.data(), (std::streamsize)nrec * sizeof(kb_bus_record));
@@ -941,8 +1041,28 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   for (auto& t : readers) t.join();
   busf.close();
   cerr << " done" << endl;
+  if (bo.paired) KB_TRY(kb_quant_get_flens(q, sample_flens[batch_mode ? (cur_sample == (size_t)-1 ? 0 : cur_sample) : 0].data()));
+  if (batch_mode) {
+    // src/main.cpp:2406-2449: sample names, their fake barcodes, the stripped index, one fragment-length line per sample
+    std::ofstream cf(opt.output + "/matrix.cells"), bf(opt.output + "/matrix.sample.barcodes");
+    for (size_t j = 0; j < n_samples; ++j) {
+      cf << "batch" << j << "\n";
+      std::string b(16, 'A');      // binaryToString(j, 16), src/BUSData.cpp:38-51
+      for (int p = 0; p < 16; ++p) b[15 - p] = "ACGT"[(j >> (2 * p)) & 3];
+      bf << b << "\n";
+    }
+  }
+  if (batch_mode || bo.paired || (bo.n_umi == 1 && bo.umi[0].fileno == -1))
+    write_index_saved(opt.index, opt.output + "/index.saved", info.k);      // :2414-2417, 2517, 2560-2563
+  if (bo.paired) {      // :2418-2449 (one line per sample) / :2511-2526
+    std::ofstream ff(opt.output + "/flens.txt");
+    for (size_t j = 0; j < n_samples; ++j) {
+      for (size_t i = 0; i < 1000; ++i) ff << (i ? " " : "") << sample_flens[j][i];
+      ff << "\n";
+    }
+  }
   // barcode / UMI lengths of the header when the technology does not fix them (src/main.cpp:2470-2508)
-  {
+  if (!batch_mode) {
     uint32_t bh[33], uh[33];
     KB_TRY(kb_bus_lengths(q, bh, uh));
     uint32_t bl = 0, ul = 0;

@@ -95,6 +95,10 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
   const double t1 = now_s();
   ix->load_seconds = t1 - t0;
   FlatIndex& f = ix->flat;
+  if (f.graphless) {      // index.saved: targets only; nothing to build on the device, only quant-tcc can use it
+    ix->build_seconds = 0;
+    return ix;
+  }
   if (f.onlist.size() != f.target_len.size())
     throw Error("kallisto_b200: indices whose on-list does not cover every target are not supported yet");
   if (f.ec_tid.size() >= 0xFFFFFFFFull) throw Error("kallisto_b200: index EC sets exceed 2^32 entries");
@@ -267,6 +271,7 @@ std::unique_ptr<Index> Index::load(const std::string& path, int device, bool loa
 // Quant
 // ------------------------------------------------------------------------------------------
 Quant::Quant(Index& ix, const QuantOptions& opt) : ix_(ix), opt_(opt), flens_(1000, 0) {
+  if (ix.flat.graphless) throw Error("kallisto_b200: this index has no k-mers (an index.saved written by `bus`): only quant-tcc can use it");
   if (!ix_.ws_in_use) {   // borrow the index's work buffers
     ix_.ws_in_use = true;
     if (!ix_.shared_emws) ix_.shared_emws = new EmWs();
@@ -521,6 +526,7 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   }
   ba.fp_fl = opt_.fp_fl;
   ba.start = cur_start_;
+  ba.start2 = cur_start2_;
   ResolveArgs ra{};
   ra.scratch = bws_->d_scratch.p;
   ra.scratch_stride = scratch_stride_;
@@ -675,6 +681,10 @@ void Quant::bus_batch_host(const char* const* bases, const uint32_t* const* offs
   uint32_t maxlen = 0;
   const uint32_t* so = offs[sp.seq_file];
   for (uint32_t i = 0; i < n_sets; ++i) maxlen = std::max(maxlen, so[i + 1] - so[i]);
+  if (sp.paired) {
+    so = offs[sp.seq2_file];
+    for (uint32_t i = 0; i < n_sets; ++i) maxlen = std::max(maxlen, so[i + 1] - so[i]);
+  }
   const uint32_t n_rec = bus_core(db, dofs, n_sets, maxlen);
   if (n_rec && records_out) {
     bus_rec_.download(records_out, n_rec, 0, st);
@@ -711,20 +721,29 @@ uint32_t Quant::bus_core(const uint8_t* const* db, const uint32_t* const* dofs, 
   if (bus_tmp_.n < tb) bus_tmp_.alloc(std::max(tb, bus_scan_bytes(opt_.max_batch_reads)));
   bus_nvalid_.zero(st);
   a.n_sets = n_sets;
-  a.set_base = n_frag_total_;
+  a.set_base = n_frag_total_ - bus_sample_base_;      // --num: read numbers restart with every sample (one reader per batch)
   a.spec = sp;
   a.barcode = (uint64_t*)bus_bc_.p; a.umi = (uint64_t*)bus_umi_.p; a.flags = bus_flags_.p; a.skip = bus_skip_.p;
   a.bc_hist = bus_hist_.p; a.umi_hist = bus_hist_.p + 33; a.n_valid = bus_nvalid_.p;
   launch_bus_fields(a, st);
   KB_CK(cudaGetLastError());
-  // the cDNA read: single-read pseudoalignment with the strand filter of the technology
-  maxlen = maxlen > (uint32_t)sp.seq_start ? maxlen - sp.seq_start : 1;
+  // the cDNA read(s): single-read or paired pseudoalignment with the strand filter of the technology
+  const uint32_t min_start = (uint32_t)(sp.paired ? std::min(sp.seq_start, sp.seq2_start) : sp.seq_start);
+  maxlen = maxlen > min_start ? maxlen - min_start : 1;
   const uint64_t base = n_frag_total_;
   cur_skip_ = bus_skip_.p;
   cur_start_ = (uint32_t)sp.seq_start;
-  run_batch(db[sp.seq_file], dofs[sp.seq_file], n_sets, 0, maxlen);
+  if (sp.paired) {
+    // two sequence reads (busopt.paired, src/ProcessReads.cpp:1550-1567,1646-1650): the pair goes through the same
+    // match x 2 / intersectKmers / strand filter / mapPair path as `quant` (one buffer per mate)
+    cur_start2_ = (uint32_t)sp.seq2_start;
+    run_batch(db[sp.seq_file], dofs[sp.seq_file], 2 * n_sets, 0, maxlen, db[sp.seq2_file], dofs[sp.seq2_file]);
+  } else {
+    run_batch(db[sp.seq_file], dofs[sp.seq_file], n_sets, 0, maxlen);
+  }
   cur_skip_ = nullptr;
   cur_start_ = 0;
+  cur_start2_ = 0;
   launch_bus_records(dd_, bws_->d_handles.p, n_sets, base, bus_next_id_, bus_idof_.p, bus_isnew_.p, bus_newrank_.p,
                      bus_ismapped_.p, bus_rank_.p, (const uint64_t*)bus_bc_.p, (const uint64_t*)bus_umi_.p, bus_flags_.p,
                      bus_rec_.p, bus_tmp_.p, bus_tmp_.n, st);
@@ -739,6 +758,17 @@ uint32_t Quant::bus_core(const uint8_t* const* db, const uint32_t* const* dofs, 
   bus_next_id_ += n_new;
   bus_valid_total_ += n_valid;
   return n_rec;
+}
+
+void Quant::bus_begin_sample(uint64_t barcode) {
+  if (!opt_.bus) throw Error("kallisto_b200: not a bus run");
+  if (opt_.bus_spec.n_bc != 0) throw Error("kallisto_b200: sample barcodes need a technology without a barcode read");
+  opt_.bus_spec.fake_bc = barcode;
+  bus_sample_base_ = n_frag_total_;
+  // per-sample fragment-length histogram and quota (batchFlens[id] / tlencounts[id], src/ProcessReads.cpp:486-493)
+  std::fill(flens_.begin(), flens_.end(), 0u);
+  tl_list_.clear();
+  tlencount_ = 0;
 }
 
 void Quant::bus_lengths(uint32_t* bc_hist, uint32_t* umi_hist) {

@@ -178,6 +178,9 @@ class Quant {
   uint32_t bus_batch_device(const uint8_t* const* d_bases, const uint32_t* const* d_offs, uint32_t n_sets, uint32_t max_seq_len);
   const BusRecord* bus_records_device() const { return bus_rec_.p; }
   void bus_lengths(uint32_t* bc_hist, uint32_t* umi_hist);
+  // Batch mode (`bus -x BULK`, src/ProcessReads.cpp:371-404,1603-1607): the read sets that follow belong to sample
+  // `barcode` (the fake barcode of their records); its fragment-length sampling starts from an empty histogram.
+  void bus_begin_sample(uint64_t barcode);
   // Same, inputs already resident in device memory; handles stay on the device
   // (device_handles(), valid until the next batch).
   void pseudoalign_device(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_reads, uint32_t fixed_len,
@@ -297,9 +300,9 @@ class Quant {
   DBuf<uint32_t> lm_off_, lm_tids_, lm_counts_;       // merge_local: receive area on the root
   DBuf<unsigned long long> lm_first_;
   uint32_t bus_next_id_ = 0;
-  uint64_t bus_valid_total_ = 0;
+  uint64_t bus_valid_total_ = 0, bus_sample_base_ = 0;
   const uint8_t* cur_skip_ = nullptr;
-  uint32_t cur_start_ = 0;
+  uint32_t cur_start_ = 0, cur_start2_ = 0;
 };
 
 std::vector<double> mean_fl_trunc_of(const uint32_t* flens /* 1000 */, double fld_mean, double fld_sd);

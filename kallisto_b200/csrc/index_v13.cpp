@@ -210,6 +210,40 @@ static void parse_nodes(const std::vector<NodeRef>& nodes, size_t begin, size_t 
   }
 }
 
+// 4-7: target lengths, names and the on-list -- the part of the file `kallisto bus` copies into index.saved
+// (KmerIndex::write(fn, false), src/KmerIndex.cpp:1296-1324)
+static void parse_targets(Cursor& c, FlatIndex& fi) {
+  // 4-6. targets (KmerIndex.cpp:1470-1519)
+  int32_t num_trans = c.get<int32_t>();
+  if ((int64_t)num_trans < (int64_t)fi.dlist_n) throw std::runtime_error("kallisto index: bad target count");
+  num_trans -= (int32_t)fi.dlist_n;
+  fi.target_len.resize(num_trans);
+  for (int32_t i = 0; i < num_trans; ++i) fi.target_len[i] = (uint32_t)c.get<int32_t>();
+  {
+    // every transcript id of every equivalence class must name a target (an index with a D-list also uses id
+    // num_trans: the off-list pseudo-target of the dummy k-mer's unitig), and the lists must be strictly ascending
+    const uint32_t limit = (uint32_t)num_trans + (fi.dlist_n ? 1u : 0u);
+    for (uint32_t e = 0; e < fi.n_ec(); ++e)
+      for (uint64_t i = fi.ec_off[e]; i < fi.ec_off[e + 1]; ++i) {
+        if (fi.ec_tid[i] >= limit) throw std::runtime_error("kallisto index: equivalence class with a transcript id out of range");
+        if (i > fi.ec_off[e] && fi.ec_tid[i] <= fi.ec_tid[i - 1]) throw std::runtime_error("kallisto index: unsorted equivalence class");
+      }
+  }
+  fi.target_name.resize(num_trans);
+  for (int32_t i = 0; i < num_trans; ++i) {
+    const uint64_t n = c.get<uint64_t>();
+    const uint8_t* s = c.bytes(n);
+    // the reference builds the name with std::string(buffer): stops at the first NUL
+    fi.target_name[i] = std::string((const char*)s, strnlen((const char*)s, n));
+  }
+  // 7. on-list, Roaring portable (KmerIndex.cpp:1522-1526)
+  {
+    const uint64_t n = c.get<uint64_t>();
+    const uint8_t* s = c.bytes(n);
+    decode_roaring_portable(s, n, fi.onlist);
+  }
+}
+
 void load_index_v13(const std::string& path, FlatIndex& fi, bool load_positions, int threads) {
   Mmap mm(path);
   Cursor c{mm.data, mm.data + mm.size};
@@ -224,7 +258,23 @@ void load_index_v13(const std::string& path, FlatIndex& fi, bool load_positions,
   // 2. Bifrost blob (KmerIndex.cpp:1362-1382): GRAPH section parsed, INDEX section skipped
   uint64_t dbg_bytes = c.get<uint64_t>();
   dbg_bytes &= (~0ULL >> 1);
-  if (dbg_bytes == 0) throw std::runtime_error("kallisto index: empty de Bruijn graph");
+  if (dbg_bytes == 0) {
+    // index.saved of `kallisto bus` (KmerIndex::write(fn, false), src/KmerIndex.cpp:1226-1327): no graph, no MPHF field,
+    // an empty D-list, no nodes -- targets only.  `quant-tcc` runs on it (the reference's loader skips the graph and the
+    // MPHF together when the size is 0, :1365-1383); k keeps the reference's default.
+    fi.graphless = true;
+    fi.k = 31;
+    fi.dlist_n = c.get<uint64_t>();
+    c.get<uint64_t>();      // overhang
+    const uint64_t n_nodes = c.get<uint64_t>();
+    if (fi.dlist_n != 0 || n_nodes != 0) throw std::runtime_error("kallisto index: empty de Bruijn graph");
+    fi.blk_off.assign(1, 0);
+    fi.blk_strand_off.assign(1, 0);
+    fi.ec_off.assign(1, 0);
+    fi.useq_byteoff.assign(1, 0);
+    parse_targets(c, fi);
+    return;
+  }
   {
     const uint8_t* gb = c.bytes(dbg_bytes);       // validates the length before the sub-cursor is formed
     Cursor g{gb, gb + dbg_bytes};
@@ -512,35 +562,7 @@ void load_index_v13(const std::string& path, FlatIndex& fi, bool load_positions,
     }
   }
 
-  // 4-6. targets (KmerIndex.cpp:1470-1519)
-  int32_t num_trans = c.get<int32_t>();
-  if ((int64_t)num_trans < (int64_t)fi.dlist_n) throw std::runtime_error("kallisto index: bad target count");
-  num_trans -= (int32_t)fi.dlist_n;
-  fi.target_len.resize(num_trans);
-  for (int32_t i = 0; i < num_trans; ++i) fi.target_len[i] = (uint32_t)c.get<int32_t>();
-  {
-    // every transcript id of every equivalence class must name a target (an index with a D-list also uses id
-    // num_trans: the off-list pseudo-target of the dummy k-mer's unitig), and the lists must be strictly ascending
-    const uint32_t limit = (uint32_t)num_trans + (fi.dlist_n ? 1u : 0u);
-    for (uint32_t e = 0; e < fi.n_ec(); ++e)
-      for (uint64_t i = fi.ec_off[e]; i < fi.ec_off[e + 1]; ++i) {
-        if (fi.ec_tid[i] >= limit) throw std::runtime_error("kallisto index: equivalence class with a transcript id out of range");
-        if (i > fi.ec_off[e] && fi.ec_tid[i] <= fi.ec_tid[i - 1]) throw std::runtime_error("kallisto index: unsorted equivalence class");
-      }
-  }
-  fi.target_name.resize(num_trans);
-  for (int32_t i = 0; i < num_trans; ++i) {
-    const uint64_t n = c.get<uint64_t>();
-    const uint8_t* s = c.bytes(n);
-    // the reference builds the name with std::string(buffer): stops at the first NUL
-    fi.target_name[i] = std::string((const char*)s, strnlen((const char*)s, n));
-  }
-  // 7. on-list, Roaring portable (KmerIndex.cpp:1522-1526)
-  {
-    const uint64_t n = c.get<uint64_t>();
-    const uint8_t* s = c.bytes(n);
-    decode_roaring_portable(s, n, fi.onlist);
-  }
+  parse_targets(c, fi);
 }
 
 }  // namespace kb

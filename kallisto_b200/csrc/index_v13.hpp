@@ -18,6 +18,7 @@ namespace kb {
 struct FlatIndex {
   int k = 0;
   int g = 0;
+  bool graphless = false;   // index.saved of `kallisto bus`: targets only, no k-mers (usable by quant-tcc alone)
   uint32_t n_long = 0, n_short = 0, n_abund = 0;   // unitig kinds, in global-id order
   uint32_t n_unitigs() const { return n_long + n_short + n_abund; }
 

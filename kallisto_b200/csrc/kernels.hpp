@@ -63,6 +63,7 @@ struct BatchArgs {
   uint8_t* skip_w;          // the same array, writable: set when the index has a D-list (dlist_scan_kernel marks fragments)
   int fp_fl;                // >= 0: apply the fragment-position filter of ProcessReads.cpp:1095-1136 with this mean fragment length
   uint32_t start;           // first base of every read that is matched (bus: BUSOptionSubstr.start of the sequence)
+  uint32_t start2;          // the same for the second mate of a pair (paired bus technologies, e.g. STORM-seq: 14)
 };
 static constexpr int KB_Q_STRIDE = 2 + KB_MAX_E + 6;   // frag, n|flags, handles, 2 strand words, 4 position-filter words
 static constexpr int KB_SPILL = 112;                   // a fragment may hit KB_MAX_E + KB_SPILL = 128 distinct EC sets
@@ -207,6 +208,10 @@ struct BusSpec {        // BUSOptions (src/common.h:38-91): where barcode / UMI 
   int umi_f[4], umi_a[4], umi_b[4];
   int seq_file, seq_start;
   int num_flag;         // --num: flags = read number
+  int paired;           // busopt.paired: two sequence reads, pseudoaligned as a pair (src/ProcessReads.cpp:1550-1567)
+  int seq2_file, seq2_start;
+  int no_umi;           // umi[0].fileno == -1 ("bulk_like", :1393): UMI field = ~0, one count in umi_len[1]
+  unsigned long long fake_bc;   // n_bc == 0: the barcode every record gets (0 = 16 x 'A'; batch mode: the sample's id, :1603-1607)
 };
 struct BusArgs {
   const uint8_t* bases[4];

@@ -166,9 +166,10 @@ __device__ __forceinline__ void read_span(const BatchArgs& ba, uint32_t ridx, co
     off = (uint64_t)i * ba.fixed_len;
     len = (int)ba.fixed_len;
   }
-  if (ba.start) {
-    off += ba.start;
-    len -= (int)ba.start;
+  const uint32_t st = (ba.paired && (ridx & 1)) ? ba.start2 : ba.start;
+  if (st) {
+    off += st;
+    len -= (int)st;
     if (len < 0) len = 0;
   }
   if (ba.skip && ba.skip[ba.paired ? (ridx >> 1) : ridx]) len = 0;

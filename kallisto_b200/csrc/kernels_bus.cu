@@ -62,12 +62,18 @@ __global__ void __launch_bounds__(256) bus_fields_kernel(BusArgs a) {
     // UMI first (a bad UMI skips the set before the barcode is looked at)
     Enc u;
     bool ok = true;
-    for (int p = 0; p < sp.n_umi && ok; ++p) ok = slice(a, i, sp.umi_f[p], sp.umi_a[p], sp.umi_b[p], u);
+    if (sp.no_umi) {
+      u.n = 1;       // "bulk_like" (:1477-1482): a one-letter dummy UMI, never encoded: the record carries umi_binary = -1
+      u.r = ~0ull;
+    } else {
+      for (int p = 0; p < sp.n_umi && ok; ++p) ok = slice(a, i, sp.umi_f[p], sp.umi_a[p], sp.umi_b[p], u);
+    }
     if (ok) {
       if (u.n <= 32) atomicAdd(&a.umi_hist[u.n], 1u);
       Enc b;
       if (sp.n_bc == 0) {
-        b.n = 16;   // BUSFORMAT_FAKE_BARCODE_LEN of 'A': binary 0
+        b.n = 16;   // BUSFORMAT_FAKE_BARCODE_LEN: 16 x 'A' (binary 0), or the sample's id in batch mode
+        b.r = sp.fake_bc;
       } else {
         for (int p = 0; p < sp.n_bc && ok; ++p) ok = slice(a, i, sp.bc_f[p], sp.bc_a[p], sp.bc_b[p], b);
       }
@@ -75,7 +81,9 @@ __global__ void __launch_bounds__(256) bus_fields_kernel(BusArgs a) {
         if (b.n <= 32) atomicAdd(&a.bc_hist[b.n], 1u);
         a.barcode[i] = b.r;
         a.umi[i] = u.r;
-        a.flags[i] = sp.num_flag ? (uint32_t)(a.set_base + i) : (b.flag() | (u.flag() << 8));
+        // without a UMI stringToBinary runs once only, so the UMI half of the flags repeats the barcode's (:1736-1743)
+        const uint32_t uf = sp.no_umi ? b.flag() : u.flag();
+        a.flags[i] = sp.num_flag ? (uint32_t)(a.set_base + i) : (b.flag() | (uf << 8));
         valid = true;
       }
     }

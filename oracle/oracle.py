@@ -294,3 +294,99 @@ def ref_ec_dump(index, outdir, files, paired=True, extra=()):
         with open(fp) as f:
             flens = np.array([int(x) for x in f.read().split()], dtype=np.uint32)
     return rec, ecs, flens
+
+
+# ------------------------------------------------------------------------------------------
+# BUS records of a read set, restated (BUSProcessor::processBuffer, src/ProcessReads.cpp:1380-1832)
+# ------------------------------------------------------------------------------------------
+def string_to_binary(s):
+    """stringToBinary (src/BUSData.cpp:8-36): 2-bit code of the first 32 letters + the N flag."""
+    r, num_n, pos_n = 0, 0, 0
+    for i, c in enumerate(s[:32]):
+        x = (c & 4) >> 1
+        if (c & 3) == 2:
+            if num_n == 0:
+                pos_n = i
+            num_n += 1
+        r = ((r << 2) | (x + ((x ^ (c & 2)) >> 1))) & 0xFFFFFFFFFFFFFFFF
+    flag = 0
+    if num_n > 0:
+        flag = (min(num_n, 3) & 3) | ((pos_n & 31) << 2)
+    return r, flag
+
+
+def bus_model(index, files, bc, umi, seq, seq2=None, strand=0, num=False, samples=None):
+    """Records, EC sets, per-sample fragment-length histograms and barcode / UMI length histograms of `kallisto bus -t 1`.
+
+    files: one list of sequences (bytes) per file of the technology; bc / umi: lists of (file, start, stop), bc == []
+    = no barcode read (fake barcode: 0, or the sample's number), umi None = no UMI ("bulk_like", :1393); seq / seq2:
+    (file, start) of the sequence read(s), seq2 given = busopt.paired; samples: list of (first set, end set) ranges that
+    are samples of their own (`-x BULK`: barcode = sample number, read numbers and fragment-length quota restart).
+    Records come out in read order (the reference writes the records of already-known ECs of a batch first,
+    src/ProcessReads.cpp:1798-1812 + :603-612 -- compare sorted)."""
+    n = len(files[0])
+    paired = seq2 is not None
+    by_sample = samples is not None
+    samples = samples or [(0, n)]
+    bc_hist = np.zeros(33, np.int64)
+    umi_hist = np.zeros(33, np.int64)
+    rec_bc, rec_umi, rec_fl, skip = [0] * n, [0] * n, [0] * n, [False] * n
+
+    def piece(i, f, a, b):          # :1505-1521 / :1592-1602: None = the slice does not fit
+        l = len(files[f][i])
+        ln = (l - a) if b == 0 else (b - a)
+        if l < a + ln or ln <= 0:
+            return None
+        return files[f][i][a:a + ln]
+
+    for si, (lo, hi) in enumerate(samples):
+        for i in range(lo, hi):
+            if umi is None:
+                ulen, uval, uflag = 1, 0xFFFFFFFFFFFFFFFF, None
+            else:
+                parts = [piece(i, *u) for u in umi]
+                if any(p is None for p in parts):
+                    skip[i] = True
+                    continue
+                us = b"".join(parts)
+                ulen = len(us)
+                uval, uflag = string_to_binary(us)
+            if ulen <= 32:
+                umi_hist[ulen] += 1
+            if bc:
+                parts = [piece(i, *b) for b in bc]
+                if any(p is None for p in parts):
+                    skip[i] = True
+                    continue
+                bs = b"".join(parts)
+                blen = len(bs)
+                bval, bflag = string_to_binary(bs)
+            else:
+                blen, bval, bflag = 16, (si if by_sample else 0), 0
+            if blen <= 32:
+                bc_hist[blen] += 1
+            if uflag is None:
+                uflag = bflag       # no UMI: stringToBinary ran once, for the barcode (:1736-1743)
+            rec_bc[i], rec_umi[i] = bval, uval
+            rec_fl[i] = (i - lo) if num else (bflag | (uflag << 8))
+    # the sequence read(s): skipped sets have no sequence (they count as processed, :1372)
+    s1 = [b"" if skip[i] else files[seq[0]][i][seq[1]:] for i in range(n)]
+    s2 = [b"" if skip[i] else files[seq2[0]][i][seq2[1]:] for i in range(n)] if paired else None
+    run = OracleRun(index, paired, strand, collect_fld=False)
+    bases, off = to_batch(s1, s2)
+    frag = run.pseudoalign(bases, off)
+    eo, et, ecn = run.ec_table()
+    flens = []
+    if paired:
+        for lo, hi in samples:      # tlencounts[id]: 10 000 samples per sample (:486-493,1397-1400)
+            r = OracleRun(index, True, strand, collect_fld=True)
+            b2, o2 = to_batch(s1[lo:hi], s2[lo:hi])
+            r.pseudoalign(b2, o2)
+            flens.append(r.flens())
+    dt = np.dtype([("barcode", "<u8"), ("umi", "<u8"), ("ec", "<i4"), ("count", "<u4"), ("flags", "<u4"), ("pad", "<u4")])
+    keep = [i for i in range(n) if frag[i] >= 0]
+    rec = np.zeros(len(keep), dt)
+    for j, i in enumerate(keep):
+        rec[j] = (rec_bc[i], rec_umi[i], int(frag[i]), 1, rec_fl[i] & 0xFFFFFFFF, 0)
+    sets = [tuple(int(x) for x in et[int(eo[e]):int(eo[e + 1])]) for e in range(len(eo) - 1)]
+    return dict(records=rec, ecs=sets, flens=flens, bc_hist=bc_hist, umi_hist=umi_hist, n_processed=n)

@@ -16,6 +16,7 @@ struct kb_index { int dummy; };
 struct kb_quant {
   uint64_t h = 1469598103934665603ULL, n = 0, bases = 0;
   int nfiles = 0;
+  uint64_t sample = 0;      // kb_bus_begin_sample
 };
 static std::string g_err;
 static void mix(kb_quant* q, const char* p, uint32_t len) {
@@ -59,7 +60,7 @@ int kb_pseudoalign_batch_pe(kb_quant* q, const char* b1, const uint32_t* o1, con
   q->n += n_pairs;
   return KB_OK;
 }
-int kb_quant_get_flens(kb_quant*, uint32_t* f) { memset(f, 0, 1000 * sizeof(uint32_t)); f[200] = 10; return KB_OK; }
+int kb_quant_get_flens(kb_quant* q, uint32_t* f) { memset(f, 0, 1000 * sizeof(uint32_t)); f[200] = 10; f[1] = (uint32_t)q->sample; return KB_OK; }
 int kb_em_run(kb_quant* q, double, double, double* est, double* eff, int32_t* rounds, double*) {
   est[0] = (double)(q->h & 0xFFFFu);
   est[1] = (double)((q->h >> 16) & 0xFFFFu);
@@ -106,11 +107,13 @@ int kb_bus_batch(kb_quant* q, const char* const* bases, const uint32_t* const* o
     for (int f = 0; f < q->nfiles; ++f) mix(q, bases[f] + offs[f][i], offs[f][i + 1] - offs[f][i]);
     memset(&rec[i], 0, sizeof(rec[i]));
     rec[i].barcode = q->h;
+    rec[i].umi = q->sample;
     rec[i].count = 1;
   }
   q->n += n_sets;
   *n_rec = n_sets;
   return KB_OK;
 }
+int kb_bus_begin_sample(kb_quant* q, uint64_t barcode) { q->sample = barcode; return KB_OK; }
 int kb_bus_lengths(kb_quant*, uint32_t* bc, uint32_t* umi) { memset(bc, 0, 33 * 4); memset(umi, 0, 33 * 4); bc[16] = 1; umi[10] = 1; return KB_OK; }
 }

@@ -28,6 +28,16 @@ def test_inspect_index_matches_reference_log_lines():
     assert info["n_ec_blocks"] == 27
 
 
+def test_inspect_index_saved_targets_only():
+    """index.saved of `kallisto bus` (KmerIndex::write(fn, false), src/KmerIndex.cpp:1226-1327; fixture written by the
+    reference): version, empty graph / D-list / node sections, then the targets.  The host parser reads it (quant-tcc
+    runs on it)."""
+    info = K.inspect_index(os.path.join(util.GOLDEN, "buspaired", "ref_bulk_paired", "index.saved"))
+    full = K.inspect_index(util.dataset("synth_small")["index"])
+    assert info["n_targets"] == full["n_targets"] == 491 and info["n_kmers"] == 0 and info["n_unitigs"] == 0
+    assert K.inspect_index(os.path.join(util.GOLDEN, "buspaired", "dlist_index.saved"))["n_targets"] == 491
+
+
 def test_bad_index_is_rejected():
     with pytest.raises(K.KallistoB200Error):
         K.inspect_index(os.path.join(util.ROOT, "include", "kallisto_b200.h"))

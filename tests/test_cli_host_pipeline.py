@@ -109,6 +109,57 @@ def test_bus_records_in_read_order(setup):
     assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 1000
 
 
+def test_bus_bulk_samples_follow_the_file_sets(setup, tmp_path):
+    """`bus -x bulk [--paired]` (src/main.cpp:1050-1107): every file (pair) is a sample.  The stub stamps the sample it was
+    told about (kb_bus_begin_sample) into the records, so the record counts per sample must equal the read counts of the
+    files whatever the batch cuts; matrix.cells, matrix.sample.barcodes and index.saved are host work and must equal the
+    reference's files (tests/golden/buspaired)."""
+    import numpy as np
+    from oracle import oracle as O
+    s = setup
+    inputs = util.buspaired_inputs(str(tmp_path))
+    ref = os.path.join(util.GOLDEN, "buspaired", "ref_bulk_paired")
+    for i, env in enumerate([{}, {"KB_CLI_BATCH_READS": "700,1100"}, {"KB_CLI_BATCH_READS": "12000,5"}]):
+        e = dict(os.environ)
+        e.update(env)
+        out = tmp_path / ("bulk%d" % i)
+        r = subprocess.run([s["exe"], "bus", "-i", s["idx"], "-o", str(out), "-x", "bulk", "--paired", "-t", "4"] +
+                           [inputs[k] for k in ("a_1", "a_2", "b_1", "b_2")], capture_output=True, text=True, env=e, timeout=600)
+        assert r.returncode == 0, r.stderr[-500:]
+        hdr, rec = O.read_bus(str(out / "output.bus"))
+        assert (hdr["bclen"], hdr["umilen"]) == (16, 1)
+        assert np.array_equal(rec["umi"], np.repeat([0, 1], [12000, 8000]))
+        for fn in ("matrix.cells", "matrix.sample.barcodes", "index.saved"):
+            assert open(out / fn, "rb").read() == open(os.path.join(ref, fn), "rb").read(), fn
+        fl = [line.split() for line in open(out / "flens.txt")]
+        assert len(fl) == 2 and all(len(x) == 1000 for x in fl) and fl[0][1] == "0" and fl[1][1] == "1"
+    # single-end: three files, three samples; no flens.txt
+    out = tmp_path / "bulk_se"
+    r = subprocess.run([s["exe"], "bus", "-i", s["idx"], "-o", str(out), "-x", "bulk", "-t", "2"] +
+                       [inputs[k] for k in ("a_1", "b_1", "a_2")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    _, rec = O.read_bus(str(out / "output.bus"))
+    assert np.array_equal(rec["umi"], np.repeat([0, 1, 2], [12000, 8000, 12000]))
+    assert not os.path.exists(out / "flens.txt") and os.path.exists(out / "index.saved")
+    assert open(out / "matrix.cells").read() == "batch0\nbatch1\nbatch2\n"
+    # an odd number of files with --paired, and --paired with a single-read technology, are refused like the reference does
+    r = subprocess.run([s["exe"], "bus", "-i", s["idx"], "-o", str(tmp_path / "bad"), "-x", "bulk", "--paired", inputs["a_1"]],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "Error: paired-end mode requires an even number of input files" in r.stderr
+    r = subprocess.run([s["exe"], "bus", "-i", s["idx"], "-o", str(tmp_path / "bad2"), "-x", "10xv2", "--paired", inputs["a_1"], inputs["a_2"]],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "Error: Paired reads are not compatible with the specified technology" in r.stderr
+
+
+def test_index_saved_of_a_dlist_index_host(setup, tmp_path):
+    dl = os.path.join(util.GOLDEN, "dlist")
+    out = tmp_path / "o"
+    r = subprocess.run([setup["exe"], "bus", "-i", os.path.join(dl, "transcripts.kidx"), "-o", str(out), "-x", "bulk", "--paired",
+                        os.path.join(dl, "reads_1.fastq.gz"), os.path.join(dl, "reads_2.fastq.gz")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert open(out / "index.saved", "rb").read() == open(os.path.join(util.GOLDEN, "buspaired", "dlist_index.saved"), "rb").read()
+
+
 def test_host_pipeline_under_thread_sanitizer(setup, tmp_path):
     s = setup
     probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", str(tmp_path / "probe")], input="int main(){}", text=True,

@@ -57,3 +57,67 @@ def handles_to_ids(frag_handles, ec_handles):
     """Translate per-fragment device handles into EC ids (order of first occurrence)."""
     m = {int(h): i for i, h in enumerate(ec_handles)}
     return np.array([m[int(h)] if h >= 0 else -1 for h in frag_handles], np.int32)
+
+
+# ---- paired / sample-per-file BUS runs (tests/golden/buspaired) -------------------------------------------------------
+# The inputs are derived from synth_small's reads by this one function, used by tests/golden/make_golden.py (which runs
+# the unmodified reference on them) and by the tests (which run this build on them), so only the outputs are stored.
+BUSPAIRED_CASES = {
+    # name: (arguments after `bus -i IDX -o OUT -t T`, input files by key)
+    "bulk_paired": (["-x", "bulk", "--paired"], ["a_1", "a_2", "b_1", "b_2"]),
+    "bulk_paired_num_fr": (["-x", "bulk", "--paired", "--num", "--fr-stranded"], ["a_1", "a_2", "b_1", "b_2"]),
+    "bulk_single": (["-x", "bulk"], ["a_1", "b_1", "a_2"]),
+    "smartseq2_paired": (["-x", "smartseq2", "--paired"], ["i_1", "i_2", "s_1", "s_2"]),
+    "smartseq2_single_rf": (["-x", "smartseq2", "--rf-stranded"], ["i_1", "i_2", "s_1"]),
+    "stormlike": (["-x", "-1,-1,-1:1,0,8:0,0,0,1,14,0", "--paired", "--rf-stranded"], ["s_1", "u_2"]),
+}
+
+
+def buspaired_inputs(dst):
+    """Writes the FASTQ files of the buspaired cases into `dst` -> {key: path}.
+    a_*/b_*: synth_small's pairs 0..11999 / 12000..19999 (two samples of `bus -x bulk`);
+    s_*: pairs 0..7999; i_1/i_2: index reads for them (SMARTSEQ2: the barcode is both index reads, whole: 6 cells,
+    some reads with an N, some 6 instead of 8 nt, three empty ones -- an empty barcode piece skips the read set,
+    src/ProcessReads.cpp:1592-1598); u_2: the second mates with a 14-nt prefix whose first 8 nt are the UMI
+    (the STORM-seq layout, src/main.cpp:1358-1365), some with an N in the UMI, some shorter than the UMI."""
+    ds = dataset("synth_small")
+    s1, s2 = ds["s1"], ds["s2"]
+    rng = np.random.default_rng(20260923)
+    A = np.frombuffer(b"ACGT", np.uint8)
+
+    def write(key, seqs):
+        p = os.path.join(dst, key + ".fq")
+        with open(p, "wb") as f:
+            for i, s in enumerate(seqs):
+                if not isinstance(s, bytes):
+                    s = s.encode()
+                f.write(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+        return p
+
+    out = {}
+    out["a_1"] = write("a_1", s1[:12000]); out["a_2"] = write("a_2", s2[:12000])
+    out["b_1"] = write("b_1", s1[12000:]); out["b_2"] = write("b_2", s2[12000:])
+    n = 8000
+    out["s_1"] = write("s_1", s1[:n]); out["s_2"] = write("s_2", s2[:n])
+    cells = A[rng.integers(0, 4, (6, 2, 8))]
+    which = rng.integers(0, 6, n)
+    i1 = [bytes(cells[c, 0]) for c in which]
+    i2 = [bytes(cells[c, 1]) for c in which]
+    for j in rng.choice(n, 80, replace=False):
+        b = bytearray(i1[j]); b[int(rng.integers(0, 8))] = ord("N"); i1[j] = bytes(b)
+    for j in rng.choice(n, 40, replace=False):
+        i2[j] = i2[j][:6]
+    for j in rng.choice(n, 3, replace=False):
+        i1[j] = b""
+    out["i_1"] = write("i_1", i1); out["i_2"] = write("i_2", i2)
+    pre = A[rng.integers(0, 4, (n, 14))]
+    u2 = []
+    for j in range(n):
+        m = s2[j] if isinstance(s2[j], bytes) else s2[j].encode()
+        u2.append(bytes(pre[j]) + m)
+    for j in rng.choice(n, 60, replace=False):
+        b = bytearray(u2[j]); b[int(rng.integers(0, 8))] = ord("N"); u2[j] = bytes(b)
+    for j in rng.choice(n, 5, replace=False):
+        u2[j] = u2[j][:int(rng.integers(1, 8))]
+    out["u_2"] = write("u_2", u2)
+    return out
