@@ -9,6 +9,7 @@
 #include <atomic>
 #include <algorithm>
 #include <charconv>
+#include <cmath>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -25,6 +26,7 @@
 
 #include "../../include/kallisto_b200.h"
 #include "fastx.hpp"
+#include "h5_writer.hpp"
 
 using std::cerr;
 using std::endl;
@@ -223,12 +225,8 @@ bool check_quant(Options& opt) {   // CheckOptionsEM, src/main.cpp:1600-1805
     cerr << "Error: number of bootstrap samples must be a non-negative integer." << endl;
     ret = false;
   }
-  if (opt.bootstrap > 0 && !opt.plaintext) {
-    cerr << "Warning: kallisto was not compiled with HDF5 support so no bootstrapping" << endl
-         << "will be performed. Run quant with --plaintext option or recompile with" << endl
-         << "HDF5 support to obtain bootstrap estimates." << endl;
-    opt.bootstrap = 0;
-  }
+  // (a reference built without HDF5 drops the bootstraps here unless --plaintext is given, src/main.cpp:1796-1803; this
+  // build writes abundance.h5 itself -- csrc/h5_writer.hpp -- and so behaves like the reference built WITH HDF5)
   return ret;
 }
 
@@ -684,16 +682,57 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
   write_abundance(opt.output + "/abundance.tsv", names, lens, eff.data(), est.data());
   pt.mark("finalize + write abundance.tsv");
   if (pt.on) cerr << endl;
+  // without --plaintext the estimates (and the bootstraps) also go into abundance.h5, as in a reference built with HDF5
+  // (H5Writer::init / write_main / write_bootstrap, src/H5Writer.cpp:4-71; src/main.cpp:2693-2702,2732-2776)
+  kb::H5Writer h5;
+  int h5_aux = -1, h5_bs = -1;
+  if (!opt.plaintext) {
+    h5.add_f64(0, "est_counts", est.data(), T);
+    h5_aux = h5.group("aux");
+    if (opt.bootstrap > 0) h5_bs = h5.group("bootstrap");
+    const int32_t nb = opt.bootstrap, np = (int32_t)st.n_processed, iv = 13;
+    h5.add_i32(h5_aux, "num_bootstrap", &nb, 1);
+    h5.add_i32(h5_aux, "num_processed", &np, 1);
+    std::vector<int32_t> fld(1000, 0);
+    if (opt.fld == 0.0) {
+      for (int i = 0; i < 1000; ++i) fld[i] = (int32_t)flens[i];
+    } else {      // trunc_gaussian_counts(0, MAX_FRAG_LEN, mean, sd, 10000), src/weights.cpp:273-296
+      double total_mass = 0.0;
+      for (int i = 0; i < 1000; ++i) { const double x = ((double)i - opt.fld) / opt.sd; total_mass += std::exp(-0.5 * x * x) / opt.sd; }
+      for (int i = 0; i < 1000; ++i) {
+        const double x = ((double)i - opt.fld) / opt.sd;
+        fld[i] = (int)std::round(std::exp(-0.5 * x * x) / opt.sd * 10000 / total_mass);
+      }
+    }
+    h5.add_i32(h5_aux, "fld", fld.data(), fld.size());
+    const std::vector<int32_t> bias_obs(4096, 1);        // no --bias in this build: the reference's untouched vectors
+    const std::vector<double> bias_norm(4096, 1.0);      // (src/main.cpp:2676, src/EMAlgorithm.h:37)
+    h5.add_i32(h5_aux, "bias_observed", bias_obs.data(), bias_obs.size());
+    h5.add_f64(h5_aux, "bias_normalized", bias_norm.data(), bias_norm.size());
+    h5.add_str(h5_aux, "kallisto_version", {KALLISTO_VERSION});
+    h5.add_i32(h5_aux, "index_version", &iv, 1);
+    h5.add_str(h5_aux, "call", {call});
+    h5.add_str(h5_aux, "start_time", {start_time});
+    h5.add_str(h5_aux, "ids", names);
+    h5.add_f64(h5_aux, "eff_lengths", eff.data(), T);
+    std::vector<int32_t> l32(lens.begin(), lens.end());
+    h5.add_i32(h5_aux, "lengths", l32.data(), T);
+  }
+  auto emit_bs = [&](int b, const double* alpha) {
+    if (opt.plaintext) write_abundance(opt.output + "/bs_abundance_" + std::to_string(b) + ".tsv", names, lens, eff.data(), alpha);
+    else h5.add_f64(h5_bs, "bs" + std::to_string(b), alpha, T);
+  };
   if (opt.bootstrap > 0 && st.n_pseudoaligned == 0) {
-    for (int b = 0; b < opt.bootstrap; ++b)
-      write_abundance(opt.output + "/bs_abundance_" + std::to_string(b) + ".tsv", names, lens, eff.data(), est.data());
+    for (int b = 0; b < opt.bootstrap; ++b) emit_bs(b, est.data());
   } else if (opt.bootstrap > 0) {
     std::vector<double> bs((size_t)opt.bootstrap * T);
     cerr << "[bstrp] running EM for " << opt.bootstrap << " bootstraps on the device" << endl;
     KB_TRY(kb_bootstrap_run(q, opt.fld, opt.sd, opt.seed, opt.bootstrap, bs.data(), nullptr, nullptr));
-    for (int b = 0; b < opt.bootstrap; ++b)
-      write_abundance(opt.output + "/bs_abundance_" + std::to_string(b) + ".tsv", names, lens, eff.data(),
-                      bs.data() + (size_t)b * T);
+    for (int b = 0; b < opt.bootstrap; ++b) emit_bs(b, bs.data() + (size_t)b * T);
+  }
+  if (!opt.plaintext && !h5.write(opt.output + "/abundance.h5")) {
+    cerr << "Error: could not write " << opt.output << "/abundance.h5" << endl;
+    exit(1);
   }
   cerr << endl;
   if (!getenv("KB_CLI_CLEANUP")) finish(st.n_pseudoaligned == 0 ? 1 : 0);

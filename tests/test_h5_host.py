@@ -1,0 +1,79 @@
+"""CPU: abundance.h5 as written by csrc/h5_writer.hpp (no libhdf5 in this build; H5Writer of the reference:
+src/H5Writer.cpp:4-71, src/h5utils.h:42-91) read back by the independent, strict reader tests/h5mini.py: every dataset the
+reference writes is there, with the reference's types (int32 / double / fixed-length NUL-terminated strings), one
+deflate-compressed chunk each, and holds exactly the numbers of abundance.tsv's run."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import h5mini, util
+from tests.test_cli_host_pipeline import build
+
+CSRC = os.path.join(util.ROOT, "kallisto_b200", "csrc")
+pytestmark = pytest.mark.skipif(not shutil.which("g++"), reason="no g++")
+
+
+@pytest.mark.parametrize("n,B", [(1, 0), (1000, 3), (5000, 300)])
+def test_writer_round_trip(tmp_path, n, B):
+    exe = str(tmp_path / "h5_driver")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + CSRC, "-o", exe, os.path.join(util.ROOT, "tests", "stub", "h5_driver.cpp"), "-lz"])
+    path = str(tmp_path / "t.h5")
+    subprocess.check_call([exe, path, str(n), str(B)])
+    f = h5mini.File(path)
+    r = f.root
+    assert f.deflate_level == 6
+    assert sorted(r) == (["aux", "bootstrap", "est_counts"] if B else ["aux", "est_counts"])
+    est = np.array([i * 0.5 + 1.0 / (i + 1) for i in range(n)])
+    assert r["est_counts"].dtype == np.dtype("<f8") and np.array_equal(r["est_counts"], est)          # bit-exact doubles
+    assert r["aux"]["ids"] == ["ENST%d%s|gene" % (i, "x" * (i % 40)) for i in range(n)]
+    assert r["aux"]["lengths"].dtype == np.dtype("<i4") and np.array_equal(r["aux"]["lengths"], 200 + 7 * np.arange(n))
+    assert list(r["aux"]["num_bootstrap"]) == [B]
+    if B:
+        assert sorted(r["bootstrap"]) == sorted("bs%d" % b for b in range(B))
+        for b in (0, B // 2, B - 1):
+            assert np.array_equal(r["bootstrap"]["bs%d" % b], est * (b + 1))
+        assert f.int_k >= (B + 7) // 8 / 2                      # all symbol table nodes of /bootstrap under one B-tree node
+
+
+def test_quant_writes_abundance_h5_like_an_hdf5_build(tmp_path):
+    """Through the command line (host side against the stub library): without --plaintext abundance.h5 appears next to
+    abundance.tsv and holds the same run (src/main.cpp:2693-2702); bootstraps go into /bootstrap instead of
+    bs_abundance_*.tsv (:2732-2776); with --plaintext there is no HDF5 file."""
+    exe = build(str(tmp_path / "stub"))
+    ds = os.path.join(util.GOLDEN, "synth_small")
+    files = [os.path.join(ds, "reads_%d.fastq.gz" % m) for m in (1, 2)]
+    idx = os.path.join(ds, "transcripts.kidx")
+    env = dict(os.environ, KB_CLI_CLEANUP="1")
+    out = tmp_path / "o"
+    r = subprocess.run([exe, "quant", "-i", idx, "-o", str(out), "-b", "11", "-t", "2"] + files, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert sorted(os.listdir(out)) == ["abundance.h5", "abundance.tsv", "run_info.json"]
+    h = h5mini.read(str(out / "abundance.h5"))
+    names, lens, eff, est, tpm = util.read_abundance(str(out / "abundance.tsv"))
+    assert sorted(h) == ["aux", "bootstrap", "est_counts"]
+    assert sorted(h["aux"]) == sorted(["num_bootstrap", "num_processed", "fld", "bias_observed", "bias_normalized", "kallisto_version",
+                                       "index_version", "call", "start_time", "ids", "eff_lengths", "lengths"])
+    assert h["aux"]["ids"] == names and np.array_equal(h["aux"]["lengths"], lens)
+    np.testing.assert_allclose(h["est_counts"], est, rtol=1e-5)         # the text file has 6 significant digits
+    np.testing.assert_allclose(h["aux"]["eff_lengths"], eff, rtol=1e-5)
+    assert list(h["aux"]["num_bootstrap"]) == [11] and list(h["aux"]["num_processed"]) == [20000] and list(h["aux"]["index_version"]) == [13]
+    assert h["aux"]["kallisto_version"] == ["0.51.1"] and h["aux"]["call"][0].startswith(exe + " quant -i ")
+    assert len(h["aux"]["fld"]) == 1000 and h["aux"]["fld"][200] == 10          # the stub's histogram
+    assert len(h["aux"]["bias_observed"]) == 4096 and set(h["aux"]["bias_observed"]) == {1} and set(h["aux"]["bias_normalized"]) == {1.0}
+    assert sorted(h["bootstrap"]) == sorted("bs%d" % b for b in range(11))
+    import json
+    assert json.load(open(out / "run_info.json"))["n_bootstraps"] == 11
+    # -l / -s: the stored distribution is the truncated Gaussian of trunc_gaussian_counts (src/weights.cpp:273-296)
+    out2 = tmp_path / "o2"
+    r = subprocess.run([exe, "quant", "-i", idx, "-o", str(out2), "--single", "-l", "200", "-s", "20", files[0]], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
+    fld = h5mini.read(str(out2 / "abundance.h5"))["aux"]["fld"]
+    x = (np.arange(1000) - 200.0) / 20.0
+    dens = np.exp(-0.5 * x * x) / 20.0
+    assert np.array_equal(fld, np.round(dens * 10000 / dens.sum()).astype(np.int32)) and 9990 <= fld.sum() <= 10010
+    out3 = tmp_path / "o3"
+    r = subprocess.run([exe, "quant", "-i", idx, "-o", str(out3), "--plaintext", "-b", "2"] + files, capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and sorted(os.listdir(out3)) == ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv", "run_info.json"]
