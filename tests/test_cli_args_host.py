@@ -40,6 +40,10 @@ CASES = [
     ["bus", "-i", IDX, "-o", "o", "-x", "0,0,16:0,16,26:1,0,0:1,0,0", B1, B2],
     ["bus", "-i", IDX, "-o", "o", "-x", "0,0,16:0,16,26:1,0,0", B1],
     ["bus", "-o", "o", "-x", "10xv2", B1, B2],
+    ["bus", "-i", IDX, "-o", "o", "-x", "bulk", "--paired", R1],
+    ["bus", "-i", IDX, "-o", "o", "-x", "10xv2", "--paired", B1, B2],
+    ["bus", "-i", IDX, "-o", "o", "-x", "STORM-seq", R1, R2],          # upper-cased before it is compared: not selectable (src/main.cpp:619,1358)
+    ["bus", "-i", IDX, "-o", "o", "-x", "smartseq2", R1, R2],          # three files without --paired
     ["quant", "-i", IDX, "-o", "o", "--single", "-l", "200", "-s", "20"],
     ["quant", "-i", IDX, "-o", "o", "-t", "-2", "--single", "-l", "200", "-s", "20", R1],
 ]
