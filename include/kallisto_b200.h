@@ -220,6 +220,11 @@ typedef struct kb_bus_opts {
                                    * pseudoaligned as a pair (match x 2 + intersectKmers + mapPair, :1646-1650,1747-1756);
                                    * the fragment-length histogram is read with kb_quant_get_flens */
   kb_bus_substr seq2;             /* second sequence read when paired; stop must be 0 */
+  const char* tag;                /* UMI tag sequence (`--tag`, SMARTSEQ3: "ATTGCGCAATG"; src/main.cpp:1447-1475,
+                                   * src/ProcessReads.cpp:1497-1530) or NULL.  umi[0] must then cover tag + UMI, as the user
+                                   * of the reference gives it; a read set whose UMI is not preceded by the tag (one mismatch
+                                   * allowed when it is longer than 5) is an internal read: UMI ~0, the sequence starts where
+                                   * the tag would have, no strand filter, and only those sample fragment lengths. */
 } kb_bus_opts;
 typedef struct kb_bus_record {    /* BUSData, src/BUSData.h:30-38: 32 bytes, as written to output.bus */
   uint64_t barcode, umi;

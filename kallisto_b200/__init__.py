@@ -53,7 +53,7 @@ class kb_bus_opts(C.Structure):
     _fields_ = [("nfiles", C.c_int32), ("n_bc", C.c_int32), ("bc", kb_bus_substr * 4), ("n_umi", C.c_int32),
                 ("umi", kb_bus_substr * 4), ("seq", kb_bus_substr), ("strand_mode", C.c_int32), ("num", C.c_int32),
                 ("max_batch_sets", C.c_uint32), ("max_batch_bases", C.c_uint64), ("paired", C.c_int32),
-                ("seq2", kb_bus_substr)]
+                ("seq2", kb_bus_substr), ("tag", C.c_char_p)]
 
 
 BUS_RECORD_DTYPE = np.dtype([("barcode", "<u8"), ("umi", "<u8"), ("ec", "<i4"), ("count", "<u4"), ("flags", "<u4"),
@@ -81,6 +81,7 @@ TECHNOLOGIES = {
     "SMARTSEQ2": (3, [(0, 0, 0), (1, 0, 0)], [(-1, -1, -1)], (2, 0, 0), 0),
     "SMARTSEQ2-PAIRED": (4, [(0, 0, 0), (1, 0, 0)], [(-1, -1, -1)], (2, 0, 0), 0, (3, 0, 0)),
     "STORM-SEQ": (2, [], [(1, 0, 8)], (0, 0, 0), 2, (1, 14, 0)),
+    "SMARTSEQ3": (4, [(0, 0, 0), (1, 0, 0)], [(2, 0, 19)], (2, 22, 0), 1, (3, 0, 0)),   # with tag="ATTGCGCAATG"
 }
 
 
@@ -421,7 +422,7 @@ class Comm:
 class BUSProcessor(MinCollector):
     """`kallisto bus` run (BUSProcessor::processBuffer + the BUS part of MasterProcessor::update)."""
 
-    def __init__(self, index, technology, strand="default", num=False, max_batch_sets=0):
+    def __init__(self, index, technology, strand="default", num=False, max_batch_sets=0, tag=None):
         self.index = index
         self.paired = False
         tech = TECHNOLOGIES[technology.upper()] if isinstance(technology, str) else technology
@@ -442,6 +443,8 @@ class BUSProcessor(MinCollector):
         o.strand_mode = dstrand if strand == "default" else {None: 0, "unstranded": 0, "fr": 1, "rf": 2}[strand]
         o.num = int(num)
         o.max_batch_sets = max_batch_sets
+        if tag:
+            o.tag = tag if isinstance(tag, bytes) else tag.encode()      # --tag / SMARTSEQ3: umi[0] covers tag + UMI
         self.nfiles = nfiles
         self._h = C.c_void_p()
         _ck(lib().kb_bus_create(index._h, C.byref(o), C.byref(self._h)))

@@ -495,6 +495,23 @@ int kb_bus_create(kb_index* ix, const kb_bus_opts* o, kb_quant** out) {
     s.seq2_file = o->paired ? o->seq2.fileno : 0;
     s.seq2_start = o->paired ? o->seq2.start : 0;
     s.fake_bc = 0;
+    s.tag_len = 0;
+    s.tag_bin = 0;
+    if (o->tag && o->tag[0]) {
+      const size_t tl = strlen(o->tag);
+      if (no_umi || tl > 31) throw std::invalid_argument("kb_bus_create: a tag sequence needs a UMI and at most 31 letters");
+      // opt.busOptions.umi[0].start += tag length; it must stay in front of the stop (src/main.cpp:1467-1475)
+      s.umi_a[0] += (int)tl;
+      if (s.umi_b[0] != 0 && s.umi_a[0] >= s.umi_b[0]) throw std::invalid_argument("Error: Tag sequence must be shorter than UMI sequence");
+      unsigned long long r = 0;                       // stringToBinary (src/BUSData.cpp:8-36)
+      for (size_t i = 0; i < tl; ++i) {
+        const unsigned c = (unsigned char)o->tag[i];
+        const unsigned long long x = (c & 4) >> 1;
+        r = (r << 2) | (x + ((x ^ (c & 2)) >> 1));
+      }
+      s.tag_len = (int)tl;
+      s.tag_bin = r;
+    }
     kb_quant* h = new kb_quant();
     h->owner = ix;
     h->q.reset(new kb::Quant(*ix->ix, q));

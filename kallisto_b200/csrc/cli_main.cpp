@@ -756,12 +756,13 @@ struct Tech {
   kb_bus_substr seq2 = {-1, 0, 0};   // paired technologies: the second sequence read
 };
 
-const std::vector<Tech>& tech_table() {   // src/main.cpp:1283-1407: every technology but SMARTSEQ3, which needs a tag sequence.
+const std::vector<Tech>& tech_table() {   // src/main.cpp:1283-1407.
                                           // SMARTSEQ2 grows a fourth file with --paired (cmd_bus).  "STORM-seq" cannot be
                                           // selected in the reference either: -x is upper-cased (:619) before it is compared
                                           // with the mixed-case name (:1358); its layout is -x -1,-1,-1:1,0,8:0,0,0,1,14,0
   static const std::vector<Tech> t = {
       {"SMARTSEQ2", 3, {{0, 0, 0}, {1, 0, 0}}, {{-1, -1, -1}}, {2, 0, 0}, 0},
+      {"SMARTSEQ3", 4, {{0, 0, 0}, {1, 0, 0}}, {{2, 0, 19}}, {2, 22, 0}, 1, {3, 0, 0}},      // + the default tag sequence, below
       {"BDWTA", 2, {{0, 0, 9}, {0, 21, 30}, {0, 43, 52}}, {{0, 52, 60}}, {1, 0, 0}, 1},
       {"VASA-SEQ", 1, {{0, 6, 14}}, {{0, 0, 6}}, {0, 14, 0}, 1},
       {"10XV1", 3, {{0, 0, 14}}, {{1, 0, 10}}, {2, 0, 0}, 1},
@@ -840,24 +841,26 @@ void usage_bus() {
             << "-o, --output-dir=STRING       Directory to write output to" << endl
             << "-x, --technology=STRING       Single-cell technology used (10xv1, 10xv2, 10xv3, visium, surecell," << endl
             << "                              dropseq, indropsv1/2/3, celseq, celseq2, split-seq, scrbseq, bdwta," << endl
-            << "                              vasa-seq, smartseq2), a custom bc:umi:seq string of file,start,stop" << endl
+            << "                              vasa-seq, smartseq2, smartseq3), a custom bc:umi:seq string of file,start,stop" << endl
             << "                              triplets, or bulk (every file or file pair is a sample of its own)" << endl << endl
             << "Optional arguments:" << endl
             << "-t, --threads=INT             Number of host threads (default: 1)" << endl
             << "-n, --num                     Output number of read in flag column" << endl
             << "    --paired                  Treat reads as paired (bulk, smartseq2, custom technologies with two" << endl
             << "                              sequence reads)" << endl
+            << "    --tag=STRING              5' tag sequence to identify UMI reads for certain technologies" << endl
             << "    --fr-stranded / --rf-stranded / --unstranded   Strand specificity" << endl
             << "    --device=INT              CUDA device ordinal (default: 0)" << endl;
 }
 
 int cmd_bus(int argc, char** argv, const std::string& call, const std::string& start_time) {
   Options opt;
-  std::string technology;
+  std::string technology, tagsequence;
   int num_flag = 0, fr = 0, rf = 0, unstranded = 0, verbose_flag = 0, paired_flag = 0;
-  const char* opt_string = "i:o:x:t:nD:";
+  const char* opt_string = "i:o:x:t:nD:T:";
   static struct option long_options[] = {{"verbose", no_argument, &verbose_flag, 1},
                                          {"paired", no_argument, &paired_flag, 1},
+                                         {"tag", required_argument, 0, 'T'},
                                          {"num", no_argument, 0, 'n'},
                                          {"fr-stranded", no_argument, &fr, 1},
                                          {"rf-stranded", no_argument, &rf, 1},
@@ -877,6 +880,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
       case 't': std::stringstream(optarg) >> opt.threads; break;
       case 'n': num_flag = 1; break;
       case 'D': std::stringstream(optarg) >> opt.device; break;
+      case 'T': std::stringstream(optarg) >> tagsequence; break;
       default: break;
     }
   }
@@ -913,6 +917,10 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     bo.umi[0] = kb_bus_substr{-1, -1, -1};
     bo.seq = kb_bus_substr{0, 0, 0};
     if (paired_flag) { bo.paired = 1; bo.seq2 = kb_bus_substr{1, 0, 0}; }
+    if (!tagsequence.empty()) {      // src/main.cpp:1191-1194
+      cerr << "Error: --tag not supported in this mode" << endl;
+      ret = false;
+    }
   } else {
     std::string up = technology;
     for (auto& ch : up) ch = (char)toupper(ch);
@@ -920,10 +928,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     for (auto& t : tech_table())
       if (up == t.name) found = &t;
     std::vector<kb_bus_substr> bc, umi, seq;
-    if (up == "SMARTSEQ3") {
-      cerr << "Error: this build does not handle UMI tag sequences (SMARTSEQ3, --tag)" << endl;
-      ret = false;
-    } else if (found) {
+    if (found) {
       bo.nfiles = found->nfiles;
       bc = found->bc; umi = found->umi; seq = {found->seq};
       tech_strand = found->strand;
@@ -978,6 +983,10 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
         if (two) { bo.paired = 1; bo.seq2 = seq[1]; }
       }
     }
+    if (ret && tagsequence.empty() && up == "SMARTSEQ3") {      // src/main.cpp:1447-1450
+      tagsequence = "ATTGCGCAATG";
+      cerr << "[bus] Using " << tagsequence << " as UMI tag sequence" << endl;
+    }
     if (ret && paired_flag && !bo.paired) {      // src/main.cpp:1472-1475
       cerr << "Error: Paired reads are not compatible with the specified technology" << endl;
       ret = false;
@@ -997,6 +1006,14 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     if (strand == 1) cerr << "[bus] Note: Strand option was not specified; setting it to --fr-stranded for specified technology" << endl;
     else if (strand == 2) cerr << "[bus] Note: Strand option was not specified; setting it to --rf-stranded for specified technology" << endl;
     else cerr << "[bus] Note: Strand option was not specified; setting it to --unstranded for specified technology" << endl;
+  }
+  if (!tagsequence.empty() && !batch_mode && bo.n_umi > 0) {      // src/main.cpp:1467-1475: the UMI starts after the tag
+    if (bo.umi[0].fileno < 0 || bo.umi[0].start + (int)tagsequence.size() >= bo.umi[0].stop || tagsequence.size() > 31) {
+      cerr << "Error: Tag sequence must be shorter than UMI sequence" << endl;
+      ret = false;
+    } else {
+      bo.tag = tagsequence.c_str();
+    }
   }
   if (opt.output.empty()) { cerr << "Error: need to specify output directory " << opt.output << endl; ret = false; }
   else if (stat(opt.output.c_str(), &stt) == 0) {
@@ -1035,6 +1052,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     return r;
   };
   uint32_t bclen = (uint32_t)spec_len(bo.bc, bo.n_bc), umilen = (uint32_t)spec_len(bo.umi, bo.n_umi);
+  if (bo.tag && umilen > 0) umilen -= (uint32_t)tagsequence.size();      // getUMILength() of the advanced UMI location
   if (batch_mode) umilen = 1;      // writeBUSHeader(busf_out, BUSFORMAT_FAKE_BARCODE_LEN, 1), src/ProcessReads.h:241-242
   const uint32_t hdr_bclen = bo.n_bc == 0 ? 16u : bclen;
   const std::string busfile = opt.output + "/output.bus";

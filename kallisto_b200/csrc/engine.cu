@@ -527,6 +527,9 @@ void Quant::run_batch(const uint8_t* d_bases, const uint32_t* d_off, uint32_t n_
   ba.fp_fl = opt_.fp_fl;
   ba.start = cur_start_;
   ba.start2 = cur_start2_;
+  ba.notag = cur_notag_;
+  ba.alt_start = cur_alt_start_;
+  ba.alt_start2 = cur_alt_start2_;
   ResolveArgs ra{};
   ra.scratch = bws_->d_scratch.p;
   ra.scratch_stride = scratch_stride_;
@@ -713,6 +716,7 @@ uint32_t Quant::bus_core(const uint8_t* const* db, const uint32_t* const* dofs, 
   const size_t n1 = (size_t)n_sets + 1;
   auto grow = [&](auto& b, size_t need) { if (b.n < need) b.alloc(std::max<size_t>(need, (size_t)opt_.max_batch_reads + 1)); };
   grow(bus_bc_, n1); grow(bus_umi_, n1); grow(bus_flags_, n1); grow(bus_skip_, n1);
+  if (sp.tag_len) grow(bus_notag_, n1);
   grow(bus_isnew_, n1); grow(bus_newrank_, n1); grow(bus_ismapped_, n1); grow(bus_rank_, n1); grow(bus_rec_, n1);
   if (bus_hist_.n < 66) { bus_hist_.alloc(66); bus_hist_.zero(st); }
   if (bus_nvalid_.n < 1) bus_nvalid_.alloc(1);
@@ -724,11 +728,21 @@ uint32_t Quant::bus_core(const uint8_t* const* db, const uint32_t* const* dofs, 
   a.set_base = n_frag_total_ - bus_sample_base_;      // --num: read numbers restart with every sample (one reader per batch)
   a.spec = sp;
   a.barcode = (uint64_t*)bus_bc_.p; a.umi = (uint64_t*)bus_umi_.p; a.flags = bus_flags_.p; a.skip = bus_skip_.p;
+  a.notag = sp.tag_len ? bus_notag_.p : nullptr;
   a.bc_hist = bus_hist_.p; a.umi_hist = bus_hist_.p + 33; a.n_valid = bus_nvalid_.p;
   launch_bus_fields(a, st);
   KB_CK(cudaGetLastError());
   // the cDNA read(s): single-read or paired pseudoalignment with the strand filter of the technology
-  const uint32_t min_start = (uint32_t)(sp.paired ? std::min(sp.seq_start, sp.seq2_start) : sp.seq_start);
+  uint32_t min_start = (uint32_t)(sp.paired ? std::min(sp.seq_start, sp.seq2_start) : sp.seq_start);
+  if (sp.tag_len) {
+    // a read set without the tag has no UMI: the sequence read that shares the UMI's file starts where the tag would
+    // have started (src/ProcessReads.cpp:1547,1553-1554), the other one where the technology says
+    const int at = sp.umi_a[0] - sp.tag_len;
+    cur_notag_ = bus_notag_.p;
+    cur_alt_start_ = (uint32_t)(sp.umi_f[0] == sp.seq_file ? at : sp.seq_start);
+    cur_alt_start2_ = (uint32_t)(sp.paired && sp.umi_f[0] == sp.seq2_file ? at : sp.seq2_start);
+    min_start = std::min(min_start, sp.paired ? std::min(cur_alt_start_, cur_alt_start2_) : cur_alt_start_);
+  }
   maxlen = maxlen > min_start ? maxlen - min_start : 1;
   const uint64_t base = n_frag_total_;
   cur_skip_ = bus_skip_.p;
@@ -744,6 +758,8 @@ uint32_t Quant::bus_core(const uint8_t* const* db, const uint32_t* const* dofs, 
   cur_skip_ = nullptr;
   cur_start_ = 0;
   cur_start2_ = 0;
+  cur_notag_ = nullptr;
+  cur_alt_start_ = cur_alt_start2_ = 0;
   launch_bus_records(dd_, bws_->d_handles.p, n_sets, base, bus_next_id_, bus_idof_.p, bus_isnew_.p, bus_newrank_.p,
                      bus_ismapped_.p, bus_rank_.p, (const uint64_t*)bus_bc_.p, (const uint64_t*)bus_umi_.p, bus_flags_.p,
                      bus_rec_.p, bus_tmp_.p, bus_tmp_.n, st);

@@ -290,7 +290,7 @@ class Quant {
   bool ecs_valid_ = false;
   struct EmWs* emws_ = nullptr;
   // bus mode
-  DBuf<uint8_t> bus_b_[4], bus_skip_;
+  DBuf<uint8_t> bus_b_[4], bus_skip_, bus_notag_;
   DBuf<uint32_t> bus_o_[4], bus_flags_, bus_hist_, bus_isnew_, bus_newrank_, bus_ismapped_, bus_rank_;
   DBuf<unsigned long long> bus_bc_, bus_umi_, bus_nvalid_;
   DBuf<int32_t> bus_idof_;
@@ -302,7 +302,8 @@ class Quant {
   uint32_t bus_next_id_ = 0;
   uint64_t bus_valid_total_ = 0, bus_sample_base_ = 0;
   const uint8_t* cur_skip_ = nullptr;
-  uint32_t cur_start_ = 0, cur_start2_ = 0;
+  uint32_t cur_start_ = 0, cur_start2_ = 0, cur_alt_start_ = 0, cur_alt_start2_ = 0;
+  const uint8_t* cur_notag_ = nullptr;
 };
 
 std::vector<double> mean_fl_trunc_of(const uint32_t* flens /* 1000 */, double fld_mean, double fld_sd);

@@ -64,6 +64,11 @@ struct BatchArgs {
   int fp_fl;                // >= 0: apply the fragment-position filter of ProcessReads.cpp:1095-1136 with this mean fragment length
   uint32_t start;           // first base of every read that is matched (bus: BUSOptionSubstr.start of the sequence)
   uint32_t start2;          // the same for the second mate of a pair (paired bus technologies, e.g. STORM-seq: 14)
+  // UMI tag sequences (bus --tag / SMARTSEQ3, src/ProcessReads.cpp:1512-1530): notag[f] = 1 marks a fragment without the
+  // tag ("ignore_umi"): its reads start at alt_start / alt_start2, the strand filter is off for it, and ONLY such
+  // fragments sample fragment lengths.  nullptr = no tag sequence in play.
+  const uint8_t* notag;
+  uint32_t alt_start, alt_start2;
 };
 static constexpr int KB_Q_STRIDE = 2 + KB_MAX_E + 6;   // frag, n|flags, handles, 2 strand words, 4 position-filter words
 static constexpr int KB_SPILL = 112;                   // a fragment may hit KB_MAX_E + KB_SPILL = 128 distinct EC sets
@@ -212,6 +217,8 @@ struct BusSpec {        // BUSOptions (src/common.h:38-91): where barcode / UMI 
   int seq2_file, seq2_start;
   int no_umi;           // umi[0].fileno == -1 ("bulk_like", :1393): UMI field = ~0, one count in umi_len[1]
   unsigned long long fake_bc;   // n_bc == 0: the barcode every record gets (0 = 16 x 'A'; batch mode: the sample's id, :1603-1607)
+  int tag_len;                  // --tag: length of the tag sequence that precedes the UMI (0 = none); umi_a[0] is already advanced by it
+  unsigned long long tag_bin;   // stringToBinary(tag)
 };
 struct BusArgs {
   const uint8_t* bases[4];
@@ -223,6 +230,7 @@ struct BusArgs {
   uint64_t* umi;
   uint32_t* flags;
   uint8_t* skip;
+  uint8_t* notag;       // tag runs: 1 = the read set does not carry the tag
   uint32_t* bc_hist;    // 33 bins
   uint32_t* umi_hist;   // 33 bins
   unsigned long long* n_valid;

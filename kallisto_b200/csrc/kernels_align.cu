@@ -166,7 +166,9 @@ __device__ __forceinline__ void read_span(const BatchArgs& ba, uint32_t ridx, co
     off = (uint64_t)i * ba.fixed_len;
     len = (int)ba.fixed_len;
   }
-  const uint32_t st = (ba.paired && (ridx & 1)) ? ba.start2 : ba.start;
+  const bool second = ba.paired && (ridx & 1);
+  uint32_t st = second ? ba.start2 : ba.start;
+  if (ba.notag && ba.notag[ba.paired ? (ridx >> 1) : ridx]) st = second ? ba.alt_start2 : ba.alt_start;
   if (st) {
     off += st;
     len -= (int)st;
@@ -421,6 +423,9 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
             } else {
               xs0 = v_cur ? (f_blk * 2u + (f_strand ? 1u : 0u)) : 0xFFFFFFFFu;
             }
+            // a fragment without the UMI tag is not strand-filtered (doStrandSpecificityIfPossible = false,
+            // ProcessReads.cpp:1526): "no first hit" for both mates makes resolve_kernel skip the filter
+            if (ba.notag && ba.notag[frag]) xs0 = xs1 = 0xFFFFFFFFu;
           }
           const bool use_first = (mate == 1) && !v_cur;     // second mate empty: the first mate's hit
           const uint32_t xf0 = use_first ? m_blk : f_blk;
@@ -508,6 +513,7 @@ __global__ void __launch_bounds__(256, KB_MATCH_MIN_BLOCKS) match_kernel(DevInde
               if (d > 0 && d < 1000) tl = (uint16_t)d;
             }
           }
+          if (ba.notag && !ba.notag[frag]) tl = 0;     // tag runs: only fragments without the tag are sampled (getFragLenIfPaired, :1525)
           ba.tl_out[frag] = tl;
         }
         // per-handle accounting, aggregated over the lanes finalised in this round

@@ -42,13 +42,15 @@ struct Enc {
   }
 };
 
-__device__ __forceinline__ bool slice(const BusArgs& a, uint32_t i, int fileno, int start, int stop, Enc& e) {
+// `back`: letters in front of the slice that are encoded with it (the tag sequence in front of the first UMI piece,
+// src/ProcessReads.cpp:1512-1514); the fit test is the slice's own
+__device__ __forceinline__ bool slice(const BusArgs& a, uint32_t i, int fileno, int start, int stop, Enc& e, int back = 0) {
   const uint32_t o0 = a.off[fileno][i], o1 = a.off[fileno][i + 1];
   const int l = (int)(o1 - o0);
   const int n = (stop == 0) ? l - start : stop - start;
   if (l < start + n || n <= 0) return false;
-  const uint8_t* s = a.bases[fileno] + o0 + start;
-  for (int j = 0; j < n; ++j) e.push(s[j]);
+  const uint8_t* s = a.bases[fileno] + o0 + start - back;
+  for (int j = 0; j < n + back; ++j) e.push(s[j]);
   return true;
 }
 
@@ -66,7 +68,25 @@ __global__ void __launch_bounds__(256) bus_fields_kernel(BusArgs a) {
       u.n = 1;       // "bulk_like" (:1477-1482): a one-letter dummy UMI, never encoded: the record carries umi_binary = -1
       u.r = ~0ull;
     } else {
-      for (int p = 0; p < sp.n_umi && ok; ++p) ok = slice(a, i, sp.umi_f[p], sp.umi_a[p], sp.umi_b[p], u);
+      for (int p = 0; p < sp.n_umi && ok; ++p) ok = slice(a, i, sp.umi_f[p], sp.umi_a[p], sp.umi_b[p], u, p == 0 ? sp.tag_len : 0);
+    }
+    bool tag_missing = false;
+    if (ok && sp.tag_len) {
+      // --tag / SMARTSEQ3 (:1512-1530): the letters in front of the UMI must be the tag (one mismatch allowed when it is
+      // longer than 5); then the UMI is what follows it, else the read set has no UMI at all
+      const int rest = u.n - sp.tag_len;                       // letters of the UMI proper
+      const unsigned long long head = (2 * rest < 64) ? (u.r >> (2 * rest)) : 0ull;
+      unsigned long long df = head ^ sp.tag_bin;
+      int d = 0;
+      for (int j = 0; j < sp.tag_len; ++j, df >>= 2) d += (df & 3ull) != 0;
+      if (d <= (sp.tag_len <= 5 ? 0 : 1)) {
+        if (rest < 32) u.r &= ~(~0ull << (2 * rest));
+        u.n = rest;
+      } else {
+        tag_missing = true;
+        u.r = ~0ull;
+        u.n = 99;                                              // no UMI length is recorded for it
+      }
     }
     if (ok) {
       if (u.n <= 32) atomicAdd(&a.umi_hist[u.n], 1u);
@@ -82,12 +102,13 @@ __global__ void __launch_bounds__(256) bus_fields_kernel(BusArgs a) {
         a.barcode[i] = b.r;
         a.umi[i] = u.r;
         // without a UMI stringToBinary runs once only, so the UMI half of the flags repeats the barcode's (:1736-1743)
-        const uint32_t uf = sp.no_umi ? b.flag() : u.flag();
+        const uint32_t uf = (sp.no_umi || sp.tag_len) ? b.flag() : u.flag();
         a.flags[i] = sp.num_flag ? (uint32_t)(a.set_base + i) : (b.flag() | (uf << 8));
         valid = true;
       }
     }
     a.skip[i] = valid ? 0 : 1;
+    if (a.notag) a.notag[i] = (valid && tag_missing) ? 1 : 0;
   }
   const unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(a.n_valid, (unsigned long long)__popc(m));

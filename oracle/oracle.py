@@ -315,13 +315,23 @@ def string_to_binary(s):
     return r, flag
 
 
-def bus_model(index, files, bc, umi, seq, seq2=None, strand=0, num=False, samples=None):
+def hamming(a, b, n):
+    """hamming (src/BUSData.cpp:55-66): differing 2-bit symbols among the low n"""
+    df = a ^ b
+    return sum(1 for i in range(n) if (df >> (2 * i)) & 3)
+
+
+def bus_model(index, files, bc, umi, seq, seq2=None, strand=0, num=False, samples=None, tag=None):
     """Records, EC sets, per-sample fragment-length histograms and barcode / UMI length histograms of `kallisto bus -t 1`.
 
     files: one list of sequences (bytes) per file of the technology; bc / umi: lists of (file, start, stop), bc == []
     = no barcode read (fake barcode: 0, or the sample's number), umi None = no UMI ("bulk_like", :1393); seq / seq2:
     (file, start) of the sequence read(s), seq2 given = busopt.paired; samples: list of (first set, end set) ranges that
-    are samples of their own (`-x BULK`: barcode = sample number, read numbers and fragment-length quota restart).
+    are samples of their own (`-x BULK`: barcode = sample number, read numbers and fragment-length quota restart);
+    tag: UMI tag sequence (`--tag`, SMARTSEQ3; umi[0].start already advanced by its length, src/main.cpp:1467-1468): a
+    read set whose UMI is preceded by the tag (<= 1 mismatch when the tag is longer than 5) is a UMI read -- strand
+    filter on, no fragment-length sampling; any other is an internal read -- UMI ~0, the whole read is sequence, no
+    strand filter, fragment lengths sampled (:1497-1530,1545-1567).
     Records come out in read order (the reference writes the records of already-known ECs of a batch first,
     src/ProcessReads.cpp:1798-1812 + :603-612 -- compare sorted)."""
     n = len(files[0])
@@ -330,27 +340,37 @@ def bus_model(index, files, bc, umi, seq, seq2=None, strand=0, num=False, sample
     samples = samples or [(0, n)]
     bc_hist = np.zeros(33, np.int64)
     umi_hist = np.zeros(33, np.int64)
-    rec_bc, rec_umi, rec_fl, skip = [0] * n, [0] * n, [0] * n, [False] * n
+    rec_bc, rec_umi, rec_fl, skip, notag = [0] * n, [0] * n, [0] * n, [False] * n, [False] * n
+    taglen = len(tag) if tag else 0
+    tag_bin = string_to_binary(tag)[0] if tag else 0
 
-    def piece(i, f, a, b):          # :1505-1521 / :1592-1602: None = the slice does not fit
+    def piece(i, f, a, b, back=0):          # :1505-1521 / :1592-1602: None = the slice does not fit
         l = len(files[f][i])
         ln = (l - a) if b == 0 else (b - a)
         if l < a + ln or ln <= 0:
             return None
-        return files[f][i][a:a + ln]
+        return files[f][i][a - back:a + ln]
 
     for si, (lo, hi) in enumerate(samples):
         for i in range(lo, hi):
             if umi is None:
                 ulen, uval, uflag = 1, 0xFFFFFFFFFFFFFFFF, None
             else:
-                parts = [piece(i, *u) for u in umi]
+                parts = [piece(i, *u, back=(taglen if j == 0 else 0)) for j, u in enumerate(umi)]
                 if any(p is None for p in parts):
                     skip[i] = True
                     continue
                 us = b"".join(parts)
                 ulen = len(us)
                 uval, uflag = string_to_binary(us)
+                if tag:
+                    uflag = None                       # stringToBinary's flag of the UMI is dropped (local f, :1512-1513)
+                    if hamming(tag_bin, uval >> (2 * (ulen - taglen)), taglen) <= (0 if taglen <= 5 else 1):
+                        uval &= (1 << (2 * (ulen - taglen))) - 1
+                        ulen -= taglen
+                    else:
+                        notag[i] = True
+                        uval, ulen = 0xFFFFFFFFFFFFFFFF, 99
             if ulen <= 32:
                 umi_hist[ulen] += 1
             if bc:
@@ -366,27 +386,59 @@ def bus_model(index, files, bc, umi, seq, seq2=None, strand=0, num=False, sample
             if blen <= 32:
                 bc_hist[blen] += 1
             if uflag is None:
-                uflag = bflag       # no UMI: stringToBinary ran once, for the barcode (:1736-1743)
+                uflag = bflag       # no UMI / tag mode: stringToBinary ran once, for the barcode (:1736-1743)
             rec_bc[i], rec_umi[i] = bval, uval
             rec_fl[i] = (i - lo) if num else (bflag | (uflag << 8))
-    # the sequence read(s): skipped sets have no sequence (they count as processed, :1372)
-    s1 = [b"" if skip[i] else files[seq[0]][i][seq[1]:] for i in range(n)]
-    s2 = [b"" if skip[i] else files[seq2[0]][i][seq2[1]:] for i in range(n)] if paired else None
-    run = OracleRun(index, paired, strand, collect_fld=False)
-    bases, off = to_batch(s1, s2)
-    frag = run.pseudoalign(bases, off)
-    eo, et, ecn = run.ec_table()
+
+    # the sequence read(s): skipped sets have no sequence (they count as processed, :1372); an internal read of a tag
+    # run starts where the tag would have started
+    def seq_of(i, sq):
+        if skip[i]:
+            return b""
+        st = sq[1]
+        if notag[i] and umi[0][0] == sq[0]:
+            st = umi[0][1] - taglen
+        return files[sq[0]][i][st:]
+
+    s1 = [seq_of(i, seq) for i in range(n)]
+    s2 = [seq_of(i, seq2) for i in range(n)] if paired else None
+    # groups of read sets that are pseudoaligned under different rules: (members, strand mode, samples fragment lengths)
+    if tag:
+        groups = [([not x for x in notag], strand, False), (list(notag), 0, True)]
+    else:
+        groups = [([True] * n, strand, True)]
+    frag_set = [None] * n
+    for members, smode, _ in groups:
+        run = OracleRun(index, paired, smode, collect_fld=False)
+        a1 = [s1[i] if members[i] else b"" for i in range(n)]
+        a2 = [s2[i] if members[i] else b"" for i in range(n)] if paired else None
+        bases, off = to_batch(a1, a2)
+        frag = run.pseudoalign(bases, off)
+        eo, et, ecn = run.ec_table()
+        sets = [tuple(int(x) for x in et[int(eo[e]):int(eo[e + 1])]) for e in range(len(eo) - 1)]
+        for i in range(n):
+            if members[i] and frag[i] >= 0:
+                frag_set[i] = sets[frag[i]]
+    ids, ecs = {}, []
+    for i in range(n):              # EC ids in order of first occurrence over the whole input
+        if frag_set[i] is not None and frag_set[i] not in ids:
+            ids[frag_set[i]] = len(ecs)
+            ecs.append(frag_set[i])
     flens = []
     if paired:
         for lo, hi in samples:      # tlencounts[id]: 10 000 samples per sample (:486-493,1397-1400)
-            r = OracleRun(index, True, strand, collect_fld=True)
-            b2, o2 = to_batch(s1[lo:hi], s2[lo:hi])
-            r.pseudoalign(b2, o2)
-            flens.append(r.flens())
+            f = np.zeros(1000, np.uint32)
+            for members, smode, want in groups:
+                if not want:
+                    continue
+                r = OracleRun(index, True, smode, collect_fld=True)
+                b2, o2 = to_batch([s1[i] if members[i] else b"" for i in range(lo, hi)], [s2[i] if members[i] else b"" for i in range(lo, hi)])
+                r.pseudoalign(b2, o2)
+                f += r.flens()
+            flens.append(f)
     dt = np.dtype([("barcode", "<u8"), ("umi", "<u8"), ("ec", "<i4"), ("count", "<u4"), ("flags", "<u4"), ("pad", "<u4")])
-    keep = [i for i in range(n) if frag[i] >= 0]
+    keep = [i for i in range(n) if frag_set[i] is not None]
     rec = np.zeros(len(keep), dt)
     for j, i in enumerate(keep):
-        rec[j] = (rec_bc[i], rec_umi[i], int(frag[i]), 1, rec_fl[i] & 0xFFFFFFFF, 0)
-    sets = [tuple(int(x) for x in et[int(eo[e]):int(eo[e + 1])]) for e in range(len(eo) - 1)]
-    return dict(records=rec, ecs=sets, flens=flens, bc_hist=bc_hist, umi_hist=umi_hist, n_processed=n)
+        rec[j] = (rec_bc[i], rec_umi[i], ids[frag_set[i]], 1, rec_fl[i] & 0xFFFFFFFF, 0)
+    return dict(records=rec, ecs=ecs, flens=flens, bc_hist=bc_hist, umi_hist=umi_hist, n_processed=n)

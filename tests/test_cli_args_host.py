@@ -44,6 +44,9 @@ CASES = [
     ["bus", "-i", IDX, "-o", "o", "-x", "10xv2", "--paired", B1, B2],
     ["bus", "-i", IDX, "-o", "o", "-x", "STORM-seq", R1, R2],          # upper-cased before it is compared: not selectable (src/main.cpp:619,1358)
     ["bus", "-i", IDX, "-o", "o", "-x", "smartseq2", R1, R2],          # three files without --paired
+    ["bus", "-i", IDX, "-o", "o", "-x", "0,0,8:1,0,8:1,22,0", "--tag", "ATTGCGCAATG", B1, B2],   # the UMI location must hold tag + UMI
+    ["bus", "-i", IDX, "-o", "o", "-x", "bulk", "--tag", "ACGTAC", R1],
+    ["bus", "-i", IDX, "-o", "o", "-x", "smartseq3", R1, R2],          # four files
     ["quant", "-i", IDX, "-o", "o", "--single", "-l", "200", "-s", "20"],
     ["quant", "-i", IDX, "-o", "o", "-t", "-2", "--single", "-l", "200", "-s", "20", R1],
 ]

@@ -35,8 +35,10 @@ def ix():
 
 
 def technology(name):
-    bc, umi, seq, seq2, strand, num, per_sample = SPECS[name]
+    bc, umi, seq, seq2, strand, num, per_sample, tag = SPECS[name]
     nfiles = 1 + max([seq[0]] + ([seq2[0]] if seq2 else []) + [b[0] for b in bc] + [u[0] for u in (umi or [])])
+    if tag:          # the library takes the UMI location as the user gives it: tag + UMI (SPECS holds it advanced by the tag)
+        umi = [(umi[0][0], umi[0][1] - len(tag), umi[0][2])] + list(umi[1:])
     t = (nfiles, bc, umi if umi is not None else [(-1, -1, -1)], (seq[0], seq[1], 0), 0)
     if seq2:
         t = t + ((seq2[0], seq2[1], 0),)
@@ -46,9 +48,9 @@ def technology(name):
 @pytest.mark.parametrize("name", sorted(SPECS))
 def test_library_records_ecs_flens_identical_to_reference(inputs, ix, name):
     d, hdr, ref, info, ref_ecs, ref_flens = read_ref(name)
-    bc, umi, seq, seq2, strand, num, per_sample = SPECS[name]
+    bc, umi, seq, seq2, strand, num, per_sample, tag = SPECS[name]
     files, samples = case_files(inputs, name)
-    bp = K.BUSProcessor(ix, technology(name), strand={0: "unstranded", 1: "fr", 2: "rf"}[strand], num=num)
+    bp = K.BUSProcessor(ix, technology(name), strand={0: "unstranded", 1: "fr", 2: "rf"}[strand], num=num, tag=tag)
     parts, flens = [], []
     for si, (lo, hi) in enumerate(samples or [(0, len(files[0]))]):
         if per_sample:

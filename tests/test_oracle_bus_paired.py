@@ -14,21 +14,24 @@ from tests import util
 
 D = os.path.join(util.GOLDEN, "buspaired")
 
-# name -> bus_model arguments: (bc, umi, seq, seq2, strand, num, per-sample)
+# name -> bus_model arguments: (bc, umi, seq, seq2, strand, num, per-sample, tag)
 SPECS = {
-    "bulk_paired": ([], None, (0, 0), (1, 0), 0, False, True),
-    "bulk_paired_num_fr": ([], None, (0, 0), (1, 0), 1, True, True),
-    "bulk_single": ([], None, (0, 0), None, 0, False, True),
-    "smartseq2_paired": ([(0, 0, 0), (1, 0, 0)], None, (2, 0), (3, 0), 0, False, False),
-    "smartseq2_single_rf": ([(0, 0, 0), (1, 0, 0)], None, (2, 0), None, 2, False, False),
-    "stormlike": ([], [(1, 0, 8)], (0, 0), (1, 14), 2, False, False),
+    "bulk_paired": ([], None, (0, 0), (1, 0), 0, False, True, None),
+    "bulk_paired_num_fr": ([], None, (0, 0), (1, 0), 1, True, True, None),
+    "bulk_single": ([], None, (0, 0), None, 0, False, True, None),
+    "smartseq2_paired": ([(0, 0, 0), (1, 0, 0)], None, (2, 0), (3, 0), 0, False, False, None),
+    "smartseq2_single_rf": ([(0, 0, 0), (1, 0, 0)], None, (2, 0), None, 2, False, False, None),
+    "stormlike": ([], [(1, 0, 8)], (0, 0), (1, 14), 2, False, False, None),
+    # UMI tag sequences: the UMI location is the technology's, advanced by the tag's length (src/main.cpp:1467-1468)
+    "smartseq3": ([(0, 0, 0), (1, 0, 0)], [(2, 11, 19)], (2, 22), (3, 0), 1, False, False, util.SMARTSEQ3_TAG),
+    "tag_single_fr": ([(0, 0, 8)], [(1, 11, 19)], (1, 22), None, 1, False, False, util.SMARTSEQ3_TAG),
 }
 
 
 def case_files(inputs, name):
     """-> (files: one list of sequences per file of the technology, sample ranges or None)"""
     keys = util.BUSPAIRED_CASES[name][1]
-    bc, umi, seq, seq2, strand, num, per_sample = SPECS[name]
+    bc, umi, seq, seq2, strand, num, per_sample, tag = SPECS[name]
     nfiles = 1 + max([seq[0]] + ([seq2[0]] if seq2 else []) + [b[0] for b in bc] + [u[0] for u in (umi or [])])
     reads = [O.read_fastq(inputs[k]) for k in keys]
     if not per_sample:
@@ -78,9 +81,9 @@ def oix():
 @pytest.mark.parametrize("name", sorted(SPECS))
 def test_bus_model_reproduces_the_reference(inputs, oix, name):
     d, hdr, ref, info, ref_ecs, ref_flens = read_ref(name)
-    bc, umi, seq, seq2, strand, num, per_sample = SPECS[name]
+    bc, umi, seq, seq2, strand, num, per_sample, tag = SPECS[name]
     files, samples = case_files(inputs, name)
-    m = O.bus_model(oix, files, bc, umi, seq, seq2, strand=strand, num=num, samples=samples)
+    m = O.bus_model(oix, files, bc, umi, seq, seq2, strand=strand, num=num, samples=samples, tag=tag)
     assert m["n_processed"] == info["n_processed"]
     assert len(m["records"]) == info["n_pseudoaligned"] == len(ref)
     assert m["ecs"] == ref_ecs                                   # same sets, same ids (order of first occurrence)

@@ -70,7 +70,10 @@ BUSPAIRED_CASES = {
     "smartseq2_paired": (["-x", "smartseq2", "--paired"], ["i_1", "i_2", "s_1", "s_2"]),
     "smartseq2_single_rf": (["-x", "smartseq2", "--rf-stranded"], ["i_1", "i_2", "s_1"]),
     "stormlike": (["-x", "-1,-1,-1:1,0,8:0,0,0,1,14,0", "--paired", "--rf-stranded"], ["s_1", "u_2"]),
+    "smartseq3": (["-x", "smartseq3"], ["i_1", "i_2", "t_1", "s_2"]),
+    "tag_single_fr": (["-x", "0,0,8:1,0,19:1,22,0", "--tag", "ATTGCGCAATG", "--fr-stranded"], ["i_1", "t_1"]),
 }
+SMARTSEQ3_TAG = b"ATTGCGCAATG"
 
 
 def buspaired_inputs(dst):
@@ -120,4 +123,24 @@ def buspaired_inputs(dst):
     for j in rng.choice(n, 5, replace=False):
         u2[j] = u2[j][:int(rng.integers(1, 8))]
     out["u_2"] = write("u_2", u2)
+    # t_1: first mates of a SMARTSEQ3 run: 40 % UMI reads = tag (11 nt) + UMI (8) + GGG + cDNA, a few of them with one
+    # wrong letter in the tag (still a UMI read: one mismatch is allowed, src/ProcessReads.cpp:1517) or with two Ns (an
+    # internal read then, like the plain 60 %)
+    kinds = rng.random(n)
+    t1 = []
+    for j in range(n):
+        r = s1[j] if isinstance(s1[j], bytes) else s1[j].encode()
+        if kinds[j] < 0.4:
+            tag = bytearray(SMARTSEQ3_TAG)
+            if kinds[j] < 0.05:
+                q = int(rng.integers(0, 11))
+                tag[q] = ord("C") if tag[q] != ord("C") else ord("A")
+            elif kinds[j] < 0.08:
+                for q in rng.choice(11, 2, replace=False):
+                    tag[int(q)] = ord("N")
+            r = bytes(tag) + bytes(A[rng.integers(0, 4, 8)]) + b"GGG" + r
+        t1.append(r)
+    for j in rng.choice(n, 4, replace=False):
+        t1[j] = t1[j][:int(rng.integers(5, 19))]          # shorter than tag + UMI: the set is skipped
+    out["t_1"] = write("t_1", t1)
     return out
