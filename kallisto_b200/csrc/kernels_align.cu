@@ -1106,7 +1106,7 @@ void launch_pseudoalign(const DevIndex& ix, const DevDict& dd, const BatchArgs& 
   if (ev) cudaEventRecord(ev[1], st);
   match_kernel<<<blocks, tpb, smem, st>>>(ix, dd, ba);
   if (ev) cudaEventRecord(ev[2], st);
-  switch (ra.group) {      // lanes per fragment (engine.cu: KB_RESOLVE_G, default 8)
+  switch (ra.group) {      // lanes per fragment (engine.cu: KB_RESOLVE_G, default 32: profiles/resolve_group_sweep_r02.jsonl)
     case 4: resolve_kernel<4><<<(ra.n_warps * 4 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra); break;
     case 8: resolve_kernel<8><<<(ra.n_warps * 8 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra); break;
     case 16: resolve_kernel<16><<<(ra.n_warps * 16 + 127) / 128, 128, 0, st>>>(ix, dd, ba, ra); break;
