@@ -111,7 +111,11 @@ for san in thread address,undefined; do
   KB_CLI_CLEANUP=1 KB_FASTX_WINDOW=30000 KB_CLI_BATCH_READS=700,1100 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o1 --plaintext -t 8 $W/data/r1.fq $W/data/r2.fq > /dev/null 2> $d/e1 || true
   KB_CLI_CLEANUP=1 KB_CLI_BATCH_READS=512,4096 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o2 --plaintext -t 8 tests/golden/synth_small/reads_1.fastq.gz tests/golden/synth_small/reads_2.fastq.gz > /dev/null 2> $d/e2 || true
   KB_CLI_BATCH_READS=300,470 $d/cli bus -i tests/golden/config1/transcripts.kidx -o $d/o3 -x 10xv2 -t 4 tests/golden/bus10x/sc_reads_1.fastq.gz tests/golden/bus10x/sc_reads_2.fastq.gz > /dev/null 2> $d/e3 || true
-  if grep -q -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3; then echo "command line under -fsanitize=$san: report"; grep -h -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3 | head; fail=1; fi
+  # sample-per-file bus run (file-set switching, flens.txt / index.saved / matrix.cells writers) and the HDF5 emitter
+  KB_CLI_CLEANUP=1 KB_CLI_BATCH_READS=700,1100 $d/cli bus -i tests/golden/synth_small/transcripts.kidx -o $d/o4 -x bulk --paired -t 4 $W/data/r1.fq $W/data/r2.fq tests/golden/synth_small/reads_1.fastq.gz tests/golden/synth_small/reads_2.fastq.gz > /dev/null 2> $d/e4 || true
+  KB_CLI_CLEANUP=1 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o5 -b 40 -t 4 $W/data/r1.fq $W/data/r2.fq > /dev/null 2> $d/e5 || true
+  [ -s $d/o4/index.saved ] && [ -s $d/o5/abundance.h5 ] || { echo "bus -x bulk / abundance.h5 outputs missing under -fsanitize=$san"; fail=1; }
+  if grep -q -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3 $d/e4 $d/e5; then echo "command line under -fsanitize=$san: report"; grep -h -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3 $d/e4 $d/e5 | head; fail=1; fi
   cmp -s $d/o1/abundance.tsv $d/o2/abundance.tsv || { echo "plain and gzip input gave different digests"; fail=1; }
 done
 [ $fail = 0 ] && echo "clean"
