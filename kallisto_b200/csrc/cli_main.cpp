@@ -3,6 +3,8 @@
 // command body), with the read pipeline, EC bookkeeping, EM and bootstrap running on the GPU through
 // the C ABI (include/kallisto_b200.h).  Host work here: option parsing, FASTQ parsing, text output.
 #include <getopt.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -799,27 +801,44 @@ bool parse_triplets(const std::string& s, std::vector<kb_bus_substr>& out) {
 // targets followed by the input file's own tail (target lengths, names, on-list), which the reference re-serialises
 // unchanged.  The tail is found by walking the sections of the v13 file.
 void write_index_saved(const std::string& in_path, const std::string& out_path, int k) {
-  std::ifstream in(in_path, std::ios::binary);
-  auto rd64 = [&]() { uint64_t v = 0; in.read((char*)&v, 8); return v; };
+  // the file is mapped and walked by pointer: a human index has ~10^6 node records to step over
+  const int fd = open(in_path.c_str(), O_RDONLY);
+  struct stat sb;
+  const uint8_t* base = nullptr;
+  if (fd >= 0 && fstat(fd, &sb) == 0 && sb.st_size > 0) {
+    void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m != MAP_FAILED) base = (const uint8_t*)m;
+  }
+  if (fd >= 0) close(fd);
+  const uint64_t size = base ? (uint64_t)sb.st_size : 0;
+  uint64_t o = 0;
+  bool ok = base != nullptr;
+  auto rd64 = [&]() -> uint64_t {
+    uint64_t v = 0;
+    if (ok && o + 8 <= size) memcpy(&v, base + o, 8); else ok = false;
+    o += 8;
+    return v;
+  };
+  auto skip = [&](uint64_t n) { if (ok && n <= size - std::min(o, size)) o += n; else ok = false; };
   const uint64_t version = rd64();
-  uint64_t dbg_bytes = rd64();
-  dbg_bytes &= ~(1ull << 63);
-  in.seekg((std::streamoff)dbg_bytes, std::ios::cur);
-  const uint64_t mphf_bytes = rd64();
-  in.seekg((std::streamoff)mphf_bytes, std::ios::cur);
+  const uint64_t dbg_bytes = rd64() & ~(1ull << 63);
+  skip(dbg_bytes);
+  if (dbg_bytes) skip(rd64());      // the MPHF section exists only next to a graph (src/KmerIndex.cpp:1365-1383)
   const uint64_t dlist_n = rd64();
   rd64();      // D-list overhang
-  in.seekg((std::streamoff)(dlist_n * 8), std::ios::cur);
+  skip(dlist_n * 8);
   const uint64_t n_nodes = rd64();
-  for (uint64_t i = 0; i < n_nodes && in; ++i) {
-    in.seekg(k, std::ios::cur);
+  for (uint64_t i = 0; i < n_nodes && ok; ++i) {
+    skip((uint64_t)k);
     uint32_t nb = 0;
-    in.read((char*)&nb, 4);
-    in.seekg(nb, std::ios::cur);
+    if (ok && o + 4 <= size) memcpy(&nb, base + o, 4); else ok = false;
+    o += 4;
+    skip(nb);
   }
   int32_t num_trans = 0;
-  in.read((char*)&num_trans, 4);
-  if (!in || version != 13) {
+  if (ok && o + 4 <= size) memcpy(&num_trans, base + o, 4); else ok = false;
+  o += 4;
+  if (!ok || version != 13) {
     cerr << "Error: could not read " << in_path << " to write index.saved" << endl;
     exit(1);
   }
@@ -828,7 +847,8 @@ void write_index_saved(const std::string& in_path, const std::string& out_path, 
   const uint64_t head[5] = {13, 0, 0, 1, 0};      // version, graph bytes, D-list size, D-list overhang, nodes
   out.write((const char*)head, sizeof(head));
   out.write((const char*)&num_trans, 4);
-  out << in.rdbuf();
+  out.write((const char*)base + o, (std::streamsize)(size - o));
+  munmap((void*)base, (size_t)size);
 }
 
 void usage_bus() {

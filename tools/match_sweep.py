@@ -28,7 +28,7 @@ def main():
     if len(sys.argv) > 1:
         configs = [json.loads(a) for a in sys.argv[1:]]
     for cfg in configs:
-        for k in ("KB_FILTER_LOG2", "KB_L2_PERSIST_MB", "KB_TABLE_FACTOR", "KB_RESOLVE_G"):
+        for k in ("KB_FILTER_LOG2", "KB_L2_PERSIST_MB", "KB_TABLE_FACTOR", "KB_RESOLVE_G", "KB_REFILL_MIN"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         ix = K.KmerIndex(idx, device=0, threads=16)
