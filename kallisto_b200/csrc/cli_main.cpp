@@ -28,6 +28,7 @@
 
 #include "../../include/kallisto_b200.h"
 #include "fastx.hpp"
+#include "h5_reader.hpp"
 #include "h5_writer.hpp"
 
 using std::cerr;
@@ -1511,6 +1512,121 @@ int cmd_quant_tcc(int argc, char** argv) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// kallisto h5dump (src/main.cpp:883-921 ParseOptionsH5Dump, 2027-2072 CheckOptionsH5Dump, 3223-3241; H5Converter,
+// src/H5Writer.cpp:75-200): abundance.h5 -> abundance.tsv, bs_abundance_<b>.tsv, run_info.json.  Host only; the file is
+// read by csrc/h5_reader.hpp.
+// ------------------------------------------------------------------------------------------------
+void usage_h5dump() {
+  std::cout << "kallisto_b200 " << KALLISTO_VERSION << endl
+            << "Converts HDF5-formatted results to plaintext" << endl << endl
+            << "Usage:  kallisto_b200 h5dump [arguments] abundance.h5" << endl << endl
+            << "Required argument:" << endl
+            << "-o, --output-dir=STRING       Directory to write output to" << endl << endl;
+}
+
+int cmd_h5dump(int argc, char** argv) {
+  std::string output;
+  std::vector<std::string> files;
+  int peek_flag = 0;
+  static struct option long_options[] = {{"peek", no_argument, &peek_flag, 1}, {"output-dir", required_argument, 0, 'o'}, {0, 0, 0, 0}};
+  int c, oi = 0;
+  while ((c = getopt_long(argc, argv, "o:", long_options, &oi)) != -1)
+    if (c == 'o') output = optarg;
+  for (int i = optind; i < argc; i++) files.push_back(argv[i]);
+  bool ret = true;
+  struct stat stt;
+  if (!peek_flag) {
+    if (output.empty()) { cerr << "Error: You must specify an output directory." << endl; ret = false; }
+    else if (stat(output.c_str(), &stt) == 0) {
+      if (!S_ISDIR(stt.st_mode)) { cerr << "Error: tried to open " << output << " but another file already exists there" << endl; ret = false; }
+    } else if (mkdir(output.c_str(), 0777) == -1) { cerr << "Error: could not create directory " << output << endl; ret = false; }
+  } else if (!output.empty()) {
+    cerr << "Error: Cannot specify output directory and '--peek'. Please specify only one." << endl;
+    ret = false;
+  }
+  if (files.empty()) { cerr << "Error: Missing H5 files" << endl; ret = false; }
+  else if (files.size() > 1) { cerr << "Error: Please specify only one H5 file" << endl; ret = false; }
+  else if (stat(files[0].c_str(), &stt) != 0) { cerr << "Error: H5 file not found " << files[0] << endl; ret = false; }
+  if (!ret) {
+    usage_h5dump();
+    return 1;
+  }
+  try {
+    kb::H5Reader h5(files[0]);
+    // H5Converter::H5Converter
+    const std::vector<std::string> ids = h5.read_str("/aux/ids");
+    cerr << "[h5dump] number of targets: " << ids.size() << endl;
+    const std::vector<int64_t> lengths = h5.read_int("/aux/lengths");
+    const std::vector<double> eff = h5.read_f64("/aux/eff_lengths");
+    if (lengths.size() != ids.size() || eff.size() != ids.size()) throw std::runtime_error("Error: /aux/ids, /aux/lengths and /aux/eff_lengths differ in size");
+    const int64_t n_bs = h5.read_int("/aux/num_bootstrap").at(0), n_proc = h5.read_int("/aux/num_processed").at(0);
+    cerr << "[h5dump] number of bootstraps: " << n_bs << endl;
+    const std::string version = h5.read_str("/aux/kallisto_version").at(0);
+    cerr << "[h5dump] kallisto version: " << version << endl;
+    const int64_t index_version = h5.read_int("/aux/index_version").at(0);
+    cerr << "[h5dump] index version: " << index_version << endl;
+    const std::string start_time = h5.read_str("/aux/start_time").at(0);
+    cerr << "[h5dump] start time: " << start_time << endl;
+    const std::string call = h5.read_str("/aux/call").at(0);
+    cerr << "[h5dump] shell call: " << call << endl;
+    if (peek_flag) return 0;
+    std::vector<uint32_t> lens(lengths.begin(), lengths.end());
+    // H5Converter::write_aux: the number of pseudoaligned reads is the rounded sum of the estimated counts, the number of
+    // unique reads and the k-mer length are not in the file ("-1", "dummy k-mer length")
+    std::vector<double> alpha = h5.read_f64("/est_counts");
+    if (alpha.size() != ids.size()) throw std::runtime_error("Error: /est_counts and /aux/ids differ in size");
+    double sum = 0.0;
+    for (double x : alpha) sum += x;
+    const int n_paln = (int)std::round(sum);
+    {
+      std::ofstream of(output + "/run_info.json");
+      double p_uniq = 0.0, p_aln = 0.0;
+      if ((double)n_proc > 0) {
+        p_uniq = 100.0 * -1.0 / (double)n_proc;
+        p_aln = 100.0 * (double)n_paln / (double)n_proc;
+      }
+      std::stringstream ss;
+      ss << std::fixed << std::setprecision(1) << p_uniq;
+      const std::string p_uniq_s = ss.str();
+      ss.str("");
+      ss << std::fixed << std::setprecision(1) << p_aln;
+      const std::string p_aln_s = ss.str();
+      of << "{" << std::endl
+         << to_json("n_targets", std::to_string(ids.size()), false) << std::endl
+         << to_json("n_bootstraps", std::to_string(n_bs), false) << std::endl
+         << to_json("n_processed", std::to_string(n_proc), false) << std::endl
+         << to_json("n_pseudoaligned", std::to_string(n_paln), false) << std::endl
+         << to_json("n_unique", "-1", false) << std::endl
+         << to_json("p_pseudoaligned", p_aln_s, false) << std::endl
+         << to_json("p_unique", p_uniq_s, false) << std::endl
+         << to_json("kallisto_version", version, true) << std::endl
+         << to_json("index_version", std::to_string(index_version), false) << std::endl
+         << to_json("k-mer length", "dummy k-mer length", false) << std::endl
+         << to_json("start_time", start_time, true) << std::endl
+         << to_json("call", call, true, false) << std::endl
+         << "}" << std::endl;
+    }
+    // H5Converter::convert
+    cerr << "[h5dump] writing abundance file: " << output << "/abundance.tsv" << endl;
+    write_abundance(output + "/abundance.tsv", ids, lens, eff.data(), alpha.data());
+    if (n_bs > 0) cerr << "[h5dump] writing bootstrap abundance files: " << output << "/bs_abundance_*.tsv" << endl;
+    int64_t i = 0;
+    for (; i < n_bs; ++i) {
+      if (i % 50 == 0 && i > 0) cerr << endl;
+      cerr << ".";
+      alpha = h5.read_f64("/bootstrap/bs" + std::to_string(i));
+      if (alpha.size() != ids.size()) throw std::runtime_error("Error: a bootstrap dataset and /aux/ids differ in size");
+      write_abundance(output + "/bs_abundance_" + std::to_string(i) + ".tsv", ids, lens, eff.data(), alpha.data());
+    }
+    if (i > 0) cerr << endl;
+  } catch (const std::exception& e) {
+    cerr << e.what() << endl;
+    return 1;
+  }
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -1529,6 +1645,8 @@ int main(int argc, char** argv) {
               << "Where <CMD> can be one of:" << endl << endl
               << "    quant         Runs the quantification algorithm (GPU)" << endl
               << "    bus           Generate BUS files for single-cell data (GPU)" << endl
+              << "    quant-tcc     Runs quantification on transcript-compatibility counts (GPU)" << endl
+              << "    h5dump        Converts HDF5-formatted results to plaintext" << endl
               << "    version       Prints version information" << endl << endl
               << "Indices are built with the reference `kallisto index` (format v13)." << endl;
     return 1;
@@ -1558,6 +1676,13 @@ int main(int argc, char** argv) {
       return 0;
     }
     return cmd_quant_tcc(argc - 1, argv + 1);
+  }
+  if (cmd == "h5dump") {
+    if (argc == 2) {
+      usage_h5dump();
+      return 1;
+    }
+    return cmd_h5dump(argc - 1, argv + 1);
   }
   cerr << "Error: invalid command " << cmd << endl;
   return 1;
