@@ -22,8 +22,16 @@ int main(int argc, char** argv) {
   const int aux = w.group("aux");
   w.add_str(aux, "ids", ids);
   w.add_i32(aux, "lengths", len.data(), len.size());
-  const int32_t nb = B;
+  const int32_t nb = B, np = 123456, iv = 13;
   w.add_i32(aux, "num_bootstrap", &nb, 1);
+  w.add_i32(aux, "num_processed", &np, 1);
+  w.add_i32(aux, "index_version", &iv, 1);
+  std::vector<double> eff(n);
+  for (int i = 0; i < n; ++i) eff[i] = len[i] - 150.25;
+  w.add_f64(aux, "eff_lengths", eff.data(), eff.size());
+  w.add_str(aux, "kallisto_version", {"0.51.1"});
+  w.add_str(aux, "call", {"h5_driver " + std::string(argv[2]) + " " + argv[3]});
+  w.add_str(aux, "start_time", {"Thu Jan  1 00:00:00 1970"});
   if (B > 0) {
     const int bs = w.group("bootstrap");
     for (int b = 0; b < B; ++b) {

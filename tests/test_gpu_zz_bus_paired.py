@@ -167,3 +167,9 @@ def test_quant_without_plaintext_writes_abundance_h5(tmp_path):
     g = util.golden_ecs(ds, "paired")
     np.testing.assert_array_equal(h["aux"]["fld"], g["flens"].astype(np.int32))
     assert list(h["aux"]["num_processed"]) == [10000] and list(h["aux"]["num_bootstrap"]) == [3]
+    # ... and back: h5dump turns the file into the reference's own text files, byte for byte (the doubles are all there)
+    dump = tmp_path / "dump"
+    r = subprocess.run([BIN, "h5dump", "-o", str(dump), str(out / "abundance.h5")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    for fn in ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv", "bs_abundance_2.tsv"]:
+        assert open(dump / fn).read() == open(os.path.join(ref, fn)).read(), fn

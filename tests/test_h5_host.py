@@ -77,3 +77,54 @@ def test_quant_writes_abundance_h5_like_an_hdf5_build(tmp_path):
     out3 = tmp_path / "o3"
     r = subprocess.run([exe, "quant", "-i", idx, "-o", str(out3), "--plaintext", "-b", "2"] + files, capture_output=True, text=True, env=env)
     assert r.returncode == 0 and sorted(os.listdir(out3)) == ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv", "run_info.json"]
+
+
+def test_h5dump_round_trip(tmp_path):
+    """`kallisto_b200 h5dump` (H5Converter, src/H5Writer.cpp:75-200) reads the file back with its own reader
+    (csrc/h5_reader.hpp) and writes the plaintext files: after quant -> abundance.h5 -> h5dump, abundance.tsv is the file
+    quant wrote itself, byte for byte (the HDF5 file holds the full doubles; the formatting code is the same), and there is
+    one bs_abundance file per bootstrap; run_info.json carries what the reference's converter can know."""
+    import json
+    exe = build(str(tmp_path / "stub"))
+    ds = os.path.join(util.GOLDEN, "synth_small")
+    files = [os.path.join(ds, "reads_%d.fastq.gz" % m) for m in (1, 2)]
+    env = dict(os.environ, KB_CLI_CLEANUP="1")
+    out = tmp_path / "o"
+    r = subprocess.run([exe, "quant", "-i", os.path.join(ds, "transcripts.kidx"), "-o", str(out), "-b", "5"] + files, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
+    dump = tmp_path / "dump"
+    r = subprocess.run([exe, "h5dump", "-o", str(dump), str(out / "abundance.h5")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert "[h5dump] number of targets: 3" in r.stderr and "[h5dump] number of bootstraps: 5" in r.stderr
+    assert sorted(os.listdir(dump)) == ["abundance.tsv"] + ["bs_abundance_%d.tsv" % b for b in range(5)] + ["run_info.json"]
+    assert open(dump / "abundance.tsv", "rb").read() == open(out / "abundance.tsv", "rb").read()
+    txt = open(dump / "run_info.json").read()
+    assert '"n_unique": -1,' in txt and '"k-mer length": dummy k-mer length,' in txt and '"n_bootstraps": 5,' in txt and '"n_processed": 20000,' in txt
+    assert json.load(open(out / "run_info.json"))["call"] in txt
+    # option checking of the reference (CheckOptionsH5Dump, src/main.cpp:2027-2072)
+    for args, msg in [([str(out / "abundance.h5")], "Error: You must specify an output directory."),
+                      (["-o", str(tmp_path / "d2")], "Error: Missing H5 files"),
+                      (["-o", str(tmp_path / "d3"), "nope.h5"], "Error: H5 file not found nope.h5"),
+                      (["-o", str(tmp_path / "d4"), str(out / "abundance.tsv")], "is not an HDF5 file")]:
+        r = subprocess.run([exe, "h5dump"] + args, capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr[-300:])
+
+
+def test_h5dump_large_file(tmp_path):
+    """5000 targets, 300 bootstraps (a /bootstrap group of 38 symbol table nodes under a B-tree node of raised order)."""
+    drv = str(tmp_path / "h5_driver")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + CSRC, "-o", drv, os.path.join(util.ROOT, "tests", "stub", "h5_driver.cpp"), "-lz"])
+    path = str(tmp_path / "t.h5")
+    subprocess.check_call([drv, path, "5000", "300"])
+    exe = build(str(tmp_path / "stub"))
+    dump = tmp_path / "dump"
+    r = subprocess.run([exe, "h5dump", "-o", str(dump), path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert len(os.listdir(dump)) == 302
+    est = np.array([i * 0.5 + 1.0 / (i + 1) for i in range(5000)])
+    names, lens, eff, got, tpm = util.read_abundance(str(dump / "bs_abundance_299.tsv"))
+    assert names[4999] == "ENST4999%s|gene" % ("x" * (4999 % 40)) and np.array_equal(lens, 200 + 7 * np.arange(5000))
+    np.testing.assert_allclose(got, est * 300, rtol=1e-5)
+    np.testing.assert_allclose(eff, lens - 150.25, rtol=1e-5)
+    x = est * 300 / (lens - 150.25)
+    np.testing.assert_allclose(tpm, x / x.sum() * 1e6, rtol=1e-4)
