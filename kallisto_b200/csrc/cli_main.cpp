@@ -876,12 +876,13 @@ void usage_bus() {
 
 int cmd_bus(int argc, char** argv, const std::string& call, const std::string& start_time) {
   Options opt;
-  std::string technology, tagsequence;
+  std::string technology, tagsequence, batch_file;
   int num_flag = 0, fr = 0, rf = 0, unstranded = 0, verbose_flag = 0, paired_flag = 0;
-  const char* opt_string = "i:o:x:t:nD:T:";
+  const char* opt_string = "i:o:x:t:nD:T:B:";
   static struct option long_options[] = {{"verbose", no_argument, &verbose_flag, 1},
                                          {"paired", no_argument, &paired_flag, 1},
                                          {"tag", required_argument, 0, 'T'},
+                                         {"batch", required_argument, 0, 'B'},
                                          {"num", no_argument, 0, 'n'},
                                          {"fr-stranded", no_argument, &fr, 1},
                                          {"rf-stranded", no_argument, &rf, 1},
@@ -902,6 +903,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
       case 'n': num_flag = 1; break;
       case 'D': std::stringstream(optarg) >> opt.device; break;
       case 'T': std::stringstream(optarg) >> tagsequence; break;
+      case 'B': batch_file = optarg; break;
       default: break;
     }
   }
@@ -913,22 +915,67 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   if (opt.index.empty()) { cerr << ERROR_STR << " kallisto index file missing" << endl; ret = false; }
   else if (stat(opt.index.c_str(), &stt) != 0) { cerr << ERROR_STR << " kallisto index file not found " << opt.index << endl; ret = false; }
   if (opt.threads <= 0) { cerr << "Error: invalid number of threads " << opt.threads << endl; ret = false; }
-  if (opt.files.empty()) { cerr << ERROR_STR << " Missing read files" << endl; ret = false; }
-  for (auto& fn : opt.files)
-    if (stat(fn.c_str(), &stt) != 0) { cerr << ERROR_STR << " file not found " << fn << endl; ret = false; }
+  std::string tech_upper = technology;
+  for (auto& ch : tech_upper) ch = (char)toupper(ch);
+  const bool from_batch_file = !batch_file.empty() && (technology.empty() || tech_upper == "BULK");
+  if (!batch_file.empty() && !from_batch_file) {
+    cerr << "Error: this build reads --batch files only without a technology (-x bulk or no -x)" << endl;
+    ret = false;
+  }
+  std::vector<std::string> sample_names;      // --batch: the ids of the lines (matrix.cells)
+  std::vector<uint64_t> sample_barcode;       // batch_id_mapping: lines with the same id share a barcode (src/ProcessReads.h:211-224)
+  if (from_batch_file) {
+    // src/main.cpp:1108-1180: "id file1 [file2]" per line, '#' lines skipped, the first line decides single / paired
+    cerr << "[bus] will try running read files supplied in batch file" << endl;
+    if (paired_flag) cerr << "[bus] --paired ignored; single/paired-end is inferred from number of files supplied" << endl;
+    if (!opt.files.empty()) { cerr << ERROR_STR << " cannot specify batch mode and supply read files" << endl; ret = false; }
+    else {
+      if (stat(batch_file.c_str(), &stt) != 0) { cerr << ERROR_STR << " file not found " << batch_file << endl; ret = false; }
+      std::ifstream bfile(batch_file);
+      std::string line;
+      bool first = true, single = true;
+      std::vector<std::pair<std::string, uint64_t>> seen;
+      while (std::getline(bfile, line)) {
+        if (line.empty()) continue;
+        std::stringstream ss(line);
+        std::string id, f1, f2;
+        ss >> id;
+        if (id.empty() || id[0] == '#') continue;
+        ss >> f1 >> f2;
+        if (first) { single = f2.empty(); first = false; }
+        sample_names.push_back(id);
+        uint64_t bcv = seen.size();
+        for (auto& pr : seen) if (pr.first == id) bcv = pr.second;
+        if (bcv == seen.size()) seen.push_back({id, bcv});
+        sample_barcode.push_back(bcv);
+        if (stat(f1.c_str(), &stt) != 0) { cerr << ERROR_STR << " file not found " << f1 << endl; ret = false; }
+        opt.files.push_back(f1);
+        if (single) {
+          if (!f2.empty()) { cerr << ERROR_STR << " batch file malformatted" << endl; ret = false; break; }
+        } else {
+          if (f2.empty()) { cerr << ERROR_STR << " batch file malformatted" << endl; ret = false; break; }
+          if (stat(f2.c_str(), &stt) != 0) { cerr << ERROR_STR << " file not found " << f2 << endl; ret = false; }
+          opt.files.push_back(f2);
+        }
+      }
+      paired_flag = single ? 0 : 1;
+    }
+  }
+  if (opt.files.empty() && !from_batch_file) { cerr << ERROR_STR << " Missing read files" << endl; ret = false; }
+  if (!from_batch_file)
+    for (auto& fn : opt.files)
+      if (stat(fn.c_str(), &stt) != 0) { cerr << ERROR_STR << " file not found " << fn << endl; ret = false; }
   kb_bus_opts bo{};
   bo.seq2 = kb_bus_substr{-1, 0, 0};
   int tech_strand = 0;
-  bool batch_mode = false;      // -x BULK: every file (pair) is a sample of its own (src/main.cpp:1050-1107)
-  std::string tech_upper = technology;
-  for (auto& ch : tech_upper) ch = (char)toupper(ch);
-  if (technology.empty()) {
+  bool batch_mode = false;      // -x BULK / --batch: every file (pair) is a sample of its own (src/main.cpp:1050-1214)
+  if (technology.empty() && !from_batch_file) {
     if (ret) cerr << "Error: the technology must be specified via -x, use \"bulk\" for regular RNA-seq reads" << endl;   // src/main.cpp:1058
     ret = false;
-  } else if (tech_upper == "BULK") {
+  } else if (tech_upper == "BULK" || from_batch_file) {
     // batch mode without a technology (:1050-1107, 1190-1214): no barcode read, no UMI, the whole read(s) are the sequence
     batch_mode = true;
-    if (ret && paired_flag && opt.files.size() % 2 != 0) {
+    if (ret && !from_batch_file && paired_flag && opt.files.size() % 2 != 0) {
       cerr << "Error: paired-end mode requires an even number of input files" << endl;
       ret = false;
     }
@@ -1108,7 +1155,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
         // samples its own fragment lengths (src/ProcessReads.cpp:371-404,486-493,1603-1607)
         if (cur_sample != (size_t)-1) KB_TRY(kb_quant_get_flens(q, sample_flens[cur_sample].data()));
         cur_sample = ls.file_set();
-        KB_TRY(kb_bus_begin_sample(q, (uint64_t)cur_sample));
+        KB_TRY(kb_bus_begin_sample(q, sample_barcode.empty() ? (uint64_t)cur_sample : sample_barcode[cur_sample]));
       }
       uint32_t nrec = 0;
       KB_TRY(kb_bus_batch(q, bp, op, (uint32_t)n, recs.data(), &nrec));
@@ -1124,9 +1171,11 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
     // src/main.cpp:2406-2449: sample names, their fake barcodes, the stripped index, one fragment-length line per sample
     std::ofstream cf(opt.output + "/matrix.cells"), bf(opt.output + "/matrix.sample.barcodes");
     for (size_t j = 0; j < n_samples; ++j) {
-      cf << "batch" << j << "\n";
-      std::string b(16, 'A');      // binaryToString(j, 16), src/BUSData.cpp:38-51
-      for (int p = 0; p < 16; ++p) b[15 - p] = "ACGT"[(j >> (2 * p)) & 3];
+      if (sample_names.empty()) cf << "batch" << j << "\n";
+      else cf << sample_names[j] << "\n";
+      const uint64_t v = sample_barcode.empty() ? (uint64_t)j : sample_barcode[j];
+      std::string b(16, 'A');      // binaryToString(v, 16), src/BUSData.cpp:38-51
+      for (int p = 0; p < 16; ++p) b[15 - p] = "ACGT"[(v >> (2 * p)) & 3];
       bf << b << "\n";
     }
   }

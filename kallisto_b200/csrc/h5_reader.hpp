@@ -199,6 +199,8 @@ class H5Reader {
       }
     }
     if (d.cls < 0 || !layout || d.elem == 0 || (d.elem > 8 && d.cls != 3)) throw std::runtime_error("Error: dataset " + path + " cannot be read");
+    // deflate expands at most ~1032 times: a size beyond that cannot come out of this file (damaged header)
+    if (d.n > (b_.size() * 1100ull + 4096) / d.elem) throw std::runtime_error("Error: dataset " + path + " is larger than the file can hold");
     const uint64_t bytes = d.n * d.elem;
     d.raw.assign(bytes, 0);
     if (layout[0] != 3 || layout_size < 3) throw std::runtime_error("Error: HDF5 data layout version " + std::to_string(layout[0]) + " is not supported");

@@ -321,13 +321,14 @@ def hamming(a, b, n):
     return sum(1 for i in range(n) if (df >> (2 * i)) & 3)
 
 
-def bus_model(index, files, bc, umi, seq, seq2=None, strand=0, num=False, samples=None, tag=None):
+def bus_model(index, files, bc, umi, seq, seq2=None, strand=0, num=False, samples=None, tag=None, sample_barcodes=None):
     """Records, EC sets, per-sample fragment-length histograms and barcode / UMI length histograms of `kallisto bus -t 1`.
 
     files: one list of sequences (bytes) per file of the technology; bc / umi: lists of (file, start, stop), bc == []
     = no barcode read (fake barcode: 0, or the sample's number), umi None = no UMI ("bulk_like", :1393); seq / seq2:
     (file, start) of the sequence read(s), seq2 given = busopt.paired; samples: list of (first set, end set) ranges that
-    are samples of their own (`-x BULK`: barcode = sample number, read numbers and fragment-length quota restart);
+    are samples of their own (`-x BULK`: barcode = sample number -- or sample_barcodes[i] for a --batch file whose lines
+    share ids --, read numbers and fragment-length quota restart);
     tag: UMI tag sequence (`--tag`, SMARTSEQ3; umi[0].start already advanced by its length, src/main.cpp:1467-1468): a
     read set whose UMI is preceded by the tag (<= 1 mismatch when the tag is longer than 5) is a UMI read -- strand
     filter on, no fragment-length sampling; any other is an internal read -- UMI ~0, the whole read is sequence, no
@@ -382,7 +383,7 @@ def bus_model(index, files, bc, umi, seq, seq2=None, strand=0, num=False, sample
                 blen = len(bs)
                 bval, bflag = string_to_binary(bs)
             else:
-                blen, bval, bflag = 16, (si if by_sample else 0), 0
+                blen, bval, bflag = 16, ((sample_barcodes[si] if sample_barcodes else si) if by_sample else 0), 0
             if blen <= 32:
                 bc_hist[blen] += 1
             if uflag is None:

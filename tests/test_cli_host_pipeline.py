@@ -151,6 +151,31 @@ def test_bus_bulk_samples_follow_the_file_sets(setup, tmp_path):
     assert r.returncode == 1 and "Error: Paired reads are not compatible with the specified technology" in r.stderr
 
 
+def test_bus_batch_file_host(setup, tmp_path):
+    """`bus --batch FILE` on the host side: sample names and barcodes (lines with the same id share one) as the reference
+    writes them (tests/golden/buspaired/ref_batchfile), the samples switch with the lines, and the reference's messages
+    for a missing batch file / read files next to --batch."""
+    import numpy as np
+    from oracle import oracle as O
+    s = setup
+    inputs = util.buspaired_inputs(str(tmp_path))
+    bf = util.write_batch_file(str(tmp_path / "batch.txt"), inputs)
+    ref = os.path.join(util.GOLDEN, "buspaired", "ref_batchfile")
+    out = tmp_path / "o"
+    r = subprocess.run([s["exe"], "bus", "-i", s["idx"], "-o", str(out), "--batch", bf, "-t", "4"], capture_output=True, text=True,
+                       env=dict(os.environ, KB_CLI_BATCH_READS="900,2000"), timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    for fn in ("matrix.cells", "matrix.sample.barcodes", "index.saved"):
+        assert open(out / fn, "rb").read() == open(os.path.join(ref, fn), "rb").read(), fn
+    _, rec = O.read_bus(str(out / "output.bus"))
+    assert np.array_equal(rec["umi"], np.repeat([0, 1, 0], [12000, 8000, 8000]))       # the stub stamps the sample barcode
+    assert len(open(out / "flens.txt").readlines()) == 3
+    r = subprocess.run([s["exe"], "bus", "-i", s["idx"], "-o", str(tmp_path / "b1"), "--batch", str(tmp_path / "nope.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error: file not found " + str(tmp_path / "nope.txt") in r.stderr
+    r = subprocess.run([s["exe"], "bus", "-i", s["idx"], "-o", str(tmp_path / "b2"), "--batch", bf, inputs["a_1"]], capture_output=True, text=True)
+    assert r.returncode == 1 and "Error: cannot specify batch mode and supply read files" in r.stderr
+
+
 def test_index_saved_of_a_dlist_index_host(setup, tmp_path):
     dl = os.path.join(util.GOLDEN, "dlist")
     out = tmp_path / "o"

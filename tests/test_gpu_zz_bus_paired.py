@@ -103,6 +103,25 @@ def test_command_line_files_identical_to_reference(inputs, name, tmp_path):
         assert ja[k] == jb[k], k
 
 
+def test_batch_file_identical_to_reference(inputs, tmp_path):
+    """`bus --batch FILE`: sample names from the file, lines with the same id share a barcode; every file the reference
+    writes (records as a sorted multiset)."""
+    d, hdr, ref, info, ref_ecs, ref_flens = read_ref("batchfile")
+    out = tmp_path / "o"
+    bf = util.write_batch_file(str(tmp_path / "batch.txt"), inputs)
+    r = subprocess.run([BIN, "bus", "-i", os.path.join(util.GOLDEN, "synth_small", "transcripts.kidx"), "-o", str(out), "-t", "4", "--batch", bf],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    got_hdr, got = O.read_bus(str(out / "output.bus"))
+    assert got_hdr == hdr
+    assert sorted_records(got.copy()).tobytes() == sorted_records(ref).tobytes()
+    for fn in ("matrix.ec", "flens.txt", "index.saved", "matrix.cells", "matrix.sample.barcodes"):
+        assert open(out / fn, "rb").read() == open(os.path.join(d, fn), "rb").read(), fn
+    ja = json.load(open(out / "run_info.json"))
+    for k in ("n_targets", "n_processed", "n_pseudoaligned", "n_unique"):
+        assert ja[k] == info[k], k
+
+
 def test_index_saved_of_a_dlist_index(tmp_path):
     dl = os.path.join(util.GOLDEN, "dlist")
     out = tmp_path / "o"

@@ -101,3 +101,29 @@ def test_bus_model_reproduces_the_reference(inputs, oix, name):
         assert (hdr["bclen"], hdr["umilen"]) == (16, 1)
     else:                                                        # src/main.cpp:2470-2508: most frequent observed lengths
         assert hdr["bclen"] == int(np.argmax(m["bc_hist"])) and hdr["umilen"] == int(np.argmax(m["umi_hist"]))
+
+
+def test_bus_model_batch_file(inputs, oix):
+    """`bus --batch FILE` (src/main.cpp:1108-1180): one sample per line; lines with the same id share the fake barcode
+    (batch_id_mapping, src/ProcessReads.h:211-224) but not the fragment-length histogram."""
+    d, hdr, ref, info, ref_ecs, ref_flens = read_ref("batchfile")
+    lines = [l for l in util.BATCHFILE_LINES if not l[0].startswith("#")]
+    files, samples = [[], []], []
+    for _, k1, k2 in lines:
+        lo = len(files[0])
+        files[0].extend(O.read_fastq(inputs[k1]))
+        files[1].extend(O.read_fastq(inputs[k2]))
+        samples.append((lo, len(files[0])))
+    ids = []
+    for name, _, _ in lines:
+        if name not in ids:
+            ids.append(name)
+    m = O.bus_model(oix, files, [], None, (0, 0), (1, 0), samples=samples, sample_barcodes=[ids.index(l[0]) for l in lines])
+    assert m["n_processed"] == info["n_processed"] and len(m["records"]) == info["n_pseudoaligned"] == len(ref)
+    assert m["ecs"] == ref_ecs
+    assert sorted_records(m["records"]).tobytes() == sorted_records(ref).tobytes()
+    assert len(ref_flens) == 3
+    for a, b in zip(m["flens"], ref_flens):
+        np.testing.assert_array_equal(a, b)
+    assert open(os.path.join(d, "matrix.cells")).read().split() == [l[0] for l in lines]
+    assert (hdr["bclen"], hdr["umilen"]) == (16, 1)

@@ -74,6 +74,16 @@ BUSPAIRED_CASES = {
     "tag_single_fr": (["-x", "0,0,8:1,0,19:1,22,0", "--tag", "ATTGCGCAATG", "--fr-stranded"], ["i_1", "t_1"]),
 }
 SMARTSEQ3_TAG = b"ATTGCGCAATG"
+# `bus --batch FILE` (src/main.cpp:1108-1180): lines "id file1 file2"; lines with the same id share a sample barcode
+BATCHFILE_LINES = [("#id", "file1", "file2"), ("cellA", "a_1", "a_2"), ("cellB", "b_1", "b_2"), ("cellA", "s_1", "s_2")]
+
+
+def write_batch_file(path, inputs):
+    with open(path, "w") as f:
+        for i, k1, k2 in BATCHFILE_LINES:
+            f.write("%s %s %s\n" % (i, inputs.get(k1, k1), inputs.get(k2, k2)))
+        f.write("\n")
+    return path
 
 
 def buspaired_inputs(dst):

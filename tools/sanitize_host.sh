@@ -114,6 +114,19 @@ for san in thread address,undefined; do
   # sample-per-file bus run (file-set switching, flens.txt / index.saved / matrix.cells writers) and the HDF5 emitter
   KB_CLI_CLEANUP=1 KB_CLI_BATCH_READS=700,1100 $d/cli bus -i tests/golden/synth_small/transcripts.kidx -o $d/o4 -x bulk --paired -t 4 $W/data/r1.fq $W/data/r2.fq tests/golden/synth_small/reads_1.fastq.gz tests/golden/synth_small/reads_2.fastq.gz > /dev/null 2> $d/e4 || true
   KB_CLI_CLEANUP=1 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o5 -b 40 -t 4 $W/data/r1.fq $W/data/r2.fq > /dev/null 2> $d/e5 || true
+  # ... and the reader behind h5dump, on the good file and on damaged copies of it
+  $d/cli h5dump -o $d/o6 $d/o5/abundance.h5 > /dev/null 2> $d/e6 || true
+  cmp -s $d/o6/abundance.tsv $d/o5/abundance.tsv || { echo "h5dump does not give abundance.tsv back under -fsanitize=$san"; fail=1; }
+  python - "$d" <<'PY'
+import random, sys
+d = sys.argv[1]; rnd = random.Random(3); good = open(d + '/o5/abundance.h5', 'rb').read()
+for i in range(40):
+    b = bytearray(good[:rnd.randrange(1, len(good))] if i % 4 == 0 else good)
+    for _ in range(rnd.choice((1, 2, 16))): b[rnd.randrange(len(b))] = rnd.randrange(256)
+    open('%s/bad_%d.h5' % (d, i), 'wb').write(bytes(b))
+PY
+  for f in $d/bad_*.h5; do $d/cli h5dump -o $d/o7 $f > /dev/null 2>> $d/e6 || true; done
+  if grep -q -E "Sanitizer|runtime error" $d/e6; then echo "h5dump under -fsanitize=$san: report"; grep -h -E "Sanitizer|runtime error" $d/e6 | head -5; fail=1; fi
   [ -s $d/o4/index.saved ] && [ -s $d/o5/abundance.h5 ] || { echo "bus -x bulk / abundance.h5 outputs missing under -fsanitize=$san"; fail=1; }
   if grep -q -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3 $d/e4 $d/e5; then echo "command line under -fsanitize=$san: report"; grep -h -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3 $d/e4 $d/e5 | head; fail=1; fi
   cmp -s $d/o1/abundance.tsv $d/o2/abundance.tsv || { echo "plain and gzip input gave different digests"; fail=1; }
