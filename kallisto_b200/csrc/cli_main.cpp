@@ -870,6 +870,8 @@ void usage_bus() {
             << "    --paired                  Treat reads as paired (bulk, smartseq2, custom technologies with two" << endl
             << "                              sequence reads)" << endl
             << "    --tag=STRING              5' tag sequence to identify UMI reads for certain technologies" << endl
+            << "    --batch=FILE              Process files listed in FILE (lines: id file1 [file2]), one sample per" << endl
+            << "                              line; without a technology only" << endl
             << "    --fr-stranded / --rf-stranded / --unstranded   Strand specificity" << endl
             << "    --device=INT              CUDA device ordinal (default: 0)" << endl;
 }
