@@ -1143,7 +1143,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   std::vector<std::thread> readers;
   start_streams(streams, readers, opt.files, max_bases, max_reads, opt.threads);
   std::vector<kb_bus_record> recs(max_reads);
-  const size_t n_samples = batch_mode ? opt.files.size() / (size_t)bo.nfiles : 1;
+  const size_t n_samples = batch_mode ? std::max<size_t>(1, opt.files.size() / (size_t)bo.nfiles) : 1;
   std::vector<std::vector<uint32_t>> sample_flens(n_samples, std::vector<uint32_t>(1000, 0));
   size_t cur_sample = (size_t)-1;
   {

@@ -215,6 +215,7 @@ class H5Reader {
       if (layout[2] != 2) throw std::runtime_error("Error: dataset " + path + " is not one-dimensional");
       const uint64_t bt = g64(layout + 3);
       const uint64_t cdim = g32(layout + 11);
+      if (cdim == 0 || cdim > d.n + (1u << 20)) throw std::runtime_error("Error: dataset " + path + " has an implausible chunk size");
       if (bt != kUndef && bytes) read_chunks(bt, cdim, deflate, d, 0);
     } else {
       throw std::runtime_error("Error: unknown HDF5 data layout");
