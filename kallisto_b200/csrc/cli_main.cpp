@@ -39,13 +39,15 @@ namespace {
 const char* KALLISTO_VERSION = "0.51.1";   // the reference version whose behaviour is reproduced
 const char* ERROR_STR = "Error:";   // src/main.cpp:29
 
+void write_index_saved(const std::string& in_path, const std::string& out_path, int k);
+
 struct Options {
   int threads = 1;
   std::string index, output;
   double fld = 0.0, sd = 0.0;
   int bootstrap = 0;
   size_t seed = 42;
-  bool plaintext = false, single_end = false, single_overhang = false, verbose = false;
+  bool plaintext = false, single_end = false, single_overhang = false, verbose = false, write_index = false;
   int strand = 0;   // 0 none, 1 FR, 2 RF
   int device = 0;
   std::vector<int> devices;   // --devices=0,1,...: reads are dealt to several GPUs, merged over NCCL (csrc/comm.cu)
@@ -105,16 +107,18 @@ void usage_quant() {
             << "    --device=INT              CUDA device ordinal (default: 0)" << endl
             << "    --devices=LIST            Comma-separated CUDA devices: batches of reads are dealt to all of them," << endl
             << "                              index replicated, equivalence classes merged over NCCL before the EM" << endl
-            << "    --verbose                 Print out progress information every 1M proccessed reads" << endl << endl
+            << "    --verbose                 Print out progress information every 1M proccessed reads" << endl
+            << "    --write-index             Also write counts.txt (reads per equivalence class) and index.saved" << endl << endl
             << "Limits of this build (a run stops with an error, never with a wrong answer): reads longer than ~12.6 kb," << endl
             << "more than 128 distinct equivalence classes hit by one fragment, more than 16.7 M targets." << endl;
 }
 
 void parse_quant(int argc, char** argv, Options& opt) {
-  int verbose_flag = 0, plaintext_flag = 0, single_flag = 0, single_overhang_flag = 0, fr = 0, rf = 0;
+  int verbose_flag = 0, plaintext_flag = 0, single_flag = 0, single_overhang_flag = 0, fr = 0, rf = 0, write_index_flag = 0;
   const char* opt_string = "t:i:l:s:o:b:d:D:";
   static struct option long_options[] = {
       {"verbose", no_argument, &verbose_flag, 1},
+      {"write-index", no_argument, &write_index_flag, 1},
       {"plaintext", no_argument, &plaintext_flag, 1},
       {"single", no_argument, &single_flag, 1},
       {"single-overhang", no_argument, &single_overhang_flag, 1},
@@ -158,6 +162,7 @@ void parse_quant(int argc, char** argv, Options& opt) {
   if (!opt.devices.empty()) opt.device = opt.devices[0];
   opt.verbose = verbose_flag;
   opt.plaintext = plaintext_flag;
+  opt.write_index = write_index_flag;
   opt.single_end = single_flag;
   opt.single_overhang = single_overhang_flag;
   if (fr) opt.strand = 1;
@@ -639,6 +644,19 @@ int cmd_quant(int argc, char** argv, const std::string& call, const std::string&
     pt.mark("merge (peer copies)");
   }
   cerr << " done" << endl;
+  if (opt.write_index) {
+    // --write-index: counts.txt = "id <tab> count" per equivalence class in id order (MinCollector::write,
+    // src/MinCollector.h:74-78, src/ProcessReads.cpp:242-249) and the stripped index (src/main.cpp:2658-2661)
+    kb_run_stats s0{};
+    KB_TRY(kb_quant_finalize(q, &s0));
+    std::vector<uint64_t> eo(s0.n_ecs + 1);
+    std::vector<uint32_t> et(std::max<uint64_t>(1, s0.n_ec_entries)), ec(std::max<uint64_t>(1, s0.n_ecs));
+    KB_TRY(kb_quant_ec_table(q, eo.data(), et.data(), ec.data(), nullptr));
+    std::ofstream cf(opt.output + "/counts.txt");
+    for (uint64_t i = 0; i < s0.n_ecs; ++i) cf << i << "\t" << ec[i] << "\n";
+    cf.close();
+    write_index_saved(opt.index, opt.output + "/index.saved", info.k);
+  }
 
   const uint32_t T = info.n_targets;
   std::vector<double> est(T), eff(T);

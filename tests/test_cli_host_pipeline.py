@@ -151,6 +151,21 @@ def test_bus_bulk_samples_follow_the_file_sets(setup, tmp_path):
     assert r.returncode == 1 and "Error: Paired reads are not compatible with the specified technology" in r.stderr
 
 
+def test_quant_write_index_host(setup, tmp_path):
+    """`quant --write-index` (src/ProcessReads.cpp:242-249, src/main.cpp:2658-2661): counts.txt and index.saved next to the
+    usual files; index.saved equals the reference's (tests/golden/config1/ref_quant_paired), counts.txt has one
+    "id <tab> count" line per equivalence class (the stub reports one class)."""
+    d = os.path.join(util.GOLDEN, "config1")
+    out = tmp_path / "o"
+    r = subprocess.run([setup["exe"], "quant", "-i", os.path.join(d, "transcripts.kidx"), "-o", str(out), "--plaintext", "--write-index",
+                        os.path.join(d, "reads_1.fastq.gz"), os.path.join(d, "reads_2.fastq.gz")], capture_output=True, text=True,
+                       env=dict(os.environ, KB_CLI_CLEANUP="1"), timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert sorted(os.listdir(out)) == ["abundance.tsv", "counts.txt", "index.saved", "run_info.json"]
+    assert open(out / "index.saved", "rb").read() == open(os.path.join(d, "ref_quant_paired", "index.saved"), "rb").read()
+    assert open(out / "counts.txt").read() == "0\t1\n"
+
+
 def test_bus_batch_file_host(setup, tmp_path):
     """`bus --batch FILE` on the host side: sample names and barcodes (lines with the same id share one) as the reference
     writes them (tests/golden/buspaired/ref_batchfile), the samples switch with the lines, and the reference's messages

@@ -192,3 +192,16 @@ def test_quant_without_plaintext_writes_abundance_h5(tmp_path):
     assert r.returncode == 0, r.stderr[-1000:]
     for fn in ["abundance.tsv", "bs_abundance_0.tsv", "bs_abundance_1.tsv", "bs_abundance_2.tsv"]:
         assert open(dump / fn).read() == open(os.path.join(ref, fn)).read(), fn
+
+
+def test_quant_write_index(tmp_path):
+    """`quant --write-index`: counts.txt (reads per equivalence class, ids of first occurrence = the reference's with -t 1)
+    and index.saved identical to the reference's files (tests/golden/config1/ref_quant_paired)."""
+    ds = util.dataset("config1")
+    out = tmp_path / "o"
+    r = subprocess.run([BIN, "quant", "-i", ds["index"], "-o", str(out), "--plaintext", "--write-index", os.path.join(ds["dir"], "reads_1.fastq.gz"),
+                        os.path.join(ds["dir"], "reads_2.fastq.gz")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-1000:]
+    ref = os.path.join(ds["dir"], "ref_quant_paired")
+    for fn in ("counts.txt", "index.saved", "abundance.tsv"):
+        assert open(out / fn, "rb").read() == open(os.path.join(ref, fn), "rb").read(), fn
