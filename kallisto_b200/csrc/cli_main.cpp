@@ -380,6 +380,93 @@ void reader_thread(std::vector<std::string> files, Stream* s, size_t max_reads, 
   s->cv.notify_all();
 }
 
+// `bus --inleaved` (src/main.cpp:583,739-741,1000-1012): ONE file holds the reads of a set one after the other (file 0's
+// read, file 1's read, ...).  One parser thread reads it and deals record j to stream j % n_streams, so the consumer sees
+// the same per-file streams as with separate files.  A trailing incomplete set is dropped.
+void interleaved_reader_thread(std::string file, std::vector<Stream>* streams, size_t max_reads, int parse_threads) {
+  const size_t nf = streams->size();
+  std::string error;
+  try {
+    for (auto& s : *streams)
+      for (auto& b : s.ring) {
+        b.bases = (char*)kb_host_alloc(b.cap_bases + 64);
+        b.off = (uint32_t*)kb_host_alloc((b.cap_reads + 1) * sizeof(uint32_t));
+        if (!b.bases || !b.off) throw std::runtime_error("Error: could not allocate pinned host memory");
+        b.clear();
+      }
+    kb::ReadBatch tmp;
+    tmp.cap_reads = max_reads * nf;
+    tmp.cap_bases = (*streams)[0].ring[0].cap_bases;
+    std::vector<char> tb(tmp.cap_bases + 64);
+    std::vector<uint32_t> to(tmp.cap_reads + 1);
+    tmp.bases = tb.data();
+    tmp.off = to.data();
+    tmp.clear();
+    kb::FastxReader f(file, parse_threads);
+    size_t slot = 0;
+    bool more = true;
+    while (more) {
+      more = f.fill(tmp, max_reads * nf);                      // appends to what was carried over
+      const size_t n_sets = tmp.n / nf;
+      if (n_sets) {
+        for (size_t s = 0; s < nf; ++s) {
+          Stream& st = (*streams)[s];
+          {
+            std::unique_lock<std::mutex> lk(st.m);
+            st.cv.wait(lk, [&] { return st.state[slot] == 0; });
+          }
+          kb::ReadBatch& b = st.ring[slot];
+          b.clear();
+          for (size_t i = 0; i < n_sets; ++i) {
+            const size_t r = i * nf + s;
+            const uint32_t len = tmp.off[r + 1] - tmp.off[r];
+            memcpy(b.bases + b.off[b.n], tmp.bases + tmp.off[r], len);
+            b.off[b.n + 1] = b.off[b.n] + len;
+            b.max_len = std::max(b.max_len, len);
+            ++b.n;
+          }
+          {
+            std::lock_guard<std::mutex> lk(st.m);
+            st.state[slot] = 1;
+          }
+          st.cv.notify_all();
+        }
+        slot = (slot + 1) % (*streams)[0].ring.size();
+      }
+      // reads of an incomplete set stay for the next round
+      const size_t used = n_sets * nf, rest = tmp.n - used;
+      const uint32_t base = tmp.off[used];
+      memmove(tmp.bases, tmp.bases + base, tmp.off[tmp.n] - base);
+      for (size_t i = 0; i <= rest; ++i) tmp.off[i] = tmp.off[used + i] - base;
+      tmp.n = rest;
+    }
+    for (size_t s = 0; s < nf; ++s) {                          // the end-of-file marker of every stream
+      Stream& st = (*streams)[s];
+      {
+        std::unique_lock<std::mutex> lk(st.m);
+        st.cv.wait(lk, [&] { return st.state[slot] == 0; });
+      }
+      st.ring[slot].clear();
+      st.ring[slot].eof = true;
+      {
+        std::lock_guard<std::mutex> lk(st.m);
+        st.state[slot] = 1;
+      }
+      st.cv.notify_all();
+    }
+  } catch (const std::exception& e) {
+    error = e.what();
+  }
+  for (auto& st : *streams) {
+    {
+      std::lock_guard<std::mutex> lk(st.m);
+      if (!error.empty()) st.error = error;
+      st.done = true;
+    }
+    st.cv.notify_all();
+  }
+}
+
 // Reads per batch of stream s.  KB_CLI_BATCH_READS="a,b,..." (tests) gives the streams different batch sizes, the
 // situation that otherwise only arises when one file's batches fill up by bytes before they fill up by reads.
 size_t stream_batch_reads(int s, size_t dflt) {
@@ -887,6 +974,7 @@ void usage_bus() {
             << "-n, --num                     Output number of read in flag column" << endl
             << "    --paired                  Treat reads as paired (bulk, smartseq2, custom technologies with two" << endl
             << "                              sequence reads)" << endl
+            << "    --inleaved                Specifies that input is an interleaved FASTQ file" << endl
             << "    --tag=STRING              5' tag sequence to identify UMI reads for certain technologies" << endl
             << "    --batch=FILE              Process files listed in FILE (lines: id file1 [file2]), one sample per" << endl
             << "                              line; without a technology only" << endl
@@ -897,10 +985,11 @@ void usage_bus() {
 int cmd_bus(int argc, char** argv, const std::string& call, const std::string& start_time) {
   Options opt;
   std::string technology, tagsequence, batch_file;
-  int num_flag = 0, fr = 0, rf = 0, unstranded = 0, verbose_flag = 0, paired_flag = 0;
+  int num_flag = 0, fr = 0, rf = 0, unstranded = 0, verbose_flag = 0, paired_flag = 0, interleaved_flag = 0;
   const char* opt_string = "i:o:x:t:nD:T:B:";
   static struct option long_options[] = {{"verbose", no_argument, &verbose_flag, 1},
                                          {"paired", no_argument, &paired_flag, 1},
+                                         {"inleaved", no_argument, &interleaved_flag, 1},
                                          {"tag", required_argument, 0, 'T'},
                                          {"batch", required_argument, 0, 'B'},
                                          {"num", no_argument, 0, 'n'},
@@ -935,6 +1024,10 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   if (opt.index.empty()) { cerr << ERROR_STR << " kallisto index file missing" << endl; ret = false; }
   else if (stat(opt.index.c_str(), &stt) != 0) { cerr << ERROR_STR << " kallisto index file not found " << opt.index << endl; ret = false; }
   if (opt.threads <= 0) { cerr << "Error: invalid number of threads " << opt.threads << endl; ret = false; }
+  if (interleaved_flag) {      // src/main.cpp:1000-1012
+    if (opt.files.size() > 1) { cerr << ERROR_STR << " interleaved input cannot consist of more than one input" << endl; ret = false; }
+    if (!batch_file.empty()) { cerr << ERROR_STR << " interleaved input cannot be specified with a batch file" << endl; ret = false; }
+  }
   std::string tech_upper = technology;
   for (auto& ch : tech_upper) ch = (char)toupper(ch);
   const bool from_batch_file = !batch_file.empty() && (technology.empty() || tech_upper == "BULK");
@@ -995,7 +1088,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   } else if (tech_upper == "BULK" || from_batch_file) {
     // batch mode without a technology (:1050-1107, 1190-1214): no barcode read, no UMI, the whole read(s) are the sequence
     batch_mode = true;
-    if (ret && !from_batch_file && paired_flag && opt.files.size() % 2 != 0) {
+    if (ret && !from_batch_file && paired_flag && opt.files.size() % 2 != 0 && !interleaved_flag) {
       cerr << "Error: paired-end mode requires an even number of input files" << endl;
       ret = false;
     }
@@ -1080,7 +1173,7 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
       ret = false;
     }
   }
-  if (ret && opt.files.size() % bo.nfiles != 0) {
+  if (ret && !interleaved_flag && opt.files.size() % bo.nfiles != 0) {
     cerr << "Error: Number of files (" << opt.files.size() << ") does not match number of input files required by "
          << "technology " << tech_upper << " (" << bo.nfiles << ")" << endl;
     ret = false;
@@ -1159,9 +1252,19 @@ int cmd_bus(int argc, char** argv, const std::string& call, const std::string& s
   const int n_streams = bo.nfiles;
   std::vector<Stream> streams(n_streams);
   std::vector<std::thread> readers;
-  start_streams(streams, readers, opt.files, max_bases, max_reads, opt.threads);
+  if (interleaved_flag) {
+    for (auto& st : streams) {
+      st.ring.resize(3);
+      st.state.assign(3, 0);
+      for (auto& b : st.ring) { b.cap_bases = max_bases; b.cap_reads = max_reads; }
+    }
+    const size_t per_stream = std::max<size_t>(1, stream_batch_reads(0, max_reads / (size_t)n_streams));
+    readers.emplace_back(interleaved_reader_thread, opt.files[0], &streams, per_stream, std::max(1, opt.threads));
+  } else {
+    start_streams(streams, readers, opt.files, max_bases, max_reads, opt.threads);
+  }
   std::vector<kb_bus_record> recs(max_reads);
-  const size_t n_samples = batch_mode ? std::max<size_t>(1, opt.files.size() / (size_t)bo.nfiles) : 1;
+  const size_t n_samples = (batch_mode && !interleaved_flag) ? std::max<size_t>(1, opt.files.size() / (size_t)bo.nfiles) : 1;
   std::vector<std::vector<uint32_t>> sample_flens(n_samples, std::vector<uint32_t>(1000, 0));
   size_t cur_sample = (size_t)-1;
   {

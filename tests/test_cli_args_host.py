@@ -47,6 +47,7 @@ CASES = [
     ["bus", "-i", IDX, "-o", "o", "-x", "0,0,8:1,0,8:1,22,0", "--tag", "ATTGCGCAATG", B1, B2],   # the UMI location must hold tag + UMI
     ["bus", "-i", IDX, "-o", "o", "-x", "bulk", "--tag", "ACGTAC", R1],
     ["bus", "-i", IDX, "-o", "o", "-x", "smartseq3", R1, R2],          # four files
+    ["bus", "-i", IDX, "-o", "o", "-x", "10xv2", "--inleaved", B1, B2],
     ["bus", "-i", IDX, "-o", "o", "--batch", "nope.txt"],
     ["bus", "-i", IDX, "-o", "o", "--batch", IDX, R1],                 # read files next to a batch file
     ["quant", "-i", IDX, "-o", "o", "--single", "-l", "200", "-s", "20"],

@@ -151,6 +151,35 @@ def test_bus_bulk_samples_follow_the_file_sets(setup, tmp_path):
     assert r.returncode == 1 and "Error: Paired reads are not compatible with the specified technology" in r.stderr
 
 
+def test_bus_interleaved_input(setup, tmp_path):
+    """`bus --inleaved` (src/main.cpp:583,739-741,1000-1012): one file with the reads of every set one after the other gives
+    the device exactly the read sets of the separate files, whatever the batch cuts; an incomplete last set is dropped."""
+    s = setup
+    d = os.path.join(util.GOLDEN, "bus10x")
+    files = [os.path.join(d, "sc_reads_1.fastq.gz"), os.path.join(d, "sc_reads_2.fastq.gz")]
+    idx = os.path.join(util.GOLDEN, "config1", "transcripts.kidx")
+    a, b = (gzip.open(f, "rb").read().split(b"\n") for f in files)
+    n = len(a) // 4
+    il = tmp_path / "il.fq"
+    with open(il, "wb") as f:
+        for i in range(n):
+            f.write(b"\n".join(a[4 * i:4 * i + 4]) + b"\n" + b"\n".join(b[4 * i:4 * i + 4]) + b"\n")
+        f.write(b"\n".join(a[:4]) + b"\n")                     # a first mate without its second: dropped
+    def run(args, env=None):
+        e = dict(os.environ, KB_CLI_CLEANUP="1")
+        e.update(env or {})
+        out = tmp_path / ("o%d" % len(os.listdir(tmp_path)))
+        r = subprocess.run([s["exe"], "bus", "-i", idx, "-o", str(out), "-x", "10xv2"] + args, capture_output=True, text=True, env=e, timeout=600)
+        assert r.returncode == 0, r.stderr[-500:]
+        return open(out / "output.bus", "rb").read()
+    want = run(["-t", "2"] + files)
+    assert run(["-t", "4", "--inleaved", str(il)]) == want
+    assert run(["-t", "1", "--inleaved", str(il)], {"KB_CLI_BATCH_READS": "333"}) == want
+    assert run(["-t", "8", "--inleaved", str(il)], {"KB_CLI_BATCH_READS": "1", "KB_FASTX_WINDOW": "5000"}) == want
+    r = subprocess.run([s["exe"], "bus", "-i", idx, "-o", str(tmp_path / "bad"), "-x", "10xv2", "--inleaved"] + files, capture_output=True, text=True)
+    assert r.returncode == 1 and "Error: interleaved input cannot consist of more than one input" in r.stderr
+
+
 def test_quant_write_index_host(setup, tmp_path):
     """`quant --write-index` (src/ProcessReads.cpp:242-249, src/main.cpp:2658-2661): counts.txt and index.saved next to the
     usual files; index.saved equals the reference's (tests/golden/config1/ref_quant_paired), counts.txt has one

@@ -111,6 +111,9 @@ for san in thread address,undefined; do
   KB_CLI_CLEANUP=1 KB_FASTX_WINDOW=30000 KB_CLI_BATCH_READS=700,1100 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o1 --plaintext -t 8 $W/data/r1.fq $W/data/r2.fq > /dev/null 2> $d/e1 || true
   KB_CLI_CLEANUP=1 KB_CLI_BATCH_READS=512,4096 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o2 --plaintext -t 8 tests/golden/synth_small/reads_1.fastq.gz tests/golden/synth_small/reads_2.fastq.gz > /dev/null 2> $d/e2 || true
   KB_CLI_BATCH_READS=300,470 $d/cli bus -i tests/golden/config1/transcripts.kidx -o $d/o3 -x 10xv2 -t 4 tests/golden/bus10x/sc_reads_1.fastq.gz tests/golden/bus10x/sc_reads_2.fastq.gz > /dev/null 2> $d/e3 || true
+  python -c "import gzip,sys; a,b=[gzip.open('tests/golden/bus10x/sc_reads_%d.fastq.gz'%m,'rb').read().split(b'\\n') for m in (1,2)]; open(sys.argv[1],'wb').write(b''.join(b'\\n'.join(x[4*i:4*i+4])+b'\\n' for i in range(len(a)//4) for x in (a,b)))" $d/il.fq
+  KB_CLI_CLEANUP=1 KB_CLI_BATCH_READS=333 $d/cli bus -i tests/golden/config1/transcripts.kidx -o $d/o3b -x 10xv2 -t 4 --inleaved $d/il.fq > /dev/null 2>> $d/e3 || true
+  cmp -s $d/o3/output.bus $d/o3b/output.bus || { echo "interleaved input gave other records under -fsanitize=$san"; fail=1; }
   # sample-per-file bus run (file-set switching, flens.txt / index.saved / matrix.cells writers) and the HDF5 emitter
   KB_CLI_CLEANUP=1 KB_CLI_BATCH_READS=700,1100 $d/cli bus -i tests/golden/synth_small/transcripts.kidx -o $d/o4 -x bulk --paired -t 4 $W/data/r1.fq $W/data/r2.fq tests/golden/synth_small/reads_1.fastq.gz tests/golden/synth_small/reads_2.fastq.gz > /dev/null 2> $d/e4 || true
   KB_CLI_CLEANUP=1 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o5 -b 40 -t 4 $W/data/r1.fq $W/data/r2.fq > /dev/null 2> $d/e5 || true
