@@ -205,3 +205,20 @@ def test_quant_write_index(tmp_path):
     ref = os.path.join(ds["dir"], "ref_quant_paired")
     for fn in ("counts.txt", "index.saved", "abundance.tsv"):
         assert open(out / fn, "rb").read() == open(os.path.join(ref, fn), "rb").read(), fn
+
+
+def test_bus_interleaved_input(tmp_path):
+    """`bus --inleaved`: one interleaved FASTQ file instead of the two of 10x v2 -> the reference's output.bus, byte for byte."""
+    import gzip
+    d = os.path.join(util.GOLDEN, "bus10x")
+    a, b = (gzip.open(os.path.join(d, "sc_reads_%d.fastq.gz" % m), "rb").read().split(b"\n") for m in (1, 2))
+    il = tmp_path / "il.fq"
+    with open(il, "wb") as f:
+        for i in range(len(a) // 4):
+            f.write(b"\n".join(a[4 * i:4 * i + 4]) + b"\n" + b"\n".join(b[4 * i:4 * i + 4]) + b"\n")
+    out = tmp_path / "o"
+    r = subprocess.run([BIN, "bus", "-i", os.path.join(util.GOLDEN, "config1", "transcripts.kidx"), "-o", str(out), "-x", "10xv2", "-t", "4",
+                        "--inleaved", str(il)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    for fn in ("output.bus", "matrix.ec"):
+        assert open(out / fn, "rb").read() == open(os.path.join(d, "ref_10xv2", fn), "rb").read(), fn
