@@ -19,7 +19,7 @@ pytestmark = pytest.mark.skipif(not shutil.which("g++"), reason="no g++")
 @pytest.mark.parametrize("n,B", [(1, 0), (1000, 3), (5000, 300)])
 def test_writer_round_trip(tmp_path, n, B):
     exe = str(tmp_path / "h5_driver")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + CSRC, "-o", exe, os.path.join(util.ROOT, "tests", "stub", "h5_driver.cpp"), "-lz"])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + CSRC, "-o", exe, os.path.join(util.ROOT, "tests", "stub", "h5_driver.cpp"), "-lz", "-pthread"])
     path = str(tmp_path / "t.h5")
     subprocess.check_call([exe, path, str(n), str(B)])
     f = h5mini.File(path)
@@ -113,7 +113,7 @@ def test_h5dump_round_trip(tmp_path):
 def test_h5dump_large_file(tmp_path):
     """5000 targets, 300 bootstraps (a /bootstrap group of 38 symbol table nodes under a B-tree node of raised order)."""
     drv = str(tmp_path / "h5_driver")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + CSRC, "-o", drv, os.path.join(util.ROOT, "tests", "stub", "h5_driver.cpp"), "-lz"])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + CSRC, "-o", drv, os.path.join(util.ROOT, "tests", "stub", "h5_driver.cpp"), "-lz", "-pthread"])
     path = str(tmp_path / "t.h5")
     subprocess.check_call([drv, path, "5000", "300"])
     exe = build(str(tmp_path / "stub"))
@@ -135,7 +135,7 @@ def test_h5dump_never_crashes_on_damaged_files(tmp_path):
     padding, with a normal conversion -- never with a signal or a hang (csrc/h5_reader.hpp bounds every address)."""
     import random
     drv = str(tmp_path / "h5_driver")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + CSRC, "-o", drv, os.path.join(util.ROOT, "tests", "stub", "h5_driver.cpp"), "-lz"])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + CSRC, "-o", drv, os.path.join(util.ROOT, "tests", "stub", "h5_driver.cpp"), "-lz", "-pthread"])
     path = str(tmp_path / "t.h5")
     subprocess.check_call([drv, path, "200", "20"])
     good = open(path, "rb").read()
