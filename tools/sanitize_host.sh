@@ -130,6 +130,9 @@ for i in range(40):
 PY
   for f in $d/bad_*.h5; do $d/cli h5dump -o $d/o7 $f > /dev/null 2>> $d/e6 || true; done
   if grep -q -E "Sanitizer|runtime error" $d/e6; then echo "h5dump under -fsanitize=$san: report"; grep -h -E "Sanitizer|runtime error" $d/e6 | head -5; fail=1; fi
+  # bootstrap text files are written by several threads
+  KB_CLI_CLEANUP=1 $d/cli quant -i tests/golden/synth_small/transcripts.kidx -o $d/o8 --plaintext -b 9 -t 4 $W/data/r1.fq $W/data/r2.fq > /dev/null 2>> $d/e5 || true
+  [ -s $d/o8/bs_abundance_8.tsv ] || { echo "bootstrap text files missing under -fsanitize=$san"; fail=1; }
   [ -s $d/o4/index.saved ] && [ -s $d/o5/abundance.h5 ] || { echo "bus -x bulk / abundance.h5 outputs missing under -fsanitize=$san"; fail=1; }
   if grep -q -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3 $d/e4 $d/e5; then echo "command line under -fsanitize=$san: report"; grep -h -E "Sanitizer|runtime error" $d/e1 $d/e2 $d/e3 $d/e4 $d/e5 | head; fail=1; fi
   cmp -s $d/o1/abundance.tsv $d/o2/abundance.tsv || { echo "plain and gzip input gave different digests"; fail=1; }
