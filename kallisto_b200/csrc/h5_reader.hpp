@@ -129,7 +129,7 @@ class H5Reader {
     return out;
   }
   void walk_group_tree(uint64_t addr, const char* names, uint64_t hsize, std::map<std::string, uint64_t>& out, int depth) const {
-    if (depth > 16) throw std::runtime_error("Error: HDF5 group B-tree too deep");
+    if (depth > 16 || ++visits_ > 4000000) throw std::runtime_error("Error: HDF5 group B-tree too deep or cyclic");
     const uint8_t* n = at(addr, 24);
     if (memcmp(n, "TREE", 4) == 0) {
       if (n[4] != 0) throw std::runtime_error("Error: HDF5 group B-tree node expected");
@@ -223,7 +223,7 @@ class H5Reader {
     return d;
   }
   void read_chunks(uint64_t addr, uint64_t cdim, bool deflate, Data& d, int depth) const {
-    if (depth > 16) throw std::runtime_error("Error: HDF5 chunk B-tree too deep");
+    if (depth > 16 || ++visits_ > 4000000) throw std::runtime_error("Error: HDF5 chunk B-tree too deep or cyclic");
     const uint8_t* n = at(addr, 24);
     if (memcmp(n, "TREE", 4) != 0 || n[4] != 1) throw std::runtime_error("Error: HDF5 chunk B-tree node expected");
     const unsigned level = n[5], used = g16(n + 6);
@@ -252,6 +252,7 @@ class H5Reader {
 
   std::vector<uint8_t> b_;
   uint64_t base_ = 0, root_header_ = 0;
+  mutable uint64_t visits_ = 0;      // B-tree nodes visited: a damaged file may point a node at itself
   std::map<uint64_t, std::map<std::string, uint64_t>> cache_;
 };
 

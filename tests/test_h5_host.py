@@ -147,6 +147,17 @@ def test_h5dump_never_crashes_on_damaged_files(tmp_path):
         for _ in range(rnd.choice((1, 1, 2, 8, 64))):
             b[rnd.randrange(len(b))] = rnd.randrange(256)
         cases.append(bytes(b))
+    # a group B-tree node whose children all point back at the node itself: bounded, not exponential
+    import re
+    import struct
+    b = bytearray(good)
+    for m in re.finditer(b"TREE\x00\x00", good):
+        if struct.unpack_from("<H", b, m.start() + 6)[0] >= 2:
+            for i in range(30):
+                struct.pack_into("<Q", b, m.start() + 32 + 16 * i, m.start())
+            struct.pack_into("<H", b, m.start() + 6, 30)
+            break
+    cases.append(bytes(b))
     n_err = 0
     for i, data in enumerate(cases):
         p = tmp_path / "bad.h5"
